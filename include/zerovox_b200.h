@@ -1,0 +1,144 @@
+/*
+ * zerovox_b200 — C ABI of the B200-native ZeroVOX inference engine (libzerovox_b200.so).
+ *
+ * The reference (gooofy/zerovox @ 56a4316) has no FFI: its boundary is the Python module API
+ * of zerovox/tts/model.py and its sub-modules.  Each entry point below replaces the eval-mode
+ * forward of one of those modules; the Python shims in zerovox_b200/tts/ keep the reference
+ * signatures and state_dict keys and call these symbols through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every tensor pointer is a DEVICE pointer on the handle's device unless it says "host";
+ *     all memory is caller-owned, fp32 row-major contiguous unless stated;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); work is enqueued on it
+ *     and the call returns without synchronising, except where stated;
+ *   - return 0 on success, non-zero on error; the message is available from zvx_last_error().
+ *     No C++ exception ever crosses the ABI;
+ *   - a handle is bound to one device and is not thread-safe (the reference is single-threaded).
+ *   - there is no CPU path: every entry point fails if no CUDA device is usable.
+ */
+#ifndef ZEROVOX_B200_H
+#define ZEROVOX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZVX_MAX_UPSAMPLES 8
+#define ZVX_MAX_RESBLOCK_KERNELS 8
+#define ZVX_MAX_DILATIONS 4
+
+#define ZVX_ABI_VERSION 1
+
+typedef struct zvx_handle zvx_handle;
+
+/* Hyper-parameters: ZeroVox.__init__ kwargs (zerovox/tts/model.py:159-201; values from
+ * configs/tts_medium.yaml:16-51) plus the HiFi-GAN config.json fields read by
+ * Generator.__init__ (zerovox/tts/hifigan.py:93-110). */
+typedef struct zvx_config {
+    int32_t abi_version;          /* must be ZVX_ABI_VERSION */
+    int32_t num_phones;           /* Symbols.num_phones (embedding has +1 rows, fs2.py:350) */
+    int32_t num_puncts;           /* Symbols.num_puncts incl. _NP_ (embedding has +1 rows, fs2.py:354) */
+    int32_t emb_dim;              /* 512 */
+    int32_t punct_emb_dim;        /* 16  -> hidden = emb_dim + punct_emb_dim = 528 */
+    int32_t max_txt_len;          /* 512 */
+    int32_t max_mel_len;          /* 1750 */
+    int32_t enc_layers;           /* 4 */
+    int32_t enc_heads;            /* 2 */
+    int32_t vp_filter_size;       /* 256 */
+    int32_t vp_kernel_size;       /* 3 */
+    int32_t ve_n_bins;            /* 256 */
+    int32_t decoder_kind;         /* 0 = fastspeech2 (FFT blocks + SCLN); 1 = styletts (not built yet) */
+    int32_t dec_layers;           /* 6 */
+    int32_t dec_heads;            /* 2 */
+    int32_t conv_filter_size;     /* 1024 */
+    int32_t conv_kernel_size[2];  /* {9, 1} */
+    int32_t dec_scln;             /* 1 */
+    int32_t resnet_layers[4];     /* {3,4,6,3} */
+    int32_t resnet_num_filters[4];/* {32,64,128,256} */
+    int32_t resnet_encoder_type;  /* 0 = SAP, 1 = ASP */
+    int32_t n_mels;               /* 80 */
+    int32_t hop_length;           /* 256 (= product of upsample rates) */
+    /* HiFi-GAN generator */
+    int32_t hg_resblock;          /* 1 or 2 */
+    int32_t hg_num_upsamples;
+    int32_t hg_upsample_rates[ZVX_MAX_UPSAMPLES];
+    int32_t hg_upsample_kernel_sizes[ZVX_MAX_UPSAMPLES];
+    int32_t hg_upsample_initial_channel;
+    int32_t hg_num_kernels;
+    int32_t hg_resblock_kernel_sizes[ZVX_MAX_RESBLOCK_KERNELS];
+    int32_t hg_num_dilations;
+    int32_t hg_resblock_dilation_sizes[ZVX_MAX_RESBLOCK_KERNELS][ZVX_MAX_DILATIONS];
+    /* numerics policy: 0 = every contraction in fp32 FMA; 1 = decoder / vocoder / speaker-net
+     * contractions on TF32 tensor cores (tcgen05), encoder + variance predictors stay fp32. */
+    int32_t tensor_core_policy;
+    int32_t reserved[7];
+} zvx_config;
+
+int zvx_abi_version(void);
+
+/* Lifetime.  zvx_create replaces ZeroVox.__init__ + .to(device) (model.py:159-257). */
+int  zvx_create(const zvx_config* cfg, int device, zvx_handle** out);
+void zvx_destroy(zvx_handle* h);
+/* Message of the last failing call on this handle (h may be NULL for zvx_create failures). */
+const char* zvx_last_error(const zvx_handle* h);
+
+/* Weights.  One call per reference state_dict entry (load_state_dict, synthesize.py:78-88;
+ * get_meldec, model.py:86-118 — vocoder keys in post-remove_weight_norm form, prefixed
+ * "_meldec.").  `data` may be a host or a device pointer (fp32, contiguous, `shape[ndim]`);
+ * it is copied.  Unknown keys return an error code > 0 but are otherwise harmless
+ * (the reference loads with strict=False). */
+int zvx_set_weight(zvx_handle* h, const char* state_dict_key, const void* data,
+                   const int64_t* shape, int ndim);
+/* Packs weights for the kernels (QKV fusion, tap-major conv weights, eval BatchNorm folded
+ * to scale/shift, SCLN affine stack, position tables) and uploads them.  Fails listing the
+ * first missing key. */
+int zvx_finalize_weights(zvx_handle* h);
+
+/* ResNetSE34V2.forward (zerovox/tts/ResNetSE34V2.py:176-212).
+ * ref_mel [B, T_ref, n_mels] -> style [B, hidden] (unit L2 norm). */
+int zvx_spkemb(zvx_handle* h, const float* ref_mel, int B, int T_ref, float* style, void* stream);
+
+/* FS2Encoder.forward up to (not including) the LengthRegulator (fs2.py:732-765, 370-401,
+ * 652-681).  phoneme/puncts int32 [B,T]; phoneme_mask uint8 [B,T] (1 = padding) or NULL;
+ * style [B,hidden]; forced_dur int32 [B,T] or NULL (force_duration, fs2.py:745).
+ * Outputs: pitch, energy, log_dur fp32 [B,T]; dur_rounded int32 [B,T]; mel_len int64 [B];
+ * xprime fp32 [B,T,hidden] (features + pitch/energy embeddings, the LengthRegulator input).
+ * If L_max_out != NULL the call synchronises `stream` ONCE and returns max(mel_len) there and,
+ * if mel_len_host != NULL (host, int64 [B]), the per-utterance lengths — the reference pays
+ * B*T + 1 such syncs (fs2.py:451, model.py:325). */
+int zvx_encode(zvx_handle* h, const int32_t* phoneme, const int32_t* puncts,
+               const uint8_t* phoneme_mask, const float* style, const int32_t* forced_dur,
+               int B, int T, float* pitch, float* energy, float* log_dur, int32_t* dur_rounded,
+               int64_t* mel_len, float* xprime, int64_t* mel_len_host, int* L_max_out, void* stream);
+
+/* LengthRegulator.forward + pad (fs2.py:403-459): features[b, f, :] = xprime[b, i, :] where i is
+ * the phoneme whose run covers frame f, zero for f >= mel_len[b].  src_index (nullable) receives
+ * i (or -1) — bit-exact integer arithmetic. */
+int zvx_length_regulate(zvx_handle* h, const float* xprime, const int32_t* dur, int B, int T,
+                        int L_max, float* features, int32_t* src_index, void* stream);
+
+/* FS2Decoder.forward (fs2.py:281-315) + the mel masking of ZeroVox.forward (model.py:283-285).
+ * features [B,L,hidden]; mask uint8 [B,L] (1 = padding) or NULL to derive it from mel_len
+ * (model.py:269-273); style [B,hidden]; zero_padded_mel != 0 applies masked_fill(mask, 0) to the
+ * mel.  Outputs (either may be NULL): mel_BLC [B,L,n_mels], mel_BCL [B,n_mels,L]. */
+int zvx_decode(zvx_handle* h, const float* features, const uint8_t* mask, const int64_t* mel_len,
+               const float* style, int B, int L, int zero_padded_mel, float* mel_BLC,
+               float* mel_BCL, void* stream);
+
+/* hifigan.Generator.forward (hifigan.py:114-130).  mel_BCL [B,n_mels,L] -> wav [B, L*hop]. */
+int zvx_vocode(zvx_handle* h, const float* mel_BCL, int B, int L, float* wav, void* stream);
+
+/* Workspace control: bytes of engine-owned scratch currently reserved on the device. */
+int64_t zvx_workspace_bytes(const zvx_handle* h);
+
+/* Number of kernels this library has launched through this handle since creation
+ * (bench.py's gpu_launches). */
+int64_t zvx_launch_count(const zvx_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZEROVOX_B200_H */

@@ -1,0 +1,618 @@
+"""CPU oracle for the ZeroVOX eval-mode phoneme -> mel -> waveform forward path.
+
+TEST INFRASTRUCTURE ONLY.  This file is the *checker*, never the product:
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it.  Nothing under ``zerovox_b200/`` does.
+
+It is a plain functional restatement (torch CPU fp32 ops + numpy integer code,
+no ``nn.Module``) of the reference's algorithm, keyed by the reference's own
+``state_dict`` names.  Every function cites the reference file:line it follows
+(paths relative to the upstream repo gooofy/zerovox @ 56a4316).
+
+Pinning status: the reference ships NO tests / golden vectors,
+so this restatement is pinned against *outputs of the reference's own modules
+run in the build container* — ``oracle/make_goldens.py`` imports
+``zerovox.tts.{fs2,hifigan,ResNetSE34V2,model}`` from /root/reference, loads
+the same seeded weights, asserts module-vs-restatement agreement and writes
+``tests/golden/*.npz`` (committed).  ``tests/test_oracle_golden.py`` re-checks
+the restatement against those fixtures on any machine.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+LRELU_SLOPE = 0.1  # hifigan.py:15
+
+
+# ----------------------------------------------------------------------------
+# configuration (configs/tts_medium.yaml:3-51 + upstream HiFi-GAN config_v{1,2,3}.json)
+# ----------------------------------------------------------------------------
+@dataclass
+class HifiGanConfig:
+    resblock: str = "1"
+    upsample_rates: tuple = (8, 8, 2, 2)
+    upsample_kernel_sizes: tuple = (16, 16, 4, 4)
+    upsample_initial_channel: int = 128
+    resblock_kernel_sizes: tuple = (3, 7, 11)
+    resblock_dilation_sizes: tuple = ((1, 3, 5), (1, 3, 5), (1, 3, 5))
+
+    @staticmethod
+    def v1():
+        return HifiGanConfig(upsample_initial_channel=512)
+
+    @staticmethod
+    def v2():
+        return HifiGanConfig(upsample_initial_channel=128)
+
+    @staticmethod
+    def v3():
+        return HifiGanConfig(resblock="2", upsample_rates=(8, 8, 4), upsample_kernel_sizes=(16, 16, 8),
+                             upsample_initial_channel=256, resblock_kernel_sizes=(3, 5, 7),
+                             resblock_dilation_sizes=((1, 2), (2, 6), (3, 12)))
+
+    def as_json_dict(self):
+        return {"resblock": self.resblock, "upsample_rates": list(self.upsample_rates),
+                "upsample_kernel_sizes": list(self.upsample_kernel_sizes),
+                "upsample_initial_channel": self.upsample_initial_channel,
+                "resblock_kernel_sizes": list(self.resblock_kernel_sizes),
+                "resblock_dilation_sizes": [list(d) for d in self.resblock_dilation_sizes]}
+
+
+@dataclass
+class ZeroVoxConfig:
+    """tts_medium.yaml; kwargs mapping of utils/train_tts.py:202-241."""
+    phones: str = "'-abcdefghijklmnopqrstuvwxyz"
+    puncts: str = " ,.;:-!?\""
+    emb_dim: int = 512
+    punct_emb_dim: int = 16
+    max_txt_len: int = 512
+    max_mel_len: int = 1750
+    enc_layers: int = 4
+    enc_heads: int = 2
+    vp_filter_size: int = 256
+    vp_kernel_size: int = 3
+    ve_n_bins: int = 256
+    decoder_kind: str = "fastspeech2"
+    dec_layers: int = 6
+    dec_heads: int = 2
+    conv_filter_size: int = 1024
+    conv_kernel_size: tuple = (9, 1)
+    dec_scln: bool = True
+    resnet_layers: tuple = (3, 4, 6, 3)
+    resnet_num_filters: tuple = (32, 64, 128, 256)
+    resnet_encoder_type: str = "ASP"
+    n_mels: int = 80
+    sampling_rate: int = 22050
+    hop_length: int = 256
+    hifigan: HifiGanConfig = field(default_factory=HifiGanConfig.v2)
+
+    @property
+    def hidden(self):
+        return self.emb_dim + self.punct_emb_dim
+
+    @property
+    def num_phones(self):  # symbols.py:35-37
+        return len(self.phones)
+
+    @property
+    def num_puncts(self):  # symbols.py:47-49 (includes _NP_)
+        return len(self.puncts) + 1
+
+    @staticmethod
+    def tiny():
+        """Small dims for fast CPU tests (same code path, every feature on)."""
+        return ZeroVoxConfig(emb_dim=80, punct_emb_dim=16, max_txt_len=24, max_mel_len=60,
+                             enc_layers=2, dec_layers=2, vp_filter_size=32, conv_filter_size=96,
+                             resnet_layers=(1, 1, 1, 1), resnet_num_filters=(8, 8, 16, 16),
+                             hifigan=HifiGanConfig(upsample_initial_channel=32))
+
+
+# ----------------------------------------------------------------------------
+# seeded weights, keyed like the reference state_dict
+# ----------------------------------------------------------------------------
+def get_sinusoid_encoding_table(n_position: int, d_hid: int) -> torch.Tensor:
+    """fs2.py:17-37 — float64 numpy table, cast to fp32 (vectorised, same arithmetic)."""
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    hid = np.arange(d_hid)[None, :]
+    table = pos / np.power(10000, 2 * (hid // 2) / d_hid)
+    table[:, 0::2] = np.sin(table[:, 0::2])
+    table[:, 1::2] = np.cos(table[:, 1::2])
+    return torch.from_numpy(table.astype(np.float32))
+
+
+def _fan_in_normal(g, shape, fan_in, gain=1.0):
+    return torch.randn(shape, generator=g, dtype=torch.float32) * (gain / math.sqrt(fan_in))
+
+
+def make_weights(cfg: ZeroVoxConfig, seed: int = 0, dur_bias: float | None = None) -> dict:
+    """Deterministic random weights with O(1) activations everywhere.
+
+    Not the reference's init (that needs the reference importable, and its
+    HiFi-GAN init N(0, 0.01) gives ~0 output, hifigan.py:17-20); any fp32 values
+    are valid parity inputs.  ``dur_bias`` sets duration_predictor.linear bias
+    (log(7) gives ~6 frames/phoneme with predicted durations).
+    """
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+    H, DI = cfg.hidden, cfg.conv_filter_size
+    k1, k2 = cfg.conv_kernel_size
+
+    def fft_stack(prefix, n_layers, scln):
+        for i in range(n_layers):
+            p = f"{prefix}.layer_stack.{i}"
+            for nm in ("w_qs", "w_ks", "w_vs", "fc"):
+                w[f"{p}.slf_attn.{nm}.weight"] = _fan_in_normal(g, (H, H), H)
+                w[f"{p}.slf_attn.{nm}.bias"] = _fan_in_normal(g, (H,), 16.0)
+            w[f"{p}.pos_ffn.w_1.weight"] = _fan_in_normal(g, (DI, H, k1), H * k1, 1.4)
+            w[f"{p}.pos_ffn.w_1.bias"] = _fan_in_normal(g, (DI,), 16.0)
+            w[f"{p}.pos_ffn.w_2.weight"] = _fan_in_normal(g, (H, DI, k2), DI * k2, 1.4)
+            w[f"{p}.pos_ffn.w_2.bias"] = _fan_in_normal(g, (H,), 16.0)
+            for ln in ("slf_attn", "pos_ffn"):
+                if scln:
+                    # bias rows first, gain rows second (fs2.py:85); |style| = 1, so unit-variance
+                    # rows give O(1) random-sign gains and biases (a non-degenerate SCLN)
+                    aff = torch.randn((2 * H, H), generator=g)
+                    w[f"{p}.{ln}.layer_norm.affine_layer.linear.weight"] = aff
+                else:
+                    w[f"{p}.{ln}.layer_norm.weight"] = 1.0 + 0.1 * torch.randn((H,), generator=g)
+                    w[f"{p}.{ln}.layer_norm.bias"] = 0.1 * torch.randn((H,), generator=g)
+
+    # encoder (fs2.py:350-368)
+    e = "_phoneme_encoder._encoder"
+    w[f"{e}.position_enc"] = get_sinusoid_encoding_table(cfg.max_txt_len + 1, H).unsqueeze(0)
+    emb = torch.randn((cfg.num_phones + 1, cfg.emb_dim), generator=g)
+    emb[0] = 0.0  # padding_idx=0 (fs2.py:350)
+    w[f"{e}.src_word_emb.weight"] = emb
+    pemb = torch.randn((cfg.num_puncts + 1, cfg.punct_emb_dim), generator=g)
+    pemb[0] = 0.0
+    w[f"{e}.punct_embed.weight"] = pemb
+    fft_stack(e, cfg.enc_layers, scln=False)
+
+    # variance adaptor (fs2.py:586-624)
+    va = "_phoneme_encoder._variance_adaptor"
+    F_, K = cfg.vp_filter_size, cfg.vp_kernel_size
+    for nm in ("duration", "pitch", "energy"):
+        p = f"{va}.{nm}_predictor"
+        w[f"{p}.conv_layer.conv1d_1.conv.weight"] = _fan_in_normal(g, (F_, H, K), H * K, 1.4)
+        w[f"{p}.conv_layer.conv1d_1.conv.bias"] = _fan_in_normal(g, (F_,), 16.0)
+        w[f"{p}.conv_layer.layer_norm_1.weight"] = 1.0 + 0.1 * torch.randn((F_,), generator=g)
+        w[f"{p}.conv_layer.layer_norm_1.bias"] = 0.1 * torch.randn((F_,), generator=g)
+        w[f"{p}.conv_layer.conv1d_2.conv.weight"] = _fan_in_normal(g, (F_, F_, K), F_ * K, 1.4)
+        w[f"{p}.conv_layer.conv1d_2.conv.bias"] = _fan_in_normal(g, (F_,), 16.0)
+        w[f"{p}.conv_layer.layer_norm_2.weight"] = 1.0 + 0.1 * torch.randn((F_,), generator=g)
+        w[f"{p}.conv_layer.layer_norm_2.bias"] = 0.1 * torch.randn((F_,), generator=g)
+        # pitch/energy predictions should span [0,1] so that many buckets are hit
+        gain = 0.35 if nm != "duration" else 0.5
+        w[f"{p}.linear_layer.weight"] = _fan_in_normal(g, (1, F_), F_, gain)
+        b = 0.5 if nm != "duration" else (dur_bias if dur_bias is not None else math.log(7.0))
+        w[f"{p}.linear_layer.bias"] = torch.full((1,), float(b))
+    w[f"{va}.pitch_embedding.weight"] = 0.5 * torch.randn((cfg.ve_n_bins, H), generator=g)
+    w[f"{va}.energy_embedding.weight"] = 0.5 * torch.randn((cfg.ve_n_bins, H), generator=g)
+
+    # speaker net (ResNetSE34V2.py:101-155)
+    s = "_spkemb"
+    nf = cfg.resnet_num_filters
+    w[f"{s}.conv1.weight"] = _fan_in_normal(g, (nf[0], 1, 3, 3), 9, 1.4)
+    w[f"{s}.conv1.bias"] = 0.1 * torch.randn((nf[0],), generator=g)
+
+    def bn(prefix, c):
+        w[f"{prefix}.weight"] = 1.0 + 0.1 * torch.randn((c,), generator=g)
+        w[f"{prefix}.bias"] = 0.1 * torch.randn((c,), generator=g)
+        w[f"{prefix}.running_mean"] = 0.1 * torch.randn((c,), generator=g)
+        w[f"{prefix}.running_var"] = 0.5 + torch.rand((c,), generator=g)
+        w[f"{prefix}.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    bn(f"{s}.bn1", nf[0])
+    inpl = nf[0]
+    for li, (planes, nblocks) in enumerate(zip(nf, cfg.resnet_layers), start=1):
+        for bi in range(nblocks):
+            p = f"{s}.layer{li}.{bi}"
+            stride = 2 if (li > 1 and bi == 0) else 1
+            w[f"{p}.conv1.weight"] = _fan_in_normal(g, (planes, inpl, 3, 3), inpl * 9, 1.4)
+            bn(f"{p}.bn1", planes)
+            w[f"{p}.conv2.weight"] = _fan_in_normal(g, (planes, planes, 3, 3), planes * 9, 1.0)
+            bn(f"{p}.bn2", planes)
+            r = planes // 8
+            w[f"{p}.se.fc.0.weight"] = _fan_in_normal(g, (r, planes), planes)
+            w[f"{p}.se.fc.0.bias"] = 0.1 * torch.randn((r,), generator=g)
+            w[f"{p}.se.fc.2.weight"] = _fan_in_normal(g, (planes, r), r)
+            w[f"{p}.se.fc.2.bias"] = 0.1 * torch.randn((planes,), generator=g)
+            if stride != 1 or inpl != planes:
+                w[f"{p}.downsample.0.weight"] = _fan_in_normal(g, (planes, inpl, 1, 1), inpl)
+                bn(f"{p}.downsample.1", planes)
+            inpl = planes
+    D = nf[3] * (cfg.n_mels // 8)
+    w[f"{s}.attention.0.weight"] = _fan_in_normal(g, (128, D, 1), D, 1.4)
+    w[f"{s}.attention.0.bias"] = 0.1 * torch.randn((128,), generator=g)
+    bn(f"{s}.attention.2", 128)
+    w[f"{s}.attention.3.weight"] = _fan_in_normal(g, (D, 128, 1), 128)
+    w[f"{s}.attention.3.bias"] = 0.1 * torch.randn((D,), generator=g)
+    out_dim = D * 2 if cfg.resnet_encoder_type == "ASP" else D
+    w[f"{s}.fc.weight"] = _fan_in_normal(g, (H, out_dim), out_dim)
+    w[f"{s}.fc.bias"] = 0.1 * torch.randn((H,), generator=g)
+
+    # mel decoder (fs2.py:264-278)
+    d = "_mel_decoder"
+    if cfg.decoder_kind == "fastspeech2":
+        w[f"{d}.position_enc"] = get_sinusoid_encoding_table(cfg.max_mel_len + 1, H).unsqueeze(0)
+        fft_stack(d, cfg.dec_layers, scln=cfg.dec_scln)
+        w[f"{d}.mel_linear.weight"] = _fan_in_normal(g, (cfg.n_mels, H), H, 2.0)
+        w[f"{d}.mel_linear.bias"] = 0.5 * torch.randn((cfg.n_mels,), generator=g)
+    else:
+        raise NotImplementedError("oracle weights for decoder_kind=%r" % cfg.decoder_kind)
+
+    # vocoder, post-remove_weight_norm form (hifigan.py:93-110, 132-139)
+    w.update({f"_meldec.{k}": v for k, v in make_hifigan_weights(cfg.hifigan, g).items()})
+    return w
+
+
+def make_hifigan_weights(h: HifiGanConfig, g: torch.Generator) -> dict:
+    w = {}
+    C0 = h.upsample_initial_channel
+    w["conv_pre.weight"] = _fan_in_normal(g, (C0, 80, 7), 80 * 7)
+    w["conv_pre.bias"] = 0.1 * torch.randn((C0,), generator=g)
+    ch = C0
+    for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+        cin, cout = C0 // (2 ** i), C0 // (2 ** (i + 1))
+        # ConvTranspose1d weight is [C_in, C_out, k]; k/u taps reach each output
+        w[f"ups.{i}.weight"] = _fan_in_normal(g, (cin, cout, k), cin * (k // u), 1.4)
+        w[f"ups.{i}.bias"] = 0.1 * torch.randn((cout,), generator=g)
+        ch = cout
+        for j, (rk, rd) in enumerate(zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes)):
+            p = f"resblocks.{i * len(h.resblock_kernel_sizes) + j}"
+            names = (["convs1", "convs2"] if h.resblock == "1" else ["convs"])
+            for nm in names:
+                for di in range(len(rd)):
+                    w[f"{p}.{nm}.{di}.weight"] = _fan_in_normal(g, (ch, ch, rk), ch * rk, 0.8)
+                    w[f"{p}.{nm}.{di}.bias"] = 0.05 * torch.randn((ch,), generator=g)
+    w["conv_post.weight"] = _fan_in_normal(g, (1, ch, 7), ch * 7, 0.7)
+    w["conv_post.bias"] = 0.05 * torch.randn((1,), generator=g)
+    return w
+
+
+def make_inputs(cfg: ZeroVoxConfig, B: int, T: int, T_ref: int, seed: int = 7,
+                ragged: bool = False, dur_lo: int = 2, dur_hi: int = 10) -> dict:
+    """Synthetic batch: phoneme~U{1..27}, puncts~U{0..9}, ref_mel~N(0,1),
+    forced durations~U{dur_lo..dur_hi}; ``ragged`` pads a random tail with phoneme_mask."""
+    g = torch.Generator().manual_seed(seed)
+    x = {
+        "phoneme": torch.randint(1, cfg.num_phones, (B, T), generator=g, dtype=torch.int32),
+        "puncts": torch.randint(0, cfg.num_puncts, (B, T), generator=g, dtype=torch.int32),
+        "ref_mel": torch.randn((B, T_ref, cfg.n_mels), generator=g),
+        "duration": torch.randint(dur_lo, dur_hi + 1, (B, T), generator=g, dtype=torch.int32),
+    }
+    if ragged:
+        lens = torch.randint(max(1, T // 2), T + 1, (B,), generator=g)
+        lens[0] = T
+        mask = torch.arange(T)[None, :] >= lens[:, None]
+        x["phoneme_mask"] = mask
+        x["phoneme"] = x["phoneme"].masked_fill(mask, 0)
+        x["puncts"] = x["puncts"].masked_fill(mask, 0)
+        x["duration"] = x["duration"].masked_fill(mask, 0)
+    return x
+
+
+# ----------------------------------------------------------------------------
+# FastSpeech2 pieces
+# ----------------------------------------------------------------------------
+def scln(x, s, affine_w, eps=1e-8):
+    """fs2.py:76-90 — unbiased std, (sigma + eps), bias rows first / gain rows second."""
+    mu = torch.mean(x, dim=-1, keepdim=True)
+    sigma = torch.std(x, dim=-1, keepdim=True)
+    y = (x - mu) / (sigma + eps)
+    H = x.shape[-1]
+    b, g = torch.split(F.linear(s, affine_w), H, dim=-1)
+    return g * y + b
+
+
+def multi_head_attention(w, p, x, spk, slf_attn_mask, n_head, scln_on):
+    """fs2.py:133-164 (+ ScaledDotProductAttention 47-58); dropout is identity in eval."""
+    B, L, H = x.shape
+    dk = H // n_head
+    residual = x
+    q = F.linear(x, w[f"{p}.w_qs.weight"], w[f"{p}.w_qs.bias"]).view(B, L, n_head, dk)
+    k = F.linear(x, w[f"{p}.w_ks.weight"], w[f"{p}.w_ks.bias"]).view(B, L, n_head, dk)
+    v = F.linear(x, w[f"{p}.w_vs.weight"], w[f"{p}.w_vs.bias"]).view(B, L, n_head, dk)
+    q = q.permute(2, 0, 1, 3).contiguous().view(-1, L, dk)
+    k = k.permute(2, 0, 1, 3).contiguous().view(-1, L, dk)
+    v = v.permute(2, 0, 1, 3).contiguous().view(-1, L, dk)
+    mask = slf_attn_mask.repeat(n_head, 1, 1)
+    attn = torch.bmm(q, k.transpose(1, 2))
+    attn = attn / np.power(dk, 0.5)
+    attn = attn.masked_fill(mask, -np.inf)
+    attn = torch.softmax(attn, dim=2)
+    out = torch.bmm(attn, v)
+    out = out.view(n_head, B, L, dk).permute(1, 2, 0, 3).contiguous().view(B, L, -1)
+    out = F.linear(out, w[f"{p}.fc.weight"], w[f"{p}.fc.bias"])
+    if scln_on:
+        return scln(out + residual, spk, w[f"{p}.layer_norm.affine_layer.linear.weight"])
+    return F.layer_norm(out + residual, (H,), w[f"{p}.layer_norm.weight"], w[f"{p}.layer_norm.bias"], 1e-5)
+
+
+def positionwise_ffn(w, p, x, spk, kernel_size, scln_on):
+    """fs2.py:196-209 — Conv1d k=9 (pad 4) -> ReLU -> Conv1d k=1, residual, (SC)LN."""
+    H = x.shape[-1]
+    residual = x
+    o = x.transpose(1, 2)
+    o = F.conv1d(o, w[f"{p}.w_1.weight"], w[f"{p}.w_1.bias"], padding=(kernel_size[0] - 1) // 2)
+    o = F.relu(o)
+    o = F.conv1d(o, w[f"{p}.w_2.weight"], w[f"{p}.w_2.bias"], padding=(kernel_size[1] - 1) // 2)
+    o = o.transpose(1, 2)
+    if scln_on:
+        return scln(o + residual, spk, w[f"{p}.layer_norm.affine_layer.linear.weight"])
+    return F.layer_norm(o + residual, (H,), w[f"{p}.layer_norm.weight"], w[f"{p}.layer_norm.bias"], 1e-5)
+
+
+def fft_block(w, p, x, spk, mask, slf_attn_mask, n_head, kernel_size, scln_on):
+    """fs2.py:221-230 — both sub-layers followed by masked_fill(mask, 0)."""
+    o = multi_head_attention(w, f"{p}.slf_attn", x, spk, slf_attn_mask, n_head, scln_on)
+    o = o.masked_fill(mask.unsqueeze(-1), 0)
+    o = positionwise_ffn(w, f"{p}.pos_ffn", o, spk, kernel_size, scln_on)
+    o = o.masked_fill(mask.unsqueeze(-1), 0)
+    return o
+
+
+def _pos_table(w, key, L, H, max_len):
+    """fs2.py:287-304 / 383-392 — parameter rows when L <= max, recomputed table otherwise (eval)."""
+    if L > max_len:
+        return get_sinusoid_encoding_table(L, H)[:L, :]
+    return w[key][0, :L, :]
+
+
+def encoder(cfg, w, phoneme, puncts, mask):
+    """fs2.py:370-401."""
+    e = "_phoneme_encoder._encoder"
+    x = F.embedding(phoneme.long(), w[f"{e}.src_word_emb.weight"])
+    xp = F.embedding(puncts.long(), w[f"{e}.punct_embed.weight"])
+    x = torch.cat((x, xp), 2)
+    B, T = phoneme.shape
+    slf = mask.unsqueeze(1).expand(-1, T, -1)
+    x = x + _pos_table(w, f"{e}.position_enc", T, cfg.hidden, cfg.max_txt_len).unsqueeze(0)
+    for i in range(cfg.enc_layers):
+        x = fft_block(w, f"{e}.layer_stack.{i}", x, None, mask, slf, cfg.enc_heads,
+                      cfg.conv_kernel_size, scln_on=False)
+    return x
+
+
+def variance_predictor(cfg, w, p, x, mask):
+    """fs2.py:522-563 — conv k3 -> ReLU -> LN -> conv k3 (padding=1) -> ReLU -> LN -> Linear -> mask0."""
+    F_ = cfg.vp_filter_size
+    K = cfg.vp_kernel_size
+    o = F.conv1d(x.transpose(1, 2), w[f"{p}.conv_layer.conv1d_1.conv.weight"],
+                 w[f"{p}.conv_layer.conv1d_1.conv.bias"], padding=(K - 1) // 2).transpose(1, 2)
+    o = F.relu(o)
+    o = F.layer_norm(o, (F_,), w[f"{p}.conv_layer.layer_norm_1.weight"], w[f"{p}.conv_layer.layer_norm_1.bias"], 1e-5)
+    o = F.conv1d(o.transpose(1, 2), w[f"{p}.conv_layer.conv1d_2.conv.weight"],
+                 w[f"{p}.conv_layer.conv1d_2.conv.bias"], padding=1).transpose(1, 2)
+    o = F.relu(o)
+    o = F.layer_norm(o, (F_,), w[f"{p}.conv_layer.layer_norm_2.weight"], w[f"{p}.conv_layer.layer_norm_2.bias"], 1e-5)
+    o = F.linear(o, w[f"{p}.linear_layer.weight"], w[f"{p}.linear_layer.bias"]).squeeze(-1)
+    return o.masked_fill(mask, 0.0)
+
+
+def bucketize(cfg, pred):
+    """fs2.py:639 / 649 — clamp(round(p * (n_bins-1)).long(), 0, n_bins-1); round = half-to-even."""
+    return torch.clamp(torch.round(pred * (cfg.ve_n_bins - 1)).long(), min=0, max=cfg.ve_n_bins - 1)
+
+
+def duration_round(log_d):
+    """fs2.py:678-681."""
+    return torch.clamp(torch.round(torch.exp(log_d) - 1), min=0)
+
+
+def length_regulator_indices(duration: np.ndarray, max_len: int | None = None):
+    """fs2.py:432-459 + pad 403-423, as pure integer index arithmetic.
+
+    Returns (src_index int32 [B, L_max] with -1 at zero-padded frames, mel_len int64 [B]).
+    Row i is repeated max(int(d_i), 0) times (fs2.py:451-452).
+    """
+    dur = np.maximum(duration.astype(np.int64), 0)
+    mel_len = dur.sum(axis=1)
+    L = int(max_len) if max_len else int(mel_len.max()) if mel_len.size else 0
+    B, T = dur.shape
+    idx = np.full((B, L), -1, dtype=np.int32)
+    for b in range(B):
+        rep = np.repeat(np.arange(T, dtype=np.int32), dur[b])
+        idx[b, : len(rep)] = rep[:L]
+    return idx, mel_len.astype(np.int64)
+
+
+def length_regulate(x, duration, max_len=None):
+    idx, mel_len = length_regulator_indices(duration.detach().cpu().numpy(), max_len)
+    idx_t = torch.from_numpy(idx).long()
+    B, L = idx_t.shape
+    g = torch.gather(x, 1, idx_t.clamp(min=0).unsqueeze(-1).expand(B, L, x.shape[-1]))
+    g = g.masked_fill((idx_t < 0).unsqueeze(-1), 0.0)
+    return g, torch.from_numpy(mel_len), idx
+
+
+def fs2_encoder(cfg, w, x, style_embed, force_duration=False):
+    """FS2Encoder.forward, fs2.py:732-775 + VarianceAdaptor.forward 652-693 (eval)."""
+    phoneme, puncts = x["phoneme"], x["puncts"]
+    mask = x["phoneme_mask"] if "phoneme_mask" in x else torch.zeros_like(phoneme, dtype=torch.bool)
+    feats = encoder(cfg, w, phoneme, puncts, mask)
+    feats = feats + style_embed.expand_as(feats)  # all positions, padded too (fs2.py:740-741)
+    va = "_phoneme_encoder._variance_adaptor"
+    log_d = variance_predictor(cfg, w, f"{va}.duration_predictor", feats, mask)
+    pitch = variance_predictor(cfg, w, f"{va}.pitch_predictor", feats, mask)
+    pb = bucketize(cfg, pitch)
+    feats = feats + F.embedding(pb, w[f"{va}.pitch_embedding.weight"])
+    energy = variance_predictor(cfg, w, f"{va}.energy_predictor", feats, mask)
+    eb = bucketize(cfg, energy)
+    feats = feats + F.embedding(eb, w[f"{va}.energy_embedding.weight"])
+    xprime = feats
+    if force_duration:
+        dur = x["duration"]
+        out, mel_len, idx = length_regulate(feats, dur)
+        masks = None
+    else:
+        dur = duration_round(log_d)
+        out, mel_len, idx = length_regulate(feats, dur)
+        L = out.shape[1]
+        mel_mask = torch.arange(L)[None, :] >= mel_len[:, None]  # fs2.py:565-573
+        masks = mel_mask.unsqueeze(2).expand(-1, -1, out.shape[2])
+    return {"pitch": pitch, "energy": energy, "log_duration": log_d, "mel_len": mel_len,
+            "features": out, "masks": masks,
+            # extras for stage-wise parity tests (not in the reference dict)
+            "_xprime": xprime, "_pitch_bucket": pb, "_energy_bucket": eb,
+            "_duration_rounded": dur, "_src_index": idx}
+
+
+def fs2_decoder(cfg, w, enc_seq, mask, spk):
+    """FS2Decoder.forward, fs2.py:281-315 (eval: no truncation to max_seq_len)."""
+    d = "_mel_decoder"
+    B, L, H = enc_seq.shape
+    slf = mask.unsqueeze(1).expand(-1, L, -1)
+    o = enc_seq + _pos_table(w, f"{d}.position_enc", L, H, cfg.max_mel_len).unsqueeze(0)
+    for i in range(cfg.dec_layers):
+        o = fft_block(w, f"{d}.layer_stack.{i}", o, spk, mask, slf, cfg.dec_heads,
+                      cfg.conv_kernel_size, scln_on=cfg.dec_scln)
+    return F.linear(o, w[f"{d}.mel_linear.weight"], w[f"{d}.mel_linear.bias"])
+
+
+# ----------------------------------------------------------------------------
+# ResNetSE34V2 speaker embedding
+# ----------------------------------------------------------------------------
+def _bn(w, p, x):
+    return F.batch_norm(x, w[f"{p}.running_mean"], w[f"{p}.running_var"], w[f"{p}.weight"], w[f"{p}.bias"],
+                        training=False, eps=1e-5)
+
+
+def se_basic_block(w, p, x, stride):
+    """ResNetSE34V2.py:83-99 — conv->ReLU->BN (!), conv->BN, SE gate, +residual, ReLU."""
+    out = F.conv2d(x, w[f"{p}.conv1.weight"], None, stride=stride, padding=1)
+    out = F.relu(out)
+    out = _bn(w, f"{p}.bn1", out)
+    out = F.conv2d(out, w[f"{p}.conv2.weight"], None, padding=1)
+    out = _bn(w, f"{p}.bn2", out)
+    y = out.mean(dim=(2, 3))  # AdaptiveAvgPool2d(1), ResNetSE34V2.py:63-67
+    y = torch.sigmoid(F.linear(F.relu(F.linear(y, w[f"{p}.se.fc.0.weight"], w[f"{p}.se.fc.0.bias"])),
+                               w[f"{p}.se.fc.2.weight"], w[f"{p}.se.fc.2.bias"]))
+    out = out * y[:, :, None, None]
+    if f"{p}.downsample.0.weight" in w:
+        res = F.conv2d(x, w[f"{p}.downsample.0.weight"], None, stride=stride)
+        res = _bn(w, f"{p}.downsample.1", res)
+    else:
+        res = x
+    return F.relu(out + res)
+
+
+def speaker_embed(cfg, w, ref_mel):
+    """ResNetSE34V2.forward, ResNetSE34V2.py:176-212 (log_input=False, model.py:223)."""
+    s = "_spkemb"
+    x = ref_mel.transpose(1, 2)
+    x = F.instance_norm(x, eps=1e-5).unsqueeze(1)
+    x = F.conv2d(x, w[f"{s}.conv1.weight"], w[f"{s}.conv1.bias"], padding=1)
+    x = F.relu(x)
+    x = _bn(w, f"{s}.bn1", x)
+    for li, nblocks in enumerate(cfg.resnet_layers, start=1):
+        for bi in range(nblocks):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            x = se_basic_block(w, f"{s}.layer{li}.{bi}", x, stride)
+    x = x.reshape(x.size(0), -1, x.size(-1))
+    a = F.conv1d(x, w[f"{s}.attention.0.weight"], w[f"{s}.attention.0.bias"])
+    a = F.relu(a)
+    a = _bn(w, f"{s}.attention.2", a)
+    a = F.conv1d(a, w[f"{s}.attention.3.weight"], w[f"{s}.attention.3.bias"])
+    a = torch.softmax(a, dim=2)
+    if cfg.resnet_encoder_type == "SAP":
+        x = torch.sum(x * a, dim=2)
+    else:
+        mu = torch.sum(x * a, dim=2)
+        sg = torch.sqrt((torch.sum((x ** 2) * a, dim=2) - mu ** 2).clamp(min=1e-5))
+        x = torch.cat((mu, sg), 1)
+    x = F.linear(x, w[f"{s}.fc.weight"], w[f"{s}.fc.bias"])
+    x = F.normalize(x, p=2, dim=1)
+    return x.unsqueeze(1)
+
+
+# ----------------------------------------------------------------------------
+# HiFi-GAN generator
+# ----------------------------------------------------------------------------
+def _get_padding(k, d=1):  # hifigan.py:22-23
+    return int((k * d - d) / 2)
+
+
+def hifigan_generator(h: HifiGanConfig, w: dict, mel: torch.Tensor, prefix: str = "_meldec.") -> torch.Tensor:
+    """Generator.forward, hifigan.py:114-130; ResBlock1 49-56, ResBlock2 78-82.  mel [B,80,L] -> [B,1,256L]."""
+    g = lambda k: w[prefix + k]
+    nk = len(h.resblock_kernel_sizes)
+    x = F.conv1d(mel, g("conv_pre.weight"), g("conv_pre.bias"), padding=3)
+    for i, (u, k) in enumerate(zip(h.upsample_rates, h.upsample_kernel_sizes)):
+        x = F.leaky_relu(x, LRELU_SLOPE)
+        x = F.conv_transpose1d(x, g(f"ups.{i}.weight"), g(f"ups.{i}.bias"), stride=u, padding=(k - u) // 2)
+        xs = None
+        for j, (rk, rd) in enumerate(zip(h.resblock_kernel_sizes, h.resblock_dilation_sizes)):
+            p = f"resblocks.{i * nk + j}"
+            r = x
+            for di, d in enumerate(rd):
+                xt = F.leaky_relu(r, LRELU_SLOPE)
+                if h.resblock == "1":
+                    xt = F.conv1d(xt, g(f"{p}.convs1.{di}.weight"), g(f"{p}.convs1.{di}.bias"),
+                                  dilation=d, padding=_get_padding(rk, d))
+                    xt = F.leaky_relu(xt, LRELU_SLOPE)
+                    xt = F.conv1d(xt, g(f"{p}.convs2.{di}.weight"), g(f"{p}.convs2.{di}.bias"),
+                                  padding=_get_padding(rk, 1))
+                else:
+                    xt = F.conv1d(xt, g(f"{p}.convs.{di}.weight"), g(f"{p}.convs.{di}.bias"),
+                                  dilation=d, padding=_get_padding(rk, d))
+                r = xt + r
+            xs = r if xs is None else xs + r
+        x = xs / nk
+    x = F.leaky_relu(x)  # default slope 0.01 (hifigan.py:126)
+    x = F.conv1d(x, g("conv_post.weight"), g("conv_post.bias"), padding=3)
+    return torch.tanh(x)
+
+
+# ----------------------------------------------------------------------------
+# model container
+# ----------------------------------------------------------------------------
+def zerovox_forward(cfg, w, x, force_duration=False, style_embed=None):
+    """ZeroVox.forward eval path, model.py:260-290, with the *intended* HiFi-GAN tail.
+
+    The reference's own eval tail (model.py:298-304) raises with hifigan.Generator
+    (ParallelWaveGAN leftovers .mean/.scale/.pqmf/c=); the tail used here is
+    ``wav = _meldec(mel.transpose(1,2)).squeeze(1)``, which is what
+    utils/export_hifigan.py:109-151 consumes.  Returns (wav [B,256*L], mel [B,80,L],
+    mel_len [B] int64, log_duration [B,T]) plus a dict of stage tensors.
+    """
+    se = speaker_embed(cfg, w, x["ref_mel"]) if style_embed is None else style_embed
+    pred = fs2_encoder(cfg, w, x, se, force_duration=force_duration)
+    masks = pred["masks"]
+    L = pred["features"].shape[1]
+    if masks is None:  # model.py:269-273
+        dec_mask = ~(torch.arange(L).expand(len(pred["mel_len"]), L) < pred["mel_len"].unsqueeze(1))
+    else:
+        dec_mask = masks[:, :, 0]
+    mel = fs2_decoder(cfg, w, pred["features"], dec_mask, se)
+    if masks is not None and mel.size(0) > 1:  # model.py:283-285
+        mel = mel.masked_fill(masks[:, :, : mel.shape[-1]], 0)
+    mel_t = mel.transpose(1, 2)
+    wav = hifigan_generator(cfg.hifigan, w, mel_t).squeeze(1)
+    stages = dict(pred)
+    stages["style_embed"] = se
+    stages["dec_mask"] = dec_mask
+    return wav, mel_t, pred["mel_len"], pred["log_duration"], stages
+
+
+def zerovox_inference_ex(cfg, w, x, style_embed, force_duration=False, min_mel_len=689):
+    """ZeroVox.inference_ex, model.py:308-347 (batch = 1).  Returns the reference 4-tuple and the
+    updated ``_min_mel_len`` (the reference mutates self._min_mel_len, model.py:331-335)."""
+    pred = fs2_encoder(cfg, w, x, style_embed, force_duration=force_duration)
+    L = pred["features"].shape[1]
+    dec_mask = ~(torch.arange(L).expand(1, L) < pred["mel_len"].unsqueeze(1))
+    mel = fs2_decoder(cfg, w, pred["features"], dec_mask, style_embed)
+    mel_len = int(pred["mel_len"][0])
+    mel = mel[0]
+    if mel_len < min_mel_len:
+        mel = F.pad(mel, (0, 0, 0, min_mel_len - mel_len))
+    elif mel_len > min_mel_len:
+        min_mel_len = mel_len
+    wav = hifigan_generator(cfg.hifigan, w, mel.T.unsqueeze(0))[0, 0]
+    mel = mel.transpose(0, 1)
+    return wav[: mel_len * cfg.hop_length], mel_len, pred["log_duration"], mel[:, :mel_len], min_mel_len

@@ -1,0 +1,893 @@
+// zerovox_b200 engine: weight packing, workspace, stage orchestration and the C ABI (include/zerovox_b200.h).
+//
+// Data layout in HBM
+//   acoustic model / speaker net : channel-last  ([B, T, C] / [B, H, W, C]) so that every Linear, Conv1d and Conv2d
+//                                  is one (implicit) GEMM with K contiguous;
+//   vocoder                      : channel-first ([B, C, T], time contiguous), the reference's own layout;
+//   weights                      : packed once at zvx_finalize_weights (tap-major [tap][N][K] for convs, fused QKV,
+//                                  stacked SCLN affine, eval-BatchNorm folded to scale/shift).
+#include "../../include/zerovox_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+#include "gemm_tc.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace zvx {
+
+namespace {
+
+std::string g_create_error;
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto s : shape) n *= s;
+        return n;
+    }
+};
+
+// Growable block workspace: pointers are stable within a call; the same call sequence re-uses the same blocks, so
+// steady state performs no cudaMalloc.
+class Workspace {
+  public:
+    ~Workspace() { release(); }
+    void reset() { cur_ = 0; off_ = 0; }
+    template <typename T>
+    T* get(long long n) {
+        size_t bytes = (size_t)round_up(std::max<long long>(n, 1) * (long long)sizeof(T), 256);
+        while (cur_ < blocks_.size() && off_ + bytes > blocks_[cur_].size) {
+            ++cur_;
+            off_ = 0;
+        }
+        if (cur_ == blocks_.size()) {
+            Block b;
+            b.size = std::max(bytes, (size_t)256 << 20);
+            ZVX_CUDA_CHECK(cudaMalloc(&b.p, b.size));
+            blocks_.push_back(b);
+            off_ = 0;
+        }
+        T* p = reinterpret_cast<T*>(static_cast<char*>(blocks_[cur_].p) + off_);
+        off_ += bytes;
+        return p;
+    }
+    int64_t bytes() const {
+        int64_t t = 0;
+        for (auto& b : blocks_) t += (int64_t)b.size;
+        return t;
+    }
+    void release() {
+        for (auto& b : blocks_) cudaFree(b.p);
+        blocks_.clear();
+        reset();
+    }
+
+  private:
+    struct Block { void* p = nullptr; size_t size = 0; };
+    std::vector<Block> blocks_;
+    size_t cur_ = 0, off_ = 0;
+};
+
+struct FFTLayer {
+    float *wqkv = nullptr, *bqkv = nullptr, *wfc = nullptr, *bfc = nullptr;
+    float *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+    float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;  // LayerNorm variant
+};
+
+struct VarPredictor {
+    float *wc1 = nullptr, *bc1 = nullptr, *ln1_g = nullptr, *ln1_b = nullptr;
+    float *wc2 = nullptr, *bc2 = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+    float *wlin = nullptr, *blin = nullptr;
+};
+
+struct SEBlock {
+    int inpl = 0, planes = 0, stride = 1, red = 0;
+    float *w1 = nullptr, *bn1_s = nullptr, *bn1_b = nullptr;
+    float *w2 = nullptr, *bn2_s = nullptr, *bn2_b = nullptr;
+    float *se_w1 = nullptr, *se_b1 = nullptr, *se_w2 = nullptr, *se_b2 = nullptr;
+    float *wd = nullptr, *bnd_s = nullptr, *bnd_b = nullptr;  // downsample (nullable)
+};
+
+struct HGConv { float* w = nullptr; float* b = nullptr; int cin = 0, cout = 0, k = 1, dil = 1; };
+
+}  // namespace
+
+class Engine {
+  public:
+    Engine(const zvx_config& c, int device) : cfg(c), dev(device) {
+        ZVX_REQUIRE(c.abi_version == ZVX_ABI_VERSION, "zvx_config.abi_version mismatch");
+        int n = 0;
+        ZVX_CUDA_CHECK(cudaGetDeviceCount(&n));
+        ZVX_REQUIRE(n > 0 && device >= 0 && device < n, "no usable CUDA device (this engine has no CPU path)");
+        ZVX_CUDA_CHECK(cudaSetDevice(device));
+        cudaDeviceProp prop{};
+        ZVX_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        ZVX_REQUIRE(prop.major == 10, "zerovox_b200 is built for sm_100a (Blackwell B200) only");
+        num_sms = prop.multiProcessorCount;
+        H = c.emb_dim + c.punct_emb_dim;
+        ZVX_REQUIRE(H % 4 == 0 && H <= 1024, "hidden size must be a multiple of 4 and <= 1024");
+        ZVX_REQUIRE(c.enc_heads > 0 && H % c.enc_heads == 0 && (H / c.enc_heads) % 4 == 0, "bad encoder head split");
+        ZVX_REQUIRE(c.decoder_kind == 0 || c.decoder_kind == 1, "decoder_kind must be 0 (fastspeech2) or 1 (styletts)");
+        ZVX_REQUIRE(c.dec_heads > 0 && H % c.dec_heads == 0 && (H / c.dec_heads) % 4 == 0, "bad decoder head split");
+        ZVX_REQUIRE(c.vp_filter_size % 4 == 0 && c.conv_filter_size % 4 == 0, "filter sizes must be multiples of 4");
+        ZVX_REQUIRE(c.n_mels % 8 == 0, "n_mels must be a multiple of 8");
+        ZVX_REQUIRE(c.hg_resblock == 1 || c.hg_resblock == 2, "hg_resblock must be 1 or 2");
+        ZVX_REQUIRE(c.hg_num_upsamples >= 1 && c.hg_num_upsamples <= ZVX_MAX_UPSAMPLES, "hg_num_upsamples");
+        ZVX_REQUIRE(c.hg_num_kernels >= 1 && c.hg_num_kernels <= ZVX_MAX_RESBLOCK_KERNELS, "hg_num_kernels");
+        ZVX_REQUIRE(c.hg_num_dilations >= 1 && c.hg_num_dilations <= ZVX_MAX_DILATIONS, "hg_num_dilations");
+        long long hop = 1;
+        for (int i = 0; i < c.hg_num_upsamples; ++i) hop *= c.hg_upsample_rates[i];
+        ZVX_REQUIRE(hop == c.hop_length, "product of upsample rates must equal hop_length");
+        ZVX_CUDA_CHECK(cudaMallocHost(&pinned_len, sizeof(int64_t) * kMaxBatch));
+    }
+
+    ~Engine() {
+        cudaSetDevice(dev);
+        for (void* p : owned) cudaFree(p);
+        if (pinned_len) cudaFreeHost(pinned_len);
+    }
+
+    // ------------------------------------------------------------------------------------------ weights
+    int set_weight(const char* key, const void* data, const int64_t* shape, int ndim) {
+        ZVX_REQUIRE(key && data && ndim >= 0 && ndim <= 8, "zvx_set_weight: bad arguments");
+        ZVX_CUDA_CHECK(cudaSetDevice(dev));
+        HostTensor t;
+        t.shape.assign(shape, shape + ndim);
+        const int64_t n = t.numel();
+        t.data.resize((size_t)n);
+        cudaPointerAttributes attr{};
+        cudaError_t e = cudaPointerGetAttributes(&attr, data);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            attr.type = cudaMemoryTypeUnregistered;
+        }
+        if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) {
+            ZVX_CUDA_CHECK(cudaMemcpy(t.data.data(), data, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+        } else {
+            std::memcpy(t.data.data(), data, (size_t)n * sizeof(float));
+        }
+        raw[key] = std::move(t);
+        finalized = false;
+        return 0;
+    }
+
+    const HostTensor& W(const std::string& key) {
+        auto it = raw.find(key);
+        if (it == raw.end()) throw Error("missing weight: " + key);
+        return it->second;
+    }
+    const HostTensor& W(const std::string& key, std::initializer_list<int64_t> shape) {
+        const HostTensor& t = W(key);
+        if (t.shape != std::vector<int64_t>(shape)) throw Error("weight has unexpected shape: " + key);
+        return t;
+    }
+
+    float* upload(const std::vector<float>& v) {
+        float* p = nullptr;
+        ZVX_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(v.size(), 4) * sizeof(float)));
+        owned.push_back(p);
+        if (!v.empty()) ZVX_CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return p;
+    }
+    float* upload(const HostTensor& t) { return upload(t.data); }
+
+    // Conv weight [N][C][k] -> tap-major [k][N][C]
+    static std::vector<float> tap_major(const HostTensor& t) {
+        const int64_t N = t.shape[0], C = t.shape[1];
+        int64_t k = 1;
+        for (size_t i = 2; i < t.shape.size(); ++i) k *= t.shape[i];
+        std::vector<float> o((size_t)(N * C * k));
+        for (int64_t n = 0; n < N; ++n)
+            for (int64_t c = 0; c < C; ++c)
+                for (int64_t j = 0; j < k; ++j) o[(size_t)((j * N + n) * C + c)] = t.data[(size_t)((n * C + c) * k + j)];
+        return o;
+    }
+
+    void bn_fold(const std::string& p, int C, float** scale, float** shift) {
+        const HostTensor &w = W(p + ".weight", {C}), &b = W(p + ".bias", {C});
+        const HostTensor &m = W(p + ".running_mean", {C}), &v = W(p + ".running_var", {C});
+        std::vector<float> s((size_t)C), sh((size_t)C);
+        for (int i = 0; i < C; ++i) {
+            const float inv = 1.0f / std::sqrt(v.data[i] + 1e-5f);
+            s[i] = w.data[i] * inv;
+            sh[i] = b.data[i] - m.data[i] * s[i];
+        }
+        *scale = upload(s);
+        *shift = upload(sh);
+    }
+
+    void pack_fft(const std::string& prefix, int n_layers, bool scln, std::vector<FFTLayer>& out,
+                  std::vector<float>* scln_stack) {
+        const int DI = cfg.conv_filter_size, k1 = cfg.conv_kernel_size[0], k2 = cfg.conv_kernel_size[1];
+        out.resize((size_t)n_layers);
+        for (int i = 0; i < n_layers; ++i) {
+            const std::string p = prefix + ".layer_stack." + std::to_string(i);
+            FFTLayer& L = out[(size_t)i];
+            std::vector<float> wqkv, bqkv;
+            for (const char* nm : {"w_qs", "w_ks", "w_vs"}) {
+                const HostTensor& w = W(p + ".slf_attn." + nm + ".weight", {H, H});
+                const HostTensor& b = W(p + ".slf_attn." + nm + ".bias", {H});
+                wqkv.insert(wqkv.end(), w.data.begin(), w.data.end());
+                bqkv.insert(bqkv.end(), b.data.begin(), b.data.end());
+            }
+            L.wqkv = upload(wqkv);
+            L.bqkv = upload(bqkv);
+            L.wfc = upload(W(p + ".slf_attn.fc.weight", {H, H}));
+            L.bfc = upload(W(p + ".slf_attn.fc.bias", {H}));
+            L.w1 = upload(tap_major(W(p + ".pos_ffn.w_1.weight", {DI, H, k1})));
+            L.b1 = upload(W(p + ".pos_ffn.w_1.bias", {DI}));
+            L.w2 = upload(tap_major(W(p + ".pos_ffn.w_2.weight", {H, DI, k2})));
+            L.b2 = upload(W(p + ".pos_ffn.w_2.bias", {H}));
+            if (scln) {
+                for (const char* sub : {"slf_attn", "pos_ffn"}) {
+                    const HostTensor& a = W(p + "." + sub + ".layer_norm.affine_layer.linear.weight", {2 * H, H});
+                    scln_stack->insert(scln_stack->end(), a.data.begin(), a.data.end());
+                }
+            } else {
+                L.ln1_g = upload(W(p + ".slf_attn.layer_norm.weight", {H}));
+                L.ln1_b = upload(W(p + ".slf_attn.layer_norm.bias", {H}));
+                L.ln2_g = upload(W(p + ".pos_ffn.layer_norm.weight", {H}));
+                L.ln2_b = upload(W(p + ".pos_ffn.layer_norm.bias", {H}));
+            }
+        }
+    }
+
+    static std::vector<float> sinusoid_table(int rows, int d, int first_row = 0) {
+        // fs2.py:17-37, float64 arithmetic then cast
+        std::vector<float> t((size_t)rows * d);
+        for (int r = 0; r < rows; ++r)
+            for (int j = 0; j < d; ++j) {
+                const double ang = (double)(first_row + r) / std::pow(10000.0, 2.0 * (double)(j / 2) / (double)d);
+                t[(size_t)r * d + j] = (float)((j & 1) ? std::cos(ang) : std::sin(ang));
+            }
+        return t;
+    }
+
+    // Position table: rows from the state_dict parameter, extended by the formula when longer inputs arrive
+    // (the reference recomputes the table in eval when L > max_len: fs2.py:287-294, 383-388).
+    const float* pos_table(bool decoder, int rows) {
+        auto& cache = decoder ? dec_pos : enc_pos;
+        auto& cache_rows = decoder ? dec_pos_rows : enc_pos_rows;
+        const int param_rows = (decoder ? cfg.max_mel_len : cfg.max_txt_len) + 1;
+        // reference semantics: parameter rows if L <= max_len else a freshly computed table
+        const bool need_formula = rows > param_rows - 1;
+        if (!need_formula) return decoder ? dec_pos_param : enc_pos_param;
+        if (rows > cache_rows) {
+            std::vector<float> t = sinusoid_table(rows, H);
+            cache = upload(t);  // old tables stay owned until destroy (rare growth)
+            cache_rows = rows;
+        }
+        return cache;
+    }
+
+    // Each section (encoder + variance adaptor, decoder, speaker net, vocoder) is packed independently so that a
+    // stand-alone Generator / ResNetSE34V2 (get_meldec, model.py:86-118; synthesize.py:141) works without the rest.
+    int finalize() {
+        ZVX_CUDA_CHECK(cudaSetDevice(dev));
+        for (void* p : owned) cudaFree(p);
+        owned.clear();
+        enc_pos = dec_pos = nullptr;
+        enc_pos_rows = dec_pos_rows = 0;
+        int ready = 0;
+        auto section = [&](int idx, void (Engine::*fn)()) {
+            try {
+                (this->*fn)();
+                sec_ready[idx] = true;
+                sec_err[idx].clear();
+                ++ready;
+            } catch (const std::exception& e) {
+                sec_ready[idx] = false;
+                sec_err[idx] = e.what();
+            }
+        };
+        section(SEC_ENC, &Engine::pack_encoder);
+        section(SEC_DEC, &Engine::pack_decoder);
+        section(SEC_SPK, &Engine::pack_spknet);
+        section(SEC_VOC, &Engine::pack_vocoder);
+        finalized = true;
+        if (ready == 0) throw Error("zvx_finalize_weights: no complete section; first problem: " + sec_err[SEC_ENC]);
+        return 0;
+    }
+
+    void pack_encoder() {
+        const int E = cfg.emb_dim, P = cfg.punct_emb_dim;
+        // encoder
+        const std::string e = "_phoneme_encoder._encoder";
+        enc_pos_param = upload(W(e + ".position_enc", {1, cfg.max_txt_len + 1, H}));
+        phon_emb = upload(W(e + ".src_word_emb.weight", {cfg.num_phones + 1, E}));
+        punct_emb = upload(W(e + ".punct_embed.weight", {cfg.num_puncts + 1, P}));
+        pack_fft(e, cfg.enc_layers, false, enc, nullptr);
+        // variance adaptor
+        const std::string va = "_phoneme_encoder._variance_adaptor";
+        const int F = cfg.vp_filter_size, K = cfg.vp_kernel_size;
+        int vi = 0;
+        for (const char* nm : {"duration", "pitch", "energy"}) {
+            const std::string p = va + "." + nm + "_predictor";
+            VarPredictor& v = vp[vi++];
+            v.wc1 = upload(tap_major(W(p + ".conv_layer.conv1d_1.conv.weight", {F, H, K})));
+            v.bc1 = upload(W(p + ".conv_layer.conv1d_1.conv.bias", {F}));
+            v.ln1_g = upload(W(p + ".conv_layer.layer_norm_1.weight", {F}));
+            v.ln1_b = upload(W(p + ".conv_layer.layer_norm_1.bias", {F}));
+            v.wc2 = upload(tap_major(W(p + ".conv_layer.conv1d_2.conv.weight", {F, F, K})));
+            v.bc2 = upload(W(p + ".conv_layer.conv1d_2.conv.bias", {F}));
+            v.ln2_g = upload(W(p + ".conv_layer.layer_norm_2.weight", {F}));
+            v.ln2_b = upload(W(p + ".conv_layer.layer_norm_2.bias", {F}));
+            v.wlin = upload(W(p + ".linear_layer.weight", {1, F}));
+            v.blin = upload(W(p + ".linear_layer.bias", {1}));
+        }
+        pitch_emb = upload(W(va + ".pitch_embedding.weight", {cfg.ve_n_bins, H}));
+        energy_emb = upload(W(va + ".energy_embedding.weight", {cfg.ve_n_bins, H}));
+    }
+
+    void pack_decoder() {
+        ZVX_REQUIRE(cfg.decoder_kind == 0, "decoder_kind=styletts has no CUDA path yet (SURVEY.md 8f row 1)");
+        const std::string d = "_mel_decoder";
+        dec_pos_param = upload(W(d + ".position_enc", {1, cfg.max_mel_len + 1, H}));
+        std::vector<float> scln_stack;
+        pack_fft(d, cfg.dec_layers, cfg.dec_scln != 0, dec, &scln_stack);
+        if (cfg.dec_scln) scln_w = upload(scln_stack);
+        mel_w = upload(W(d + ".mel_linear.weight", {cfg.n_mels, H}));
+        mel_b = upload(W(d + ".mel_linear.bias", {cfg.n_mels}));
+    }
+
+    void pack_spknet() {
+        const std::string s = "_spkemb";
+        const int* nf = cfg.resnet_num_filters;
+        {
+            const HostTensor& w = W(s + ".conv1.weight", {nf[0], 1, 3, 3});
+            std::vector<float> t((size_t)9 * nf[0]);
+            for (int c = 0; c < nf[0]; ++c)
+                for (int j = 0; j < 9; ++j) t[(size_t)j * nf[0] + c] = w.data[(size_t)c * 9 + j];
+            stem_w = upload(t);
+            stem_b = upload(W(s + ".conv1.bias", {nf[0]}));
+            bn_fold(s + ".bn1", nf[0], &stem_s, &stem_sh);
+        }
+        se_blocks.clear();
+        int inpl = nf[0];
+        for (int li = 0; li < 4; ++li) {
+            const int planes = nf[li];
+            ZVX_REQUIRE(planes % 8 == 0, "resnet_num_filters must be multiples of 8");
+            for (int bi = 0; bi < cfg.resnet_layers[li]; ++bi) {
+                const std::string p = s + ".layer" + std::to_string(li + 1) + "." + std::to_string(bi);
+                SEBlock b;
+                b.inpl = inpl;
+                b.planes = planes;
+                b.stride = (li > 0 && bi == 0) ? 2 : 1;
+                b.red = planes / 8;
+                b.w1 = upload(tap_major(W(p + ".conv1.weight", {planes, inpl, 3, 3})));
+                bn_fold(p + ".bn1", planes, &b.bn1_s, &b.bn1_b);
+                b.w2 = upload(tap_major(W(p + ".conv2.weight", {planes, planes, 3, 3})));
+                bn_fold(p + ".bn2", planes, &b.bn2_s, &b.bn2_b);
+                b.se_w1 = upload(W(p + ".se.fc.0.weight", {b.red, planes}));
+                b.se_b1 = upload(W(p + ".se.fc.0.bias", {b.red}));
+                b.se_w2 = upload(W(p + ".se.fc.2.weight", {planes, b.red}));
+                b.se_b2 = upload(W(p + ".se.fc.2.bias", {planes}));
+                if (b.stride != 1 || inpl != planes) {
+                    b.wd = upload(W(p + ".downsample.0.weight", {planes, inpl, 1, 1}));
+                    bn_fold(p + ".downsample.1", planes, &b.bnd_s, &b.bnd_b);
+                }
+                se_blocks.push_back(b);
+                inpl = planes;
+            }
+        }
+        spk_D = nf[3] * (cfg.n_mels / 8);
+        att_w0 = upload(W(s + ".attention.0.weight", {128, spk_D, 1}));
+        att_b0 = upload(W(s + ".attention.0.bias", {128}));
+        bn_fold(s + ".attention.2", 128, &att_bn_s, &att_bn_b);
+        att_w3 = upload(W(s + ".attention.3.weight", {spk_D, 128, 1}));
+        att_b3 = upload(W(s + ".attention.3.bias", {spk_D}));
+        const int out_dim = cfg.resnet_encoder_type == 1 ? 2 * spk_D : spk_D;
+        spk_fc_w = upload(W(s + ".fc.weight", {H, out_dim}));
+        spk_fc_b = upload(W(s + ".fc.bias", {H}));
+    }
+
+    void pack_vocoder() {
+        // vocoder: conv weights [Cout][Cin][k] -> [Cin][k][Cout]; transposed convs [Cin][Cout][k] -> [Cin][k][Cout]
+        auto pack_conv = [&](const std::string& key, int cout, int cin, int k, int dil) {
+            const HostTensor& w = W("_meldec." + key + ".weight", {cout, cin, k});
+            std::vector<float> t((size_t)cout * cin * k);
+            for (int co = 0; co < cout; ++co)
+                for (int ci = 0; ci < cin; ++ci)
+                    for (int j = 0; j < k; ++j)
+                        t[((size_t)ci * k + j) * cout + co] = w.data[((size_t)co * cin + ci) * k + j];
+            HGConv c;
+            c.w = upload(t);
+            c.b = upload(W("_meldec." + key + ".bias", {cout}));
+            c.cin = cin; c.cout = cout; c.k = k; c.dil = dil;
+            return c;
+        };
+        const int C0 = cfg.hg_upsample_initial_channel;
+        hg_pre = pack_conv("conv_pre", C0, cfg.n_mels, 7, 1);
+        hg_ups.clear();
+        hg_c1.clear();
+        hg_c2.clear();
+        int ch = C0;
+        for (int i = 0; i < cfg.hg_num_upsamples; ++i) {
+            const int cin = C0 >> i, cout = C0 >> (i + 1), k = cfg.hg_upsample_kernel_sizes[i];
+            ZVX_REQUIRE(cout >= 1, "too many upsample stages for upsample_initial_channel");
+            const HostTensor& w = W("_meldec.ups." + std::to_string(i) + ".weight", {cin, cout, k});
+            std::vector<float> t((size_t)cin * cout * k);
+            for (int ci = 0; ci < cin; ++ci)
+                for (int co = 0; co < cout; ++co)
+                    for (int j = 0; j < k; ++j)
+                        t[((size_t)ci * k + j) * cout + co] = w.data[((size_t)ci * cout + co) * k + j];
+            HGConv c;
+            c.w = upload(t);
+            c.b = upload(W("_meldec.ups." + std::to_string(i) + ".bias", {cout}));
+            c.cin = cin; c.cout = cout; c.k = k; c.dil = 1;
+            hg_ups.push_back(c);
+            ch = cout;
+            for (int j = 0; j < cfg.hg_num_kernels; ++j) {
+                const std::string p = "resblocks." + std::to_string(i * cfg.hg_num_kernels + j);
+                const int rk = cfg.hg_resblock_kernel_sizes[j];
+                for (int di = 0; di < cfg.hg_num_dilations; ++di) {
+                    const int dl = cfg.hg_resblock_dilation_sizes[j][di];
+                    if (cfg.hg_resblock == 1) {
+                        hg_c1.push_back(pack_conv(p + ".convs1." + std::to_string(di), ch, ch, rk, dl));
+                        hg_c2.push_back(pack_conv(p + ".convs2." + std::to_string(di), ch, ch, rk, 1));
+                    } else {
+                        hg_c1.push_back(pack_conv(p + ".convs." + std::to_string(di), ch, ch, rk, dl));
+                    }
+                }
+            }
+        }
+        hg_post = pack_conv("conv_post", 1, ch, 7, 1);
+    }
+
+    // ------------------------------------------------------------------------------------------ helpers
+    void gemm(const GemmArgs& a, bool tensor_core_ok, cudaStream_t st) {
+        if (tensor_core_ok && cfg.tensor_core_policy != 0 && gemm_tc_supported(a)) {
+            gemm_tc(a, st);
+        } else {
+            gemm_simt(a, st);
+        }
+    }
+
+    void linear(const float* x, int M, int K, const float* w, const float* b, int N, float* y, bool tc,
+                cudaStream_t st, const float* R = nullptr, int relu_first = 0, const float* scale = nullptr,
+                const float* shift = nullptr) {
+        GemmArgs a;
+        a.A = x; a.lda = K; a.W = w; a.ldw = K; a.C = y; a.ldc = N; a.bias = b; a.M = M; a.N = N; a.K = K;
+        a.R = R; a.ldr = N; a.relu_first = relu_first; a.scale = scale; a.shift = shift;
+        gemm(a, tc, st);
+    }
+
+    void conv1d_cl(const float* x, int B, int L, int Cin, const float* w, const float* b, int Cout, int k, int pad,
+                   float* y, bool tc, cudaStream_t st, const float* R = nullptr, int relu_first = 0) {
+        GemmArgs a;
+        a.A = x; a.lda = Cin; a.W = w; a.ldw = Cin; a.w_tap_stride = (long long)Cout * Cin; a.C = y; a.ldc = Cout;
+        a.bias = b; a.M = B * L; a.N = Cout; a.K = Cin; a.taps = k; a.R = R; a.ldr = Cout; a.relu_first = relu_first;
+        if (k > 1) {
+            a.mode = ROW_CONV1D; a.Lout = L; a.Lin = L; a.stride = 1; a.pad = pad; a.dil = 1;
+        }
+        gemm(a, tc, st);
+    }
+
+    struct FFTScratch {
+        float *qkv = nullptr, *att = nullptr, *y = nullptr, *S = nullptr, *h1 = nullptr;
+        int Lq_max = 0, ldS = 0;
+    };
+
+    FFTScratch fft_scratch(int B, int L, int n_head) {
+        FFTScratch s;
+        const long long rows = (long long)B * L;
+        const int DI = cfg.conv_filter_size;
+        s.qkv = ws.get<float>(rows * 3 * H);
+        s.att = ws.get<float>(rows * H);
+        s.y = ws.get<float>(rows * H);
+        // attention is chunked over query rows so that the score matrix stays below kScoreBytes
+        s.ldS = (int)round_up(L, 4);
+        const long long max_q = kScoreBytes / ((long long)B * n_head * s.ldS * (long long)sizeof(float));
+        s.Lq_max = (int)std::max<long long>(1, std::min<long long>(L, max_q));
+        s.S = ws.get<float>((long long)B * n_head * s.Lq_max * s.ldS);
+        // position-wise feed-forward hidden: re-use the qkv buffer when it is large enough
+        s.h1 = (3 * H >= DI) ? s.qkv : ws.get<float>(rows * DI);
+        return s;
+    }
+
+    // FFTBlock.forward (fs2.py:221-230) in place on x [B, L, H].
+    void fft_block(float* x, int B, int L, int n_head, const FFTLayer& ly, const uint8_t* mask, bool scln,
+                   const float* gb1, const float* gb2, int gb_ld, bool tc, const FFTScratch& sc, cudaStream_t st) {
+        const int dk = H / n_head, DI = cfg.conv_filter_size;
+        const int k1 = cfg.conv_kernel_size[0], k2 = cfg.conv_kernel_size[1];
+        const long long rows = (long long)B * L;
+        float *qkv = sc.qkv, *att = sc.att, *y = sc.y, *S = sc.S;
+        const int ldS = sc.ldS, Lq_max = sc.Lq_max;
+        const int nz = B * n_head;
+        linear(x, (int)rows, H, ly.wqkv, ly.bqkv, 3 * H, qkv, tc, st);
+        const float temperature = (float)std::pow((double)dk, 0.5);  // np.power(d_k, 0.5), fs2.py:122
+        for (int q0 = 0; q0 < L; q0 += Lq_max) {
+            const int Lq = std::min(Lq_max, L - q0);
+            GemmArgs s;
+            s.A = qkv + (long long)q0 * 3 * H; s.lda = 3 * H; s.W = qkv + H; s.ldw = 3 * H; s.C = S; s.ldc = ldS;
+            s.M = Lq; s.N = L; s.K = dk; s.nz = nz; s.nzh = n_head;
+            s.sA_b = (long long)L * 3 * H; s.sA_h = dk; s.sW_b = (long long)L * 3 * H; s.sW_h = dk;
+            s.sC_b = (long long)n_head * Lq * ldS; s.sC_h = (long long)Lq * ldS;
+            gemm(s, tc, st);
+            attn_softmax(S, nz, n_head, Lq, L, ldS, mask, L, temperature, st);
+            GemmArgs o;
+            o.A = S; o.lda = ldS; o.W = qkv + 2 * H; o.ldw = 3 * H; o.b_kn = 1; o.C = att + (long long)q0 * H; o.ldc = H;
+            o.M = Lq; o.N = dk; o.K = L; o.nz = nz; o.nzh = n_head;
+            o.sA_b = (long long)n_head * Lq * ldS; o.sA_h = (long long)Lq * ldS;
+            o.sW_b = (long long)L * 3 * H; o.sW_h = dk; o.sC_b = (long long)L * H; o.sC_h = dk;
+            gemm(o, tc, st);
+        }
+        linear(att, (int)rows, H, ly.wfc, ly.bfc, H, y, tc, st, /*R=*/x);
+        NormArgs n;
+        n.x = y; n.out = x; n.rows = (int)rows; n.C = H; n.rows_per_batch = L; n.mask = mask;
+        if (scln) { n.scln = 1; n.gb = gb1; n.gb_ld = gb_ld; n.eps = 1e-8f; }
+        else { n.gamma = ly.ln1_g; n.beta = ly.ln1_b; n.eps = 1e-5f; }
+        layer_norm(n, st);
+        // position-wise feed-forward (fs2.py:196-209)
+        float* h1 = sc.h1;
+        conv1d_cl(x, B, L, H, ly.w1, ly.b1, DI, k1, (k1 - 1) / 2, h1, tc, st, nullptr, /*relu_first=*/1);
+        conv1d_cl(h1, B, L, DI, ly.w2, ly.b2, H, k2, (k2 - 1) / 2, y, tc, st, /*R=*/x);
+        n.x = y; n.out = x;
+        if (scln) n.gb = gb2; else { n.gamma = ly.ln2_g; n.beta = ly.ln2_b; }
+        layer_norm(n, st);
+    }
+
+    void variance_predictor(const float* x, int B, int T, const VarPredictor& v, const uint8_t* mask, float* out,
+                            cudaStream_t st) {
+        const int F = cfg.vp_filter_size, K = cfg.vp_kernel_size;
+        const long long rows = (long long)B * T;
+        float* c1 = ws.get<float>(rows * F);
+        float* c2 = ws.get<float>(rows * F);
+        conv1d_cl(x, B, T, H, v.wc1, v.bc1, F, K, (K - 1) / 2, c1, false, st, nullptr, 1);
+        NormArgs n;
+        n.x = c1; n.out = c1; n.rows = (int)rows; n.C = F; n.gamma = v.ln1_g; n.beta = v.ln1_b; n.eps = 1e-5f;
+        layer_norm(n, st);
+        conv1d_cl(c1, B, T, F, v.wc2, v.bc2, F, K, 1, c2, false, st, nullptr, 1);  // padding=1 (fs2.py:543)
+        n.x = c2; n.out = nullptr; n.gamma = v.ln2_g; n.beta = v.ln2_b;
+        n.dot_w = v.wlin; n.dot_b = v.blin; n.dot_out = out; n.mask = mask;
+        layer_norm(n, st);
+    }
+
+    void check_ready(int sec) {
+        ZVX_REQUIRE(finalized, "weights not finalized: call zvx_finalize_weights first");
+        if (!sec_ready[sec]) throw Error("weights for this stage are incomplete: " + sec_err[sec]);
+        ZVX_CUDA_CHECK(cudaSetDevice(dev));
+    }
+
+    // ------------------------------------------------------------------------------------------ stages
+    int spkemb(const float* ref_mel, int B, int T, float* style, cudaStream_t st) {
+        check_ready(SEC_SPK);
+        ZVX_REQUIRE(B >= 0 && T >= 8, "zvx_spkemb: need T_ref >= 8 frames");
+        ws.reset();
+        const int M = cfg.n_mels;
+        const int* nf = cfg.resnet_num_filters;
+        const bool tc = true;
+        float* x0 = ws.get<float>((long long)B * M * T);
+        instance_norm_time(ref_mel, B, T, M, x0, st);
+        long long big = (long long)B * M * T * nf[0];
+        float* buf[4];
+        for (int i = 0; i < 4; ++i) buf[i] = ws.get<float>(big);
+        float* pooled = ws.get<float>((long long)B * 1024);
+        float* gate = ws.get<float>((long long)B * 1024);
+        float* x = buf[0];
+        stem_conv3x3(x0, stem_w, stem_b, stem_s, stem_sh, B, M, T, nf[0], x, st);
+        int Hh = M, Ww = T;
+        int xi = 0;
+        for (const SEBlock& b : se_blocks) {
+            ZVX_REQUIRE(b.planes <= 1024, "resnet filters > 1024");
+            const int Ho = (Hh - 1) / b.stride + 1, Wo = (Ww - 1) / b.stride + 1;
+            float* t1 = buf[(xi + 1) & 3];
+            float* t2 = buf[(xi + 2) & 3];
+            float* rs = buf[(xi + 3) & 3];
+            GemmArgs c;
+            c.A = x; c.lda = b.inpl; c.W = b.w1; c.ldw = b.inpl; c.w_tap_stride = (long long)b.planes * b.inpl;
+            c.C = t1; c.ldc = b.planes; c.M = B * Ho * Wo; c.N = b.planes; c.K = b.inpl; c.taps = 9;
+            c.mode = ROW_CONV2D; c.Ho = Ho; c.Wo = Wo; c.Hi = Hh; c.Wi = Ww; c.ksize = 3; c.stride = b.stride; c.pad = 1;
+            c.relu_first = 1; c.scale = b.bn1_s; c.shift = b.bn1_b;
+            gemm(c, tc, st);
+            GemmArgs c2;
+            c2.A = t1; c2.lda = b.planes; c2.W = b.w2; c2.ldw = b.planes; c2.w_tap_stride = (long long)b.planes * b.planes;
+            c2.C = t2; c2.ldc = b.planes; c2.M = B * Ho * Wo; c2.N = b.planes; c2.K = b.planes; c2.taps = 9;
+            c2.mode = ROW_CONV2D; c2.Ho = Ho; c2.Wo = Wo; c2.Hi = Ho; c2.Wi = Wo; c2.ksize = 3; c2.stride = 1; c2.pad = 1;
+            c2.scale = b.bn2_s; c2.shift = b.bn2_b;
+            gemm(c2, tc, st);
+            hw_mean(t2, B, Ho * Wo, b.planes, pooled, st);
+            se_excite(pooled, b.se_w1, b.se_b1, b.se_w2, b.se_b2, B, b.planes, b.red, gate, st);
+            const float* res = x;
+            if (b.wd) {
+                GemmArgs dn;
+                dn.A = x; dn.lda = b.inpl; dn.W = b.wd; dn.ldw = b.inpl; dn.C = rs; dn.ldc = b.planes;
+                dn.M = B * Ho * Wo; dn.N = b.planes; dn.K = b.inpl; dn.taps = 1;
+                dn.mode = ROW_CONV2D; dn.Ho = Ho; dn.Wo = Wo; dn.Hi = Hh; dn.Wi = Ww; dn.ksize = 1; dn.stride = b.stride; dn.pad = 0;
+                dn.scale = b.bnd_s; dn.shift = b.bnd_b;
+                gemm(dn, tc, st);
+                res = rs;
+            }
+            se_scale_add_relu(t2, gate, res, B, Ho * Wo, b.planes, t1, st);  // t1 is free again
+            x = t1;
+            xi = (xi + 1) & 3;
+            Hh = Ho;
+            Ww = Wo;
+        }
+        // attentive statistics pooling head (ResNetSE34V2.py:196-208)
+        const int C3 = nf[3];
+        ZVX_REQUIRE(Hh * C3 == spk_D, "speaker net: unexpected feature-map height");
+        float* flat = ws.get<float>((long long)B * Ww * spk_D);
+        float* a1 = ws.get<float>((long long)B * Ww * 128);
+        float* lg = ws.get<float>((long long)B * Ww * spk_D);
+        const int asp = cfg.resnet_encoder_type == 1;
+        float* stats = ws.get<float>((long long)B * spk_D * 2);
+        spk_flatten(x, B, Hh, Ww, C3, flat, st);
+        linear(flat, B * Ww, spk_D, att_w0, att_b0, 128, a1, tc, st, nullptr, 1, att_bn_s, att_bn_b);
+        linear(a1, B * Ww, 128, att_w3, att_b3, spk_D, lg, tc, st);
+        attentive_pool(flat, lg, B, Ww, spk_D, asp, stats, st);
+        linear(stats, B, asp ? 2 * spk_D : spk_D, spk_fc_w, spk_fc_b, H, style, false, st);
+        l2_normalize(style, B, H, st);
+        return 0;
+    }
+
+    int encode(const int32_t* phoneme, const int32_t* puncts, const uint8_t* mask, const float* style,
+               const int32_t* forced, int B, int T, float* pitch, float* energy, float* log_dur, int32_t* dur,
+               int64_t* mel_len, float* xprime, int64_t* mel_len_host, int* L_max_out, cudaStream_t st) {
+        check_ready(SEC_ENC);
+        ZVX_REQUIRE(B >= 1 && T >= 1, "zvx_encode: empty batch");
+        ZVX_REQUIRE(B <= kMaxBatch, "zvx_encode: batch too large");
+        ws.reset();
+        float* x = xprime;
+        embed_posenc(phoneme, puncts, phon_emb, punct_emb, pos_table(false, T), B, T, cfg.emb_dim, cfg.punct_emb_dim, x, st);
+        const FFTScratch sc = fft_scratch(B, T, cfg.enc_heads);
+        for (int i = 0; i < cfg.enc_layers; ++i)
+            fft_block(x, B, T, cfg.enc_heads, enc[(size_t)i], mask, false, nullptr, nullptr, 0, /*tc=*/false, sc, st);
+        add_batch_vector(x, style, B, T, H, st);  // all positions, padded ones too (fs2.py:740-741)
+        variance_predictor(x, B, T, vp[0], mask, log_dur, st);
+        variance_predictor(x, B, T, vp[1], mask, pitch, st);
+        bucket_embed_add(x, pitch, pitch_emb, B * T, H, cfg.ve_n_bins, nullptr, st);
+        variance_predictor(x, B, T, vp[2], mask, energy, st);
+        bucket_embed_add(x, energy, energy_emb, B * T, H, cfg.ve_n_bins, nullptr, st);
+        duration_round(log_dur, forced, dur, B * T, st);
+        int32_t* cum = ws.get<int32_t>((long long)B * T);
+        duration_scan(dur, B, T, cum, mel_len, st);
+        if (L_max_out) {
+            ZVX_CUDA_CHECK(cudaMemcpyAsync(pinned_len, mel_len, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, st));
+            ZVX_CUDA_CHECK(cudaStreamSynchronize(st));  // the one inherent sync (the reference: B*T + 1)
+            int64_t mx = 0;
+            for (int b = 0; b < B; ++b) mx = std::max(mx, pinned_len[b]);
+            ZVX_REQUIRE(mx < (1LL << 30), "zvx_encode: implausible mel length");
+            *L_max_out = (int)mx;
+            if (mel_len_host) std::memcpy(mel_len_host, pinned_len, sizeof(int64_t) * B);
+        }
+        return 0;
+    }
+
+    int length_regulate(const float* xprime, const int32_t* dur, int B, int T, int L_max, float* features,
+                        int32_t* src_index, cudaStream_t st) {
+        ZVX_CUDA_CHECK(cudaSetDevice(dev));
+        ZVX_REQUIRE(B >= 1 && T >= 1 && L_max >= 0 && B <= 65535, "zvx_length_regulate: bad sizes");
+        ws.reset();
+        int32_t* cum = ws.get<int32_t>((long long)B * T);
+        duration_scan(dur, B, T, cum, nullptr, st);
+        length_regulate_gather(xprime, cum, B, T, H, L_max, features, src_index, st);
+        return 0;
+    }
+
+    int decode(const float* features, const uint8_t* mask, const int64_t* mel_len, const float* style, int B, int L,
+               int zero_padded_mel, float* mel_BLC, float* mel_BCL, cudaStream_t st) {
+        check_ready(SEC_DEC);
+        ZVX_REQUIRE(B >= 1 && L >= 1, "zvx_decode: empty batch");
+        ZVX_REQUIRE(mask || mel_len, "zvx_decode: need mask or mel_len");
+        ws.reset();
+        const bool tc = true;
+        if (!mask) {
+            uint8_t* m = ws.get<uint8_t>((long long)B * L);
+            mask_from_lengths(mel_len, B, L, m, st);
+            mask = m;
+        }
+        const int nscln = cfg.dec_layers * 2;
+        float* gb = nullptr;
+        if (cfg.dec_scln) {
+            gb = ws.get<float>((long long)B * nscln * 2 * H);
+            linear(style, B, H, scln_w, nullptr, nscln * 2 * H, gb, false, st);
+        }
+        float* x = ws.get<float>((long long)B * L * H);
+        add_posenc(features, pos_table(true, L), B, L, H, x, st);
+        const FFTScratch sc = fft_scratch(B, L, cfg.dec_heads);
+        for (int i = 0; i < cfg.dec_layers; ++i) {
+            const float* gb1 = gb ? gb + (long long)(2 * i) * 2 * H : nullptr;
+            const float* gb2 = gb ? gb + (long long)(2 * i + 1) * 2 * H : nullptr;
+            fft_block(x, B, L, cfg.dec_heads, dec[(size_t)i], mask, cfg.dec_scln != 0, gb1, gb2, nscln * 2 * H, tc, sc, st);
+        }
+        float* mel = mel_BLC ? mel_BLC : ws.get<float>((long long)B * L * cfg.n_mels);
+        linear(x, B * L, H, mel_w, mel_b, cfg.n_mels, mel, tc, st);
+        if (mel_BCL || zero_padded_mel)
+            transpose_mel(mel, mask, zero_padded_mel, B, L, cfg.n_mels, mel_BCL, zero_padded_mel ? mel : nullptr, st);
+        return 0;
+    }
+
+    int vocode(const float* mel, int B, int L, float* wav, cudaStream_t st) {
+        check_ready(SEC_VOC);
+        ZVX_REQUIRE(B >= 1 && L >= 1 && B <= 65535, "zvx_vocode: bad sizes");
+        ws.reset();
+        const int C0 = cfg.hg_upsample_initial_channel;
+        const int nk = cfg.hg_num_kernels, nd = cfg.hg_num_dilations;
+        // largest activation: max over stages of C * T
+        long long big = (long long)C0 * L, t = L;
+        for (int i = 0; i < cfg.hg_num_upsamples; ++i) {
+            t *= cfg.hg_upsample_rates[i];
+            big = std::max(big, (long long)(C0 >> (i + 1)) * t);
+        }
+        big *= B;
+        float* x = ws.get<float>(big);
+        float* y = ws.get<float>(big);
+        float* ra = ws.get<float>(big);
+        float* rb = ws.get<float>(big);
+        float* tmp = ws.get<float>(big);
+        Conv1dArgs a;
+        a.x = mel; a.w = hg_pre.w; a.bias = hg_pre.b; a.B = B; a.Cin = cfg.n_mels; a.Cout = C0; a.T = L; a.k = 7;
+        a.dil = 1; a.in_slope = 1.f; a.out = x;
+        conv1d_cf(a, st);
+        int T = L;
+        size_t ci = 0;
+        for (int i = 0; i < cfg.hg_num_upsamples; ++i) {
+            const HGConv& up = hg_ups[(size_t)i];
+            conv_transpose1d_cf(x, up.w, up.b, B, up.cin, up.cout, T, up.k, cfg.hg_upsample_rates[i], 0.1f, y, st);
+            T *= cfg.hg_upsample_rates[i];
+            const int ch = up.cout;
+            for (int j = 0; j < nk; ++j) {
+                const float* r = y;
+                for (int di = 0; di < nd; ++di, ++ci) {
+                    const bool last = (di == nd - 1);
+                    float* rn = (r == ra) ? rb : ra;
+                    Conv1dArgs c;
+                    c.B = B; c.Cin = ch; c.Cout = ch; c.T = T; c.in_slope = 0.1f;
+                    if (cfg.hg_resblock == 1) {
+                        const HGConv &c1 = hg_c1[ci], &c2 = hg_c2[ci];
+                        c.x = r; c.w = c1.w; c.bias = c1.b; c.k = c1.k; c.dil = c1.dil; c.out = tmp;
+                        conv1d_cf(c, st);
+                        c.x = tmp; c.w = c2.w; c.bias = c2.b; c.k = c2.k; c.dil = 1; c.res = r;
+                    } else {
+                        const HGConv& c1 = hg_c1[ci];
+                        c.x = r; c.w = c1.w; c.bias = c1.b; c.k = c1.k; c.dil = c1.dil; c.res = r;
+                    }
+                    if (last) {  // xs (+)= resblock(x); x = xs / num_kernels   (hifigan.py:119-125)
+                        c.out = nullptr; c.acc = x; c.acc_init = (j == 0); c.acc_scale = 1.f / (float)nk;
+                    } else {
+                        c.out = rn;
+                    }
+                    conv1d_cf(c, st);
+                    r = rn;
+                }
+            }
+        }
+        Conv1dArgs p;
+        p.x = x; p.w = hg_post.w; p.bias = hg_post.b; p.B = B; p.Cin = hg_post.cin; p.Cout = 1; p.T = T; p.k = 7;
+        p.dil = 1; p.in_slope = 0.01f; p.tanh_out = 1; p.out = wav;  // F.leaky_relu default slope (hifigan.py:126)
+        conv1d_cf(p, st);
+        return 0;
+    }
+
+    static constexpr int kMaxBatch = 65536;
+    static constexpr long long kScoreBytes = 1LL << 30;  // attention-score chunk budget
+
+    zvx_config cfg;
+    int dev = 0;
+    int num_sms = 0;
+    int H = 0;
+    std::string err;
+    std::map<std::string, HostTensor> raw;
+    std::vector<void*> owned;
+    bool finalized = false;
+    enum { SEC_ENC = 0, SEC_DEC = 1, SEC_SPK = 2, SEC_VOC = 3 };
+    bool sec_ready[4] = {false, false, false, false};
+    std::string sec_err[4];
+    Workspace ws;
+    int64_t* pinned_len = nullptr;
+
+    float *enc_pos_param = nullptr, *dec_pos_param = nullptr, *enc_pos = nullptr, *dec_pos = nullptr;
+    int enc_pos_rows = 0, dec_pos_rows = 0;
+    float *phon_emb = nullptr, *punct_emb = nullptr, *pitch_emb = nullptr, *energy_emb = nullptr;
+    std::vector<FFTLayer> enc, dec;
+    VarPredictor vp[3];
+    float *scln_w = nullptr, *mel_w = nullptr, *mel_b = nullptr;
+    float *stem_w = nullptr, *stem_b = nullptr, *stem_s = nullptr, *stem_sh = nullptr;
+    std::vector<SEBlock> se_blocks;
+    int spk_D = 0;
+    float *att_w0 = nullptr, *att_b0 = nullptr, *att_bn_s = nullptr, *att_bn_b = nullptr, *att_w3 = nullptr,
+          *att_b3 = nullptr, *spk_fc_w = nullptr, *spk_fc_b = nullptr;
+    HGConv hg_pre, hg_post;
+    std::vector<HGConv> hg_ups, hg_c1, hg_c2;
+};
+
+}  // namespace zvx
+
+// -------------------------------------------------------------------------------------------------- C ABI
+struct zvx_handle {
+    std::unique_ptr<zvx::Engine> eng;
+};
+
+#define ZVX_GUARD(h, body)                                                     \
+    if (!(h) || !(h)->eng) return -1;                                          \
+    try {                                                                      \
+        body;                                                                  \
+    } catch (const std::exception& e) {                                        \
+        (h)->eng->err = e.what();                                              \
+        return 1;                                                              \
+    } catch (...) {                                                            \
+        (h)->eng->err = "unknown error";                                       \
+        return 2;                                                              \
+    }
+
+extern "C" {
+
+int zvx_abi_version(void) { return ZVX_ABI_VERSION; }
+
+int zvx_create(const zvx_config* cfg, int device, zvx_handle** out) {
+    if (!cfg || !out) {
+        zvx::g_create_error = "zvx_create: null argument";
+        return -1;
+    }
+    try {
+        auto* h = new zvx_handle();
+        h->eng.reset(new zvx::Engine(*cfg, device));
+        *out = h;
+        return 0;
+    } catch (const std::exception& e) {
+        zvx::g_create_error = e.what();
+        return 1;
+    } catch (...) {
+        zvx::g_create_error = "unknown error";
+        return 2;
+    }
+}
+
+void zvx_destroy(zvx_handle* h) { delete h; }
+
+const char* zvx_last_error(const zvx_handle* h) {
+    if (!h || !h->eng) return zvx::g_create_error.c_str();
+    return h->eng->err.c_str();
+}
+
+int zvx_set_weight(zvx_handle* h, const char* key, const void* data, const int64_t* shape, int ndim) {
+    ZVX_GUARD(h, return h->eng->set_weight(key, data, shape, ndim));
+}
+
+int zvx_finalize_weights(zvx_handle* h) { ZVX_GUARD(h, return h->eng->finalize()); }
+
+int zvx_spkemb(zvx_handle* h, const float* ref_mel, int B, int T_ref, float* style, void* stream) {
+    ZVX_GUARD(h, return h->eng->spkemb(ref_mel, B, T_ref, style, (cudaStream_t)stream));
+}
+
+int zvx_encode(zvx_handle* h, const int32_t* phoneme, const int32_t* puncts, const uint8_t* phoneme_mask,
+               const float* style, const int32_t* forced_dur, int B, int T, float* pitch, float* energy,
+               float* log_dur, int32_t* dur_rounded, int64_t* mel_len, float* xprime, int64_t* mel_len_host,
+               int* L_max_out, void* stream) {
+    ZVX_GUARD(h, return h->eng->encode(phoneme, puncts, phoneme_mask, style, forced_dur, B, T, pitch, energy,
+                                       log_dur, dur_rounded, mel_len, xprime, mel_len_host, L_max_out,
+                                       (cudaStream_t)stream));
+}
+
+int zvx_length_regulate(zvx_handle* h, const float* xprime, const int32_t* dur, int B, int T, int L_max,
+                        float* features, int32_t* src_index, void* stream) {
+    ZVX_GUARD(h, return h->eng->length_regulate(xprime, dur, B, T, L_max, features, src_index, (cudaStream_t)stream));
+}
+
+int zvx_decode(zvx_handle* h, const float* features, const uint8_t* mask, const int64_t* mel_len,
+               const float* style, int B, int L, int zero_padded_mel, float* mel_BLC, float* mel_BCL, void* stream) {
+    ZVX_GUARD(h, return h->eng->decode(features, mask, mel_len, style, B, L, zero_padded_mel, mel_BLC, mel_BCL,
+                                       (cudaStream_t)stream));
+}
+
+int zvx_vocode(zvx_handle* h, const float* mel_BCL, int B, int L, float* wav, void* stream) {
+    ZVX_GUARD(h, return h->eng->vocode(mel_BCL, B, L, wav, (cudaStream_t)stream));
+}
+
+int64_t zvx_workspace_bytes(const zvx_handle* h) { return (h && h->eng) ? h->eng->ws.bytes() : 0; }
+
+int64_t zvx_launch_count(const zvx_handle* h) {
+    (void)h;
+    return zvx::g_launches;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Launchers for the non-GEMM kernels (HBM-bound gather / normalise / elementwise work).
+#pragma once
+#include "common.cuh"
+
+namespace zvx {
+
+// ---- FastSpeech2 acoustic model (kernels_fs2.cu) ---------------------------------------------------
+// K1: out[b,t,:] = cat(phon_emb[phoneme[b,t]], punct_emb[puncts[b,t]]) + pos[t]      (fs2.py:372-392)
+void embed_posenc(const int32_t* phoneme, const int32_t* puncts, const float* phon_emb, const float* punct_emb,
+                  const float* pos, int B, int T, int E, int P, float* out, cudaStream_t st);
+
+// K6: LayerNorm (eps inside sqrt, biased variance) or SCLN (unbiased std, sigma + eps; fs2.py:76-90).
+struct NormArgs {
+    const float* x = nullptr;     // [rows, C]
+    float* out = nullptr;         // [rows, C] (may alias x); ignored when dot_w != nullptr
+    int rows = 0, C = 0;
+    int rows_per_batch = 1;       // L: batch index of a row = row / L
+    int scln = 0;
+    const float* gamma = nullptr; // LN weight [C]
+    const float* beta = nullptr;  // LN bias [C]
+    const float* gb = nullptr;    // SCLN: per-batch affine rows, bias at gb[b*gb_ld + 0..C), gain at +C..2C
+    int gb_ld = 0;
+    float eps = 1e-5f;
+    const uint8_t* mask = nullptr;  // [rows], 1 = padding -> output row (or dot) is 0   (fs2.py:225,228,560-561)
+    const float* dot_w = nullptr;   // optional fused Linear(C -> 1): dot_out[row] = <norm(x), dot_w> + dot_b[0]
+    const float* dot_b = nullptr;
+    float* dot_out = nullptr;
+};
+void layer_norm(const NormArgs& a, cudaStream_t st);
+
+// K4 (softmax part): in-place over S[z][q][0..L) with z = b*nh + h:  softmax_j( S/temperature, key mask -> -inf ).
+// Columns [L, ldS) are zeroed so S can feed a K-padded GEMM.
+void attn_softmax(float* S, int nz, int nh, int Lq, int L, int ldS, const uint8_t* key_mask /*[B,L]*/, int mask_ld,
+                  float temperature, cudaStream_t st);
+
+// x[b,t,:] += v[b,:]   (fs2.py:740-741)
+void add_batch_vector(float* x, const float* v, int B, int T, int C, cudaStream_t st);
+
+// K9: x[b,t,:] += table[clamp(rint(pred[b,t]*(n_bins-1)), 0, n_bins-1), :]   (fs2.py:639, 649, 668, 672)
+void bucket_embed_add(float* x, const float* pred, const float* table, int rows, int C, int n_bins,
+                      int32_t* bucket_out /*nullable*/, cudaStream_t st);
+
+// K10: dur[b,t] = forced ? forced[b,t] : clamp(rint(exp(log_d) - 1), 0)      (fs2.py:674-681)
+void duration_round(const float* log_d, const int32_t* forced, int32_t* dur, int n, cudaStream_t st);
+
+// K11a: inclusive scan of max(dur,0) along T; total -> mel_len (int64).      (fs2.py:447-455)
+void duration_scan(const int32_t* dur, int B, int T, int32_t* cum, int64_t* mel_len, cudaStream_t st);
+
+// K11b: gather. features[b,f,:] = x[b, idx, :], idx = upper_bound(cum[b], f); zero rows past mel_len. (fs2.py:403-459)
+void length_regulate_gather(const float* x, const int32_t* cum, int B, int T, int C, int L_max, float* features,
+                            int32_t* src_index /*nullable*/, cudaStream_t st);
+
+// K12: out[b,l,:] = x[b,l,:] + pos[l,:]      (fs2.py:287-304)
+void add_posenc(const float* x, const float* pos, int B, int L, int C, float* out, cudaStream_t st);
+
+// mask[b,l] = l >= mel_len[b]      (model.py:269-273, fs2.py:565-573)
+void mask_from_lengths(const int64_t* mel_len, int B, int L, uint8_t* mask, cudaStream_t st);
+
+// [B,L,C] -> [B,C,L], rows with mask==1 zeroed when zero_masked (model.py:283-285); also optionally fixes up the
+// [B,L,C] copy in place.
+void transpose_mel(const float* mel_BLC, const uint8_t* mask, int zero_masked, int B, int L, int C, float* mel_BCL,
+                   float* mel_BLC_inplace /*nullable*/, cudaStream_t st);
+
+// ---- HiFi-GAN (kernels_hifigan.cu), channel-first [B, C, T] ------------------------------------------
+struct Conv1dArgs {
+    const float* x = nullptr;   // [B, Cin, T]
+    const float* w = nullptr;   // packed [Cin][k][Cout]
+    const float* bias = nullptr;  // [Cout]
+    int B = 0, Cin = 0, Cout = 0, T = 0, k = 1, dil = 1;  // 'same' padding (k*d - d)/2      (hifigan.py:22-23)
+    float in_slope = 1.f;       // leaky-ReLU slope applied to x on load (1 = identity)
+    const float* res = nullptr; // optional residual [B, Cout, T] added to the result
+    float* out = nullptr;       // optional plain output
+    float* acc = nullptr;       // optional accumulator: acc = (acc_init ? 0 : acc) + result * acc_scale
+    int acc_init = 0;
+    float acc_scale = 1.f;
+    int tanh_out = 0;
+};
+void conv1d_cf(const Conv1dArgs& a, cudaStream_t st);
+
+// ConvTranspose1d(stride u, kernel k, padding (k-u)/2) with leaky-ReLU on load   (hifigan.py:99-102, 117-118)
+// x [B,Cin,T] -> out [B,Cout,T*u]; w packed [Cin][k][Cout].
+void conv_transpose1d_cf(const float* x, const float* w, const float* bias, int B, int Cin, int Cout, int T, int k,
+                         int u, float in_slope, float* out, cudaStream_t st);
+
+// ---- ResNetSE34V2 (kernels_spk.cu), channel-last [B, H, W, C] ---------------------------------------
+// InstanceNorm1d over time (no affine, biased var, eps 1e-5): ref_mel [B,T,n_mels] -> out [B, n_mels(H), T(W)]
+void instance_norm_time(const float* ref_mel, int B, int T, int n_mels, float* out, cudaStream_t st);
+// stem: Conv2d(1->C, 3x3, pad 1, bias) -> ReLU -> BN(scale, shift); in [B,H,W] -> out [B,H,W,C]
+void stem_conv3x3(const float* in, const float* w /*[9][C]*/, const float* bias, const float* scale,
+                  const float* shift, int B, int H, int W, int C, float* out, cudaStream_t st);
+// SE squeeze: mean over HW -> [B, C]
+void hw_mean(const float* x, int B, int HW, int C, float* out, cudaStream_t st);
+// SE excitation: y = sigmoid(W2 relu(W1 p + b1) + b2), p [B,C], W1 [R,C], W2 [C,R]
+void se_excite(const float* p, const float* w1, const float* b1, const float* w2, const float* b2, int B, int C,
+               int R, float* y, cudaStream_t st);
+// out = relu(x * y[b,c] + res)
+void se_scale_add_relu(const float* x, const float* y, const float* res, int B, int HW, int C, float* out,
+                       cudaStream_t st);
+// [B, Hh, W, C] -> [B, W, C*Hh] with feature index c*Hh + h  (x.reshape(B, -1, W), ResNetSE34V2.py:196)
+void spk_flatten(const float* x, int B, int Hh, int W, int C, float* out, cudaStream_t st);
+// softmax over time of logits [B,W,D], then attentive statistics (mu, sigma) of feat [B,W,D] -> out [B, 2D] (ASP)
+// or weighted mean only -> out [B, D] (SAP)       (ResNetSE34V2.py:198-204)
+void attentive_pool(const float* feat, const float* logits, int B, int W, int D, int asp, float* out,
+                    cudaStream_t st);
+// x[b,:] /= max(||x[b,:]||_2, 1e-12)       (F.normalize, ResNetSE34V2.py:207-208)
+void l2_normalize(float* x, int B, int C, cudaStream_t st);
+
+}  // namespace zvx

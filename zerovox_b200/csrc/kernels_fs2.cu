@@ -1,0 +1,403 @@
+// HBM-bound kernels of the FastSpeech2 acoustic model: embedding gather, (SC)LayerNorm, masked softmax,
+// variance-adaptor bucketing, duration rounding / scan and the LengthRegulator gather.
+// All row kernels use 128-bit accesses where the channel count allows and one warp per row.
+#include "kernels.cuh"
+
+namespace zvx {
+
+long long g_launches = 0;
+
+// ------------------------------------------------------------------------------------------------
+// K1 embedding + position encoding (fs2.py:372-392)
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_posenc_kernel(const int32_t* __restrict__ phoneme, const int32_t* __restrict__ puncts,
+                                    const float* __restrict__ phon_emb, const float* __restrict__ punct_emb,
+                                    const float* __restrict__ pos, int rows, int T, int E, int P,
+                                    float* __restrict__ out) {
+    const int row = blockIdx.x;
+    if (row >= rows) return;
+    const int t = row % T;
+    const int C = E + P;
+    const float* pe = phon_emb + (long long)phoneme[row] * E;
+    const float* qe = punct_emb + (long long)puncts[row] * P;
+    const float* ps = pos + (long long)t * C;
+    float* o = out + (long long)row * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v = (c < E) ? __ldg(pe + c) : __ldg(qe + (c - E));
+        o[c] = v + __ldg(ps + c);
+    }
+}
+
+void embed_posenc(const int32_t* phoneme, const int32_t* puncts, const float* phon_emb, const float* punct_emb,
+                  const float* pos, int B, int T, int E, int P, float* out, cudaStream_t st) {
+    if (B * T == 0) return;
+    embed_posenc_kernel<<<B * T, 128, 0, st>>>(phoneme, puncts, phon_emb, punct_emb, pos, B * T, T, E, P, out);
+    ZVX_POST_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6 LayerNorm / SCLN, one warp per row, row held in registers (C <= 1024)
+// ------------------------------------------------------------------------------------------------
+constexpr int NORM_MAXV = 8;  // float4 per lane -> C <= 32*4*8 = 1024
+
+__global__ void __launch_bounds__(256) layer_norm_kernel(const NormArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.rows) return;
+    const int row = warp;
+    const bool masked = a.mask && a.mask[row];
+    if (masked) {
+        if (a.dot_w) {
+            if (lane == 0) a.dot_out[row] = 0.f;
+        } else {
+            float4* o = reinterpret_cast<float4*>(a.out + (long long)row * a.C);
+            for (int c4 = lane; c4 < a.C / 4; c4 += 32) o[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
+    const int C4 = a.C >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(a.x + (long long)row * a.C);
+    float4 v[NORM_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c4 = lane + i * 32;
+        if (c4 < C4) {
+            v[i] = xr[c4];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mu = warp_sum(s) / (float)a.C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c4 = lane + i * 32;
+        if (c4 < C4) {
+            float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
+            q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+    }
+    q = warp_sum(q);
+    float inv;
+    const float *gp, *bp;
+    if (a.scln) {
+        const float sigma = sqrtf(q / (float)(a.C - 1));  // torch.std: unbiased
+        inv = 1.f / (sigma + a.eps);
+        const float* gb = a.gb + (long long)(row / a.rows_per_batch) * a.gb_ld;
+        bp = gb;          // bias rows first  (fs2.py:85)
+        gp = gb + a.C;    // gain rows second
+    } else {
+        inv = rsqrtf(q / (float)a.C + a.eps);
+        gp = a.gamma;
+        bp = a.beta;
+    }
+    float dot = 0.f;
+    float4* o = a.dot_w ? nullptr : reinterpret_cast<float4*>(a.out + (long long)row * a.C);
+#pragma unroll
+    for (int i = 0; i < NORM_MAXV; ++i) {
+        const int c4 = lane + i * 32;
+        if (c4 < C4) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gp) + c4);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bp) + c4);
+            float4 y;
+            if (a.scln) {
+                // o = g * ((x - mu) / (sigma + eps)) + b
+                y.x = fmaf(g.x, (v[i].x - mu) * inv, b.x);
+                y.y = fmaf(g.y, (v[i].y - mu) * inv, b.y);
+                y.z = fmaf(g.z, (v[i].z - mu) * inv, b.z);
+                y.w = fmaf(g.w, (v[i].w - mu) * inv, b.w);
+            } else {
+                y.x = fmaf((v[i].x - mu) * inv, g.x, b.x);
+                y.y = fmaf((v[i].y - mu) * inv, g.y, b.y);
+                y.z = fmaf((v[i].z - mu) * inv, g.z, b.z);
+                y.w = fmaf((v[i].w - mu) * inv, g.w, b.w);
+            }
+            if (a.dot_w) {
+                const float4 w = __ldg(reinterpret_cast<const float4*>(a.dot_w) + c4);
+                dot += (y.x * w.x + y.y * w.y) + (y.z * w.z + y.w * w.w);
+            } else {
+                o[c4] = y;
+            }
+        }
+    }
+    if (a.dot_w) {
+        dot = warp_sum(dot);
+        if (lane == 0) a.dot_out[row] = dot + (a.dot_b ? __ldg(a.dot_b) : 0.f);
+    }
+}
+
+void layer_norm(const NormArgs& a, cudaStream_t st) {
+    if (a.rows == 0) return;
+    ZVX_REQUIRE(a.C % 4 == 0 && a.C <= 128 * NORM_MAXV, "layer_norm: C must be a multiple of 4 and <= 1024");
+    ZVX_REQUIRE(!a.scln || (a.gb && (a.gb_ld % 4) == 0 && a.C > 1), "layer_norm: SCLN needs per-batch affine rows");
+    const int warps_per_block = 8;
+    layer_norm_kernel<<<cdiv(a.rows, warps_per_block), warps_per_block * 32, 0, st>>>(a);
+    ZVX_POST_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 masked softmax over keys, one block per (z, q) row  (fs2.py:49-55)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_softmax_kernel(float* __restrict__ S, int nh, int Lq, int L, int ldS,
+                                                           const uint8_t* __restrict__ key_mask, int mask_ld,
+                                                           float temperature) {
+    const long long rowid = blockIdx.x;  // z*Lq + q
+    const int z = (int)(rowid / Lq);
+    const int b = z / nh;
+    float* s = S + rowid * ldS;
+    const uint8_t* km = key_mask ? key_mask + (long long)b * mask_ld : nullptr;
+    __shared__ float red[4];
+    __shared__ float bcast;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    float m = -INFINITY;
+    for (int j = tid; j < L; j += 128) {
+        float v = s[j] / temperature;
+        if (km && km[j]) v = -INFINITY;
+        s[j] = v;
+        m = fmaxf(m, v);
+    }
+    m = warp_max(m);
+    if (lane == 0) red[wid] = m;
+    __syncthreads();
+    if (tid == 0) bcast = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    m = bcast;
+    float sum = 0.f;
+    for (int j = tid; j < L; j += 128) {
+        float e = expf(s[j] - m);
+        s[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[wid] = sum;
+    __syncthreads();
+    if (tid == 0) bcast = (red[0] + red[1]) + (red[2] + red[3]);
+    __syncthreads();
+    const float tot = bcast;
+    for (int j = tid; j < ldS; j += 128) s[j] = (j < L) ? s[j] / tot : 0.f;
+}
+
+void attn_softmax(float* S, int nz, int nh, int Lq, int L, int ldS, const uint8_t* key_mask, int mask_ld,
+                  float temperature, cudaStream_t st) {
+    const long long rows = (long long)nz * Lq;
+    if (rows == 0) return;
+    ZVX_REQUIRE(rows < 2147483647LL, "attn_softmax: too many rows");
+    attn_softmax_kernel<<<(unsigned)rows, 128, 0, st>>>(S, nh, Lq, L, ldS, key_mask, mask_ld, temperature);
+    ZVX_POST_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------------
+// small elementwise kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void add_batch_vector_kernel(float* __restrict__ x, const float* __restrict__ v, long long n4, int TC4,
+                                        int C4) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int b = (int)(i / TC4);
+    const int c4 = (int)(i % C4);
+    float4 a = reinterpret_cast<float4*>(x)[i];
+    const float4 s = __ldg(reinterpret_cast<const float4*>(v) + (long long)b * C4 + c4);
+    a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+    reinterpret_cast<float4*>(x)[i] = a;
+}
+
+void add_batch_vector(float* x, const float* v, int B, int T, int C, cudaStream_t st) {
+    ZVX_REQUIRE(C % 4 == 0, "add_batch_vector: C % 4");
+    const long long n4 = (long long)B * T * C / 4;
+    if (n4 == 0) return;
+    add_batch_vector_kernel<<<cdiv(n4, 256), 256, 0, st>>>(x, v, n4, T * C / 4, C / 4);
+    ZVX_POST_LAUNCH();
+}
+
+__global__ void bucket_embed_add_kernel(float* __restrict__ x, const float* __restrict__ pred,
+                                        const float* __restrict__ table, int rows, int C, int n_bins,
+                                        int32_t* __restrict__ bucket_out) {
+    const int row = blockIdx.x;
+    if (row >= rows) return;
+    // torch.round = round-half-to-even = rintf in the default rounding mode; the product is a separate fp32
+    // multiply in the reference, so keep it un-fused.
+    const float scaled = __fmul_rn(pred[row], (float)(n_bins - 1));
+    float r = rintf(scaled);
+    r = fminf(fmaxf(r, 0.f), (float)(n_bins - 1));
+    const int bkt = (int)r;
+    if (bucket_out && threadIdx.x == 0) bucket_out[row] = bkt;
+    const float4* e = reinterpret_cast<const float4*>(table + (long long)bkt * C);
+    float4* o = reinterpret_cast<float4*>(x + (long long)row * C);
+    for (int c4 = threadIdx.x; c4 < C / 4; c4 += blockDim.x) {
+        float4 a = o[c4];
+        const float4 b = __ldg(e + c4);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        o[c4] = a;
+    }
+}
+
+void bucket_embed_add(float* x, const float* pred, const float* table, int rows, int C, int n_bins,
+                      int32_t* bucket_out, cudaStream_t st) {
+    ZVX_REQUIRE(C % 4 == 0, "bucket_embed_add: C % 4");
+    if (rows == 0) return;
+    bucket_embed_add_kernel<<<rows, 128, 0, st>>>(x, pred, table, rows, C, n_bins, bucket_out);
+    ZVX_POST_LAUNCH();
+}
+
+__global__ void duration_round_kernel(const float* __restrict__ log_d, const int32_t* __restrict__ forced,
+                                      int32_t* __restrict__ dur, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (forced) {
+        dur[i] = forced[i];
+    } else {
+        float d = rintf(__fsub_rn(expf(log_d[i]), 1.f));
+        d = fminf(fmaxf(d, 0.f), 1.0e6f);
+        dur[i] = (int32_t)d;
+    }
+}
+
+void duration_round(const float* log_d, const int32_t* forced, int32_t* dur, int n, cudaStream_t st) {
+    if (n == 0) return;
+    duration_round_kernel<<<cdiv(n, 256), 256, 0, st>>>(log_d, forced, dur, n);
+    ZVX_POST_LAUNCH();
+}
+
+// one block per utterance; chunked block scan
+__global__ void __launch_bounds__(256) duration_scan_kernel(const int32_t* __restrict__ dur, int T,
+                                                            int32_t* __restrict__ cum, int64_t* __restrict__ mel_len) {
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ int wsum[8];
+    __shared__ int carry_s;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < T; t0 += 256) {
+        const int t = t0 + tid;
+        int v = (t < T) ? max(dur[(long long)b * T + t], 0) : 0;  // max(int(d), 0)  (fs2.py:452)
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += n;
+        }
+        if (lane == 31) wsum[wid] = s;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < wid; ++w) woff += wsum[w];
+        const int carry = carry_s;
+        if (t < T) cum[(long long)b * T + t] = carry + woff + s;
+        __syncthreads();
+        if (tid == 255) carry_s = carry + woff + s;
+        __syncthreads();
+    }
+    if (tid == 0 && mel_len) mel_len[b] = (int64_t)carry_s;
+}
+
+void duration_scan(const int32_t* dur, int B, int T, int32_t* cum, int64_t* mel_len, cudaStream_t st) {
+    if (B == 0) return;
+    duration_scan_kernel<<<B, 256, 0, st>>>(dur, T, cum, mel_len);
+    ZVX_POST_LAUNCH();
+}
+
+// one warp per output frame: binary search of the run that covers it, then a coalesced 128-bit row copy
+__global__ void __launch_bounds__(256) length_regulate_gather_kernel(const float* __restrict__ x,
+                                                                     const int32_t* __restrict__ cum, int T, int C4,
+                                                                     int L_max, float* __restrict__ features,
+                                                                     int32_t* __restrict__ src_index) {
+    const int b = blockIdx.y;
+    const int f = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= L_max) return;
+    const int32_t* c = cum + (long long)b * T;
+    const int total = T > 0 ? c[T - 1] : 0;
+    float4* o = reinterpret_cast<float4*>(features) + ((long long)b * L_max + f) * C4;
+    if (f >= total) {
+        for (int c4 = lane; c4 < C4; c4 += 32) o[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src_index && lane == 0) src_index[(long long)b * L_max + f] = -1;
+        return;
+    }
+    int lo = 0, hi = T - 1;  // first i with cum[i] > f
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (c[mid] > f) hi = mid; else lo = mid + 1;
+    }
+    const float4* src = reinterpret_cast<const float4*>(x) + ((long long)b * T + lo) * C4;
+    for (int c4 = lane; c4 < C4; c4 += 32) o[c4] = __ldg(src + c4);
+    if (src_index && lane == 0) src_index[(long long)b * L_max + f] = lo;
+}
+
+void length_regulate_gather(const float* x, const int32_t* cum, int B, int T, int C, int L_max, float* features,
+                            int32_t* src_index, cudaStream_t st) {
+    ZVX_REQUIRE(C % 4 == 0, "length_regulate: C % 4");
+    if (B == 0 || L_max == 0) return;
+    dim3 grid(cdiv(L_max, 8), B);
+    length_regulate_gather_kernel<<<grid, 256, 0, st>>>(x, cum, T, C / 4, L_max, features, src_index);
+    ZVX_POST_LAUNCH();
+}
+
+__global__ void add_posenc_kernel(const float* __restrict__ x, const float* __restrict__ pos, long long n4, int LC4,
+                                  float* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos) + (i % LC4));
+    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+    reinterpret_cast<float4*>(out)[i] = a;
+}
+
+void add_posenc(const float* x, const float* pos, int B, int L, int C, float* out, cudaStream_t st) {
+    ZVX_REQUIRE(C % 4 == 0, "add_posenc: C % 4");
+    const long long n4 = (long long)B * L * C / 4;
+    if (n4 == 0) return;
+    add_posenc_kernel<<<cdiv(n4, 256), 256, 0, st>>>(x, pos, n4, L * C / 4, out);
+    ZVX_POST_LAUNCH();
+}
+
+__global__ void mask_from_lengths_kernel(const int64_t* __restrict__ mel_len, int B, int L, uint8_t* __restrict__ mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * L) return;
+    const int b = (int)(i / L), l = (int)(i % L);
+    mask[i] = (l >= mel_len[b]) ? 1 : 0;
+}
+
+void mask_from_lengths(const int64_t* mel_len, int B, int L, uint8_t* mask, cudaStream_t st) {
+    if ((long long)B * L == 0) return;
+    mask_from_lengths_kernel<<<cdiv((long long)B * L, 256), 256, 0, st>>>(mel_len, B, L, mask);
+    ZVX_POST_LAUNCH();
+}
+
+// 32x32 smem-tiled transpose [B,L,C] -> [B,C,L]
+__global__ void transpose_mel_kernel(const float* __restrict__ in, const uint8_t* __restrict__ mask, int zero_masked,
+                                     int L, int C, float* __restrict__ out, float* __restrict__ inplace) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int l0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int l = l0 + i, c = c0 + tx;
+        float v = 0.f;
+        if (l < L && c < C) {
+            const long long idx = ((long long)b * L + l) * C + c;
+            v = in[idx];
+            if (zero_masked && mask && mask[(long long)b * L + l]) {
+                v = 0.f;
+                if (inplace) inplace[idx] = 0.f;
+            }
+        }
+        tile[i][tx] = v;
+    }
+    __syncthreads();
+    if (!out) return;
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, l = l0 + tx;
+        if (l < L && c < C) out[((long long)b * C + c) * L + l] = tile[tx][i];
+    }
+}
+
+void transpose_mel(const float* mel_BLC, const uint8_t* mask, int zero_masked, int B, int L, int C, float* mel_BCL,
+                   float* mel_BLC_inplace, cudaStream_t st) {
+    if (B == 0 || L == 0) return;
+    dim3 grid(cdiv(L, 32), cdiv(C, 32), B);
+    transpose_mel_kernel<<<grid, dim3(32, 8), 0, st>>>(mel_BLC, mask, zero_masked, L, C, mel_BCL, mel_BLC_inplace);
+    ZVX_POST_LAUNCH();
+}
+
+}  // namespace zvx

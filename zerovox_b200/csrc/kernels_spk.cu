@@ -1,0 +1,247 @@
+// ResNetSE34V2 speaker-embedding kernels that are not GEMM-shaped (ResNetSE34V2.py:176-212).
+// Activations are channel-last [B, H(mel), W(time), C]; the 3x3 / 1x1 convolutions run through the
+// implicit-GEMM path (ROW_CONV2D) with ReLU / folded-BatchNorm epilogues.
+#include "kernels.cuh"
+
+namespace zvx {
+
+// InstanceNorm1d(n_mels) over time, no affine (ResNetSE34V2.py:123, 182); also performs the
+// transpose(1,2) of line 178: in [B,T,M] -> out [B,M,T].  One block per utterance; each warp owns
+// mel channels m = warp, warp+nw, ...; two passes (mean, then biased variance) like ATen.
+__global__ void __launch_bounds__(256) instance_norm_time_kernel(const float* __restrict__ in, int T, int M,
+                                                                 float* __restrict__ out) {
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float* x = in + (long long)b * T * M;
+    float* o = out + (long long)b * M * T;
+    for (int m = wid; m < M; m += nw) {
+        float s = 0.f;
+        for (int t = lane; t < T; t += 32) s += x[(long long)t * M + m];
+        const float mu = warp_sum(s) / (float)T;
+        float q = 0.f;
+        for (int t = lane; t < T; t += 32) {
+            const float d = x[(long long)t * M + m] - mu;
+            q += d * d;
+        }
+        const float inv = rsqrtf(warp_sum(q) / (float)T + 1e-5f);
+        for (int t = lane; t < T; t += 32) o[(long long)m * T + t] = (x[(long long)t * M + m] - mu) * inv;
+    }
+}
+
+void instance_norm_time(const float* ref_mel, int B, int T, int n_mels, float* out, cudaStream_t st) {
+    if (B == 0) return;
+    instance_norm_time_kernel<<<B, 256, 0, st>>>(ref_mel, T, n_mels, out);
+    ZVX_POST_LAUNCH();
+}
+
+// stem Conv2d(1 -> C, 3x3, pad 1) + bias -> ReLU -> BN (ResNetSE34V2.py:184-186).  One thread per output
+// pixel-channel; C is the fastest index so stores are coalesced and the 9 input taps are warp-broadcast.
+__global__ void stem_conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                    const float* __restrict__ bias, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int H, int W, int C, long long total,
+                                    float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int x = (int)(p % W);
+    p /= W;
+    const int y = (int)(p % H);
+    const int b = (int)(p / H);
+    const float* ib = in + (long long)b * H * W;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        const int yi = y + dy - 1;
+        if (yi < 0 || yi >= H) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int xi = x + dx - 1;
+            if (xi < 0 || xi >= W) continue;
+            acc = fmaf(__ldg(ib + (long long)yi * W + xi), __ldg(w + (dy * 3 + dx) * C + c), acc);
+        }
+    }
+    float v = fmaxf(acc + __ldg(bias + c), 0.f);
+    out[i] = fmaf(v, __ldg(scale + c), __ldg(shift + c));
+}
+
+void stem_conv3x3(const float* in, const float* w, const float* bias, const float* scale, const float* shift, int B,
+                  int H, int W, int C, float* out, cudaStream_t st) {
+    const long long total = (long long)B * H * W * C;
+    if (total == 0) return;
+    stem_conv3x3_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, w, bias, scale, shift, H, W, C, total, out);
+    ZVX_POST_LAUNCH();
+}
+
+// SE squeeze (AdaptiveAvgPool2d(1), ResNetSE34V2.py:63-64): x [B, HW, C] -> mean over HW.
+// grid (B, ceil(C/32)); block 32 x 8: threadIdx.x = channel (coalesced), threadIdx.y strides over HW.
+__global__ void hw_mean_kernel(const float* __restrict__ x, int HW, int C, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int b = blockIdx.x;
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    float s = 0.f;
+    if (c < C) {
+        const float* p = x + (long long)b * HW * C + c;
+        for (int i = threadIdx.y; i < HW; i += 8) s += p[(long long)i * C];
+    }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        out[(long long)b * C + c] = t / (float)HW;
+    }
+}
+
+void hw_mean(const float* x, int B, int HW, int C, float* out, cudaStream_t st) {
+    if (B == 0) return;
+    dim3 grid(B, cdiv(C, 32));
+    hw_mean_kernel<<<grid, dim3(32, 8), 0, st>>>(x, HW, C, out);
+    ZVX_POST_LAUNCH();
+}
+
+// SE excitation (ResNetSE34V2.py:55-60, 65): one block per utterance.
+__global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict__ p, const float* __restrict__ w1,
+                                                        const float* __restrict__ b1, const float* __restrict__ w2,
+                                                        const float* __restrict__ b2, int C, int R,
+                                                        float* __restrict__ y) {
+    extern __shared__ float sh[];  // [C] pooled, [R] hidden
+    float* ps = sh;
+    float* hs = sh + C;
+    const int b = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) ps[c] = p[(long long)b * C + c];
+    __syncthreads();
+    for (int r = wid; r < R; r += nw) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(w1 + (long long)r * C + c), ps[c], s);
+        s = warp_sum(s);
+        if (lane == 0) hs[r] = fmaxf(s + __ldg(b1 + r), 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = __ldg(b2 + c);
+        for (int r = 0; r < R; ++r) s = fmaf(__ldg(w2 + (long long)c * R + r), hs[r], s);
+        y[(long long)b * C + c] = 1.f / (1.f + expf(-s));
+    }
+}
+
+void se_excite(const float* p, const float* w1, const float* b1, const float* w2, const float* b2, int B, int C,
+               int R, float* y, cudaStream_t st) {
+    if (B == 0) return;
+    se_excite_kernel<<<B, 256, (C + R) * sizeof(float), st>>>(p, w1, b1, w2, b2, C, R, y);
+    ZVX_POST_LAUNCH();
+}
+
+// out = relu(x * y[b, c] + res)   (ResNetSE34V2.py:66-67, 97-98)
+__global__ void se_scale_add_relu_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                         const float* __restrict__ res, long long n4, long long HWC4, int C4,
+                                         float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int b = (int)(i / HWC4);
+    const int c4 = (int)(i % C4);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(y) + (long long)b * C4 + c4);
+    const float4 r = __ldg(reinterpret_cast<const float4*>(res) + i);
+    float4 o;
+    o.x = fmaxf(fmaf(a.x, g.x, r.x), 0.f);
+    o.y = fmaxf(fmaf(a.y, g.y, r.y), 0.f);
+    o.z = fmaxf(fmaf(a.z, g.z, r.z), 0.f);
+    o.w = fmaxf(fmaf(a.w, g.w, r.w), 0.f);
+    reinterpret_cast<float4*>(out)[i] = o;
+}
+
+void se_scale_add_relu(const float* x, const float* y, const float* res, int B, int HW, int C, float* out,
+                       cudaStream_t st) {
+    ZVX_REQUIRE(C % 4 == 0, "se_scale_add_relu: C % 4");
+    const long long n4 = (long long)B * HW * C / 4;
+    if (n4 == 0) return;
+    se_scale_add_relu_kernel<<<cdiv(n4, 256), 256, 0, st>>>(x, y, res, n4, (long long)HW * C / 4, C / 4, out);
+    ZVX_POST_LAUNCH();
+}
+
+// [B, Hh, W, C] -> [B, W, C*Hh], feature f = c*Hh + h   (x.reshape(B, -1, W) of an NCHW tensor, line 196)
+__global__ void spk_flatten_kernel(const float* __restrict__ x, int Hh, int W, int C, long long total,
+                                   float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int D = C * Hh;
+    const int f = (int)(i % D);
+    long long p = i / D;
+    const int w = (int)(p % W);
+    const int b = (int)(p / W);
+    const int c = f / Hh, h = f - c * Hh;
+    out[i] = __ldg(x + (((long long)b * Hh + h) * W + w) * C + c);
+}
+
+void spk_flatten(const float* x, int B, int Hh, int W, int C, float* out, cudaStream_t st) {
+    const long long total = (long long)B * Hh * W * C;
+    if (total == 0) return;
+    spk_flatten_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, Hh, W, C, total, out);
+    ZVX_POST_LAUNCH();
+}
+
+// Softmax over time + attentive statistics pooling (ResNetSE34V2.py:139-147, 198-204).
+// One thread per (b, feature); consecutive threads = consecutive features -> coalesced over D.
+__global__ void attentive_pool_kernel(const float* __restrict__ feat, const float* __restrict__ logits, int W, int D,
+                                      int asp, long long total, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int d = (int)(i % D);
+    const int b = (int)(i / D);
+    const float* lg = logits + (long long)b * W * D + d;
+    const float* ft = feat + (long long)b * W * D + d;
+    float m = -INFINITY;
+    for (int t = 0; t < W; ++t) m = fmaxf(m, lg[(long long)t * D]);
+    float den = 0.f;
+    for (int t = 0; t < W; ++t) den += expf(lg[(long long)t * D] - m);
+    float mu = 0.f, sq = 0.f;
+    for (int t = 0; t < W; ++t) {
+        const float wgt = expf(lg[(long long)t * D] - m) / den;
+        const float x = ft[(long long)t * D];
+        mu = fmaf(x, wgt, mu);
+        sq = fmaf(x * x, wgt, sq);
+    }
+    if (asp) {
+        out[(long long)b * 2 * D + d] = mu;
+        out[(long long)b * 2 * D + D + d] = sqrtf(fmaxf(sq - mu * mu, 1e-5f));
+    } else {
+        out[(long long)b * D + d] = mu;
+    }
+}
+
+void attentive_pool(const float* feat, const float* logits, int B, int W, int D, int asp, float* out,
+                    cudaStream_t st) {
+    const long long total = (long long)B * D;
+    if (total == 0) return;
+    attentive_pool_kernel<<<cdiv(total, 128), 128, 0, st>>>(feat, logits, W, D, asp, total, out);
+    ZVX_POST_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) l2_normalize_kernel(float* __restrict__ x, int C) {
+    __shared__ float red[8];
+    __shared__ float inv;
+    float* r = x + (long long)blockIdx.x * C;
+    float s = 0.f;
+    for (int c = threadIdx.x; c < C; c += 256) s = fmaf(r[c], r[c], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        inv = 1.f / fmaxf(sqrtf(t), 1e-12f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) r[c] *= inv;
+}
+
+void l2_normalize(float* x, int B, int C, cudaStream_t st) {
+    if (B == 0) return;
+    l2_normalize_kernel<<<B, 256, 0, st>>>(x, C);
+    ZVX_POST_LAUNCH();
+}
+
+}  // namespace zvx

@@ -1,0 +1,198 @@
+"""ZeroVox model container with the reference's public interface (zerovox/tts/model.py:86-118, 158-351):
+same constructor kwargs, ``forward`` / ``inference_ex`` / ``inference`` signatures and return tuples, same
+attribute names (``_phoneme_encoder``, ``_spkemb``, ``_mel_decoder``, ``_meldec``, ``_min_mel_len``,
+``_hop_length``, ``hparams``) and the same ``state_dict`` keys, so zerovox/tts/synthesize.py, zerovox/demo.py and
+utils/export_hifigan.py drive it unchanged.  Eval-mode arithmetic runs in the CUDA engine; there is no CPU or
+training path here (see INTEGRATION.md for how training keeps using the reference modules).
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from pathlib import Path
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from ._context import EngineContext
+from .fs2 import FS2Decoder, FS2Encoder
+from .hifigan import Generator
+from .ResNetSE34V2 import ResNetSE34V2
+from .symbols import Symbols
+
+DEFAULT_MELDEC_MODEL_NAME = "zerovox-hifigan-vctk-v2-en-1"  # model.py:84
+
+
+class AttrDict(dict):
+    """dict with attribute access, for HiFi-GAN config.json (model.py:39-42)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.__dict__ = self
+
+
+def model_cache_path(model: str, relpath: str) -> Path:
+    """Cache layout of model.py:66-82: $CACHED_PATH_ZEROVOX (default ~/.cache/zerovox)/model_repo/<model>/<relpath>.
+    Files must already be there — this engine never downloads."""
+    cache = Path(os.getenv("CACHED_PATH_ZEROVOX", Path.home() / ".cache" / "zerovox"))
+    path = cache / "model_repo" / model / relpath
+    if not path.exists():
+        raise FileNotFoundError(f"{path} not found (zerovox_b200 does not download models; place the file there)")
+    return path
+
+
+def get_meldec(modelspec, infer_device="cpu", verbose=False):
+    """model.py:86-118: build the Generator from <dir>/config.json + generator.ckpt['generator'] (weight-norm form),
+    eval(), remove_weight_norm()."""
+    if os.path.isdir(modelspec):
+        config_path, gen_path = Path(modelspec) / "config.json", Path(modelspec) / "generator.ckpt"
+    else:
+        config_path = model_cache_path(str(modelspec), "config.json")
+        gen_path = model_cache_path(str(modelspec), "generator.ckpt")
+    if verbose:
+        print("meldec: using config    : ", config_path)
+        print("meldec: using checkpoint: ", gen_path)
+    with open(config_path) as f:
+        config = AttrDict(json.loads(f.read()))
+    device = torch.device(infer_device)
+    generator = Generator(config).to(device)
+    state = torch.load(gen_path, map_location=device)
+    generator.load_state_dict(state["generator"])
+    generator.eval()
+    generator.remove_weight_norm()
+    return generator.to(device)
+
+
+_CHILD_ROLES = {"_phoneme_encoder": "encoder", "_mel_decoder": "decoder", "_spkemb": "spkemb", "_meldec": "vocoder"}
+
+
+class ZeroVox(nn.Module):
+
+    def __init__(self, symbols: Symbols, meldec_model, sampling_rate, hop_length, n_mels, lr, weight_decay,
+                 max_epochs, warmup_epochs, betas, eps, embed_dim, punct_embed_dim, dpe_embed_dim, emb_reduction,
+                 max_mel_len, max_txt_len, fs2enc_layer, fs2enc_head, fs2enc_dropout, vp_filter_size,
+                 vp_kernel_size, vp_dropout, ve_n_bins, resnet_layers, resnet_num_filters, resnet_encoder_type,
+                 decoder_kind, decoder_n_layers, decoder_n_head, decoder_conv_filter_size, decoder_conv_kernel_size,
+                 decoder_dropout, decoder_scln, verbose=False):
+        super().__init__()
+        hp = dict(locals())
+        for k in ("self", "__class__", "meldec_model", "verbose"):
+            hp.pop(k, None)
+        self.hparams = SimpleNamespace(**hp)  # save_hyperparameters(ignore=[...]) stand-in (model.py:204)
+        object.__setattr__(self, "_shared_ctx", EngineContext())
+
+        emb_size = embed_dim + punct_embed_dim
+        self._phoneme_encoder = FS2Encoder(
+            symbols=symbols, max_txt_len=max_txt_len, embed_dim=embed_dim, encoder_layer=fs2enc_layer,
+            encoder_head=fs2enc_head, conv_filter_size=decoder_conv_filter_size,
+            conv_kernel_size=decoder_conv_kernel_size, encoder_dropout=fs2enc_dropout,
+            punct_embed_dim=punct_embed_dim, vp_filter_size=vp_filter_size, vp_kernel_size=vp_kernel_size,
+            vp_dropout=vp_dropout, ve_n_bins=ve_n_bins)
+        self._spkemb = ResNetSE34V2(layers=resnet_layers, num_filters=resnet_num_filters, nOut=emb_size,
+                                    encoder_type=resnet_encoder_type, n_mels=n_mels, log_input=False)
+        if decoder_kind == "fastspeech2":
+            self._mel_decoder = FS2Decoder(
+                dec_max_seq_len=max_mel_len, dec_hidden=emb_size, dec_n_layers=decoder_n_layers,
+                dec_n_head=decoder_n_head, dec_conv_filter_size=decoder_conv_filter_size,
+                dec_conv_kernel_size=decoder_conv_kernel_size, dec_dropout=decoder_dropout, dec_scln=decoder_scln,
+                n_mel_channels=n_mels, spk_emb_size=emb_size)
+        elif decoder_kind == "styletts":
+            raise NotImplementedError("zerovox_b200: decoder_kind='styletts' has no CUDA path yet (SURVEY.md 8f)")
+        else:
+            raise Exception(f"unknown decoder kind: '{decoder_kind}'")
+        self._meldec = get_meldec(modelspec=meldec_model, verbose=verbose) if meldec_model else None
+        self._min_mel_len = 689  # model.py:254
+        self._hop_length = hop_length
+        self._verbose = verbose
+
+    # children share one engine handle ------------------------------------------------------------------
+    def __setattr__(self, name, value):
+        super().__setattr__(name, value)
+        role = _CHILD_ROLES.get(name)
+        if role is not None and isinstance(value, nn.Module) and hasattr(value, "_fill_config"):
+            self._shared_ctx.attach(role, value)
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._shared_ctx.mark_stale()
+        return r
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        r = super().load_state_dict(state_dict, strict=strict, assign=assign)
+        self._shared_ctx.mark_stale()
+        return r
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):
+        """Lightning-style .ckpt ingestion (synthesize.py:78-88): ``hyper_parameters`` + ``state_dict``;
+        kwargs override / complete the hyper-parameters, unknown ones are dropped."""
+        import inspect
+        ckpt = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        hp = dict(ckpt.get("hyper_parameters", {}))
+        hp.update(kwargs)
+        allowed = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        model = cls(**{k: v for k, v in hp.items() if k in allowed})
+        model.load_state_dict(ckpt["state_dict"], strict=strict)
+        return model
+
+    # forward -------------------------------------------------------------------------------------------
+    def forward(self, x, force_duration=False, normalize_before=True):
+        """Batched eval forward (model.py:260-306).  Returns (wav [B, L_max*hop], mel [B, n_mels, L_max],
+        mel_len int64 [B], log_duration [B, T]) — the tuple utils/export_hifigan.py:109-151 consumes.  The
+        reference's own eval tail (model.py:298-304) is ParallelWaveGAN leftover code that raises with
+        hifigan.Generator; the intended semantics ``wav = _meldec(mel.transpose(1,2)).squeeze(1)`` are built."""
+        if self.training:
+            raise NotImplementedError("ZeroVox.forward in training mode is outside the zerovox_b200 hot path")
+        if self._meldec is None:
+            raise RuntimeError("ZeroVox.forward: no vocoder (_meldec is None)")
+        eng = self._shared_ctx.get(next(self.parameters()).device)
+        dev = eng.device
+        style = eng.spkemb(x["ref_mel"].to(dev, non_blocking=True))
+        mask = x["phoneme_mask"].to(dev, non_blocking=True) if "phoneme_mask" in x else None
+        forced = x["duration"].to(dev, non_blocking=True) if force_duration else None
+        r = eng.encode(x["phoneme"].to(dev, non_blocking=True), x["puncts"].to(dev, non_blocking=True), style, mask,
+                       forced, need_lengths=True)
+        feats = eng.length_regulate(r["xprime"], r["duration_rounded"], r["L_max"])
+        # model.py:283-285: the mel is zero-filled at padded frames only when the mel mask exists (predicted
+        # durations) and B > 1
+        zero_pad = (not force_duration) and feats.shape[0] > 1
+        _, mel = eng.decode(feats, style, mel_len=r["mel_len"], zero_padded_mel=zero_pad, want_blc=False)
+        wav = eng.vocode(mel).squeeze(1)
+        return wav, mel, r["mel_len"], r["log_duration"]
+
+    def inference_ex(self, x, style_embed, normalize_before=True, force_duration=False):
+        """Batch-1 path (model.py:308-347): zero-pads the mel to the stateful ``_min_mel_len`` before vocoding and
+        trims the waveform to mel_len*hop.  Returns (wav, mel_len, log_duration, mel [n_mels, mel_len])."""
+        start_time = time.time()
+        eng = self._shared_ctx.get(next(self.parameters()).device)
+        dev = eng.device
+        forced = x["duration"].to(dev) if force_duration else None
+        mask = x["phoneme_mask"].to(dev) if "phoneme_mask" in x else None
+        r = eng.encode(x["phoneme"].to(dev), x["puncts"].to(dev), style_embed.to(dev), mask, forced)
+        if len(r["mel_len_host"]) != 1:
+            raise RuntimeError("inference_ex is the batch-1 path (model.py:325); use forward() for batches")
+        mel_len = int(r["mel_len_host"][0])
+        feats = eng.length_regulate(r["xprime"], r["duration_rounded"], r["L_max"])
+        pe_time = time.time()
+        _, mel = eng.decode(feats, style_embed.to(dev), mel_len=r["mel_len"], want_blc=False)
+        dec_time = time.time()
+        if mel_len < self._min_mel_len:
+            padded = torch.zeros((1, mel.shape[1], self._min_mel_len), device=dev, dtype=mel.dtype)
+            padded[:, :, :mel_len] = mel
+        else:
+            self._min_mel_len = max(self._min_mel_len, mel_len)
+            padded = mel
+        wav = eng.vocode(padded)[0, 0]
+        if self._verbose:
+            torch.cuda.synchronize(dev)
+            now = time.time()
+            print(f"synthesis timing stats: pe={pe_time - start_time}s, dec={dec_time - pe_time}s, "
+                  f"meldec={now - dec_time}s")
+        return wav[: mel_len * self._hop_length], mel_len, r["log_duration"], mel[0, :, :mel_len]
+
+    def inference(self, x, style_embed, normalize_before=True):
+        wav, mel_len, log_duration, _ = self.inference_ex(x=x, style_embed=style_embed,
+                                                           normalize_before=normalize_before)
+        return wav, mel_len, log_duration
