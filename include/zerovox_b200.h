@@ -131,6 +131,18 @@ int zvx_decode(zvx_handle* h, const float* features, const uint8_t* mask, const 
 /* hifigan.Generator.forward (hifigan.py:114-130).  mel_BCL [B,n_mels,L] -> wav [B, L*hop]. */
 int zvx_vocode(zvx_handle* h, const float* mel_BCL, int B, int L, float* wav, void* stream);
 
+/* Per-kernel-class device timing (CUDA events on the launching stream around every launch of the class),
+ * used by bench.py for the roofline figures.  Enable, run any stage calls, then read (synchronises).
+ * flops / bytes are the ALGORITHMIC work of the recorded launches (2*M*N*K*taps; operand + result bytes). */
+#define ZVX_PROF_GEMM_FP32    0   /* fp32 FMA GEMM / implicit conv (encoder, variance predictors, bring-up) */
+#define ZVX_PROF_GEMM_TC      1   /* tcgen05 TF32 GEMM / implicit conv */
+#define ZVX_PROF_VOC_CONV     2   /* HiFi-GAN dilated Conv1d (+ fused lrelu / residual / MRF mean / tanh) */
+#define ZVX_PROF_VOC_UPSAMPLE 3   /* HiFi-GAN polyphase ConvTranspose1d */
+#define ZVX_PROF_NUM_CLASSES  4
+int zvx_profile_enable(zvx_handle* h, int on);
+int zvx_profile_read(zvx_handle* h, int kernel_class, double* ms, int64_t* launches, double* flops,
+                     double* bytes);
+
 /* Workspace control: bytes of engine-owned scratch currently reserved on the device. */
 int64_t zvx_workspace_bytes(const zvx_handle* h);
 

@@ -72,6 +72,9 @@ SYMBOLS = {
     "zvx_length_regulate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "zvx_decode": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "zvx_vocode": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "zvx_profile_enable": (C.c_int, [_P, C.c_int]),
+    "zvx_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
+                                   C.POINTER(C.c_double)]),
     "zvx_workspace_bytes": (C.c_int64, [_P]),
     "zvx_launch_count": (C.c_int64, [_P]),
 }

@@ -98,6 +98,50 @@ struct SEBlock {
 
 struct HGConv { float* w = nullptr; float* b = nullptr; int cin = 0, cout = 0, k = 1, dil = 1; };
 
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline numbers).
+// Classes: see ZVX_PROF_* in the header.
+struct Profiler {
+    struct Rec { int cls; cudaEvent_t a, b; double flops, bytes; };
+    bool on = false;
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t ev() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        ZVX_CUDA_CHECK(cudaEventCreate(&e));
+        return e;
+    }
+    void begin(int cls, double flops, double bytes, cudaStream_t st) {
+        if (!on) return;
+        Rec r{cls, ev(), ev(), flops, bytes};
+        ZVX_CUDA_CHECK(cudaEventRecord(r.a, st));
+        recs.push_back(r);
+    }
+    void end(cudaStream_t st) {
+        if (!on) return;
+        ZVX_CUDA_CHECK(cudaEventRecord(recs.back().b, st));
+    }
+    // Synchronises; returns totals for one class and recycles nothing (call reset() afterwards).
+    void read(int cls, double* ms, int64_t* launches, double* flops, double* bytes) {
+        *ms = 0; *launches = 0; *flops = 0; *bytes = 0;
+        for (auto& r : recs) {
+            if (r.cls != cls) continue;
+            ZVX_CUDA_CHECK(cudaEventSynchronize(r.b));
+            float t = 0.f;
+            ZVX_CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+            *ms += t; *launches += 1; *flops += r.flops; *bytes += r.bytes;
+        }
+    }
+    void reset() {
+        for (auto& r : recs) { pool.push_back(r.a); pool.push_back(r.b); }
+        recs.clear();
+    }
+    ~Profiler() {
+        reset();
+        for (auto e : pool) cudaEventDestroy(e);
+    }
+};
+
 }  // namespace
 
 class Engine {
@@ -444,11 +488,19 @@ class Engine {
 
     // ------------------------------------------------------------------------------------------ helpers
     void gemm(const GemmArgs& a, bool tensor_core_ok, cudaStream_t st) {
-        if (tensor_core_ok && cfg.tensor_core_policy != 0 && gemm_tc_supported(a)) {
-            gemm_tc(a, st);
-        } else {
-            gemm_simt(a, st);
-        }
+        const bool tc = tensor_core_ok && cfg.tensor_core_policy != 0 && gemm_tc_supported(a);
+        const double flops = 2.0 * a.M * a.N * a.K * a.taps * a.nz;
+        const double bytes = 4.0 * a.nz * ((double)a.M * a.K + (double)a.N * a.K * a.taps + (double)a.M * a.N);
+        prof.begin(tc ? ZVX_PROF_GEMM_TC : ZVX_PROF_GEMM_FP32, flops, bytes, st);
+        if (tc) gemm_tc(a, st); else gemm_simt(a, st);
+        prof.end(st);
+    }
+
+    void vconv(const Conv1dArgs& c, cudaStream_t st) {
+        prof.begin(ZVX_PROF_VOC_CONV, 2.0 * c.B * c.T * c.Cin * c.Cout * c.k,
+                   4.0 * c.B * c.T * (c.Cin + c.Cout * (1 + (c.res ? 1 : 0) + (c.acc && !c.acc_init ? 1 : 0))), st);
+        conv1d_cf(c, st);
+        prof.end(st);
     }
 
     void linear(const float* x, int M, int K, const float* w, const float* b, int N, float* y, bool tc,
@@ -727,12 +779,15 @@ class Engine {
         Conv1dArgs a;
         a.x = mel; a.w = hg_pre.w; a.bias = hg_pre.b; a.B = B; a.Cin = cfg.n_mels; a.Cout = C0; a.T = L; a.k = 7;
         a.dil = 1; a.in_slope = 1.f; a.out = x;
-        conv1d_cf(a, st);
+        vconv(a, st);
         int T = L;
         size_t ci = 0;
         for (int i = 0; i < cfg.hg_num_upsamples; ++i) {
             const HGConv& up = hg_ups[(size_t)i];
+            prof.begin(ZVX_PROF_VOC_UPSAMPLE, 2.0 * B * T * up.cin * up.cout * up.k,
+                       4.0 * B * T * (up.cin + (double)up.cout * cfg.hg_upsample_rates[i]), st);
             conv_transpose1d_cf(x, up.w, up.b, B, up.cin, up.cout, T, up.k, cfg.hg_upsample_rates[i], 0.1f, y, st);
+            prof.end(st);
             T *= cfg.hg_upsample_rates[i];
             const int ch = up.cout;
             for (int j = 0; j < nk; ++j) {
@@ -745,7 +800,7 @@ class Engine {
                     if (cfg.hg_resblock == 1) {
                         const HGConv &c1 = hg_c1[ci], &c2 = hg_c2[ci];
                         c.x = r; c.w = c1.w; c.bias = c1.b; c.k = c1.k; c.dil = c1.dil; c.out = tmp;
-                        conv1d_cf(c, st);
+                        vconv(c, st);
                         c.x = tmp; c.w = c2.w; c.bias = c2.b; c.k = c2.k; c.dil = 1; c.res = r;
                     } else {
                         const HGConv& c1 = hg_c1[ci];
@@ -756,7 +811,7 @@ class Engine {
                     } else {
                         c.out = rn;
                     }
-                    conv1d_cf(c, st);
+                    vconv(c, st);
                     r = rn;
                 }
             }
@@ -764,7 +819,7 @@ class Engine {
         Conv1dArgs p;
         p.x = x; p.w = hg_post.w; p.bias = hg_post.b; p.B = B; p.Cin = hg_post.cin; p.Cout = 1; p.T = T; p.k = 7;
         p.dil = 1; p.in_slope = 0.01f; p.tanh_out = 1; p.out = wav;  // F.leaky_relu default slope (hifigan.py:126)
-        conv1d_cf(p, st);
+        vconv(p, st);
         return 0;
     }
 
@@ -783,6 +838,7 @@ class Engine {
     bool sec_ready[4] = {false, false, false, false};
     std::string sec_err[4];
     Workspace ws;
+    Profiler prof;
     int64_t* pinned_len = nullptr;
 
     float *enc_pos_param = nullptr, *dec_pos_param = nullptr, *enc_pos = nullptr, *dec_pos = nullptr;
@@ -881,6 +937,18 @@ int zvx_decode(zvx_handle* h, const float* features, const uint8_t* mask, const 
 
 int zvx_vocode(zvx_handle* h, const float* mel_BCL, int B, int L, float* wav, void* stream) {
     ZVX_GUARD(h, return h->eng->vocode(mel_BCL, B, L, wav, (cudaStream_t)stream));
+}
+
+int zvx_profile_enable(zvx_handle* h, int on) {
+    ZVX_GUARD(h, { h->eng->prof.reset(); h->eng->prof.on = (on != 0); return 0; });
+}
+
+int zvx_profile_read(zvx_handle* h, int kernel_class, double* ms, int64_t* launches, double* flops, double* bytes) {
+    ZVX_GUARD(h, {
+        ZVX_REQUIRE(ms && launches && flops && bytes, "zvx_profile_read: null output");
+        h->eng->prof.read(kernel_class, ms, launches, flops, bytes);
+        return 0;
+    });
 }
 
 int64_t zvx_workspace_bytes(const zvx_handle* h) { return (h && h->eng) ? h->eng->ws.bytes() : 0; }

@@ -259,6 +259,21 @@ class Engine:
         return wav
 
     # ------------------------------------------------------------------ introspection
+    PROF_CLASSES = {"gemm_fp32": 0, "gemm_tf32_tcgen05": 1, "vocoder_conv1d": 2, "vocoder_upsample": 3}
+
+    def profile(self, on: bool):
+        self._check(self.lib.zvx_profile_enable(self._h, 1 if on else 0), "zvx_profile_enable")
+
+    def profile_read(self) -> dict:
+        """{class: {ms, launches, flops, bytes}} for the launches recorded since profile(True) (synchronises)."""
+        out = {}
+        for name, cls in self.PROF_CLASSES.items():
+            ms, n, fl, by = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+            self._check(self.lib.zvx_profile_read(self._h, cls, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)),
+                        "zvx_profile_read")
+            out[name] = {"ms": ms.value, "launches": n.value, "flops": fl.value, "bytes": by.value}
+        return out
+
     def workspace_bytes(self) -> int:
         return int(self.lib.zvx_workspace_bytes(self._h))
 
