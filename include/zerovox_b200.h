@@ -143,6 +143,21 @@ int zvx_profile_enable(zvx_handle* h, int on);
 int zvx_profile_read(zvx_handle* h, int kernel_class, double* ms, int64_t* launches, double* flops,
                      double* bytes);
 
+/* Kernel-level test hook for the two contraction kernels every Linear / Conv1d / Conv2d of the acoustic
+ * model and speaker net lowers to (nn.Linear, nn.Conv1d, nn.Conv2d call sites of fs2.py:143-162, 198-202,
+ * 537-552 and ResNetSE34V2.py:81-92, 184-186), channel-last operands:
+ *   C[m, n] = epilogue( sum_tap sum_k A[rowmap(m, tap), k] * W[tap][n, k] )
+ *   mode 0 plain GEMM; mode 1 Conv1d over [M/L, L, K] ('same' padding given by pad, dilation dil);
+ *   mode 2 Conv2d ksize x ksize over [M/(Hh*Ww), Hh, Ww, K] (stride 1, padding pad)
+ *   epilogue: + bias[n]; relu_first; * scale[n] + shift[n]; + R[m, n]; relu_last.
+ * use_tc = 0: fp32 FMA kernel; 1: tcgen05 TF32 kernel (fails if the layout is not TMA-addressable). */
+typedef struct zvx_gemm_desc {
+    const float* A; const float* W; float* C;
+    const float* bias; const float* scale; const float* shift; const float* R;
+    int32_t M, N, K, taps, mode, L, Hh, Ww, ksize, pad, dil, relu_first, relu_last, lda, ldw, ldc;
+} zvx_gemm_desc;
+int zvx_debug_gemm(zvx_handle* h, const zvx_gemm_desc* d, int use_tc, void* stream);
+
 /* Workspace control: bytes of engine-owned scratch currently reserved on the device. */
 int64_t zvx_workspace_bytes(const zvx_handle* h);
 

@@ -57,6 +57,13 @@ class ZvxConfig(C.Structure):
     ]
 
 
+class ZvxGemmDesc(C.Structure):
+    """Mirror of ``struct zvx_gemm_desc`` (kernel-level test hook)."""
+    _fields_ = [(n, C.c_void_p) for n in ("A", "W", "C", "bias", "scale", "shift", "R")] + \
+               [(n, C.c_int32) for n in ("M", "N", "K", "taps", "mode", "L", "Hh", "Ww", "ksize", "pad", "dil",
+                                         "relu_first", "relu_last", "lda", "ldw", "ldc")]
+
+
 # every symbol include/zerovox_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -72,6 +79,7 @@ SYMBOLS = {
     "zvx_length_regulate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "zvx_decode": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "zvx_vocode": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "zvx_debug_gemm": (C.c_int, [_P, C.POINTER(ZvxGemmDesc), C.c_int, _P]),
     "zvx_profile_enable": (C.c_int, [_P, C.c_int]),
     "zvx_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                    C.POINTER(C.c_double)]),

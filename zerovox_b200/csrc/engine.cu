@@ -487,12 +487,22 @@ class Engine {
     }
 
     // ------------------------------------------------------------------------------------------ helpers
+    bool tc_enabled(bool tensor_core_ok) const { return tensor_core_ok && cfg.tensor_core_policy != 0; }
+
     void gemm(const GemmArgs& a, bool tensor_core_ok, cudaStream_t st) {
-        const bool tc = tensor_core_ok && cfg.tensor_core_policy != 0 && gemm_tc_supported(a);
+        TcGemmArgs t;
+        const bool tc = tc_enabled(tensor_core_ok) && gemm_tc_from(a, &t);
         const double flops = 2.0 * a.M * a.N * a.K * a.taps * a.nz;
         const double bytes = 4.0 * a.nz * ((double)a.M * a.K + (double)a.N * a.K * a.taps + (double)a.M * a.N);
         prof.begin(tc ? ZVX_PROF_GEMM_TC : ZVX_PROF_GEMM_FP32, flops, bytes, st);
-        if (tc) gemm_tc(a, st); else gemm_simt(a, st);
+        if (tc) gemm_tc(t, st); else gemm_simt(a, st);
+        prof.end(st);
+    }
+
+    void gemm_tc_prof(const TcGemmArgs& t, cudaStream_t st) {
+        const double pos = (double)t.IMG * t.Ho * t.Wo;
+        prof.begin(ZVX_PROF_GEMM_TC, t.flops(), 4.0 * (pos * t.K + pos * t.N + (double)t.N * t.K * t.ksx * t.ksy), st);
+        gemm_tc(t, st);
         prof.end(st);
     }
 
@@ -532,7 +542,7 @@ class Engine {
         FFTScratch s;
         const long long rows = (long long)B * L;
         const int DI = cfg.conv_filter_size;
-        s.qkv = ws.get<float>(rows * 3 * H);
+        s.qkv = ws.get<float>(rows * 3 * H + 4LL * B * H);   // + slack: tensor-core path keeps V transposed, rows padded to 4
         s.att = ws.get<float>(rows * H);
         s.y = ws.get<float>(rows * H);
         // attention is chunked over query rows so that the score matrix stays below kScoreBytes
@@ -554,8 +564,37 @@ class Engine {
         float *qkv = sc.qkv, *att = sc.att, *y = sc.y, *S = sc.S;
         const int ldS = sc.ldS, Lq_max = sc.Lq_max;
         const int nz = B * n_head;
-        linear(x, (int)rows, H, ly.wqkv, ly.bqkv, 3 * H, qkv, tc, st);
         const float temperature = (float)std::pow((double)dk, 0.5);  // np.power(d_k, 0.5), fs2.py:122
+        const bool tc_attn = tc_enabled(tc) && (dk % 4 == 0) && rows >= 64 && Lq_max == L;
+        if (tc_attn) {
+            // tcgen05 path: [Q|K] row-major [rows, 2H]; V written transposed per utterance, Vt[b][c][t] (row pitch Lp),
+            // so that both attention contractions read K-major operands through TMA.
+            const int Lp = (int)round_up(L, 4);
+            float* qk = qkv;
+            float* vt = qkv + rows * 2 * H;
+            linear(x, (int)rows, H, ly.wqkv, ly.bqkv, 2 * H, qk, true, st);
+            TcGemmArgs v;
+            v.A = x; v.K = H; v.Wi = v.Wo = L; v.Hi = v.Ho = B; v.a_sx = H; v.a_sy = (long long)L * H;
+            v.W = ly.wqkv + (long long)2 * H * H; v.N = H; v.w_sn = H; v.bias = ly.bqkv + 2 * H;
+            v.C = vt; v.c_sy = (long long)H * Lp; v.c_sx = 1; v.c_sn = Lp;
+            gemm_tc_prof(v, st);
+            TcGemmArgs sq;   // S[b,h,q,j] = <Q[b,q,h,:], K[b,j,h,:]>
+            sq.A = qk; sq.K = dk; sq.Wi = sq.Wo = L; sq.Hi = sq.Ho = n_head; sq.IMG = B;
+            sq.a_sx = 2 * H; sq.a_sy = dk; sq.a_simg = (long long)L * 2 * H;
+            sq.W = qk + H; sq.N = L; sq.Z1 = n_head; sq.Z2 = B; sq.w_sn = 2 * H; sq.w_s1 = dk; sq.w_s2 = (long long)L * 2 * H;
+            sq.b_batched = 1;
+            sq.C = S; sq.c_simg = (long long)n_head * L * ldS; sq.c_sy = (long long)L * ldS; sq.c_sx = ldS; sq.c_sn = 1;
+            gemm_tc_prof(sq, st);
+            attn_softmax(S, nz, n_head, L, L, ldS, mask, L, temperature, st);
+            TcGemmArgs pv;   // att[b,q,h*dk + c] = sum_j P[b,h,q,j] * Vt[b, h*dk + c, j]
+            pv.A = S; pv.K = L; pv.Wi = pv.Wo = L; pv.Hi = pv.Ho = n_head; pv.IMG = B;
+            pv.a_sx = ldS; pv.a_sy = (long long)L * ldS; pv.a_simg = (long long)n_head * L * ldS;
+            pv.W = vt; pv.N = dk; pv.Z1 = n_head; pv.Z2 = B; pv.w_sn = Lp; pv.w_s1 = (long long)dk * Lp; pv.w_s2 = (long long)H * Lp;
+            pv.b_batched = 1;
+            pv.C = att; pv.c_simg = (long long)L * H; pv.c_sy = dk; pv.c_sx = H; pv.c_sn = 1;
+            gemm_tc_prof(pv, st);
+        } else {
+        linear(x, (int)rows, H, ly.wqkv, ly.bqkv, 3 * H, qkv, tc, st);
         for (int q0 = 0; q0 < L; q0 += Lq_max) {
             const int Lq = std::min(Lq_max, L - q0);
             GemmArgs s;
@@ -571,6 +610,7 @@ class Engine {
             o.sA_b = (long long)n_head * Lq * ldS; o.sA_h = (long long)Lq * ldS;
             o.sW_b = (long long)L * 3 * H; o.sW_h = dk; o.sC_b = (long long)L * H; o.sC_h = dk;
             gemm(o, tc, st);
+        }
         }
         linear(att, (int)rows, H, ly.wfc, ly.bfc, H, y, tc, st, /*R=*/x);
         NormArgs n;
@@ -947,6 +987,30 @@ int zvx_profile_read(zvx_handle* h, int kernel_class, double* ms, int64_t* launc
     ZVX_GUARD(h, {
         ZVX_REQUIRE(ms && launches && flops && bytes, "zvx_profile_read: null output");
         h->eng->prof.read(kernel_class, ms, launches, flops, bytes);
+        return 0;
+    });
+}
+
+int zvx_debug_gemm(zvx_handle* h, const zvx_gemm_desc* d, int use_tc, void* stream) {
+    ZVX_GUARD(h, {
+        ZVX_REQUIRE(d && d->A && d->W && d->C, "zvx_debug_gemm: null operand");
+        ZVX_CUDA_CHECK(cudaSetDevice(h->eng->dev));
+        zvx::GemmArgs a;
+        a.A = d->A; a.lda = d->lda; a.W = d->W; a.ldw = d->ldw; a.w_tap_stride = (long long)d->N * d->ldw;
+        a.C = d->C; a.ldc = d->ldc; a.bias = d->bias; a.scale = d->scale; a.shift = d->shift; a.R = d->R; a.ldr = d->ldc;
+        a.M = d->M; a.N = d->N; a.K = d->K; a.taps = d->taps; a.relu_first = d->relu_first; a.relu_last = d->relu_last;
+        if (d->mode == 1) {
+            a.mode = zvx::ROW_CONV1D; a.Lout = a.Lin = d->L; a.stride = 1; a.pad = d->pad; a.dil = d->dil;
+        } else if (d->mode == 2) {
+            a.mode = zvx::ROW_CONV2D; a.Ho = a.Hi = d->Hh; a.Wo = a.Wi = d->Ww; a.ksize = d->ksize; a.stride = 1; a.pad = d->pad;
+        }
+        if (use_tc) {
+            zvx::TcGemmArgs t;
+            ZVX_REQUIRE(zvx::gemm_tc_from(a, &t), "zvx_debug_gemm: layout not supported by the tcgen05 path");
+            zvx::gemm_tc(t, (cudaStream_t)stream);
+        } else {
+            zvx::gemm_simt(a, (cudaStream_t)stream);
+        }
         return 0;
     });
 }

@@ -1,5 +1,478 @@
+// TF32 GEMM / implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// Persistent, warp-specialised kernel, one CTA per SM (gemm_tc.cuh states the generalised problem):
+//   warp 0      TMA producer : cp.async.bulk.tensor.4d loads of the A tile (128 positions x 32 k, one per filter tap —
+//                              the tap is a coordinate shift, the zero padding is TMA out-of-bounds fill) and of the
+//                              W tile (BN x 32 k) into a ring of 128B-swizzled shared-memory stages;
+//   warp 1      MMA issuer   : one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = BN, K = 8) straight
+//                              from shared memory into one of two TMEM accumulators (2 x 256 columns), releases stages
+//                              with tcgen05.commit;
+//   warps 2..5  epilogue     : tcgen05.ld the finished accumulator (lane = output position), apply bias / ReLU /
+//                              folded BatchNorm / residual, store row-major or transposed, hand the TMEM buffer back —
+//                              overlapping the next tile's main loop.
+// Operands are fp32 in HBM, rounded to TF32 (10-bit mantissa, round-to-nearest) by the TMA unit on their way to
+// shared memory; accumulation is fp32.
 #include "gemm_tc.cuh"
+
+#include <cuda.h>
+
+#include <cstdlib>
+#include <mutex>
+
 namespace zvx {
-bool gemm_tc_supported(const GemmArgs&) { return false; }
-void gemm_tc(const GemmArgs&, cudaStream_t) { throw Error("gemm_tc: not built"); }
+
+namespace {
+
+constexpr int BM = 128;                  // output positions per tile (MMA M)
+constexpr int BK = 32;                   // fp32 elements per 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * BK * 4;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;          // TMEM columns between the two accumulators
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct TcParams {
+    int num_tiles, tiles_n, tiles_x, tiles_y;
+    int TW, TH, BN;
+    int ksx, taps, kchunks, dil, pad_x, pad_y;
+    int b_batched;
+    int stages, stage_bytes, b_tile_bytes;
+    uint32_t idesc;
+    int Wo, Ho, N;
+    float* C;
+    const float* R;
+    long long c_simg, c_sy, c_sx, c_sn;
+    const float* bias;
+    const float* scale;
+    const float* shift;
+    int relu_first, relu_last, vec4;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    long long t0 = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile (rows of 32 fp32 = 128 B, 8-row atoms of 1024 B): matrix descriptor.
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, 16-byte units               bits [0,14)
+    d |= (uint64_t)1 << 16;                     // leading byte offset (unused: one atom in K)  bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset: next 8-row atom          bits [32,46)
+    d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)               bits [46,48)
+    d |= (uint64_t)2 << 61;                     // layout type: SWIZZLE_128B                    bits [61,64)
+    return d;
+}
+
+struct Tile { int n0, x0, y0, img; };
+__device__ __forceinline__ Tile decode_tile(const TcParams& p, int t) {
+    Tile c;
+    const int nt = t % p.tiles_n; t /= p.tiles_n;
+    const int xt = t % p.tiles_x; t /= p.tiles_x;
+    const int yt = t % p.tiles_y;
+    c.img = t / p.tiles_y;
+    c.n0 = nt * p.BN; c.x0 = xt * p.TW; c.y0 = yt * p.TH;
+    return c;
+}
+
+__device__ __forceinline__ float epi(const TcParams& p, float x, int n) {
+    if (p.bias) x += __ldg(p.bias + n);
+    if (p.relu_first) x = fmaxf(x, 0.f);
+    if (p.scale) x = fmaf(x, __ldg(p.scale + n), __ldg(p.shift + n));
+    return x;
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bars = smem_base + (uint32_t)(p.stages * p.stage_bytes);
+    // barrier i at bars + 8*i : full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | tmem base slot
+    auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(p.stages + s); };
+    auto tfull_bar = [&](int b) { return bars + 8u * (uint32_t)(2 * p.stages + b); };
+    auto tempty_bar = [&](int b) { return bars + 8u * (uint32_t)(2 * p.stages + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (uint32_t)(2 * p.stages + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem + p.stages * p.stage_bytes + 8 * (2 * p.stages + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int ksteps = p.taps * p.kchunks;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t tx_bytes = (uint32_t)(A_TILE_BYTES + p.b_tile_bytes);
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const Tile c = decode_tile(p, t);
+                for (int s = 0; s < ksteps; ++s) {
+                    const int tap = s / p.kchunks, kc = s - tap * p.kchunks;
+                    const int dy = tap / p.ksx, dx = tap - dy * p.ksx;
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
+                    const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
+                    tma_load_4d(&mapA, full_bar(stage), sa, kc * BK, c.x0 + dx * p.dil - p.pad_x,
+                                c.y0 + dy * p.dil - p.pad_y, c.img);
+                    tma_load_4d(&mapB, full_bar(stage), sa + A_TILE_BYTES, kc * BK, c.n0, p.b_batched ? c.y0 : tap,
+                                p.b_batched ? c.img : 0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t par = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty_bar(buf), par ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
+                for (int s = 0; s < ksteps; ++s) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
+                    const uint64_t da = sw128_desc(sa), db = sw128_desc(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes = 2 descriptor units per MMA
+                        umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (s | k) ? 1u : 0u);
+                    umma_commit(empty_bar(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(buf));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================================================ epilogue (warps 2..5)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;            // position within the tile
+        const int ty = r / p.TW, tx = r - ty * p.TW;
+        int it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t par = (uint32_t)(it >> 1) & 1u;
+            const Tile c = decode_tile(p, t);
+            const int y = c.y0 + ty, x = c.x0 + tx;
+            const bool valid = (y < p.Ho) && (x < p.Wo);
+            const long long off = (long long)c.img * p.c_simg + (long long)y * p.c_sy + (long long)x * p.c_sx;
+            float* __restrict__ cp = p.C + off;
+            const float* __restrict__ rp = p.R ? p.R + off : nullptr;
+            mbar_wait(tfull_bar(buf), par);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                uint32_t v[32];
+                __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
+                tmem_ld16(trow + (uint32_t)c0, v);
+                if (c0 + 16 < p.BN) tmem_ld16(trow + (uint32_t)(c0 + 16), v + 16);
+                tmem_wait_ld();
+                if (!valid) continue;
+                const int ncols = min(32, p.BN - c0);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = c.n0 + c0 + j;
+                    if (j >= ncols || n >= p.N) continue;
+                    if (p.vec4 && n + 4 <= p.N) {
+                        float4 o;
+                        o.x = epi(p, __uint_as_float(v[j + 0]), n + 0);
+                        o.y = epi(p, __uint_as_float(v[j + 1]), n + 1);
+                        o.z = epi(p, __uint_as_float(v[j + 2]), n + 2);
+                        o.w = epi(p, __uint_as_float(v[j + 3]), n + 3);
+                        if (rp) {
+                            const float4 rr = *reinterpret_cast<const float4*>(rp + n);
+                            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                        }
+                        if (p.relu_last) {
+                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                        }
+                        *reinterpret_cast<float4*>(cp + n) = o;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (n + e < p.N) {
+                                float o = epi(p, __uint_as_float(v[j + e]), n + e);
+                                const long long a = (long long)(n + e) * p.c_sn;
+                                if (rp) o += rp[a];
+                                if (p.relu_last) o = fmaxf(o, 0.f);
+                                cp[a] = o;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    });
+    if (!fn) throw Error("cuTensorMapEncodeTiled is not available from this driver");
+    return fn;
+}
+
+// 4-D fp32 tensor map, dim 0 contiguous, 128-byte swizzle, zero fill out of bounds.
+CUtensorMap make_map(const float* base, const long long dims[4], const long long strides_elems[3], const int box[4]) {
+    CUtensorMap m;
+    cuuint64_t gd[4], gs[3];
+    cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+    long long prev = 16;
+    for (int i = 0; i < 4; ++i) {
+        gd[i] = (cuuint64_t)std::max<long long>(dims[i], 1);
+        bx[i] = (cuuint32_t)box[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+        long long s = strides_elems[i] * 4;
+        if (dims[i + 1] <= 1 && s <= 0) s = prev;   // unit dims: any valid stride
+        gs[i] = (cuuint64_t)s;
+        prev = std::max<long long>(s, 16);
+    }
+    // TFLOAT32 element type: the TMA unit rounds fp32 -> tf32 (nearest) in flight.  With plain FLOAT32 the tensor core
+    // truncates the low 13 mantissa bits, a systematic -7e-4 relative bias per contraction (measured, tools/diag_tf32.py;
+    // ZVX_TMAP_F32=1 restores that behaviour for the experiment).
+    static const bool f32_type = getenv("ZVX_TMAP_F32") != nullptr;
+    const CUresult rc = encode_fn()(&m, f32_type ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), gd, gs, bx, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        char buf[256];
+        snprintf(buf, sizeof(buf),
+                 "cuTensorMapEncodeTiled failed (%d): dims %lld %lld %lld %lld strides(B) %lld %lld %lld box %d %d %d %d",
+                 (int)rc, dims[0], dims[1], dims[2], dims[3], (long long)gs[0], (long long)gs[1], (long long)gs[2], box[0],
+                 box[1], box[2], box[3]);
+        throw Error(buf);
+    }
+    return m;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+bool mult4(long long v) { return (v & 3) == 0; }
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        ZVX_CUDA_CHECK(cudaGetDevice(&dev));
+        ZVX_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return n;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const TcGemmArgs& a) {
+    if (!a.A || !a.W || !a.C) return false;
+    if (a.K < 8 || a.N < 8 || a.Wo < 1 || a.Ho < 1 || a.IMG < 1) return false;
+    if (!aligned16(a.A) || !aligned16(a.W)) return false;
+    if (!mult4(a.a_sx) || !mult4(a.a_sy) || !mult4(a.a_simg) || !mult4(a.w_sn) || !mult4(a.w_s1) || !mult4(a.w_s2))
+        return false;
+    if (a.a_sx <= 0 || a.w_sn <= 0) return false;
+    if ((long long)a.IMG * a.Ho * a.Wo < 64) return false;   // tiny problems stay on the fp32 FMA kernel
+    return true;
+}
+
+void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
+    ZVX_REQUIRE(gemm_tc_supported(a), "gemm_tc: operand layout not supported by the TMA path");
+    TcParams p{};
+    // tile shape: TH x TW = 128 positions, least padding first, wider rows on ties
+    long long best = -1;
+    for (int tw = 128; tw >= (a.b_batched ? 128 : 8); tw >>= 1) {   // per-(y,img) W operands: one y per tile
+        const int th = BM / tw;
+        const long long padded = round_up(a.Wo, tw) * round_up(a.Ho, th);
+        if (best < 0 || padded < best) { best = padded; p.TW = tw; p.TH = th; }
+    }
+    // column tile: multiple of 16, <= 256, least padding over a few tile counts
+    {
+        const int t0 = cdiv(a.N, 256);
+        long long bw = -1;
+        for (int tn = t0; tn <= t0 + 4; ++tn) {
+            const int bn = (int)std::min<long long>(256, round_up(cdiv(a.N, tn), 16));
+            const int tiles = cdiv(a.N, bn);
+            const long long waste = (long long)tiles * bn - a.N;
+            if (bw < 0 || waste < bw) { bw = waste; p.BN = bn; p.tiles_n = tiles; }
+        }
+    }
+    p.tiles_x = cdiv(a.Wo, p.TW);
+    p.tiles_y = cdiv(a.Ho, p.TH);
+    const long long nt = (long long)a.IMG * p.tiles_y * p.tiles_x * p.tiles_n;
+    ZVX_REQUIRE(nt < (1LL << 30), "gemm_tc: too many tiles");
+    p.num_tiles = (int)nt;
+    p.ksx = a.ksx; p.taps = a.ksx * a.ksy; p.kchunks = cdiv(a.K, BK); p.dil = a.dil; p.pad_x = a.pad_x; p.pad_y = a.pad_y;
+    p.b_batched = a.b_batched;
+    p.b_tile_bytes = p.BN * BK * 4;
+    p.stage_bytes = A_TILE_BYTES + (int)round_up(p.b_tile_bytes, 1024);
+    p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes);
+    // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3, M >> 4
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    p.Wo = a.Wo; p.Ho = a.Ho; p.N = a.N;
+    p.C = a.C; p.R = a.R; p.c_simg = a.c_simg; p.c_sy = a.c_sy; p.c_sx = a.c_sx; p.c_sn = a.c_sn;
+    p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.relu_first = a.relu_first; p.relu_last = a.relu_last;
+    ZVX_REQUIRE(!a.scale || a.shift, "gemm_tc: scale needs shift");
+    p.vec4 = (a.c_sn == 1) && mult4(a.c_simg) && mult4(a.c_sy) && mult4(a.c_sx) && aligned16(a.C) &&
+             (!a.R || aligned16(a.R));
+
+    const long long adims[4] = {a.K, a.Wi, a.Hi, a.IMG};
+    const long long astr[3] = {a.a_sx, a.a_sy, a.a_simg};
+    const int abox[4] = {BK, p.TW, p.TH, 1};
+    const long long wdims[4] = {a.K, a.N, a.Z1, a.Z2};
+    const long long wstr[3] = {a.w_sn, a.w_s1, a.w_s2};
+    const int wbox[4] = {BK, p.BN, 1, 1};
+    const CUtensorMap mapA = make_map(a.A, adims, astr, abox);
+    const CUtensorMap mapB = make_map(a.W, wdims, wstr, wbox);
+
+    const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 1024;
+    static bool attr = false;
+    if (!attr) {
+        ZVX_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        attr = true;
+    }
+    ZVX_REQUIRE(smem <= SMEM_LIMIT && smem > 116 * 1024, "gemm_tc: shared-memory plan out of range");
+    const int grid = std::min(p.num_tiles, num_sms());
+    gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, p);
+    ZVX_POST_LAUNCH();
+}
+
+bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* o) {
+    if (g.b_kn || g.nz != 1 || g.stride != 1) return false;
+    TcGemmArgs a;
+    a.A = g.A; a.K = g.K; a.W = g.W; a.N = g.N; a.w_sn = g.ldw; a.Z1 = g.taps; a.w_s1 = g.w_tap_stride; a.Z2 = 1;
+    a.C = g.C; a.R = g.R; a.bias = g.bias; a.scale = g.scale; a.shift = g.shift;
+    a.relu_first = g.relu_first; a.relu_last = g.relu_last; a.c_sn = 1;
+    if (g.R && g.ldr != g.ldc) return false;
+    if (g.mode == ROW_PLAIN) {
+        if (g.taps != 1) return false;
+        a.Wi = a.Wo = g.M; a.a_sx = g.lda; a.c_sx = g.ldc;
+    } else if (g.mode == ROW_CONV1D) {
+        if (g.Lin != g.Lout || g.M % g.Lout != 0) return false;
+        a.Wi = a.Wo = g.Lout; a.Hi = a.Ho = g.M / g.Lout;
+        a.a_sx = g.lda; a.a_sy = (long long)g.Lin * g.lda;
+        a.c_sx = g.ldc; a.c_sy = (long long)g.Lout * g.ldc;
+        a.ksx = g.taps; a.ksy = 1; a.dil = g.dil; a.pad_x = g.pad; a.pad_y = 0;
+    } else {
+        if (g.Hi != g.Ho || g.Wi != g.Wo || g.taps != g.ksize * g.ksize) return false;
+        a.Wi = a.Wo = g.Wo; a.Hi = a.Ho = g.Ho; a.IMG = g.M / (g.Ho * g.Wo);
+        a.a_sx = g.lda; a.a_sy = (long long)g.Wi * g.lda; a.a_simg = (long long)g.Hi * g.Wi * g.lda;
+        a.c_sx = g.ldc; a.c_sy = (long long)g.Wo * g.ldc; a.c_simg = (long long)g.Ho * g.Wo * g.ldc;
+        a.ksx = a.ksy = g.ksize; a.dil = 1; a.pad_x = a.pad_y = g.pad;
+    }
+    *o = a;
+    return gemm_tc_supported(a);
+}
+
 }  // namespace zvx

@@ -4,9 +4,43 @@
 
 namespace zvx {
 
-// True when `a` can run on the tcgen05 path (alignment / layout constraints of the TMA descriptors).
-bool gemm_tc_supported(const GemmArgs& a);
-// Same contract as gemm_simt, operands rounded to TF32 by the tensor core, fp32 accumulation.
-void gemm_tc(const GemmArgs& a, cudaStream_t st);
+// Generalised problem of the tcgen05 kernel.
+//
+//   out[img, y, x, n] = epilogue( sum_{dy,dx} sum_k A[img, y + dy*dil - pad_y, x + dx*dil - pad_x, k] * W[z1, z2][n, k] )
+//
+// A is a 4-D view (K contiguous) addressed through one TMA tensor map; positions outside [0,Hi)x[0,Wi) read as
+// zero (TMA out-of-bounds fill = the convolutions' zero padding).  W is a 4-D view (K contiguous) with
+//   (z1, z2) = (tap, 0)   tap = dy*ksx + dx      for weights shared by all tiles (Linear / Conv1d / Conv2d), or
+//   (z1, z2) = (y, img)                          for per-(y,img) operands (attention: y = head, img = utterance).
+// An output tile is TH x TW = 128 positions of one image (M of the MMA) by BN columns.
+// Plain GEMM: Hi = Ho = IMG = 1, Wi = Wo = M.   Conv1d over [B, L, C]: Hi = Ho = B, Wi = Wo = L, ksy = 1.
+// epilogue: v = acc + bias[n]; relu_first; v = v*scale[n] + shift[n]; v += R[...]; relu_last
+// out / R element offset: img*c_simg + y*c_sy + x*c_sx + n*c_sn  (c_sn = 1: row-major; c_sx = 1: transposed store).
+struct TcGemmArgs {
+    const float* A = nullptr;
+    int K = 0, Wi = 1, Hi = 1, IMG = 1;
+    long long a_sx = 0, a_sy = 0, a_simg = 0;   // element strides of the x / y / img dims (K stride = 1)
+    const float* W = nullptr;
+    int N = 0, Z1 = 1, Z2 = 1;
+    long long w_sn = 0, w_s1 = 0, w_s2 = 0;     // element strides of the n / z1 / z2 dims
+    int b_batched = 0;
+    int Wo = 1, Ho = 1;
+    int ksx = 1, ksy = 1, dil = 1, pad_x = 0, pad_y = 0;
+    float* C = nullptr;
+    long long c_simg = 0, c_sy = 0, c_sx = 0, c_sn = 1;
+    const float* R = nullptr;
+    const float* bias = nullptr;
+    const float* scale = nullptr;
+    const float* shift = nullptr;
+    int relu_first = 0, relu_last = 0;
+    double flops() const { return 2.0 * IMG * Ho * Wo * (double)N * K * ksx * ksy; }
+};
+
+// Constraints of the TMA descriptors (16-byte aligned base pointers and strides) and of the tile shapes.
+bool gemm_tc_supported(const TcGemmArgs& a);
+void gemm_tc(const TcGemmArgs& a, cudaStream_t st);
+
+// Conversion from the SIMT kernel's argument block (ROW_PLAIN / ROW_CONV1D / ROW_CONV2D with stride 1, nz == 1).
+bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* out);
 
 }  // namespace zvx
