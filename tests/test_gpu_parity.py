@@ -4,10 +4,17 @@ mirror modules, against the CPU oracle on the same seeded inputs and against the
 Tolerances (stated per stage, fp32 unless marked):
   * integer outputs (mel_len, forced durations, LengthRegulator indices and gathered rows): bit-exact;
   * fp32 FMA path (tensor_core_policy=0; encoder + variance predictors always): |err| <= 2e-4 * max|ref| + 2e-5;
-  * TF32 tensor-core path (policy 1; decoder / vocoder / speaker net): mel |err| <= 1e-2 * max|ref|,
-    wav |err| <= 2e-2 (SURVEY.md §7: TF32 operands give rel-RMS ~3e-4; max-abs is ~10-30x the RMS);
+  * TF32 tensor-core path (policy 1; decoder / vocoder / speaker net; operands rounded to nearest TF32, fp32
+    accumulation): mel |err| <= 5e-3 * max|ref|, wav |err| <= 2e-2 (CPU emulation of TF32 operand rounding in the
+    oracle's decoder, tools/diag_tf32_oracle.py: rel-RMS ~5e-4, max-abs ~7e-4 * max|ref|);
   * pitch / energy buckets and predicted durations: exact wherever the oracle's float input to the rounding step is
     more than 1e-3 away from a rounding boundary (reported otherwise).
+  * end-to-end runs under policy 1: the speaker net runs in TF32, so its style vector differs from the reference's by
+    ~1e-3; the encoder adds that vector to every phoneme before the variance predictors, whose outputs are ROUNDED to
+    buckets / durations (fs2.py:639, 649, 678-681) — a 1e-3 nudge can flip one bucket and change a whole phoneme's
+    frames.  That is a property of the reference's arithmetic, not a kernel error, so the policy-1 end-to-end tests
+    (a) check the engine's style vector against the reference's within the TF32 tolerance and (b) compare everything
+    downstream with the oracle fed that same style vector (stage-wise parity, SURVEY.md §7 "hard parts").
 """
 import os
 
@@ -39,7 +46,7 @@ def check(name, got, ref, rtol, atol=2e-5):
 
 
 FP32 = dict(rtol=2e-4)
-TC_MEL = dict(rtol=1e-2)
+TC_MEL = dict(rtol=5e-3)
 TC_WAV = dict(rtol=0.0, atol=2e-2)
 
 
@@ -181,7 +188,8 @@ def test_decoder(tiny, medium, which, B, L, policy):
 
 
 @pytest.mark.parametrize("policy", [0, 1])
-@pytest.mark.parametrize("v,B,L", [("v2", 2, 9), ("v1", 1, 7), ("v3", 2, 5), ("v2", 3, 70), ("v2", 1, 1)])
+@pytest.mark.parametrize("v,B,L", [("v2", 2, 9), ("v1", 1, 7), ("v3", 2, 5), ("v2", 3, 70), ("v2", 1, 1),
+                                   ("v1", 2, 40), ("v3", 3, 33), ("v2", 1, 300)])
 def test_vocoder_variants(golden_dir, v, B, L, policy):
     h = getattr(zo.HifiGanConfig, v)()
     g = torch.Generator().manual_seed(11)
@@ -222,14 +230,21 @@ def test_forward_against_reference_goldens(golden_dir, name, policy):
     force = bool(g["force"])
     with torch.no_grad():
         wav, mel, mel_len, logd = model(dict(x), force_duration=force)  # host tensors in, like export_hifigan.py
-    check("log_duration", logd, g["log_duration"], **FP32)
-    if not np.array_equal(mel_len.cpu().numpy(), g["mel_len"]):
+    ref = {k: g[k] for k in ("wav", "mel", "mel_len", "log_duration")}
+    if policy == 1:  # stage-wise: style vector vs the reference's, the rest vs the oracle fed the engine's style vector
+        with torch.no_grad():
+            style_e = model._spkemb(x["ref_mel"].to(DEV)).cpu()
+            check("style_embed (TF32 speaker net)", style_e, g["style_embed"], **TC_MEL)
+            owav, omel, olen, ologd, _ = zo.zerovox_forward(cfg, w, dict(x), force_duration=force, style_embed=style_e)
+        ref = {"wav": owav.numpy(), "mel": omel.numpy(), "mel_len": olen.numpy(), "log_duration": ologd.numpy()}
+    check("log_duration", logd, ref["log_duration"], **FP32)
+    if not np.array_equal(mel_len.cpu().numpy(), ref["mel_len"]):
         # only legitimate when a predicted duration sat on a rounding boundary
         assert not force
         pytest.skip("predicted duration flipped at a rounding boundary (documented in DESIGN.md)")
-    assert wav.shape == g["wav"].shape and mel.shape == g["mel"].shape
-    check("mel", mel, g["mel"], **tol(policy, "mel"))
-    check("wav", wav, g["wav"], **tol(policy, "wav"))
+    assert wav.shape == ref["wav"].shape and mel.shape == ref["mel"].shape
+    check("mel", mel, ref["mel"], **tol(policy, "mel"))
+    check("wav", wav, ref["wav"], **tol(policy, "wav"))
     assert float(wav.abs().max()) <= 1.0
     # batch-1 inference_ex with the stateful _min_mel_len padding (model.py:308-347)
     x1 = {k: v[:1] for k, v in x.items() if k != "phoneme_mask"}
@@ -251,8 +266,9 @@ def test_forward_matches_oracle_ragged_batch(medium, policy):
     cfg = medium.cfg
     x = zo.make_inputs(cfg, 4, 21, 64, seed=13, ragged=True)
     with torch.no_grad():
-        owav, omel, olen, ologd, st = zo.zerovox_forward(cfg, medium.w, dict(x), force_duration=True)
         wav, mel, mel_len, logd = medium.model(policy)(dict(x), force_duration=True)
+        style_e = medium.model(policy)._spkemb(x["ref_mel"].to(DEV)).cpu() if policy else None   # see module docstring
+        owav, omel, olen, ologd, st = zo.zerovox_forward(cfg, medium.w, dict(x), force_duration=True, style_embed=style_e)
     assert torch.equal(mel_len.cpu(), olen)
     check("log_duration", logd, ologd, **FP32)
     check("mel", mel, omel, **tol(policy, "mel"))

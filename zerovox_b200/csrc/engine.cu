@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -484,6 +485,88 @@ class Engine {
             }
         }
         hg_post = pack_conv("conv_post", 1, ch, 7, 1);
+        pack_vocoder_tc();
+    }
+
+    // Tensor-core (channel-last) image of the vocoder weights, used when tensor_core_policy != 0 and every stage has a
+    // channel count one of the tcgen05 kernels covers: C in {8,16,32} -> fused pair kernel (voc_tc.cu); C >= 64 (and a
+    // multiple of 4) -> generic TMA-fed implicit GEMM (gemm_tc.cu).
+    void pack_vocoder_tc() {
+        hg_tc_ok = false;
+        hg_stage_kind.clear(); hg_ups_tc_w.clear(); hg_ups_tc_b.clear(); hg_c1_tc.clear(); hg_c2_tc.clear();
+        const int C0 = cfg.hg_upsample_initial_channel, nk = cfg.hg_num_kernels, nd = cfg.hg_num_dilations;
+        if (C0 % 4 != 0 || C0 < 8 || cfg.n_mels % 4 != 0) return;
+        for (int i = 0; i < cfg.hg_num_upsamples; ++i) {
+            const int ch = C0 >> (i + 1), u = cfg.hg_upsample_rates[i];
+            if (cfg.hg_upsample_kernel_sizes[i] != 2 * u || (u & 1) || (C0 >> i) % 4 != 0 || (C0 >> i) < 8) return;
+            int kind = 0;
+            if (ch == 8 || ch == 16 || ch == 32) {
+                kind = 1;
+                for (int j = 0; j < nk; ++j)
+                    for (int di = 0; di < nd; ++di)
+                        if (!voc_pair_supported(ch, cfg.hg_resblock_kernel_sizes[j], cfg.hg_resblock_dilation_sizes[j][di]))
+                            kind = 0;
+            } else if (ch >= 64 && ch % 4 == 0) {
+                kind = 2;
+            }
+            if (kind == 0) return;
+            hg_stage_kind.push_back(kind);
+        }
+        auto rn_tf32 = [](float v) {
+            uint32_t u;
+            std::memcpy(&u, &v, 4);
+            u = (u + 0x0FFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
+            std::memcpy(&v, &u, 4);
+            return v;
+        };
+        (void)rn_tf32;
+        hg_pre_tc = upload(tap_major(W("_meldec.conv_pre.weight", {C0, cfg.n_mels, 7})));
+        size_t ci = 0;
+        for (int i = 0; i < cfg.hg_num_upsamples; ++i) {
+            const int cin = C0 >> i, cout = C0 >> (i + 1), u = cfg.hg_upsample_rates[i], k = 2 * u;
+            // ConvTranspose1d as a 2-tap GEMM over input positions q: out[q*u + r - p, co] = W[ci,co,r] x[q] + W[ci,co,r+u] x[q-1]
+            // tap 0 pairs with x[q-1], tap 1 with x[q]; GEMM column n = r*cout + co.
+            const HostTensor& w = W("_meldec.ups." + std::to_string(i) + ".weight", {cin, cout, k});
+            const HostTensor& b = W("_meldec.ups." + std::to_string(i) + ".bias", {cout});
+            std::vector<float> wg((size_t)2 * u * cout * cin), bg((size_t)u * cout);
+            for (int r = 0; r < u; ++r)
+                for (int co = 0; co < cout; ++co) {
+                    bg[(size_t)r * cout + co] = b.data[(size_t)co];
+                    for (int c = 0; c < cin; ++c) {
+                        wg[((size_t)0 * u * cout + (size_t)r * cout + co) * cin + c] = w.data[((size_t)c * cout + co) * k + r + u];
+                        wg[((size_t)1 * u * cout + (size_t)r * cout + co) * cin + c] = w.data[((size_t)c * cout + co) * k + r];
+                    }
+                }
+            hg_ups_tc_w.push_back(upload(wg));
+            hg_ups_tc_b.push_back(upload(bg));
+            for (int j = 0; j < nk; ++j) {
+                const std::string p = "resblocks." + std::to_string(i * nk + j);
+                const int rk = cfg.hg_resblock_kernel_sizes[j];
+                for (int di = 0; di < nd; ++di, ++ci) {
+                    auto pack = [&](const std::string& key) {
+                        const HostTensor& t = W("_meldec." + key + ".weight", {cout, cout, rk});
+                        return hg_stage_kind[(size_t)i] == 1 ? upload(voc_pack_weight(t.data.data(), cout, cout, rk))
+                                                              : upload(tap_major(t));
+                    };
+                    if (cfg.hg_resblock == 1) {
+                        hg_c1_tc.push_back(pack(p + ".convs1." + std::to_string(di)));
+                        hg_c2_tc.push_back(pack(p + ".convs2." + std::to_string(di)));
+                    } else {
+                        hg_c1_tc.push_back(pack(p + ".convs." + std::to_string(di)));
+                    }
+                }
+            }
+        }
+        {
+            const int ch = hg_post.cin;
+            if (ch % 4 != 0) return;
+            const HostTensor& w = W("_meldec.conv_post.weight", {1, ch, 7});
+            std::vector<float> t((size_t)7 * ch);
+            for (int c = 0; c < ch; ++c)
+                for (int j = 0; j < 7; ++j) t[(size_t)j * ch + c] = w.data[(size_t)c * 7 + j];
+            hg_post_tc = upload(t);
+        }
+        hg_tc_ok = true;
     }
 
     // ------------------------------------------------------------------------------------------ helpers
@@ -565,7 +648,9 @@ class Engine {
         const int ldS = sc.ldS, Lq_max = sc.Lq_max;
         const int nz = B * n_head;
         const float temperature = (float)std::pow((double)dk, 0.5);  // np.power(d_k, 0.5), fs2.py:122
-        const bool tc_attn = tc_enabled(tc) && (dk % 4 == 0) && rows >= 64 && Lq_max == L;
+        // debug bisection switches (tools/diag_golden.py): ZVX_TC_MASK bit0 attention, bit1 fc, bit2 w_1, bit3 w_2
+        static const int tc_mask = getenv("ZVX_TC_MASK") ? atoi(getenv("ZVX_TC_MASK")) : 15;
+        const bool tc_attn = tc_enabled(tc) && (tc_mask & 1) && (dk % 4 == 0) && rows >= 64 && Lq_max == L;
         if (tc_attn) {
             // tcgen05 path: [Q|K] row-major [rows, 2H]; V written transposed per utterance, Vt[b][c][t] (row pitch Lp),
             // so that both attention contractions read K-major operands through TMA.
@@ -612,7 +697,7 @@ class Engine {
             gemm(o, tc, st);
         }
         }
-        linear(att, (int)rows, H, ly.wfc, ly.bfc, H, y, tc, st, /*R=*/x);
+        linear(att, (int)rows, H, ly.wfc, ly.bfc, H, y, tc && (tc_mask & 2), st, /*R=*/x);
         NormArgs n;
         n.x = y; n.out = x; n.rows = (int)rows; n.C = H; n.rows_per_batch = L; n.mask = mask;
         if (scln) { n.scln = 1; n.gb = gb1; n.gb_ld = gb_ld; n.eps = 1e-8f; }
@@ -620,8 +705,8 @@ class Engine {
         layer_norm(n, st);
         // position-wise feed-forward (fs2.py:196-209)
         float* h1 = sc.h1;
-        conv1d_cl(x, B, L, H, ly.w1, ly.b1, DI, k1, (k1 - 1) / 2, h1, tc, st, nullptr, /*relu_first=*/1);
-        conv1d_cl(h1, B, L, DI, ly.w2, ly.b2, H, k2, (k2 - 1) / 2, y, tc, st, /*R=*/x);
+        conv1d_cl(x, B, L, H, ly.w1, ly.b1, DI, k1, (k1 - 1) / 2, h1, tc && (tc_mask & 4), st, nullptr, /*relu_first=*/1);
+        conv1d_cl(h1, B, L, DI, ly.w2, ly.b2, H, k2, (k2 - 1) / 2, y, tc && (tc_mask & 8), st, /*R=*/x);
         n.x = y; n.out = x;
         if (scln) n.gb = gb2; else { n.gamma = ly.ln2_g; n.beta = ly.ln2_b; }
         layer_norm(n, st);
@@ -798,10 +883,120 @@ class Engine {
         return 0;
     }
 
+    struct View { float* p; long long bs; };
+
+    // Channel-last tensor-core vocoder (gemm_tc.cu + voc_tc.cu); same arithmetic graph as vocode_simt below.
+    int vocode_tc(const float* mel_BCL, int B, int L, float* wav, cudaStream_t st) {
+        const int C0 = cfg.hg_upsample_initial_channel, M = cfg.n_mels;
+        const int nk = cfg.hg_num_kernels, nd = cfg.hg_num_dilations, nu = cfg.hg_num_upsamples;
+        long long big = std::max((long long)B * L * C0, (long long)B * L * M), t = L;
+        for (int i = 0; i < nu; ++i) {
+            t *= cfg.hg_upsample_rates[i];
+            big = std::max(big, (long long)B * (t + 16) * (C0 >> (i + 1)));
+        }
+        float* bX = ws.get<float>(big);    // stage output (MRF accumulator), raw
+        float* bXA = ws.get<float>(big);   // its leaky-ReLU'd copy (upsampler operand)
+        float* bY = ws.get<float>(big);    // upsampler output, raw
+        float* bYA = ws.get<float>(big);
+        float* bRA = ws.get<float>(big);
+        float* bRAa = ws.get<float>(big);
+        float* bRB = ws.get<float>(big);
+        float* bRBa = ws.get<float>(big);
+        float* bT = ws.get<float>(big);
+        float* mel = ws.get<float>((long long)B * L * M);
+        transpose_mel(mel_BCL, nullptr, 0, B, /*rows=*/M, /*cols=*/L, mel, nullptr, st);   // [B,M,L] -> [B,L,M]
+        {   // conv_pre, stored leaky-ReLU'd: its only consumer is the first upsampler
+            TcGemmArgs g;
+            g.A = mel; g.K = M; g.Wi = g.Wo = L; g.Hi = g.Ho = B; g.a_sx = M; g.a_sy = (long long)L * M;
+            g.W = hg_pre_tc; g.N = C0; g.w_sn = M; g.Z1 = 7; g.w_s1 = (long long)C0 * M; g.ksx = 7; g.pad_x = 3;
+            g.bias = hg_pre.b; g.C = bXA; g.c_sx = C0; g.c_sy = (long long)L * C0; g.act_slope = 0.1f;
+            gemm_tc_prof(g, st);
+        }
+        View xa{bXA, (long long)L * C0};
+        int T = L;
+        size_t ci = 0;
+        for (int i = 0; i < nu; ++i) {
+            const int cin = C0 >> i, ch = C0 >> (i + 1), u = cfg.hg_upsample_rates[i], pd = u / 2;
+            const int kind = hg_stage_kind[(size_t)i];
+            const int Tout = T * u;
+            const long long ybs = (long long)(Tout + u) * ch;
+            {   // ConvTranspose1d: 2-tap GEMM over the T+1 input positions, N = u*ch columns = u consecutive output samples
+                TcGemmArgs g;
+                g.A = xa.p; g.K = cin; g.Wi = T; g.Wo = T + 1; g.Hi = g.Ho = B; g.a_sx = cin; g.a_sy = xa.bs;
+                g.W = hg_ups_tc_w[(size_t)i]; g.N = u * ch; g.w_sn = cin; g.Z1 = 2; g.w_s1 = (long long)u * ch * cin;
+                g.ksx = 2; g.pad_x = 1; g.bias = hg_ups_tc_b[(size_t)i];
+                g.C = bY; g.c_sx = (long long)u * ch; g.c_sy = ybs;
+                if (kind == 2) { g.C2 = bYA; g.slope2 = 0.1f; }
+                gemm_tc_prof(g, st);
+            }
+            T = Tout;
+            const View y{bY + (long long)pd * ch, ybs}, ya{bYA + (long long)pd * ch, ybs};
+            const long long bs = (long long)T * ch;
+            const bool more = (i + 1 < nu);
+            for (int j = 0; j < nk; ++j) {
+                View r = y, ra = ya;
+                const int rk = cfg.hg_resblock_kernel_sizes[j];
+                for (int di = 0; di < nd; ++di, ++ci) {
+                    const bool last = (di == nd - 1);
+                    const bool first_buf = (r.p != bRA);
+                    const View rn{first_buf ? bRA : bRB, bs}, rna{first_buf ? bRAa : bRBa, bs};
+                    const int dl = cfg.hg_resblock_dilation_sizes[j][di];
+                    const bool pair = (cfg.hg_resblock == 1);
+                    if (kind == 1) {
+                        VocPairArgs a;
+                        a.x = r.p; a.x_bs = r.bs; a.B = B; a.T = T; a.C = ch; a.k = rk; a.d1 = dl;
+                        a.w1 = hg_c1_tc[ci]; a.b1 = hg_c1[ci].b;
+                        if (pair) { a.w2 = hg_c2_tc[ci]; a.b2 = hg_c2[ci].b; }
+                        if (last) {
+                            a.acc = bX; a.acc_bs = bs; a.acc_init = (j == 0); a.acc_scale = 1.f / (float)nk;
+                            if (j == nk - 1 && more) { a.act_out = bXA; a.act_bs = bs; a.act_slope = 0.1f; }
+                        } else {
+                            a.out = rn.p; a.out_bs = rn.bs;
+                        }
+                        prof.begin(ZVX_PROF_VOC_TC, 2.0 * B * T * ch * ch * rk * (pair ? 2 : 1),
+                                   4.0 * B * T * ch * (last && j > 0 ? 3.0 : 2.0), st);
+                        voc_pair_tc(a, st);
+                        prof.end(st);
+                    } else {
+                        TcGemmArgs g;   // conv over the leaky-ReLU'd copy
+                        g.K = ch; g.Wi = g.Wo = T; g.Hi = g.Ho = B; g.a_sx = ch; g.N = ch; g.w_sn = ch; g.Z1 = rk;
+                        g.w_s1 = (long long)ch * ch; g.ksx = rk; g.c_sx = ch;
+                        if (pair) {
+                            g.A = ra.p; g.a_sy = ra.bs; g.W = hg_c1_tc[ci]; g.bias = hg_c1[ci].b; g.dil = dl;
+                            g.pad_x = (rk - 1) / 2 * dl; g.C = bT; g.c_sy = bs; g.act_slope = 0.1f;
+                            gemm_tc_prof(g, st);
+                            g.A = bT; g.a_sy = bs; g.W = hg_c2_tc[ci]; g.bias = hg_c2[ci].b; g.dil = 1; g.pad_x = (rk - 1) / 2;
+                            g.act_slope = 1.f;
+                        } else {
+                            g.A = ra.p; g.a_sy = ra.bs; g.W = hg_c1_tc[ci]; g.bias = hg_c1[ci].b; g.dil = dl;
+                            g.pad_x = (rk - 1) / 2 * dl;
+                        }
+                        g.R = r.p; g.r_sx = ch; g.r_sy = r.bs;
+                        if (last) {
+                            g.C = bX; g.c_sy = bs; g.acc_mode = 1; g.acc_init = (j == 0); g.acc_scale = 1.f / (float)nk;
+                            if (j == nk - 1 && more) { g.C2 = bXA; g.slope2 = 0.1f; }
+                        } else {
+                            g.C = rn.p; g.c_sy = rn.bs; g.C2 = rna.p; g.slope2 = 0.1f;
+                        }
+                        gemm_tc_prof(g, st);
+                    }
+                    r = rn; ra = rna;
+                }
+            }
+            xa = View{bXA, bs};
+        }
+        const int chl = hg_post.cin;
+        prof.begin(ZVX_PROF_VOC_CONV, 2.0 * B * T * chl * 7, 4.0 * B * T * (chl + 1), st);
+        conv_post_cl(bX, (long long)T * chl, hg_post_tc, hg_post.b, B, T, chl, 7, 0.01f, wav, st);  // F.leaky_relu default slope (hifigan.py:126)
+        prof.end(st);
+        return 0;
+    }
+
     int vocode(const float* mel, int B, int L, float* wav, cudaStream_t st) {
         check_ready(SEC_VOC);
         ZVX_REQUIRE(B >= 1 && L >= 1 && B <= 65535, "zvx_vocode: bad sizes");
         ws.reset();
+        if (cfg.tensor_core_policy != 0 && hg_tc_ok) return vocode_tc(mel, B, L, wav, st);
         const int C0 = cfg.hg_upsample_initial_channel;
         const int nk = cfg.hg_num_kernels, nd = cfg.hg_num_dilations;
         // largest activation: max over stages of C * T
@@ -894,6 +1089,10 @@ class Engine {
           *att_b3 = nullptr, *spk_fc_w = nullptr, *spk_fc_b = nullptr;
     HGConv hg_pre, hg_post;
     std::vector<HGConv> hg_ups, hg_c1, hg_c2;
+    bool hg_tc_ok = false;
+    std::vector<int> hg_stage_kind;   // per upsample stage: 1 = fused pair kernel, 2 = generic tcgen05 implicit GEMM
+    float *hg_pre_tc = nullptr, *hg_post_tc = nullptr;
+    std::vector<float*> hg_ups_tc_w, hg_ups_tc_b, hg_c1_tc, hg_c2_tc;
 };
 
 }  // namespace zvx

@@ -13,6 +13,7 @@
 // Operands are fp32 in HBM, rounded to TF32 (10-bit mantissa, round-to-nearest) by the TMA unit on their way to
 // shared memory; accumulation is fp32.
 #include "gemm_tc.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda.h>
 
@@ -43,75 +44,15 @@ struct TcParams {
     float* C;
     const float* R;
     long long c_simg, c_sy, c_sx, c_sn;
+    long long r_simg, r_sy, r_sx;
     const float* bias;
     const float* scale;
     const float* shift;
     int relu_first, relu_last, vec4;
+    float act_slope;          // leaky-ReLU slope applied to the value stored in C (1 = identity)
+    float* C2; float slope2;  // optional second output lrelu(v, slope2), same addressing as C
+    int acc_mode, acc_init; float acc_scale;   // C = (acc_init ? 0 : C) + v * acc_scale
 };
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    long long t0 = 0;
-    for (;;) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        const long long now = clock64();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 4000000000LL) __trap();
-    }
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled operand tile (rows of 32 fp32 = 128 B, 8-row atoms of 1024 B): matrix descriptor.
 __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
@@ -134,6 +75,8 @@ __device__ __forceinline__ Tile decode_tile(const TcParams& p, int t) {
     c.n0 = nt * p.BN; c.x0 = xt * p.TW; c.y0 = yt * p.TH;
     return c;
 }
+
+__device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 __device__ __forceinline__ float epi(const TcParams& p, float x, int n) {
     if (p.bias) x += __ldg(p.bias + n);
@@ -248,7 +191,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const bool valid = (y < p.Ho) && (x < p.Wo);
             const long long off = (long long)c.img * p.c_simg + (long long)y * p.c_sy + (long long)x * p.c_sx;
             float* __restrict__ cp = p.C + off;
-            const float* __restrict__ rp = p.R ? p.R + off : nullptr;
+            const float* __restrict__ rp =
+                p.R ? p.R + ((long long)c.img * p.r_simg + (long long)y * p.r_sy + (long long)x * p.r_sx) : nullptr;
             mbar_wait(tfull_bar(buf), par);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
@@ -264,29 +208,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int j = 0; j < 32; j += 4) {
                     const int n = c.n0 + c0 + j;
                     if (j >= ncols || n >= p.N) continue;
-                    if (p.vec4 && n + 4 <= p.N) {
-                        float4 o;
-                        o.x = epi(p, __uint_as_float(v[j + 0]), n + 0);
-                        o.y = epi(p, __uint_as_float(v[j + 1]), n + 1);
-                        o.z = epi(p, __uint_as_float(v[j + 2]), n + 2);
-                        o.w = epi(p, __uint_as_float(v[j + 3]), n + 3);
+                    float o[4];
+                    const bool full = (n + 4 <= p.N);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = (n + e < p.N) ? epi(p, __uint_as_float(v[j + e]), n + e) : 0.f;
+                    if (p.vec4 && full) {
                         if (rp) {
                             const float4 rr = *reinterpret_cast<const float4*>(rp + n);
-                            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
                         }
                         if (p.relu_last) {
-                            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
                         }
-                        *reinterpret_cast<float4*>(cp + n) = o;
+                        if (p.acc_mode) {
+                            float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (!p.acc_init) old = *reinterpret_cast<const float4*>(cp + n);
+                            o[0] = fmaf(o[0], p.acc_scale, old.x); o[1] = fmaf(o[1], p.acc_scale, old.y);
+                            o[2] = fmaf(o[2], p.acc_scale, old.z); o[3] = fmaf(o[3], p.acc_scale, old.w);
+                        }
+                        *reinterpret_cast<float4*>(cp + n) =
+                            make_float4(lrelu_f(o[0], p.act_slope), lrelu_f(o[1], p.act_slope), lrelu_f(o[2], p.act_slope),
+                                        lrelu_f(o[3], p.act_slope));
+                        if (p.C2)
+                            *reinterpret_cast<float4*>(p.C2 + off + n) =
+                                make_float4(lrelu_f(o[0], p.slope2), lrelu_f(o[1], p.slope2), lrelu_f(o[2], p.slope2),
+                                            lrelu_f(o[3], p.slope2));
                     } else {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             if (n + e < p.N) {
-                                float o = epi(p, __uint_as_float(v[j + e]), n + e);
+                                float x = o[e];
                                 const long long a = (long long)(n + e) * p.c_sn;
-                                if (rp) o += rp[a];
-                                if (p.relu_last) o = fmaxf(o, 0.f);
-                                cp[a] = o;
+                                if (rp) x += rp[a];
+                                if (p.relu_last) x = fmaxf(x, 0.f);
+                                if (p.acc_mode) x = fmaf(x, p.acc_scale, p.acc_init ? 0.f : cp[a]);
+                                cp[a] = lrelu_f(x, p.act_slope);
+                                if (p.C2) p.C2[off + a] = lrelu_f(x, p.slope2);
                             }
                         }
                     }
@@ -383,7 +341,6 @@ bool gemm_tc_supported(const TcGemmArgs& a) {
     if (!mult4(a.a_sx) || !mult4(a.a_sy) || !mult4(a.a_simg) || !mult4(a.w_sn) || !mult4(a.w_s1) || !mult4(a.w_s2))
         return false;
     if (a.a_sx <= 0 || a.w_sn <= 0) return false;
-    if ((long long)a.IMG * a.Ho * a.Wo < 64) return false;   // tiny problems stay on the fp32 FMA kernel
     return true;
 }
 
@@ -422,10 +379,14 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     p.Wo = a.Wo; p.Ho = a.Ho; p.N = a.N;
     p.C = a.C; p.R = a.R; p.c_simg = a.c_simg; p.c_sy = a.c_sy; p.c_sx = a.c_sx; p.c_sn = a.c_sn;
+    const bool rs = a.r_sx != 0;   // residual strides default to the output's
+    p.r_simg = rs ? a.r_simg : a.c_simg; p.r_sy = rs ? a.r_sy : a.c_sy; p.r_sx = rs ? a.r_sx : a.c_sx;
     p.bias = a.bias; p.scale = a.scale; p.shift = a.shift; p.relu_first = a.relu_first; p.relu_last = a.relu_last;
+    p.act_slope = a.act_slope; p.C2 = a.C2; p.slope2 = a.slope2;
+    p.acc_mode = a.acc_mode; p.acc_init = a.acc_init; p.acc_scale = a.acc_scale;
     ZVX_REQUIRE(!a.scale || a.shift, "gemm_tc: scale needs shift");
     p.vec4 = (a.c_sn == 1) && mult4(a.c_simg) && mult4(a.c_sy) && mult4(a.c_sx) && aligned16(a.C) &&
-             (!a.R || aligned16(a.R));
+             (!a.R || (aligned16(a.R) && mult4(p.r_simg) && mult4(p.r_sy) && mult4(p.r_sx))) && (!a.C2 || aligned16(a.C2));
 
     const long long adims[4] = {a.K, a.Wi, a.Hi, a.IMG};
     const long long astr[3] = {a.a_sx, a.a_sy, a.a_simg};
@@ -472,6 +433,7 @@ bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* o) {
         a.ksx = a.ksy = g.ksize; a.dil = 1; a.pad_x = a.pad_y = g.pad;
     }
     *o = a;
+    if (g.M < 64) return false;   // tiny problems stay on the fp32 FMA kernel
     return gemm_tc_supported(a);
 }
 

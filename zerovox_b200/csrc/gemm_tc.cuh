@@ -29,10 +29,16 @@ struct TcGemmArgs {
     float* C = nullptr;
     long long c_simg = 0, c_sy = 0, c_sx = 0, c_sn = 1;
     const float* R = nullptr;
+    long long r_simg = 0, r_sy = 0, r_sx = 0;   // residual strides (all 0: same as the output's); n stride = c_sn
     const float* bias = nullptr;
     const float* scale = nullptr;
     const float* shift = nullptr;
     int relu_first = 0, relu_last = 0;
+    // vocoder extras, applied after the above:  v = v*acc_scale + (acc_init ? 0 : C)  when acc_mode;
+    // C = lrelu(v, act_slope); C2 = lrelu(v, slope2) (optional second output, addressed like C)
+    float act_slope = 1.f;
+    float* C2 = nullptr; float slope2 = 1.f;
+    int acc_mode = 0, acc_init = 0; float acc_scale = 1.f;
     double flops() const { return 2.0 * IMG * Ho * Wo * (double)N * K * ksx * ksy; }
 };
 

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <vector>
+
 namespace zvx {
 
 // ---- FastSpeech2 acoustic model (kernels_fs2.cu) ---------------------------------------------------
@@ -81,6 +83,29 @@ void conv1d_cf(const Conv1dArgs& a, cudaStream_t st);
 // x [B,Cin,T] -> out [B,Cout,T*u]; w packed [Cin][k][Cout].
 void conv_transpose1d_cf(const float* x, const float* w, const float* bias, int B, int Cin, int Cout, int T, int k,
                          int u, float in_slope, float* out, cudaStream_t st);
+
+// ---- HiFi-GAN on the tensor cores (voc_tc.cu), channel-last [B, T, C] ---------------------------------
+// Fused ResBlock1 pair  x + conv_{k,1}(lrelu(conv_{k,d1}(lrelu(x))))  (w2 != null) or single ResBlock2 conv
+// x + conv_{k,d1}(lrelu(x))  (w2 == null), C in {8, 16, 32}.  Weights in the packed image of voc_pack_weight.
+struct VocPairArgs {
+    const float* x = nullptr; long long x_bs = 0;      // raw input [B][T][C], batch stride in elements
+    const float* w1 = nullptr; const float* b1 = nullptr;
+    const float* w2 = nullptr; const float* b2 = nullptr;
+    int B = 0, T = 0, C = 0, k = 1, d1 = 1;
+    float in_slope = 0.1f, mid_slope = 0.1f;
+    int residual = 1;
+    float* out = nullptr; long long out_bs = 0;        // plain result
+    float* acc = nullptr; long long acc_bs = 0;        // acc = (acc_init ? 0 : acc) + result * acc_scale
+    int acc_init = 0; float acc_scale = 1.f;
+    float* act_out = nullptr; long long act_bs = 0; float act_slope = 0.1f;  // lrelu(acc or result) copy
+};
+bool voc_pair_supported(int C, int k, int dil);
+void voc_pair_tc(const VocPairArgs& a, cudaStream_t st);
+std::vector<float> voc_pack_weight(const float* w, int cout, int cin, int k);
+
+// conv_post on channel-last input: wav[b,t] = tanh(bias + sum_{j,c} w[j][c] * lrelu(x[b, t+j-(k-1)/2, c], slope))
+void conv_post_cl(const float* x, long long x_bs, const float* w /*[k][C]*/, const float* bias, int B, int T, int C,
+                  int k, float slope, float* wav, cudaStream_t st);
 
 // ---- ResNetSE34V2 (kernels_spk.cu), channel-last [B, H, W, C] ---------------------------------------
 // InstanceNorm1d over time (no affine, biased var, eps 1e-5): ref_mel [B,T,n_mels] -> out [B, n_mels(H), T(W)]

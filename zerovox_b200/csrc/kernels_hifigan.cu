@@ -197,7 +197,44 @@ void launch_convtr(const float* x, const float* w, const float* bias, int B, int
     ZVX_POST_LAUNCH();
 }
 
+__global__ void __launch_bounds__(256) conv_post_cl_kernel(const float* __restrict__ x, long long x_bs,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           int T, int C, int k, float slope, float* __restrict__ wav) {
+    extern __shared__ float wsm[];   // [k][C]
+    for (int i = threadIdx.x; i < k * C; i += blockDim.x) wsm[i] = w[i];
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (t >= T) return;
+    const float* xb = x + (long long)b * x_bs;
+    float acc = __ldg(bias);
+    const int half = (k - 1) / 2;
+    for (int j = 0; j < k; ++j) {
+        const int tt = t + j - half;
+        if (tt < 0 || tt >= T) continue;
+        const float4* row = reinterpret_cast<const float4*>(xb + (long long)tt * C);
+        for (int cq = 0; cq < C / 4; ++cq) {
+            const float4 v = __ldg(row + cq);
+            const float* ww = wsm + j * C + cq * 4;
+            acc = fmaf(lrelu(v.x, slope), ww[0], acc);
+            acc = fmaf(lrelu(v.y, slope), ww[1], acc);
+            acc = fmaf(lrelu(v.z, slope), ww[2], acc);
+            acc = fmaf(lrelu(v.w, slope), ww[3], acc);
+        }
+    }
+    wav[(long long)b * T + t] = tanhf(acc);
+}
+
 }  // namespace
+
+void conv_post_cl(const float* x, long long x_bs, const float* w, const float* bias, int B, int T, int C, int k,
+                  float slope, float* wav, cudaStream_t st) {
+    if (B == 0 || T == 0) return;
+    ZVX_REQUIRE(C % 4 == 0 && (k & 1) == 1 && B <= 65535, "conv_post_cl: bad shape");
+    dim3 grid(cdiv(T, 256), B);
+    conv_post_cl_kernel<<<grid, 256, (size_t)k * C * sizeof(float), st>>>(x, x_bs, w, bias, T, C, k, slope, wav);
+    ZVX_POST_LAUNCH();
+}
 
 void conv1d_cf(const Conv1dArgs& a, cudaStream_t st) {
     if (a.B == 0 || a.T == 0) return;
