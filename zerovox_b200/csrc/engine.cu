@@ -697,17 +697,18 @@ class Engine {
             gemm(o, tc, st);
         }
         }
-        linear(att, (int)rows, H, ly.wfc, ly.bfc, H, y, tc && (tc_mask & 2), st, /*R=*/x);
+        // the residual adds of fs2.py:158-162 / 205-208 are fused into the normalisation kernel (same fp32 add)
+        linear(att, (int)rows, H, ly.wfc, ly.bfc, H, y, tc && (tc_mask & 2), st);
         NormArgs n;
-        n.x = y; n.out = x; n.rows = (int)rows; n.C = H; n.rows_per_batch = L; n.mask = mask;
+        n.x = y; n.res = x; n.out = x; n.rows = (int)rows; n.C = H; n.rows_per_batch = L; n.mask = mask;
         if (scln) { n.scln = 1; n.gb = gb1; n.gb_ld = gb_ld; n.eps = 1e-8f; }
         else { n.gamma = ly.ln1_g; n.beta = ly.ln1_b; n.eps = 1e-5f; }
         layer_norm(n, st);
         // position-wise feed-forward (fs2.py:196-209)
         float* h1 = sc.h1;
         conv1d_cl(x, B, L, H, ly.w1, ly.b1, DI, k1, (k1 - 1) / 2, h1, tc && (tc_mask & 4), st, nullptr, /*relu_first=*/1);
-        conv1d_cl(h1, B, L, DI, ly.w2, ly.b2, H, k2, (k2 - 1) / 2, y, tc && (tc_mask & 8), st, /*R=*/x);
-        n.x = y; n.out = x;
+        conv1d_cl(h1, B, L, DI, ly.w2, ly.b2, H, k2, (k2 - 1) / 2, y, tc && (tc_mask & 8), st);
+        n.x = y; n.res = x; n.out = x;
         if (scln) n.gb = gb2; else { n.gamma = ly.ln2_g; n.beta = ly.ln2_b; }
         layer_norm(n, st);
     }

@@ -7,7 +7,7 @@
 //   warp 1      MMA issuer   : one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = BN, K = 8) straight
 //                              from shared memory into one of two TMEM accumulators (2 x 256 columns), releases stages
 //                              with tcgen05.commit;
-//   warps 2..5  epilogue     : tcgen05.ld the finished accumulator (lane = output position), apply bias / ReLU /
+//   warps 2..9  epilogue     : tcgen05.ld the finished accumulator (lane = output position), apply bias / ReLU /
 //                              folded BatchNorm / residual, store row-major or transposed, hand the TMEM buffer back —
 //                              overlapping the next tile's main loop.
 // Operands are fp32 in HBM, rounded to TF32 (10-bit mantissa, round-to-nearest) by the TMA unit on their way to
@@ -27,7 +27,7 @@ namespace {
 constexpr int BM = 128;                  // output positions per tile (MMA M)
 constexpr int BK = 32;                   // fp32 elements per 128-byte swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 4;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;          // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;          // TMEM columns between the two accumulators
 constexpr int MAX_STAGES = 8;
@@ -85,6 +85,7 @@ __device__ __forceinline__ float epi(const TcParams& p, float x, int n) {
     return x;
 }
 
+template <bool GENERAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -111,7 +112,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), 4);
+            mbar_init(tempty_bar(b), 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -178,8 +179,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         __syncwarp();
     } else {
-        // ================================================================ epilogue (warps 2..5)
+        // ================================================================ epilogue (warps 2..9)
+        // Two warps per TMEM lane quarter; they take alternate 16-column chunks of the accumulator.
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;
         const int r = q * 32 + lane;            // position within the tile
         const int ty = r / p.TW, tx = r - ty * p.TW;
         int it = 0;
@@ -196,55 +199,109 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait(tfull_bar(buf), par);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
-                uint32_t v[32];
+            for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
+                uint32_t v[16];
                 __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
                 tmem_ld16(trow + (uint32_t)c0, v);
-                if (c0 + 16 < p.BN) tmem_ld16(trow + (uint32_t)(c0 + 16), v + 16);
-                tmem_wait_ld();
-                if (!valid) continue;
-                const int ncols = min(32, p.BN - c0);
+                const int n = c.n0 + c0;
+                if (p.vec4 && n + 16 <= p.N) {
+                    // ---- vector path: every global access of the chunk is issued before the first use
+                    float4 bb[4], rr[4], oo[4];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int n = c.n0 + c0 + j;
-                    if (j >= ncols || n >= p.N) continue;
-                    float o[4];
-                    const bool full = (n + 4 <= p.N);
+                    for (int g = 0; g < 4; ++g) {
+                        bb[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        rr[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        oo[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (p.bias) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) o[e] = (n + e < p.N) ? epi(p, __uint_as_float(v[j + e]), n + e) : 0.f;
-                    if (p.vec4 && full) {
-                        if (rp) {
-                            const float4 rr = *reinterpret_cast<const float4*>(rp + n);
-                            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+                        for (int g = 0; g < 4; ++g) bb[g] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + g);
+                    }
+                    if (valid && rp) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) rr[g] = *(reinterpret_cast<const float4*>(rp + n) + g);
+                    }
+                    if (GENERAL && valid && p.acc_mode && !p.acc_init) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) oo[g] = *(reinterpret_cast<const float4*>(cp + n) + g);
+                    }
+                    tmem_wait_ld();
+                    float o[16];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        o[4 * g + 0] = __uint_as_float(v[4 * g + 0]) + bb[g].x;
+                        o[4 * g + 1] = __uint_as_float(v[4 * g + 1]) + bb[g].y;
+                        o[4 * g + 2] = __uint_as_float(v[4 * g + 2]) + bb[g].z;
+                        o[4 * g + 3] = __uint_as_float(v[4 * g + 3]) + bb[g].w;
+                    }
+                    if (p.relu_first) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) o[e] = fmaxf(o[e], 0.f);
+                    }
+                    if (GENERAL && p.scale) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n) + g);
+                            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n) + g);
+                            o[4 * g + 0] = fmaf(o[4 * g + 0], sc.x, sh.x); o[4 * g + 1] = fmaf(o[4 * g + 1], sc.y, sh.y);
+                            o[4 * g + 2] = fmaf(o[4 * g + 2], sc.z, sh.z); o[4 * g + 3] = fmaf(o[4 * g + 3], sc.w, sh.w);
                         }
-                        if (p.relu_last) {
+                    }
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
-                        }
-                        if (p.acc_mode) {
-                            float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (!p.acc_init) old = *reinterpret_cast<const float4*>(cp + n);
-                            o[0] = fmaf(o[0], p.acc_scale, old.x); o[1] = fmaf(o[1], p.acc_scale, old.y);
-                            o[2] = fmaf(o[2], p.acc_scale, old.z); o[3] = fmaf(o[3], p.acc_scale, old.w);
-                        }
-                        *reinterpret_cast<float4*>(cp + n) =
-                            make_float4(lrelu_f(o[0], p.act_slope), lrelu_f(o[1], p.act_slope), lrelu_f(o[2], p.act_slope),
-                                        lrelu_f(o[3], p.act_slope));
-                        if (p.C2)
-                            *reinterpret_cast<float4*>(p.C2 + off + n) =
-                                make_float4(lrelu_f(o[0], p.slope2), lrelu_f(o[1], p.slope2), lrelu_f(o[2], p.slope2),
-                                            lrelu_f(o[3], p.slope2));
-                    } else {
+                    for (int g = 0; g < 4; ++g) {
+                        o[4 * g + 0] += rr[g].x; o[4 * g + 1] += rr[g].y; o[4 * g + 2] += rr[g].z; o[4 * g + 3] += rr[g].w;
+                    }
+                    if (p.relu_last) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (n + e < p.N) {
-                                float x = o[e];
-                                const long long a = (long long)(n + e) * p.c_sn;
-                                if (rp) x += rp[a];
-                                if (p.relu_last) x = fmaxf(x, 0.f);
-                                if (p.acc_mode) x = fmaf(x, p.acc_scale, p.acc_init ? 0.f : cp[a]);
-                                cp[a] = lrelu_f(x, p.act_slope);
-                                if (p.C2) p.C2[off + a] = lrelu_f(x, p.slope2);
+                        for (int e = 0; e < 16; ++e) o[e] = fmaxf(o[e], 0.f);
+                    }
+                    if (GENERAL && p.acc_mode) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            o[4 * g + 0] = fmaf(o[4 * g + 0], p.acc_scale, oo[g].x);
+                            o[4 * g + 1] = fmaf(o[4 * g + 1], p.acc_scale, oo[g].y);
+                            o[4 * g + 2] = fmaf(o[4 * g + 2], p.acc_scale, oo[g].z);
+                            o[4 * g + 3] = fmaf(o[4 * g + 3], p.acc_scale, oo[g].w);
+                        }
+                    }
+                    if (valid) {
+                        if (GENERAL) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                *(reinterpret_cast<float4*>(cp + n) + g) =
+                                    make_float4(lrelu_f(o[4 * g + 0], p.act_slope), lrelu_f(o[4 * g + 1], p.act_slope),
+                                                lrelu_f(o[4 * g + 2], p.act_slope), lrelu_f(o[4 * g + 3], p.act_slope));
+                            if (p.C2) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g)
+                                    *(reinterpret_cast<float4*>(p.C2 + off + n) + g) =
+                                        make_float4(lrelu_f(o[4 * g + 0], p.slope2), lrelu_f(o[4 * g + 1], p.slope2),
+                                                    lrelu_f(o[4 * g + 2], p.slope2), lrelu_f(o[4 * g + 3], p.slope2));
+                            }
+                        } else {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                *(reinterpret_cast<float4*>(cp + n) + g) =
+                                    make_float4(o[4 * g + 0], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+                        }
+                    }
+                } else {
+                    // ---- element path: column tails, unaligned or transposed (c_sn != 1) outputs
+                    tmem_wait_ld();
+                    if (!valid) continue;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        if (c0 + e < p.BN && n + e < p.N) {
+                            float xv = epi(p, __uint_as_float(v[e]), n + e);
+                            const long long a = (long long)(n + e) * p.c_sn;
+                            if (rp) xv += rp[a];
+                            if (p.relu_last) xv = fmaxf(xv, 0.f);
+                            if (GENERAL) {
+                                if (p.acc_mode) xv = fmaf(xv, p.acc_scale, p.acc_init ? 0.f : cp[a]);
+                                cp[a] = lrelu_f(xv, p.act_slope);
+                                if (p.C2) p.C2[off + a] = lrelu_f(xv, p.slope2);
+                            } else {
+                                cp[a] = xv;
                             }
                         }
                     }
@@ -386,7 +443,8 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.acc_mode = a.acc_mode; p.acc_init = a.acc_init; p.acc_scale = a.acc_scale;
     ZVX_REQUIRE(!a.scale || a.shift, "gemm_tc: scale needs shift");
     p.vec4 = (a.c_sn == 1) && mult4(a.c_simg) && mult4(a.c_sy) && mult4(a.c_sx) && aligned16(a.C) &&
-             (!a.R || (aligned16(a.R) && mult4(p.r_simg) && mult4(p.r_sy) && mult4(p.r_sx))) && (!a.C2 || aligned16(a.C2));
+             (!a.R || (aligned16(a.R) && mult4(p.r_simg) && mult4(p.r_sy) && mult4(p.r_sx))) && (!a.C2 || aligned16(a.C2)) &&
+             (!a.bias || aligned16(a.bias)) && (!a.scale || (aligned16(a.scale) && aligned16(a.shift)));
 
     const long long adims[4] = {a.K, a.Wi, a.Hi, a.IMG};
     const long long astr[3] = {a.a_sx, a.a_sy, a.a_simg};
@@ -400,12 +458,15 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 1024;
     static bool attr = false;
     if (!attr) {
-        ZVX_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        ZVX_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        ZVX_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr = true;
     }
     ZVX_REQUIRE(smem <= SMEM_LIMIT && smem > 116 * 1024, "gemm_tc: shared-memory plan out of range");
     const int grid = std::min(p.num_tiles, num_sms());
-    gemm_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, p);
+    const bool general = a.scale || a.acc_mode || a.act_slope != 1.f || a.C2;
+    if (general) gemm_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, p);
+    else gemm_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, p);
     ZVX_POST_LAUNCH();
 }
 

@@ -14,6 +14,7 @@ void embed_posenc(const int32_t* phoneme, const int32_t* puncts, const float* ph
 // K6: LayerNorm (eps inside sqrt, biased variance) or SCLN (unbiased std, sigma + eps; fs2.py:76-90).
 struct NormArgs {
     const float* x = nullptr;     // [rows, C]
+    const float* res = nullptr;   // optional residual [rows, C] added to x before normalising (fs2.py:158-162, 205-208)
     float* out = nullptr;         // [rows, C] (may alias x); ignored when dot_w != nullptr
     int rows = 0, C = 0;
     int rows_per_batch = 1;       // L: batch index of a row = row / L

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const NormArgs a) {
     }
     const int C4 = a.C >> 2;
     const float4* xr = reinterpret_cast<const float4*>(a.x + (long long)row * a.C);
+    const float4* rr = a.res ? reinterpret_cast<const float4*>(a.res + (long long)row * a.C) : nullptr;
     float4 v[NORM_MAXV];
     float s = 0.f;
 #pragma unroll
@@ -64,6 +65,10 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const NormArgs a) {
         const int c4 = lane + i * 32;
         if (c4 < C4) {
             v[i] = xr[c4];
+            if (rr) {
+                const float4 t = rr[c4];
+                v[i].x += t.x; v[i].y += t.y; v[i].z += t.z; v[i].w += t.w;
+            }
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
     }
