@@ -138,8 +138,10 @@ class ZeroVox(nn.Module):
         return model
 
     # forward -------------------------------------------------------------------------------------------
-    def forward(self, x, force_duration=False, normalize_before=True):
-        """Batched eval forward (model.py:260-306).  Returns (wav [B, L_max*hop], mel [B, n_mels, L_max],
+    def forward(self, x, force_duration=False, normalize_before=True, pad_to=None):
+        """Batched eval forward (model.py:260-306).  ``pad_to`` (extension, used by zerovox_b200.parallel): an int or a
+        callable ``local_L_max -> L`` giving the frame count to pad the batch to (>= the batch's own maximum), so that a
+        shard reproduces the tail behaviour of the unsharded batch.  Returns (wav [B, L_max*hop], mel [B, n_mels, L_max],
         mel_len int64 [B], log_duration [B, T]) — the tuple utils/export_hifigan.py:109-151 consumes.  The
         reference's own eval tail (model.py:298-304) is ParallelWaveGAN leftover code that raises with
         hifigan.Generator; the intended semantics ``wav = _meldec(mel.transpose(1,2)).squeeze(1)`` are built."""
@@ -154,7 +156,10 @@ class ZeroVox(nn.Module):
         forced = x["duration"].to(dev, non_blocking=True) if force_duration else None
         r = eng.encode(x["phoneme"].to(dev, non_blocking=True), x["puncts"].to(dev, non_blocking=True), style, mask,
                        forced, need_lengths=True)
-        feats = eng.length_regulate(r["xprime"], r["duration_rounded"], r["L_max"])
+        L = r["L_max"]
+        if pad_to is not None:
+            L = max(L, int(pad_to(L) if callable(pad_to) else pad_to))
+        feats = eng.length_regulate(r["xprime"], r["duration_rounded"], L)
         # model.py:283-285: the mel is zero-filled at padded frames only when the mel mask exists (predicted
         # durations) and B > 1
         zero_pad = (not force_duration) and feats.shape[0] > 1
