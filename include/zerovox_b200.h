@@ -72,7 +72,8 @@ typedef struct zvx_config {
     int32_t hg_num_dilations;
     int32_t hg_resblock_dilation_sizes[ZVX_MAX_RESBLOCK_KERNELS][ZVX_MAX_DILATIONS];
     /* numerics policy: 0 = every contraction in fp32 FMA; 1 = decoder / vocoder / speaker-net
-     * contractions on TF32 tensor cores (tcgen05), encoder + variance predictors stay fp32. */
+     * contractions on TF32 tensor cores (tcgen05), encoder + variance predictors in 3xTF32 split
+     * arithmetic on the tensor cores (fp32-grade products, fp32 accumulation). */
     int32_t tensor_core_policy;
     int32_t reserved[7];
 } zvx_config;
@@ -139,7 +140,8 @@ int zvx_vocode(zvx_handle* h, const float* mel_BCL, int B, int L, float* wav, vo
 #define ZVX_PROF_VOC_CONV     2   /* HiFi-GAN dilated Conv1d (+ fused lrelu / residual / MRF mean / tanh) */
 #define ZVX_PROF_VOC_UPSAMPLE 3   /* HiFi-GAN polyphase ConvTranspose1d */
 #define ZVX_PROF_VOC_TC       4   /* HiFi-GAN fused ResBlock conv pair on tcgen05 (C = 8/16/32) */
-#define ZVX_PROF_NUM_CLASSES  5
+#define ZVX_PROF_GEMM_TC3     5   /* tcgen05 3xTF32 split GEMM (fp32-grade products: encoder, variance predictors) */
+#define ZVX_PROF_NUM_CLASSES  6
 int zvx_profile_enable(zvx_handle* h, int on);
 int zvx_profile_read(zvx_handle* h, int kernel_class, double* ms, int64_t* launches, double* flops,
                      double* bytes);
@@ -151,7 +153,8 @@ int zvx_profile_read(zvx_handle* h, int kernel_class, double* ms, int64_t* launc
  *   mode 0 plain GEMM; mode 1 Conv1d over [M/L, L, K] ('same' padding given by pad, dilation dil);
  *   mode 2 Conv2d ksize x ksize over [M/(Hh*Ww), Hh, Ww, K] (stride 1, padding pad)
  *   epilogue: + bias[n]; relu_first; * scale[n] + shift[n]; + R[m, n]; relu_last.
- * use_tc = 0: fp32 FMA kernel; 1: tcgen05 TF32 kernel (fails if the layout is not TMA-addressable). */
+ * use_tc = 0: fp32 FMA kernel; 1: tcgen05 TF32 kernel (fails if the layout is not TMA-addressable);
+ * 2: tcgen05 3xTF32 split (fp32-grade products; the low parts of A and W are prepared internally). */
 typedef struct zvx_gemm_desc {
     const float* A; const float* W; float* C;
     const float* bias; const float* scale; const float* shift; const float* R;

@@ -250,7 +250,7 @@ class Engine {
     }
 
     void pack_fft(const std::string& prefix, int n_layers, bool scln, std::vector<FFTLayer>& out,
-                  std::vector<float>* scln_stack) {
+                  std::vector<float>* scln_stack, bool exact) {
         const int DI = cfg.conv_filter_size, k1 = cfg.conv_kernel_size[0], k2 = cfg.conv_kernel_size[1];
         out.resize((size_t)n_layers);
         for (int i = 0; i < n_layers; ++i) {
@@ -271,6 +271,12 @@ class Engine {
             L.b1 = upload(W(p + ".pos_ffn.w_1.bias", {DI}));
             L.w2 = upload(tap_major(W(p + ".pos_ffn.w_2.weight", {H, DI, k2})));
             L.b2 = upload(W(p + ".pos_ffn.w_2.bias", {H}));
+            if (exact) {
+                register_lo(L.wqkv, (size_t)3 * H * H);
+                register_lo(L.wfc, (size_t)H * H);
+                register_lo(L.w1, (size_t)DI * H * k1);
+                register_lo(L.w2, (size_t)H * DI * k2);
+            }
             if (scln) {
                 for (const char* sub : {"slf_attn", "pos_ffn"}) {
                     const HostTensor& a = W(p + "." + sub + ".layer_norm.affine_layer.linear.weight", {2 * H, H});
@@ -319,6 +325,7 @@ class Engine {
         ZVX_CUDA_CHECK(cudaSetDevice(dev));
         for (void* p : owned) cudaFree(p);
         owned.clear();
+        w_lo.clear();
         enc_pos = dec_pos = nullptr;
         enc_pos_rows = dec_pos_rows = 0;
         int ready = 0;
@@ -337,6 +344,7 @@ class Engine {
         section(SEC_DEC, &Engine::pack_decoder);
         section(SEC_SPK, &Engine::pack_spknet);
         section(SEC_VOC, &Engine::pack_vocoder);
+        ZVX_CUDA_CHECK(cudaDeviceSynchronize());   // weight uploads / low-part splits ran on the default stream
         finalized = true;
         if (ready == 0) throw Error("zvx_finalize_weights: no complete section; first problem: " + sec_err[SEC_ENC]);
         return 0;
@@ -349,7 +357,7 @@ class Engine {
         enc_pos_param = upload(W(e + ".position_enc", {1, cfg.max_txt_len + 1, H}));
         phon_emb = upload(W(e + ".src_word_emb.weight", {cfg.num_phones + 1, E}));
         punct_emb = upload(W(e + ".punct_embed.weight", {cfg.num_puncts + 1, P}));
-        pack_fft(e, cfg.enc_layers, false, enc, nullptr);
+        pack_fft(e, cfg.enc_layers, false, enc, nullptr, /*exact=*/true);
         // variance adaptor
         const std::string va = "_phoneme_encoder._variance_adaptor";
         const int F = cfg.vp_filter_size, K = cfg.vp_kernel_size;
@@ -365,6 +373,8 @@ class Engine {
             v.bc2 = upload(W(p + ".conv_layer.conv1d_2.conv.bias", {F}));
             v.ln2_g = upload(W(p + ".conv_layer.layer_norm_2.weight", {F}));
             v.ln2_b = upload(W(p + ".conv_layer.layer_norm_2.bias", {F}));
+            register_lo(v.wc1, (size_t)F * H * K);
+            register_lo(v.wc2, (size_t)F * F * K);
             v.wlin = upload(W(p + ".linear_layer.weight", {1, F}));
             v.blin = upload(W(p + ".linear_layer.bias", {1}));
         }
@@ -377,7 +387,7 @@ class Engine {
         const std::string d = "_mel_decoder";
         dec_pos_param = upload(W(d + ".position_enc", {1, cfg.max_mel_len + 1, H}));
         std::vector<float> scln_stack;
-        pack_fft(d, cfg.dec_layers, cfg.dec_scln != 0, dec, &scln_stack);
+        pack_fft(d, cfg.dec_layers, cfg.dec_scln != 0, dec, &scln_stack, /*exact=*/false);
         if (cfg.dec_scln) scln_w = upload(scln_stack);
         mel_w = upload(W(d + ".mel_linear.weight", {cfg.n_mels, H}));
         mel_b = upload(W(d + ".mel_linear.bias", {cfg.n_mels}));
@@ -570,21 +580,60 @@ class Engine {
     }
 
     // ------------------------------------------------------------------------------------------ helpers
-    bool tc_enabled(bool tensor_core_ok) const { return tensor_core_ok && cfg.tensor_core_policy != 0; }
+    // Precision classes of a contraction.  P_EXACT: fp32-grade products (encoder, variance predictors — their outputs
+    // are rounded to integers / buckets): 3xTF32 split on the tensor cores when policy != 0, else the fp32 FMA kernel.
+    // P_TF32: TF32 tensor cores when policy != 0 (decoder, vocoder, speaker net).
+    enum { P_EXACT = 0, P_TF32 = 1 };
+    bool tc_enabled(int prec) const { return cfg.tensor_core_policy != 0 && (prec == P_TF32 || split_on); }
 
-    void gemm(const GemmArgs& a, bool tensor_core_ok, cudaStream_t st) {
+    // TF32-exact low part of a packed weight (3xTF32 split), created once at finalize.
+    void register_lo(const float* w, size_t n) {
+        if (n % 4 != 0 || cfg.tensor_core_policy == 0) return;
+        float* lo = nullptr;
+        ZVX_CUDA_CHECK(cudaMalloc(&lo, n * sizeof(float)));
+        owned.push_back(lo);
+        tf32_split_lo(w, lo, (long long)n, 0);
+        w_lo[w] = lo;
+    }
+    const float* lo_of(const float* w) const {
+        auto it = w_lo.find(w);
+        return it == w_lo.end() ? nullptr : it->second;
+    }
+
+    static long long a_extent(const GemmArgs& a) {
+        long long rows = a.M;
+        if (a.mode == ROW_CONV1D) rows = (long long)(a.M / a.Lout) * a.Lin;
+        else if (a.mode == ROW_CONV2D) rows = (long long)(a.M / (a.Ho * a.Wo)) * a.Hi * a.Wi;
+        return (rows - 1) * a.lda + a.K;
+    }
+
+    void gemm(const GemmArgs& a, int prec, cudaStream_t st) {
         TcGemmArgs t;
-        const bool tc = tc_enabled(tensor_core_ok) && gemm_tc_from(a, &t);
+        bool tc = tc_enabled(prec) && gemm_tc_from(a, &t);
+        bool split = false;
+        if (tc && prec == P_EXACT) {
+            const float* wlo = lo_of(a.W);
+            const long long n = a_extent(a);
+            if (wlo && lo_buf && n <= lo_cap) {
+                tf32_split_lo(a.A, lo_buf, n, st);
+                t.A_lo = lo_buf;
+                t.W_lo = wlo;
+                split = true;
+            } else {
+                tc = false;
+            }
+        }
         const double flops = 2.0 * a.M * a.N * a.K * a.taps * a.nz;
         const double bytes = 4.0 * a.nz * ((double)a.M * a.K + (double)a.N * a.K * a.taps + (double)a.M * a.N);
-        prof.begin(tc ? ZVX_PROF_GEMM_TC : ZVX_PROF_GEMM_FP32, flops, bytes, st);
+        prof.begin(split ? ZVX_PROF_GEMM_TC3 : tc ? ZVX_PROF_GEMM_TC : ZVX_PROF_GEMM_FP32, flops, bytes, st);
         if (tc) gemm_tc(t, st); else gemm_simt(a, st);
         prof.end(st);
     }
 
     void gemm_tc_prof(const TcGemmArgs& t, cudaStream_t st) {
         const double pos = (double)t.IMG * t.Ho * t.Wo;
-        prof.begin(ZVX_PROF_GEMM_TC, t.flops(), 4.0 * (pos * t.K + pos * t.N + (double)t.N * t.K * t.ksx * t.ksy), st);
+        prof.begin(t.A_lo ? ZVX_PROF_GEMM_TC3 : ZVX_PROF_GEMM_TC, t.flops(),
+                   4.0 * (pos * t.K + pos * t.N + (double)t.N * t.K * t.ksx * t.ksy), st);
         gemm_tc(t, st);
         prof.end(st);
     }
@@ -596,7 +645,7 @@ class Engine {
         prof.end(st);
     }
 
-    void linear(const float* x, int M, int K, const float* w, const float* b, int N, float* y, bool tc,
+    void linear(const float* x, int M, int K, const float* w, const float* b, int N, float* y, int tc,
                 cudaStream_t st, const float* R = nullptr, int relu_first = 0, const float* scale = nullptr,
                 const float* shift = nullptr) {
         GemmArgs a;
@@ -606,7 +655,7 @@ class Engine {
     }
 
     void conv1d_cl(const float* x, int B, int L, int Cin, const float* w, const float* b, int Cout, int k, int pad,
-                   float* y, bool tc, cudaStream_t st, const float* R = nullptr, int relu_first = 0) {
+                   float* y, int tc, cudaStream_t st, const float* R = nullptr, int relu_first = 0) {
         GemmArgs a;
         a.A = x; a.lda = Cin; a.W = w; a.ldw = Cin; a.w_tap_stride = (long long)Cout * Cin; a.C = y; a.ldc = Cout;
         a.bias = b; a.M = B * L; a.N = Cout; a.K = Cin; a.taps = k; a.R = R; a.ldr = Cout; a.relu_first = relu_first;
@@ -618,21 +667,29 @@ class Engine {
 
     struct FFTScratch {
         float *qkv = nullptr, *att = nullptr, *y = nullptr, *S = nullptr, *h1 = nullptr;
+        float *lo_qkv = nullptr, *lo_S = nullptr;   // 3xTF32 split: low parts of the attention operands
+        long long qkv_elems = 0, S_elems = 0;
         int Lq_max = 0, ldS = 0;
     };
 
-    FFTScratch fft_scratch(int B, int L, int n_head) {
+    FFTScratch fft_scratch(int B, int L, int n_head, int prec) {
         FFTScratch s;
         const long long rows = (long long)B * L;
         const int DI = cfg.conv_filter_size;
-        s.qkv = ws.get<float>(rows * 3 * H + 4LL * B * H);   // + slack: tensor-core path keeps V transposed, rows padded to 4
+        s.qkv_elems = rows * 3 * H + 4LL * B * H;   // + slack: tensor-core path keeps V transposed, rows padded to 4
+        s.qkv = ws.get<float>(s.qkv_elems);
         s.att = ws.get<float>(rows * H);
         s.y = ws.get<float>(rows * H);
         // attention is chunked over query rows so that the score matrix stays below kScoreBytes
         s.ldS = (int)round_up(L, 4);
         const long long max_q = kScoreBytes / ((long long)B * n_head * s.ldS * (long long)sizeof(float));
         s.Lq_max = (int)std::max<long long>(1, std::min<long long>(L, max_q));
-        s.S = ws.get<float>((long long)B * n_head * s.Lq_max * s.ldS);
+        s.S_elems = (long long)B * n_head * s.Lq_max * s.ldS;
+        s.S = ws.get<float>(s.S_elems);
+        if (prec == P_EXACT && tc_enabled(prec)) {
+            s.lo_qkv = ws.get<float>(s.qkv_elems);
+            s.lo_S = ws.get<float>(s.S_elems);
+        }
         // position-wise feed-forward hidden: re-use the qkv buffer when it is large enough
         s.h1 = (3 * H >= DI) ? s.qkv : ws.get<float>(rows * DI);
         return s;
@@ -640,7 +697,7 @@ class Engine {
 
     // FFTBlock.forward (fs2.py:221-230) in place on x [B, L, H].
     void fft_block(float* x, int B, int L, int n_head, const FFTLayer& ly, const uint8_t* mask, bool scln,
-                   const float* gb1, const float* gb2, int gb_ld, bool tc, const FFTScratch& sc, cudaStream_t st) {
+                   const float* gb1, const float* gb2, int gb_ld, int tc, const FFTScratch& sc, cudaStream_t st) {
         const int dk = H / n_head, DI = cfg.conv_filter_size;
         const int k1 = cfg.conv_kernel_size[0], k2 = cfg.conv_kernel_size[1];
         const long long rows = (long long)B * L;
@@ -648,35 +705,45 @@ class Engine {
         const int ldS = sc.ldS, Lq_max = sc.Lq_max;
         const int nz = B * n_head;
         const float temperature = (float)std::pow((double)dk, 0.5);  // np.power(d_k, 0.5), fs2.py:122
-        // debug bisection switches (tools/diag_golden.py): ZVX_TC_MASK bit0 attention, bit1 fc, bit2 w_1, bit3 w_2
-        static const int tc_mask = getenv("ZVX_TC_MASK") ? atoi(getenv("ZVX_TC_MASK")) : 15;
-        const bool tc_attn = tc_enabled(tc) && (tc_mask & 1) && (dk % 4 == 0) && rows >= 64 && Lq_max == L;
+        static const int tc_mask = getenv("ZVX_TC_MASK") ? atoi(getenv("ZVX_TC_MASK")) : 15;   // bit0: tensor-core attention
+        const bool split = (tc == P_EXACT);
+        const float* wqkv_lo = split ? lo_of(ly.wqkv) : nullptr;
+        const bool tc_attn = tc_enabled(tc) && (tc_mask & 1) && (dk % 4 == 0) && rows >= 64 && Lq_max == L &&
+                             (!split || (wqkv_lo && sc.lo_qkv && lo_buf && rows * H <= lo_cap));
         if (tc_attn) {
             // tcgen05 path: [Q|K] row-major [rows, 2H]; V written transposed per utterance, Vt[b][c][t] (row pitch Lp),
             // so that both attention contractions read K-major operands through TMA.
             const int Lp = (int)round_up(L, 4);
             float* qk = qkv;
             float* vt = qkv + rows * 2 * H;
-            linear(x, (int)rows, H, ly.wqkv, ly.bqkv, 2 * H, qk, true, st);
+            linear(x, (int)rows, H, ly.wqkv, ly.bqkv, 2 * H, qk, tc, st);
             TcGemmArgs v;
             v.A = x; v.K = H; v.Wi = v.Wo = L; v.Hi = v.Ho = B; v.a_sx = H; v.a_sy = (long long)L * H;
             v.W = ly.wqkv + (long long)2 * H * H; v.N = H; v.w_sn = H; v.bias = ly.bqkv + 2 * H;
             v.C = vt; v.c_sy = (long long)H * Lp; v.c_sx = 1; v.c_sn = Lp;
+            if (split) {
+                tf32_split_lo(x, lo_buf, rows * H, st);
+                v.A_lo = lo_buf; v.W_lo = wqkv_lo + (long long)2 * H * H;
+            }
             gemm_tc_prof(v, st);
+            if (split) tf32_split_lo(qkv, sc.lo_qkv, rows * 2 * H + (long long)B * H * Lp, st);
             TcGemmArgs sq;   // S[b,h,q,j] = <Q[b,q,h,:], K[b,j,h,:]>
             sq.A = qk; sq.K = dk; sq.Wi = sq.Wo = L; sq.Hi = sq.Ho = n_head; sq.IMG = B;
             sq.a_sx = 2 * H; sq.a_sy = dk; sq.a_simg = (long long)L * 2 * H;
             sq.W = qk + H; sq.N = L; sq.Z1 = n_head; sq.Z2 = B; sq.w_sn = 2 * H; sq.w_s1 = dk; sq.w_s2 = (long long)L * 2 * H;
             sq.b_batched = 1;
             sq.C = S; sq.c_simg = (long long)n_head * L * ldS; sq.c_sy = (long long)L * ldS; sq.c_sx = ldS; sq.c_sn = 1;
+            if (split) { sq.A_lo = sc.lo_qkv; sq.W_lo = sc.lo_qkv + H; }
             gemm_tc_prof(sq, st);
             attn_softmax(S, nz, n_head, L, L, ldS, mask, L, temperature, st);
+            if (split) tf32_split_lo(S, sc.lo_S, (long long)nz * L * ldS, st);
             TcGemmArgs pv;   // att[b,q,h*dk + c] = sum_j P[b,h,q,j] * Vt[b, h*dk + c, j]
             pv.A = S; pv.K = L; pv.Wi = pv.Wo = L; pv.Hi = pv.Ho = n_head; pv.IMG = B;
             pv.a_sx = ldS; pv.a_sy = (long long)L * ldS; pv.a_simg = (long long)n_head * L * ldS;
             pv.W = vt; pv.N = dk; pv.Z1 = n_head; pv.Z2 = B; pv.w_sn = Lp; pv.w_s1 = (long long)dk * Lp; pv.w_s2 = (long long)H * Lp;
             pv.b_batched = 1;
             pv.C = att; pv.c_simg = (long long)L * H; pv.c_sy = dk; pv.c_sx = H; pv.c_sn = 1;
+            if (split) { pv.A_lo = sc.lo_S; pv.W_lo = sc.lo_qkv + rows * 2 * H; }
             gemm_tc_prof(pv, st);
         } else {
         linear(x, (int)rows, H, ly.wqkv, ly.bqkv, 3 * H, qkv, tc, st);
@@ -698,7 +765,7 @@ class Engine {
         }
         }
         // the residual adds of fs2.py:158-162 / 205-208 are fused into the normalisation kernel (same fp32 add)
-        linear(att, (int)rows, H, ly.wfc, ly.bfc, H, y, tc && (tc_mask & 2), st);
+        linear(att, (int)rows, H, ly.wfc, ly.bfc, H, y, tc, st);
         NormArgs n;
         n.x = y; n.res = x; n.out = x; n.rows = (int)rows; n.C = H; n.rows_per_batch = L; n.mask = mask;
         if (scln) { n.scln = 1; n.gb = gb1; n.gb_ld = gb_ld; n.eps = 1e-8f; }
@@ -706,8 +773,8 @@ class Engine {
         layer_norm(n, st);
         // position-wise feed-forward (fs2.py:196-209)
         float* h1 = sc.h1;
-        conv1d_cl(x, B, L, H, ly.w1, ly.b1, DI, k1, (k1 - 1) / 2, h1, tc && (tc_mask & 4), st, nullptr, /*relu_first=*/1);
-        conv1d_cl(h1, B, L, DI, ly.w2, ly.b2, H, k2, (k2 - 1) / 2, y, tc && (tc_mask & 8), st);
+        conv1d_cl(x, B, L, H, ly.w1, ly.b1, DI, k1, (k1 - 1) / 2, h1, tc, st, nullptr, /*relu_first=*/1);
+        conv1d_cl(h1, B, L, DI, ly.w2, ly.b2, H, k2, (k2 - 1) / 2, y, tc, st);
         n.x = y; n.res = x; n.out = x;
         if (scln) n.gb = gb2; else { n.gamma = ly.ln2_g; n.beta = ly.ln2_b; }
         layer_norm(n, st);
@@ -719,11 +786,11 @@ class Engine {
         const long long rows = (long long)B * T;
         float* c1 = ws.get<float>(rows * F);
         float* c2 = ws.get<float>(rows * F);
-        conv1d_cl(x, B, T, H, v.wc1, v.bc1, F, K, (K - 1) / 2, c1, false, st, nullptr, 1);
+        conv1d_cl(x, B, T, H, v.wc1, v.bc1, F, K, (K - 1) / 2, c1, P_EXACT, st, nullptr, 1);
         NormArgs n;
         n.x = c1; n.out = c1; n.rows = (int)rows; n.C = F; n.gamma = v.ln1_g; n.beta = v.ln1_b; n.eps = 1e-5f;
         layer_norm(n, st);
-        conv1d_cl(c1, B, T, F, v.wc2, v.bc2, F, K, 1, c2, false, st, nullptr, 1);  // padding=1 (fs2.py:543)
+        conv1d_cl(c1, B, T, F, v.wc2, v.bc2, F, K, 1, c2, P_EXACT, st, nullptr, 1);  // padding=1 (fs2.py:543)
         n.x = c2; n.out = nullptr; n.gamma = v.ln2_g; n.beta = v.ln2_b;
         n.dot_w = v.wlin; n.dot_b = v.blin; n.dot_out = out; n.mask = mask;
         layer_norm(n, st);
@@ -742,13 +809,12 @@ class Engine {
         ws.reset();
         const int M = cfg.n_mels;
         const int* nf = cfg.resnet_num_filters;
-        const bool tc = true;
+        const int tc = P_TF32;
         float* x0 = ws.get<float>((long long)B * M * T);
         instance_norm_time(ref_mel, B, T, M, x0, st);
         long long big = (long long)B * M * T * nf[0];
         float* buf[4];
         for (int i = 0; i < 4; ++i) buf[i] = ws.get<float>(big);
-        float* pooled = ws.get<float>((long long)B * 1024);
         float* gate = ws.get<float>((long long)B * 1024);
         float* x = buf[0];
         stem_conv3x3(x0, stem_w, stem_b, stem_s, stem_sh, B, M, T, nf[0], x, st);
@@ -772,8 +838,10 @@ class Engine {
             c2.mode = ROW_CONV2D; c2.Ho = Ho; c2.Wo = Wo; c2.Hi = Ho; c2.Wi = Wo; c2.ksize = 3; c2.stride = 1; c2.pad = 1;
             c2.scale = b.bn2_s; c2.shift = b.bn2_b;
             gemm(c2, tc, st);
-            hw_mean(t2, B, Ho * Wo, b.planes, pooled, st);
-            se_excite(pooled, b.se_w1, b.se_b1, b.se_w2, b.se_b2, B, b.planes, b.red, gate, st);
+            const int S = hw_mean_splits(B, Ho * Wo);
+            float* pooled = ws.get<float>((long long)B * S * b.planes);
+            hw_sum_partial(t2, B, Ho * Wo, b.planes, S, pooled, st);
+            se_excite(pooled, S, Ho * Wo, b.se_w1, b.se_b1, b.se_w2, b.se_b2, B, b.planes, b.red, gate, st);
             const float* res = x;
             if (b.wd) {
                 GemmArgs dn;
@@ -802,7 +870,7 @@ class Engine {
         linear(flat, B * Ww, spk_D, att_w0, att_b0, 128, a1, tc, st, nullptr, 1, att_bn_s, att_bn_b);
         linear(a1, B * Ww, 128, att_w3, att_b3, spk_D, lg, tc, st);
         attentive_pool(flat, lg, B, Ww, spk_D, asp, stats, st);
-        linear(stats, B, asp ? 2 * spk_D : spk_D, spk_fc_w, spk_fc_b, H, style, false, st);
+        linear(stats, B, asp ? 2 * spk_D : spk_D, spk_fc_w, spk_fc_b, H, style, P_EXACT, st);
         l2_normalize(style, B, H, st);
         return 0;
     }
@@ -816,9 +884,13 @@ class Engine {
         ws.reset();
         float* x = xprime;
         embed_posenc(phoneme, puncts, phon_emb, punct_emb, pos_table(false, T), B, T, cfg.emb_dim, cfg.punct_emb_dim, x, st);
-        const FFTScratch sc = fft_scratch(B, T, cfg.enc_heads);
+        if (tc_enabled(P_EXACT)) {   // scratch for the low part of a split GEMM's A operand
+            lo_cap = (long long)B * T * std::max(std::max(3 * H, cfg.conv_filter_size), cfg.vp_filter_size);
+            lo_buf = ws.get<float>(lo_cap);
+        }
+        const FFTScratch sc = fft_scratch(B, T, cfg.enc_heads, P_EXACT);
         for (int i = 0; i < cfg.enc_layers; ++i)
-            fft_block(x, B, T, cfg.enc_heads, enc[(size_t)i], mask, false, nullptr, nullptr, 0, /*tc=*/false, sc, st);
+            fft_block(x, B, T, cfg.enc_heads, enc[(size_t)i], mask, false, nullptr, nullptr, 0, P_EXACT, sc, st);
         add_batch_vector(x, style, B, T, H, st);  // all positions, padded ones too (fs2.py:740-741)
         variance_predictor(x, B, T, vp[0], mask, log_dur, st);
         variance_predictor(x, B, T, vp[1], mask, pitch, st);
@@ -828,6 +900,8 @@ class Engine {
         duration_round(log_dur, forced, dur, B * T, st);
         int32_t* cum = ws.get<int32_t>((long long)B * T);
         duration_scan(dur, B, T, cum, mel_len, st);
+        lo_buf = nullptr;
+        lo_cap = 0;
         if (L_max_out) {
             ZVX_CUDA_CHECK(cudaMemcpyAsync(pinned_len, mel_len, sizeof(int64_t) * B, cudaMemcpyDeviceToHost, st));
             ZVX_CUDA_CHECK(cudaStreamSynchronize(st));  // the one inherent sync (the reference: B*T + 1)
@@ -857,7 +931,7 @@ class Engine {
         ZVX_REQUIRE(B >= 1 && L >= 1, "zvx_decode: empty batch");
         ZVX_REQUIRE(mask || mel_len, "zvx_decode: need mask or mel_len");
         ws.reset();
-        const bool tc = true;
+        const int tc = P_TF32;
         if (!mask) {
             uint8_t* m = ws.get<uint8_t>((long long)B * L);
             mask_from_lengths(mel_len, B, L, m, st);
@@ -867,11 +941,11 @@ class Engine {
         float* gb = nullptr;
         if (cfg.dec_scln) {
             gb = ws.get<float>((long long)B * nscln * 2 * H);
-            linear(style, B, H, scln_w, nullptr, nscln * 2 * H, gb, false, st);
+            linear(style, B, H, scln_w, nullptr, nscln * 2 * H, gb, P_EXACT, st);
         }
         float* x = ws.get<float>((long long)B * L * H);
         add_posenc(features, pos_table(true, L), B, L, H, x, st);
-        const FFTScratch sc = fft_scratch(B, L, cfg.dec_heads);
+        const FFTScratch sc = fft_scratch(B, L, cfg.dec_heads, tc);
         for (int i = 0; i < cfg.dec_layers; ++i) {
             const float* gb1 = gb ? gb + (long long)(2 * i) * 2 * H : nullptr;
             const float* gb2 = gb ? gb + (long long)(2 * i + 1) * 2 * H : nullptr;
@@ -1075,6 +1149,10 @@ class Engine {
     std::string sec_err[4];
     Workspace ws;
     Profiler prof;
+    bool split_on = getenv("ZVX_NO_SPLIT") == nullptr;   // 3xTF32 for P_EXACT contractions (debug switch)
+    std::map<const float*, const float*> w_lo;
+    float* lo_buf = nullptr;
+    long long lo_cap = 0;
     int64_t* pinned_len = nullptr;
 
     float *enc_pos_param = nullptr, *dec_pos_param = nullptr, *enc_pos = nullptr, *dec_pos = nullptr;
@@ -1103,10 +1181,10 @@ struct zvx_handle {
     std::unique_ptr<zvx::Engine> eng;
 };
 
-#define ZVX_GUARD(h, body)                                                     \
+#define ZVX_GUARD(h, ...)                                                      \
     if (!(h) || !(h)->eng) return -1;                                          \
     try {                                                                      \
-        body;                                                                  \
+        __VA_ARGS__;                                                           \
     } catch (const std::exception& e) {                                        \
         (h)->eng->err = e.what();                                              \
         return 1;                                                              \
@@ -1207,7 +1285,22 @@ int zvx_debug_gemm(zvx_handle* h, const zvx_gemm_desc* d, int use_tc, void* stre
         if (use_tc) {
             zvx::TcGemmArgs t;
             ZVX_REQUIRE(zvx::gemm_tc_from(a, &t), "zvx_debug_gemm: layout not supported by the tcgen05 path");
+            float *alo = nullptr, *wlo = nullptr;
+            if (use_tc == 2) {   // 3xTF32 split: prepare the low parts (test hook only: allocates)
+                const long long na = zvx::Engine::a_extent(a), nw = (long long)a.taps * a.N * a.ldw;
+                ZVX_REQUIRE(na % 4 == 0 && nw % 4 == 0, "zvx_debug_gemm: split mode needs sizes that are multiples of 4");
+                ZVX_CUDA_CHECK(cudaMalloc(&alo, (size_t)na * sizeof(float)));
+                ZVX_CUDA_CHECK(cudaMalloc(&wlo, (size_t)nw * sizeof(float)));
+                zvx::tf32_split_lo(a.A, alo, na, (cudaStream_t)stream);
+                zvx::tf32_split_lo(a.W, wlo, nw, (cudaStream_t)stream);
+                t.A_lo = alo; t.W_lo = wlo;
+            }
             zvx::gemm_tc(t, (cudaStream_t)stream);
+            if (alo) {
+                ZVX_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+                cudaFree(alo);
+                cudaFree(wlo);
+            }
         } else {
             zvx::gemm_simt(a, (cudaStream_t)stream);
         }

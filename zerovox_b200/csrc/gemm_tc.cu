@@ -31,6 +31,8 @@ constexpr int NUM_THREADS = 320;          // TMA warp, MMA warp, 8 epilogue warp
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;          // TMEM columns between the two accumulators
 constexpr int MAX_STAGES = 8;
+constexpr int SPLIT_PHASE = 8;           // k-steps per accumulation phase of the 3xTF32 mode (32 hi*hi MMAs per chain)
+constexpr int LO_OFFSET = 128;           // TMEM column offset of the cross-term accumulator (split mode, BN <= 128)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 struct TcParams {
@@ -38,7 +40,7 @@ struct TcParams {
     int TW, TH, BN;
     int ksx, taps, kchunks, dil, pad_x, pad_y;
     int b_batched;
-    int stages, stage_bytes, b_tile_bytes;
+    int stages, stage_bytes, b_tile_bytes, b_tile_stride;
     uint32_t idesc;
     int Wo, Ho, N;
     float* C;
@@ -85,9 +87,13 @@ __device__ __forceinline__ float epi(const TcParams& p, float x, int n) {
     return x;
 }
 
-template <bool GENERAL>
+// SPLIT (3xTF32, fp32-grade products): each operand arrives as a pair (raw fp32 tile, whose low 13 mantissa bits the
+// tensor core ignores = hi; and a TF32-exact tile lo = rn(x - hi) prepared by tf32_split_lo) and every k-step issues
+// A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same fp32 accumulator; the dropped lo*lo term is ~2^-22 relative.
+template <bool GENERAL, bool SPLIT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t smem_base = smem_u32(smem);
@@ -106,6 +112,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (threadIdx.x == 0) {
         prefetch_tmap(&mapA);
         prefetch_tmap(&mapB);
+        if (SPLIT) {
+            prefetch_tmap(&mapAlo);
+            prefetch_tmap(&mapBlo);
+        }
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -127,13 +137,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int ksteps = p.taps * p.kchunks;
+    // SPLIT: the tensor core's fp32 accumulate truncates, a bias that grows with the accumulation chain; the chain is
+    // cut every SPLIT_PHASE k-steps and the partial sums are added in registers (round-to-nearest) by the epilogue warps.
+    const int phase_len = SPLIT ? SPLIT_PHASE : ksteps;
 
     if (warp == 0) {
         // ================================================================ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)(A_TILE_BYTES + p.b_tile_bytes);
+            const uint32_t tx_bytes = (uint32_t)(A_TILE_BYTES + p.b_tile_bytes) * (SPLIT ? 2u : 1u);
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const Tile c = decode_tile(p, t);
                 for (int s = 0; s < ksteps; ++s) {
@@ -146,6 +159,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 c.y0 + dy * p.dil - p.pad_y, c.img);
                     tma_load_4d(&mapB, full_bar(stage), sa + A_TILE_BYTES, kc * BK, c.n0, p.b_batched ? c.y0 : tap,
                                 p.b_batched ? c.img : 0);
+                    if (SPLIT) {
+                        const uint32_t sl = sa + (uint32_t)(A_TILE_BYTES + p.b_tile_stride);
+                        tma_load_4d(&mapAlo, full_bar(stage), sl, kc * BK, c.x0 + dx * p.dil - p.pad_x,
+                                    c.y0 + dy * p.dil - p.pad_y, c.img);
+                        tma_load_4d(&mapBlo, full_bar(stage), sl + A_TILE_BYTES, kc * BK, c.n0, p.b_batched ? c.y0 : tap,
+                                    p.b_batched ? c.img : 0);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -156,25 +176,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-                const int buf = it & 1;
-                const uint32_t par = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(tempty_bar(buf), par ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
-                for (int s = 0; s < ksteps; ++s) {
-                    mbar_wait(full_bar(stage), phase);
+            uint32_t cnt = 0;   // accumulation phases issued so far (one per tile unless SPLIT)
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                for (int s0 = 0; s0 < ksteps; s0 += phase_len, ++cnt) {
+                    const int buf = (int)(cnt & 1u);
+                    const uint32_t par = (cnt >> 1) & 1u;
+                    mbar_wait(tempty_bar(buf), par ^ 1u);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
-                    const uint64_t da = sw128_desc(sa), db = sw128_desc(sa + A_TILE_BYTES);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
+                    const int s1 = min(ksteps, s0 + phase_len);
+                    for (int s = s0; s < s1; ++s) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
+                        const uint64_t da = sw128_desc(sa), db = sw128_desc(sa + A_TILE_BYTES);
+                        const int first = (s == s0);
+                        if (SPLIT) {
+                            const uint32_t sl = sa + (uint32_t)(A_TILE_BYTES + p.b_tile_stride);
+                            const uint64_t la = sw128_desc(sl), lb = sw128_desc(sl + A_TILE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes = 2 descriptor units per MMA
-                        umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (s | k) ? 1u : 0u);
-                    umma_commit(empty_bar(stage));
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                            for (int k = 0; k < BK / 8; ++k) {
+                                const uint32_t accum = (first && k == 0) ? 0u : 1u;
+                                umma_tf32(d_tmem + LO_OFFSET, la + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, accum);
+                                umma_tf32(d_tmem + LO_OFFSET, da + (uint64_t)(2 * k), lb + (uint64_t)(2 * k), p.idesc, 1u);
+                                umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, accum);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes = 2 descriptor units per MMA
+                                umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
+                                          (first && k == 0) ? 0u : 1u);
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(tfull_bar(buf));
                 }
-                umma_commit(tfull_bar(buf));
             }
         }
         __syncwarp();
@@ -185,10 +222,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int half = (warp - 2) >> 2;
         const int r = q * 32 + lane;            // position within the tile
         const int ty = r / p.TW, tx = r - ty * p.TW;
-        int it = 0;
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-            const int buf = it & 1;
-            const uint32_t par = (uint32_t)(it >> 1) & 1u;
+        uint32_t cnt = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             const Tile c = decode_tile(p, t);
             const int y = c.y0 + ty, x = c.x0 + tx;
             const bool valid = (y < p.Ho) && (x < p.Wo);
@@ -196,6 +231,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             float* __restrict__ cp = p.C + off;
             const float* __restrict__ rp =
                 p.R ? p.R + ((long long)c.img * p.r_simg + (long long)y * p.r_sy + (long long)x * p.r_sx) : nullptr;
+            if (SPLIT) {
+                // ---- 3xTF32: sum the per-phase partial accumulators (hi*hi and the cross terms) in registers
+                float acc[4][16];
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[ci][e] = 0.f;
+                for (int s0 = 0; s0 < ksteps; s0 += phase_len, ++cnt) {
+                    const int buf = (int)(cnt & 1u);
+                    mbar_wait(tfull_bar(buf), (cnt >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const int c0 = half * 16 + ci * 32;
+                        if (c0 < p.BN) {
+                            uint32_t v[16], w[16];
+                            tmem_ld16(trow + (uint32_t)c0, v);
+                            tmem_ld16(trow + (uint32_t)(LO_OFFSET + c0), w);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) acc[ci][e] += __uint_as_float(v[e]) + __uint_as_float(w[e]);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(buf));
+                }
+                if (valid) {
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const int c0 = half * 16 + ci * 32;
+                        const int n = c.n0 + c0;
+                        if (c0 >= p.BN || n >= p.N) continue;
+                        float o[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            o[e] = 0.f;
+                            if (n + e < p.N) {
+                                float xv = epi(p, acc[ci][e], n + e);
+                                if (rp) xv += rp[(long long)(n + e) * p.c_sn];
+                                if (p.relu_last) xv = fmaxf(xv, 0.f);
+                                o[e] = xv;
+                            }
+                        }
+                        if (p.vec4 && n + 16 <= p.N) {
+#pragma unroll
+                            for (int g = 0; g < 4; ++g)
+                                *(reinterpret_cast<float4*>(cp + n) + g) =
+                                    make_float4(o[4 * g + 0], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; ++e)
+                                if (n + e < p.N && c0 + e < p.BN) cp[(long long)(n + e) * p.c_sn] = o[e];
+                        }
+                    }
+                }
+                continue;
+            }
+            const int buf = (int)(cnt & 1u);
+            const uint32_t par = (cnt >> 1) & 1u;
+            ++cnt;
             mbar_wait(tfull_bar(buf), par);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
@@ -343,7 +440,8 @@ EncodeTiledFn encode_fn() {
 }
 
 // 4-D fp32 tensor map, dim 0 contiguous, 128-byte swizzle, zero fill out of bounds.
-CUtensorMap make_map(const float* base, const long long dims[4], const long long strides_elems[3], const int box[4]) {
+CUtensorMap make_map(const float* base, const long long dims[4], const long long strides_elems[3], const int box[4],
+                     bool raw_f32 = false) {
     CUtensorMap m;
     cuuint64_t gd[4], gs[3];
     cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
@@ -361,7 +459,8 @@ CUtensorMap make_map(const float* base, const long long dims[4], const long long
     // TFLOAT32 element type: the TMA unit rounds fp32 -> tf32 (nearest) in flight.  With plain FLOAT32 the tensor core
     // truncates the low 13 mantissa bits, a systematic -7e-4 relative bias per contraction (measured, tools/diag_tf32.py;
     // ZVX_TMAP_F32=1 restores that behaviour for the experiment).
-    static const bool f32_type = getenv("ZVX_TMAP_F32") != nullptr;
+    static const bool f32_env = getenv("ZVX_TMAP_F32") != nullptr;
+    const bool f32_type = f32_env || raw_f32;   // split mode: hi = the tensor core's own truncation of the raw bits
     const CUresult rc = encode_fn()(&m, f32_type ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), gd, gs, bx, es,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -391,6 +490,25 @@ int num_sms() {
 
 }  // namespace
 
+namespace {
+// lo = rn_tf32(x - trunc_tf32(x)): the part of x the tensor core drops when it reads raw fp32 bits as TF32
+__global__ void tf32_split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, long long n4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(x + i);
+    auto f = [](float a) { return rn_tf32(a - __uint_as_float(__float_as_uint(a) & 0xFFFFE000u)); };
+    lo[i] = make_float4(f(v.x), f(v.y), f(v.z), f(v.w));
+}
+}  // namespace
+
+void tf32_split_lo(const float* x, float* lo, long long n, cudaStream_t st) {
+    if (n <= 0) return;
+    ZVX_REQUIRE(aligned16(x) && aligned16(lo), "tf32_split_lo: unaligned");
+    const long long n4 = (n + 3) / 4;   // buffers are padded to 16 bytes by the workspace / weight uploader
+    tf32_split_lo_kernel<<<cdiv(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(lo), n4);
+    ZVX_POST_LAUNCH();
+}
+
 bool gemm_tc_supported(const TcGemmArgs& a) {
     if (!a.A || !a.W || !a.C) return false;
     if (a.K < 8 || a.N < 8 || a.Wo < 1 || a.Ho < 1 || a.IMG < 1) return false;
@@ -403,6 +521,8 @@ bool gemm_tc_supported(const TcGemmArgs& a) {
 
 void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     ZVX_REQUIRE(gemm_tc_supported(a), "gemm_tc: operand layout not supported by the TMA path");
+    const bool split = a.A_lo != nullptr || a.W_lo != nullptr;
+    ZVX_REQUIRE(!split || (a.A_lo && a.W_lo && aligned16(a.A_lo) && aligned16(a.W_lo)), "gemm_tc: split mode needs both lo operands");
     TcParams p{};
     // tile shape: TH x TW = 128 positions, least padding first, wider rows on ties
     long long best = -1;
@@ -413,10 +533,11 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     }
     // column tile: multiple of 16, <= 256, least padding over a few tile counts
     {
-        const int t0 = cdiv(a.N, 256);
+        const int bn_max = split ? 128 : 256;   // split stages hold four operand tiles
+        const int t0 = cdiv(a.N, bn_max);
         long long bw = -1;
         for (int tn = t0; tn <= t0 + 4; ++tn) {
-            const int bn = (int)std::min<long long>(256, round_up(cdiv(a.N, tn), 16));
+            const int bn = (int)std::min<long long>(bn_max, round_up(cdiv(a.N, tn), 16));
             const int tiles = cdiv(a.N, bn);
             const long long waste = (long long)tiles * bn - a.N;
             if (bw < 0 || waste < bw) { bw = waste; p.BN = bn; p.tiles_n = tiles; }
@@ -430,7 +551,8 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.ksx = a.ksx; p.taps = a.ksx * a.ksy; p.kchunks = cdiv(a.K, BK); p.dil = a.dil; p.pad_x = a.pad_x; p.pad_y = a.pad_y;
     p.b_batched = a.b_batched;
     p.b_tile_bytes = p.BN * BK * 4;
-    p.stage_bytes = A_TILE_BYTES + (int)round_up(p.b_tile_bytes, 1024);
+    p.b_tile_stride = (int)round_up(p.b_tile_bytes, 1024);
+    p.stage_bytes = (A_TILE_BYTES + p.b_tile_stride) * (split ? 2 : 1);
     p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes);
     // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3, M >> 4
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -452,21 +574,26 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     const long long wdims[4] = {a.K, a.N, a.Z1, a.Z2};
     const long long wstr[3] = {a.w_sn, a.w_s1, a.w_s2};
     const int wbox[4] = {BK, p.BN, 1, 1};
-    const CUtensorMap mapA = make_map(a.A, adims, astr, abox);
-    const CUtensorMap mapB = make_map(a.W, wdims, wstr, wbox);
+    const CUtensorMap mapA = make_map(a.A, adims, astr, abox, split);
+    const CUtensorMap mapB = make_map(a.W, wdims, wstr, wbox, split);
+    const CUtensorMap mapAlo = split ? make_map(a.A_lo, adims, astr, abox) : mapA;
+    const CUtensorMap mapBlo = split ? make_map(a.W_lo, wdims, wstr, wbox) : mapB;
 
     const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 1024;
     static bool attr = false;
     if (!attr) {
-        ZVX_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        ZVX_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        ZVX_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        ZVX_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        ZVX_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         attr = true;
     }
-    ZVX_REQUIRE(smem <= SMEM_LIMIT && smem > 116 * 1024, "gemm_tc: shared-memory plan out of range");
+    // > 116 KB keeps the kernel at one CTA per SM (each CTA allocates all 512 TMEM columns)
+    ZVX_REQUIRE(p.stages >= 2 && smem <= SMEM_LIMIT && smem > 116 * 1024, "gemm_tc: shared-memory plan out of range");
     const int grid = std::min(p.num_tiles, num_sms());
     const bool general = a.scale || a.acc_mode || a.act_slope != 1.f || a.C2;
-    if (general) gemm_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, p);
-    else gemm_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, p);
+    if (split) gemm_tc_kernel<true, true><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
+    else if (general) gemm_tc_kernel<true, false><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
+    else gemm_tc_kernel<false, false><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
     ZVX_POST_LAUNCH();
 }
 

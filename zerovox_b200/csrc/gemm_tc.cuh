@@ -24,6 +24,9 @@ struct TcGemmArgs {
     int N = 0, Z1 = 1, Z2 = 1;
     long long w_sn = 0, w_s1 = 0, w_s2 = 0;     // element strides of the n / z1 / z2 dims
     int b_batched = 0;
+    // 3xTF32 split mode (fp32-grade products): TF32-exact low parts of A and W (tf32_split_lo), same layout / strides
+    const float* A_lo = nullptr;
+    const float* W_lo = nullptr;
     int Wo = 1, Ho = 1;
     int ksx = 1, ksy = 1, dil = 1, pad_x = 0, pad_y = 0;
     float* C = nullptr;
@@ -39,12 +42,16 @@ struct TcGemmArgs {
     float act_slope = 1.f;
     float* C2 = nullptr; float slope2 = 1.f;
     int acc_mode = 0, acc_init = 0; float acc_scale = 1.f;
-    double flops() const { return 2.0 * IMG * Ho * Wo * (double)N * K * ksx * ksy; }
+    double flops() const { return 2.0 * IMG * Ho * Wo * (double)N * K * ksx * ksy; }   // algorithmic (split issues 3x)
 };
 
 // Constraints of the TMA descriptors (16-byte aligned base pointers and strides) and of the tile shapes.
 bool gemm_tc_supported(const TcGemmArgs& a);
 void gemm_tc(const TcGemmArgs& a, cudaStream_t st);
+
+// lo[i] = rn_tf32(x[i] - trunc_tf32(x[i])) for i < n (n rounded up to a multiple of 4; both buffers 16-byte aligned and
+// padded accordingly).
+void tf32_split_lo(const float* x, float* lo, long long n, cudaStream_t st);
 
 // Conversion from the SIMT kernel's argument block (ROW_PLAIN / ROW_CONV1D / ROW_CONV2D with stride 1, nz == 1).
 bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* out);

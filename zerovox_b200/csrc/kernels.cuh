@@ -114,11 +114,12 @@ void instance_norm_time(const float* ref_mel, int B, int T, int n_mels, float* o
 // stem: Conv2d(1->C, 3x3, pad 1, bias) -> ReLU -> BN(scale, shift); in [B,H,W] -> out [B,H,W,C]
 void stem_conv3x3(const float* in, const float* w /*[9][C]*/, const float* bias, const float* scale,
                   const float* shift, int B, int H, int W, int C, float* out, cudaStream_t st);
-// SE squeeze: mean over HW -> [B, C]
-void hw_mean(const float* x, int B, int HW, int C, float* out, cudaStream_t st);
-// SE excitation: y = sigmoid(W2 relu(W1 p + b1) + b2), p [B,C], W1 [R,C], W2 [C,R]
-void se_excite(const float* p, const float* w1, const float* b1, const float* w2, const float* b2, int B, int C,
-               int R, float* y, cudaStream_t st);
+// SE squeeze: S partial sums over HW -> [B, S, C] (S = hw_mean_splits(B, HW)); se_excite finishes the mean
+int hw_mean_splits(int B, int HW);
+void hw_sum_partial(const float* x, int B, int HW, int C, int S, float* out, cudaStream_t st);
+// SE excitation: p = (sum_s partial[b,s,:]) / HW; y = sigmoid(W2 relu(W1 p + b1) + b2), W1 [R,C], W2 [C,R]
+void se_excite(const float* partial, int S, int HW, const float* w1, const float* b1, const float* w2, const float* b2,
+               int B, int C, int R, float* y, cudaStream_t st);
 // out = relu(x * y[b,c] + res)
 void se_scale_add_relu(const float* x, const float* y, const float* res, int B, int HW, int C, float* out,
                        cudaStream_t st);

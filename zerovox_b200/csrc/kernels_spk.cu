@@ -3,6 +3,8 @@
 // implicit-GEMM path (ROW_CONV2D) with ReLU / folded-BatchNorm epilogues.
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace zvx {
 
 // InstanceNorm1d(n_mels) over time, no affine (ResNetSE34V2.py:123, 182); also performs the
@@ -73,45 +75,60 @@ void stem_conv3x3(const float* in, const float* w, const float* bias, const floa
     ZVX_POST_LAUNCH();
 }
 
-// SE squeeze (AdaptiveAvgPool2d(1), ResNetSE34V2.py:63-64): x [B, HW, C] -> mean over HW.
-// grid (B, ceil(C/32)); block 32 x 8: threadIdx.x = channel (coalesced), threadIdx.y strides over HW.
-__global__ void hw_mean_kernel(const float* __restrict__ x, int HW, int C, float* __restrict__ out) {
-    __shared__ float red[8][33];
-    const int b = blockIdx.x;
-    const int c = blockIdx.y * 32 + threadIdx.x;
-    float s = 0.f;
-    if (c < C) {
-        const float* p = x + (long long)b * HW * C + c;
-        for (int i = threadIdx.y; i < HW; i += 8) s += p[(long long)i * C];
+// SE squeeze (AdaptiveAvgPool2d(1), ResNetSE34V2.py:63-64): x [B, HW, C] -> sums over HW, split into S partial sums so
+// that the whole GPU streams the tensor once: grid (S, B); block = 256 threads = (256 / (C/4)) rows x C/4 float4 columns.
+// out[b][s][c] = sum over the s-th slice of HW (deterministic order); se_excite adds the S partials and divides.
+__global__ void __launch_bounds__(256) hw_sum_partial_kernel(const float* __restrict__ x, int HW, int C4, int rows_per,
+                                                             float* __restrict__ out) {
+    __shared__ float4 red[256];
+    const int s = blockIdx.x, b = blockIdx.y, S = gridDim.x;
+    const int c4 = threadIdx.x % C4, r0 = threadIdx.x / C4, nr = 256 / C4;
+    const int lo = s * rows_per, hi = min(HW, lo + rows_per);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 < nr) {
+        const float4* p = reinterpret_cast<const float4*>(x) + (long long)b * HW * C4 + c4;
+        for (int i = lo + r0; i < hi; i += nr) {
+            const float4 v = __ldg(p + (long long)i * C4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
     }
-    red[threadIdx.y][threadIdx.x] = s;
+    red[threadIdx.x] = acc;
     __syncthreads();
-    if (threadIdx.y == 0 && c < C) {
-        float t = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
-        out[(long long)b * C + c] = t / (float)HW;
+    if (r0 == 0) {
+        for (int r = 1; r < nr; ++r) {
+            const float4 v = red[r * C4 + c4];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(out)[((long long)b * S + s) * C4 + c4] = acc;
     }
 }
 
-void hw_mean(const float* x, int B, int HW, int C, float* out, cudaStream_t st) {
+int hw_mean_splits(int B, int HW) {
+    return std::max(1, std::min(cdiv(HW, 32), cdiv(4 * 148, std::max(B, 1))));
+}
+
+void hw_sum_partial(const float* x, int B, int HW, int C, int S, float* out, cudaStream_t st) {
     if (B == 0) return;
-    dim3 grid(B, cdiv(C, 32));
-    hw_mean_kernel<<<grid, dim3(32, 8), 0, st>>>(x, HW, C, out);
+    ZVX_REQUIRE(C % 4 == 0 && C / 4 <= 256, "hw_sum_partial: C must be a multiple of 4, <= 1024");
+    hw_sum_partial_kernel<<<dim3(S, B), 256, 0, st>>>(x, HW, C / 4, cdiv(HW, S), out);
     ZVX_POST_LAUNCH();
 }
 
 // SE excitation (ResNetSE34V2.py:55-60, 65): one block per utterance.
-__global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict__ p, const float* __restrict__ w1,
-                                                        const float* __restrict__ b1, const float* __restrict__ w2,
-                                                        const float* __restrict__ b2, int C, int R,
-                                                        float* __restrict__ y) {
+__global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict__ p, int S, float inv_hw,
+                                                        const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2,
+                                                        int C, int R, float* __restrict__ y) {
     extern __shared__ float sh[];  // [C] pooled, [R] hidden
     float* ps = sh;
     float* hs = sh + C;
     const int b = blockIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) ps[c] = p[(long long)b * C + c];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int s = 0; s < S; ++s) t += p[((long long)b * S + s) * C + c];
+        ps[c] = t * inv_hw;
+    }
     __syncthreads();
     for (int r = wid; r < R; r += nw) {
         float s = 0.f;
@@ -127,10 +144,10 @@ __global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict_
     }
 }
 
-void se_excite(const float* p, const float* w1, const float* b1, const float* w2, const float* b2, int B, int C,
-               int R, float* y, cudaStream_t st) {
+void se_excite(const float* p, int S, int HW, const float* w1, const float* b1, const float* w2, const float* b2, int B,
+               int C, int R, float* y, cudaStream_t st) {
     if (B == 0) return;
-    se_excite_kernel<<<B, 256, (C + R) * sizeof(float), st>>>(p, w1, b1, w2, b2, C, R, y);
+    se_excite_kernel<<<B, 256, (C + R) * sizeof(float), st>>>(p, S, 1.f / (float)HW, w1, b1, w2, b2, C, R, y);
     ZVX_POST_LAUNCH();
 }
 

@@ -260,7 +260,7 @@ class Engine:
 
     # ------------------------------------------------------------------ introspection
     PROF_CLASSES = {"gemm_fp32": 0, "gemm_tf32_tcgen05": 1, "vocoder_conv1d": 2, "vocoder_upsample": 3,
-                    "vocoder_pair_tcgen05": 4}
+                    "vocoder_pair_tcgen05": 4, "gemm_3xtf32_tcgen05": 5}
 
     def profile(self, on: bool):
         self._check(self.lib.zvx_profile_enable(self._h, 1 if on else 0), "zvx_profile_enable")
