@@ -151,7 +151,7 @@ int zvx_profile_read(zvx_handle* h, int kernel_class, double* ms, int64_t* launc
  * 537-552 and ResNetSE34V2.py:81-92, 184-186), channel-last operands:
  *   C[m, n] = epilogue( sum_tap sum_k A[rowmap(m, tap), k] * W[tap][n, k] )
  *   mode 0 plain GEMM; mode 1 Conv1d over [M/L, L, K] ('same' padding given by pad, dilation dil);
- *   mode 2 Conv2d ksize x ksize over [M/(Hh*Ww), Hh, Ww, K] (stride 1, padding pad)
+ *   mode 2 Conv2d ksize x ksize over [IMG, Hh, Ww, K] (stride 1 or 2, padding pad), M = IMG*Ho*Wo
  *   epilogue: + bias[n]; relu_first; * scale[n] + shift[n]; + R[m, n]; relu_last.
  * use_tc = 0: fp32 FMA kernel; 1: tcgen05 TF32 kernel (fails if the layout is not TMA-addressable);
  * 2: tcgen05 3xTF32 split (fp32-grade products; the low parts of A and W are prepared internally). */
@@ -159,6 +159,7 @@ typedef struct zvx_gemm_desc {
     const float* A; const float* W; float* C;
     const float* bias; const float* scale; const float* shift; const float* R;
     int32_t M, N, K, taps, mode, L, Hh, Ww, ksize, pad, dil, relu_first, relu_last, lda, ldw, ldc;
+    int32_t stride;   /* mode 2 only: 0/1 = unit stride, 2 = stride-2 Conv2d (Hh, Ww are the INPUT sizes) */
 } zvx_gemm_desc;
 int zvx_debug_gemm(zvx_handle* h, const zvx_gemm_desc* d, int use_tc, void* stream);
 

@@ -24,9 +24,11 @@ def eng():
 
 
 def run(eng, mode, A, W, bias=None, scale=None, shift=None, R=None, relu_first=0, relu_last=0, use_tc=1, L=0, Hh=0,
-        Ww=0, ksize=1, pad=0, dil=1):
+        Ww=0, ksize=1, pad=0, dil=1, stride=1, M_out=None):
     """A [M, K]; W [taps, N, K] -> C [M, N] on the device."""
     M, K = A.shape
+    if M_out is not None:
+        M = M_out
     taps, N, _ = W.shape
     Cout = torch.full((M, N), float("nan"), device=DEV)
     keep = [t.to(DEV).contiguous() if t is not None else None for t in (A, W, bias, scale, shift, R)]
@@ -36,6 +38,7 @@ def run(eng, mode, A, W, bias=None, scale=None, shift=None, R=None, relu_first=0
     d.C = Cout.data_ptr()
     d.M, d.N, d.K, d.taps, d.mode, d.L, d.Hh, d.Ww, d.ksize, d.pad, d.dil = M, N, K, taps, mode, L, Hh, Ww, ksize, pad, dil
     d.relu_first, d.relu_last, d.lda, d.ldw, d.ldc = relu_first, relu_last, K, K, N
+    d.stride = stride
     rc = eng.lib.zvx_debug_gemm(eng._h, C.byref(d), use_tc, None)
     assert rc == 0, eng.lib.zvx_last_error(eng._h).decode()
     torch.cuda.synchronize()
@@ -107,3 +110,31 @@ def test_conv2d_3x3(eng, B, Hh, Ww, Cin, Cout, use_tc):
     ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), padding=1).relu()
     ref = (ref * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]).permute(0, 2, 3, 1)
     check(got, ref.reshape(-1, Cout).float(), use_tc, 1.0)
+
+
+@pytest.mark.parametrize("use_tc", [0, 1])
+@pytest.mark.parametrize("B,Hh,Ww,Cin,Cout,ksize", [(2, 80, 48, 32, 64, 3), (3, 40, 55, 64, 128, 3), (2, 20, 27, 128, 256, 3),
+                                                    (2, 80, 48, 32, 64, 1), (1, 21, 33, 64, 128, 1)])
+def test_conv2d_stride2(eng, B, Hh, Ww, Cin, Cout, ksize, use_tc):
+    """Strided stage-entry convolutions of ResNetSE34V2 (3x3 pad 1 and the 1x1 downsample, ResNetSE34V2.py:81-92, 161-167):
+    on the tensor-core path the stride is a TMA element stride."""
+    pad = ksize // 2
+    x, w = rnd(B, Hh, Ww, Cin, seed=12), rnd(Cout, Cin, ksize, ksize, seed=13) / (Cin * ksize * ksize) ** 0.5
+    scale, shift = rnd(Cout, seed=14).abs() + 0.5, rnd(Cout, seed=15)
+    Wt = w.permute(2, 3, 0, 1).reshape(ksize * ksize, Cout, Cin).contiguous()
+    ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), padding=pad, stride=2)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    ref = (ref * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]).permute(0, 2, 3, 1)
+    got = run(eng, 2, x.reshape(-1, Cin), Wt, scale=scale, shift=shift, use_tc=use_tc, Hh=Hh, Ww=Ww, ksize=ksize, pad=pad,
+              stride=2, M_out=B * Ho * Wo)
+    check(got, ref.reshape(-1, Cout).float(), use_tc, 1.0)
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 528, 5120), (5, 1056, 528), (64, 100, 300), (1, 528, 5120), (33, 8, 256)])
+def test_skinny_gemm(eng, M, N, K):
+    """M <= 64 rows (speaker-net fc 5120 -> 528, SCLN affine stack): the fp32 FMA path switches to the skinny kernel."""
+    A, W = rnd(M, K, seed=21), rnd(1, N, K, seed=22)
+    bias, R = rnd(N, seed=23), rnd(M, N, seed=24)
+    got = run(eng, 0, A, W, bias=bias, R=R, relu_last=1, use_tc=0)
+    ref = epilogue((A.double() @ W[0].double().T).float(), bias, None, None, R, 0, 1)
+    check(got, ref, 0, K)

@@ -61,7 +61,7 @@ class ZvxGemmDesc(C.Structure):
     """Mirror of ``struct zvx_gemm_desc`` (kernel-level test hook)."""
     _fields_ = [(n, C.c_void_p) for n in ("A", "W", "C", "bias", "scale", "shift", "R")] + \
                [(n, C.c_int32) for n in ("M", "N", "K", "taps", "mode", "L", "Hh", "Ww", "ksize", "pad", "dil",
-                                         "relu_first", "relu_last", "lda", "ldw", "ldc")]
+                                         "relu_first", "relu_last", "lda", "ldw", "ldc", "stride")]
 
 
 # every symbol include/zerovox_b200.h declares: name -> (restype, argtypes)

@@ -95,6 +95,8 @@ struct GemmArgs {
     long long sA_b = 0, sA_h = 0, sW_b = 0, sW_h = 0, sC_b = 0, sC_h = 0;
 };
 
-void gemm_simt(const GemmArgs& a, cudaStream_t st);
+void gemm_simt(const GemmArgs& a, cudaStream_t st);   // dispatches skinny problems (M <= 64, plain) to gemm_skinny
+bool gemm_skinny_supported(const GemmArgs& a);
+void gemm_skinny(const GemmArgs& a, cudaStream_t st);
 
 }  // namespace zvx

@@ -513,9 +513,9 @@ class Engine {
             if (ch == 8 || ch == 16 || ch == 32) {
                 kind = 1;
                 for (int j = 0; j < nk; ++j)
-                    for (int di = 0; di < nd; ++di)
-                        if (!voc_pair_supported(ch, cfg.hg_resblock_kernel_sizes[j], cfg.hg_resblock_dilation_sizes[j][di]))
-                            kind = 0;
+                    if (!voc_resblock_supported(ch, cfg.hg_resblock_kernel_sizes[j], cfg.hg_resblock_dilation_sizes[j], nd,
+                                                cfg.hg_resblock == 1))
+                        kind = 0;
             } else if (ch >= 64 && ch % 4 == 0) {
                 kind = 2;
             }
@@ -1009,30 +1009,40 @@ class Engine {
             const long long bs = (long long)T * ch;
             const bool more = (i + 1 < nu);
             for (int j = 0; j < nk; ++j) {
-                View r = y, ra = ya;
                 const int rk = cfg.hg_resblock_kernel_sizes[j];
+                const bool pair = (cfg.hg_resblock == 1);
+                if (kind == 1) {
+                    // whole resblock in one launch; MRF mean accumulated in bX, the last one emits the next operand
+                    VocResArgs a;
+                    a.x = y.p; a.x_bs = y.bs; a.B = B; a.T = T; a.C = ch; a.k = rk;
+                    for (int di = 0; di < nd; ++di, ++ci) {
+                        const int dl = cfg.hg_resblock_dilation_sizes[j][di];
+                        if (pair) {
+                            a.steps[a.nsteps].w = hg_c1_tc[ci]; a.steps[a.nsteps].b = hg_c1[ci].b;
+                            a.steps[a.nsteps].dil = dl; a.steps[a.nsteps++].kind = 0;
+                            a.steps[a.nsteps].w = hg_c2_tc[ci]; a.steps[a.nsteps].b = hg_c2[ci].b;
+                            a.steps[a.nsteps].dil = 1; a.steps[a.nsteps++].kind = 1;
+                        } else {
+                            a.steps[a.nsteps].w = hg_c1_tc[ci]; a.steps[a.nsteps].b = hg_c1[ci].b;
+                            a.steps[a.nsteps].dil = dl; a.steps[a.nsteps++].kind = 1;
+                        }
+                    }
+                    if (j > 0) { a.acc_in = bX; a.acc_in_bs = bs; }
+                    a.out_scale = 1.f / (float)nk;
+                    const bool emit_act = (j == nk - 1) && more;
+                    a.out = emit_act ? bXA : bX; a.out_bs = bs; a.out_slope = emit_act ? 0.1f : 1.f;
+                    prof.begin(ZVX_PROF_VOC_TC, 2.0 * B * T * ch * ch * rk * a.nsteps, 4.0 * B * T * ch * (j > 0 ? 3.0 : 2.0), st);
+                    voc_resblock_tc(a, st);
+                    prof.end(st);
+                    continue;
+                }
+                View r = y, ra = ya;
                 for (int di = 0; di < nd; ++di, ++ci) {
                     const bool last = (di == nd - 1);
                     const bool first_buf = (r.p != bRA);
                     const View rn{first_buf ? bRA : bRB, bs}, rna{first_buf ? bRAa : bRBa, bs};
                     const int dl = cfg.hg_resblock_dilation_sizes[j][di];
-                    const bool pair = (cfg.hg_resblock == 1);
-                    if (kind == 1) {
-                        VocPairArgs a;
-                        a.x = r.p; a.x_bs = r.bs; a.B = B; a.T = T; a.C = ch; a.k = rk; a.d1 = dl;
-                        a.w1 = hg_c1_tc[ci]; a.b1 = hg_c1[ci].b;
-                        if (pair) { a.w2 = hg_c2_tc[ci]; a.b2 = hg_c2[ci].b; }
-                        if (last) {
-                            a.acc = bX; a.acc_bs = bs; a.acc_init = (j == 0); a.acc_scale = 1.f / (float)nk;
-                            if (j == nk - 1 && more) { a.act_out = bXA; a.act_bs = bs; a.act_slope = 0.1f; }
-                        } else {
-                            a.out = rn.p; a.out_bs = rn.bs;
-                        }
-                        prof.begin(ZVX_PROF_VOC_TC, 2.0 * B * T * ch * ch * rk * (pair ? 2 : 1),
-                                   4.0 * B * T * ch * (last && j > 0 ? 3.0 : 2.0), st);
-                        voc_pair_tc(a, st);
-                        prof.end(st);
-                    } else {
+                    {
                         TcGemmArgs g;   // conv over the leaky-ReLU'd copy
                         g.K = ch; g.Wi = g.Wo = T; g.Hi = g.Ho = B; g.a_sx = ch; g.N = ch; g.w_sn = ch; g.Z1 = rk;
                         g.w_s1 = (long long)ch * ch; g.ksx = rk; g.c_sx = ch;
@@ -1280,7 +1290,10 @@ int zvx_debug_gemm(zvx_handle* h, const zvx_gemm_desc* d, int use_tc, void* stre
         if (d->mode == 1) {
             a.mode = zvx::ROW_CONV1D; a.Lout = a.Lin = d->L; a.stride = 1; a.pad = d->pad; a.dil = d->dil;
         } else if (d->mode == 2) {
-            a.mode = zvx::ROW_CONV2D; a.Ho = a.Hi = d->Hh; a.Wo = a.Wi = d->Ww; a.ksize = d->ksize; a.stride = 1; a.pad = d->pad;
+            a.mode = zvx::ROW_CONV2D; a.Hi = d->Hh; a.Wi = d->Ww; a.ksize = d->ksize; a.stride = d->stride > 1 ? d->stride : 1;
+            a.pad = d->pad;
+            a.Ho = (a.Hi + 2 * a.pad - a.ksize) / a.stride + 1;
+            a.Wo = (a.Wi + 2 * a.pad - a.ksize) / a.stride + 1;
         }
         if (use_tc) {
             zvx::TcGemmArgs t;

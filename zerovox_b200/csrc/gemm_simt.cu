@@ -247,13 +247,73 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmArgs a, const i
     }
 }
 
+// Skinny GEMM (M <= 32 rows, any K): every warp owns one output column and strides over K, so the weight matrix is
+// streamed exactly once by the whole grid (the tiled kernel above would run such a problem on a handful of blocks).
+// Block = 8 warps = 8 columns sharing a [32 x 128] slab of A through shared memory.  fp32 FMA throughout.
+constexpr int SK_KC = 128;
+__global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmArgs a) {
+    __shared__ float As[32][SK_KC + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n = blockIdx.x * 8 + wid;
+    const int m0 = blockIdx.y * 32;
+    const int mrows = min(32, a.M - m0);
+    float acc[32];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) acc[m] = 0.f;
+    const float* wrow = a.W + (long long)min(n, a.N - 1) * a.ldw;
+    for (int k0 = 0; k0 < a.K; k0 += SK_KC) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * SK_KC; i += 256) {
+            const int m = i / SK_KC, k = i - m * SK_KC;
+            As[m][k] = (m < mrows && k0 + k < a.K) ? __ldg(a.A + (long long)(m0 + m) * a.lda + k0 + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < SK_KC; kk += 32) {
+            const int k = k0 + kk + lane;
+            const float w = (k < a.K) ? __ldg(wrow + k) : 0.f;
+#pragma unroll
+            for (int m = 0; m < 32; ++m) acc[m] = fmaf(As[m][kk + lane], w, acc[m]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 32; ++m) acc[m] = warp_sum(acc[m]);
+    if (n >= a.N) return;
+    // lane m finishes row m0 + m
+    float x = 0.f;
+#pragma unroll
+    for (int m = 0; m < 32; ++m)
+        if (lane == m) x = acc[m];
+    if (lane < mrows) {
+        const int m = m0 + lane;
+        if (a.bias) x += __ldg(a.bias + n);
+        if (a.relu_first) x = fmaxf(x, 0.f);
+        if (a.scale) x = fmaf(x, __ldg(a.scale + n), __ldg(a.shift + n));
+        if (a.R) x += a.R[(long long)m * a.ldr + n];
+        if (a.relu_last) x = fmaxf(x, 0.f);
+        a.C[(long long)m * a.ldc + n] = x;
+    }
+}
+
 }  // namespace
+
+bool gemm_skinny_supported(const GemmArgs& a) {
+    return a.mode == ROW_PLAIN && a.taps == 1 && a.nz == 1 && !a.b_kn && a.M >= 1 && a.M <= 64 && a.K >= 256 && a.N >= 8;
+}
+
+void gemm_skinny(const GemmArgs& a, cudaStream_t st) {
+    ZVX_REQUIRE(gemm_skinny_supported(a), "gemm_skinny: unsupported problem");
+    dim3 grid(cdiv(a.N, 8), cdiv(a.M, 32));
+    gemm_skinny_kernel<<<grid, 256, 0, st>>>(a);
+    ZVX_POST_LAUNCH();
+}
 
 void gemm_simt(const GemmArgs& a, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || a.nz <= 0) return;
     ZVX_REQUIRE(a.K > 0 && a.taps >= 1, "gemm: bad K/taps");
     ZVX_REQUIRE(!a.b_kn || a.taps == 1, "gemm: b_kn operands cannot have taps");
     ZVX_REQUIRE(a.R == nullptr || a.ldr > 0, "gemm: residual needs ldr");
+    if (gemm_skinny_supported(a)) return gemm_skinny(a, st);
     auto al4 = [](long long v) { return (v & 3) == 0; };
     const int a_vec = al4(a.lda) && al4(a.sA_b) && al4(a.sA_h) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
     const int w_vec = al4(a.ldw) && al4(a.sW_b) && al4(a.sW_h) && al4(a.w_tap_stride) &&

@@ -38,7 +38,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 struct TcParams {
     int num_tiles, tiles_n, tiles_x, tiles_y;
     int TW, TH, BN;
-    int ksx, taps, kchunks, dil, pad_x, pad_y;
+    int ksx, taps, kchunks, dil, pad_x, pad_y, stride, stride_y;
     int b_batched;
     int stages, stage_bytes, b_tile_bytes, b_tile_stride;
     uint32_t idesc;
@@ -155,14 +155,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
                     const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
-                    tma_load_4d(&mapA, full_bar(stage), sa, kc * BK, c.x0 + dx * p.dil - p.pad_x,
-                                c.y0 + dy * p.dil - p.pad_y, c.img);
+                    tma_load_4d(&mapA, full_bar(stage), sa, kc * BK, c.x0 * p.stride + dx * p.dil - p.pad_x,
+                                c.y0 * p.stride_y + dy * p.dil - p.pad_y, c.img);
                     tma_load_4d(&mapB, full_bar(stage), sa + A_TILE_BYTES, kc * BK, c.n0, p.b_batched ? c.y0 : tap,
                                 p.b_batched ? c.img : 0);
                     if (SPLIT) {
                         const uint32_t sl = sa + (uint32_t)(A_TILE_BYTES + p.b_tile_stride);
-                        tma_load_4d(&mapAlo, full_bar(stage), sl, kc * BK, c.x0 + dx * p.dil - p.pad_x,
-                                    c.y0 + dy * p.dil - p.pad_y, c.img);
+                        tma_load_4d(&mapAlo, full_bar(stage), sl, kc * BK, c.x0 * p.stride + dx * p.dil - p.pad_x,
+                                    c.y0 * p.stride_y + dy * p.dil - p.pad_y, c.img);
                         tma_load_4d(&mapBlo, full_bar(stage), sl + A_TILE_BYTES, kc * BK, c.n0, p.b_batched ? c.y0 : tap,
                                     p.b_batched ? c.img : 0);
                     }
@@ -440,15 +440,17 @@ EncodeTiledFn encode_fn() {
 }
 
 // 4-D fp32 tensor map, dim 0 contiguous, 128-byte swizzle, zero fill out of bounds.
+// estride: traversal step of dims 1 / 2 (strided convolutions): the box spans box[i]*estride elements, every
+// estride-th one is fetched, so the shared-memory tile keeps box[i] rows.
 CUtensorMap make_map(const float* base, const long long dims[4], const long long strides_elems[3], const int box[4],
-                     bool raw_f32 = false) {
+                     bool raw_f32 = false, int estride_x = 1, int estride_y = 1) {
     CUtensorMap m;
     cuuint64_t gd[4], gs[3];
-    cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+    cuuint32_t bx[4], es[4] = {1, (cuuint32_t)estride_x, (cuuint32_t)estride_y, 1};
     long long prev = 16;
     for (int i = 0; i < 4; ++i) {
         gd[i] = (cuuint64_t)std::max<long long>(dims[i], 1);
-        bx[i] = (cuuint32_t)box[i];
+        bx[i] = (cuuint32_t)box[i] * es[i];
     }
     for (int i = 0; i < 3; ++i) {
         long long s = strides_elems[i] * 4;
@@ -574,9 +576,12 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     const long long wdims[4] = {a.K, a.N, a.Z1, a.Z2};
     const long long wstr[3] = {a.w_sn, a.w_s1, a.w_s2};
     const int wbox[4] = {BK, p.BN, 1, 1};
-    const CUtensorMap mapA = make_map(a.A, adims, astr, abox, split);
+    ZVX_REQUIRE(a.stride >= 1 && a.stride <= 2 && p.TW * a.stride <= 256 && p.TH * a.stride <= 256, "gemm_tc: unsupported stride");
+    const int sy = (a.ksy > 1 || a.Hi != a.Ho) ? a.stride : 1;   // Conv1d rows (y = utterance) are never strided
+    p.stride = a.stride; p.stride_y = sy;
+    const CUtensorMap mapA = make_map(a.A, adims, astr, abox, split, a.stride, sy);
     const CUtensorMap mapB = make_map(a.W, wdims, wstr, wbox, split);
-    const CUtensorMap mapAlo = split ? make_map(a.A_lo, adims, astr, abox) : mapA;
+    const CUtensorMap mapAlo = split ? make_map(a.A_lo, adims, astr, abox, false, a.stride, sy) : mapA;
     const CUtensorMap mapBlo = split ? make_map(a.W_lo, wdims, wstr, wbox) : mapB;
 
     const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 1024;
@@ -598,7 +603,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
 }
 
 bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* o) {
-    if (g.b_kn || g.nz != 1 || g.stride != 1) return false;
+    if (g.b_kn || g.nz != 1) return false;
     TcGemmArgs a;
     a.A = g.A; a.K = g.K; a.W = g.W; a.N = g.N; a.w_sn = g.ldw; a.Z1 = g.taps; a.w_s1 = g.w_tap_stride; a.Z2 = 1;
     a.C = g.C; a.R = g.R; a.bias = g.bias; a.scale = g.scale; a.shift = g.shift;
@@ -608,14 +613,15 @@ bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* o) {
         if (g.taps != 1) return false;
         a.Wi = a.Wo = g.M; a.a_sx = g.lda; a.c_sx = g.ldc;
     } else if (g.mode == ROW_CONV1D) {
-        if (g.Lin != g.Lout || g.M % g.Lout != 0) return false;
+        if (g.Lin != g.Lout || g.M % g.Lout != 0 || g.stride != 1) return false;
         a.Wi = a.Wo = g.Lout; a.Hi = a.Ho = g.M / g.Lout;
         a.a_sx = g.lda; a.a_sy = (long long)g.Lin * g.lda;
         a.c_sx = g.ldc; a.c_sy = (long long)g.Lout * g.ldc;
         a.ksx = g.taps; a.ksy = 1; a.dil = g.dil; a.pad_x = g.pad; a.pad_y = 0;
     } else {
-        if (g.Hi != g.Ho || g.Wi != g.Wo || g.taps != g.ksize * g.ksize) return false;
-        a.Wi = a.Wo = g.Wo; a.Hi = a.Ho = g.Ho; a.IMG = g.M / (g.Ho * g.Wo);
+        if (g.taps != g.ksize * g.ksize || g.stride < 1 || g.stride > 2) return false;
+        if (g.Ho != (g.Hi + 2 * g.pad - g.ksize) / g.stride + 1 || g.Wo != (g.Wi + 2 * g.pad - g.ksize) / g.stride + 1) return false;
+        a.Wi = g.Wi; a.Wo = g.Wo; a.Hi = g.Hi; a.Ho = g.Ho; a.IMG = g.M / (g.Ho * g.Wo); a.stride = g.stride;
         a.a_sx = g.lda; a.a_sy = (long long)g.Wi * g.lda; a.a_simg = (long long)g.Hi * g.Wi * g.lda;
         a.c_sx = g.ldc; a.c_sy = (long long)g.Wo * g.ldc; a.c_simg = (long long)g.Ho * g.Wo * g.ldc;
         a.ksx = a.ksy = g.ksize; a.dil = 1; a.pad_x = a.pad_y = g.pad;

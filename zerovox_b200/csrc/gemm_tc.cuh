@@ -6,7 +6,7 @@ namespace zvx {
 
 // Generalised problem of the tcgen05 kernel.
 //
-//   out[img, y, x, n] = epilogue( sum_{dy,dx} sum_k A[img, y + dy*dil - pad_y, x + dx*dil - pad_x, k] * W[z1, z2][n, k] )
+//   out[img, y, x, n] = epilogue( sum_{dy,dx} sum_k A[img, y*s + dy*dil - pad_y, x*s + dx*dil - pad_x, k] * W[z1, z2][n, k] )
 //
 // A is a 4-D view (K contiguous) addressed through one TMA tensor map; positions outside [0,Hi)x[0,Wi) read as
 // zero (TMA out-of-bounds fill = the convolutions' zero padding).  W is a 4-D view (K contiguous) with
@@ -29,6 +29,7 @@ struct TcGemmArgs {
     const float* W_lo = nullptr;
     int Wo = 1, Ho = 1;
     int ksx = 1, ksy = 1, dil = 1, pad_x = 0, pad_y = 0;
+    int stride = 1;                             // output stride of a Conv2d (1 or 2; TMA element strides), x and y alike
     float* C = nullptr;
     long long c_simg = 0, c_sy = 0, c_sx = 0, c_sn = 1;
     const float* R = nullptr;

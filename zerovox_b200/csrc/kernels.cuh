@@ -104,6 +104,23 @@ bool voc_pair_supported(int C, int k, int dil);
 void voc_pair_tc(const VocPairArgs& a, cudaStream_t st);
 std::vector<float> voc_pack_weight(const float* w, int cout, int cin, int k);
 
+// Whole MRF residual block fused (voc_res.cu): ResBlock1 = [conv_{k,d} (kind 0), conv_{k,1} (kind 1)] per dilation,
+// ResBlock2 = [conv_{k,d} (kind 1)] per dilation; kind 1 steps add the residual.  Result:
+//   out = lrelu( resblock(x) * out_scale + (acc_in ? acc_in : 0), out_slope )      (acc_in may alias out)
+struct VocResArgs {
+    static constexpr int MAX_STEPS = 8;
+    struct Step { const float* w = nullptr; const float* b = nullptr; int dil = 1; int kind = 1; };
+    const float* x = nullptr; long long x_bs = 0;      // raw input [B][T][C], batch stride in elements
+    int B = 0, T = 0, C = 0, k = 1, nsteps = 0;
+    Step steps[MAX_STEPS];                             // weights in the packed image of voc_pack_weight
+    float in_slope = 0.1f, mid_slope = 0.1f;
+    const float* acc_in = nullptr; long long acc_in_bs = 0;
+    float out_scale = 1.f, out_slope = 1.f;
+    float* out = nullptr; long long out_bs = 0;
+};
+bool voc_resblock_supported(int C, int k, const int* dils, int nd, bool pair);
+void voc_resblock_tc(const VocResArgs& a, cudaStream_t st);
+
 // conv_post on channel-last input: wav[b,t] = tanh(bias + sum_{j,c} w[j][c] * lrelu(x[b, t+j-(k-1)/2, c], slope))
 void conv_post_cl(const float* x, long long x_bs, const float* w /*[k][C]*/, const float* bias, int B, int T, int C,
                   int k, float slope, float* wav, cudaStream_t st);

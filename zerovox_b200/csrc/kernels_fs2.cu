@@ -184,12 +184,77 @@ __global__ void __launch_bounds__(128) attn_softmax_kernel(float* __restrict__ S
     for (int j = tid; j < ldS; j += 128) s[j] = (j < L) ? s[j] / tot : 0.f;
 }
 
+// Same arithmetic, one warp per row with the row held in registers (one read + one write of S): rows of up to
+// 32 * 4 * NV keys.  8 rows per block.
+template <int NV>
+__global__ void __launch_bounds__(256) attn_softmax_warp_kernel(float* __restrict__ S, int nh, int Lq, int L, int ldS,
+                                                                const uint8_t* __restrict__ key_mask, int mask_ld,
+                                                                float temperature, long long rows) {
+    const long long rowid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (rowid >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int b = (int)(rowid / Lq) / nh;
+    float4* s4 = reinterpret_cast<float4*>(S + rowid * ldS);
+    const uint8_t* km = key_mask ? key_mask + (long long)b * mask_ld : nullptr;
+    const int n4 = ldS >> 2;
+    float v[NV][4];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < n4) t = s4[idx];
+        const float in[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = idx * 4 + e;
+            float x = -INFINITY;
+            if (j < L && !(km && km[j])) x = in[e] / temperature;
+            v[i][e] = x;
+            m = fmaxf(m, x);
+        }
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[i][e] = expf(v[i][e] - m);
+            sum += v[i][e];
+        }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < n4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = (idx * 4 + e < L) ? v[i][e] / sum : 0.f;
+            s4[idx] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 void attn_softmax(float* S, int nz, int nh, int Lq, int L, int ldS, const uint8_t* key_mask, int mask_ld,
                   float temperature, cudaStream_t st) {
     const long long rows = (long long)nz * Lq;
     if (rows == 0) return;
     ZVX_REQUIRE(rows < 2147483647LL, "attn_softmax: too many rows");
-    attn_softmax_kernel<<<(unsigned)rows, 128, 0, st>>>(S, nh, Lq, L, ldS, key_mask, mask_ld, temperature);
+    const int n4 = ldS / 4;
+    const bool vec = (ldS % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && n4 <= 32 * 16;
+    if (vec) {
+        const unsigned grid = (unsigned)((rows + 7) / 8);
+#define ZVX_SOFTMAX(NV) attn_softmax_warp_kernel<NV><<<grid, 256, 0, st>>>(S, nh, Lq, L, ldS, key_mask, mask_ld, temperature, rows)
+        if (n4 <= 32) ZVX_SOFTMAX(1);
+        else if (n4 <= 64) ZVX_SOFTMAX(2);
+        else if (n4 <= 128) ZVX_SOFTMAX(4);
+        else if (n4 <= 256) ZVX_SOFTMAX(8);
+        else ZVX_SOFTMAX(16);
+#undef ZVX_SOFTMAX
+    } else {
+        attn_softmax_kernel<<<(unsigned)rows, 128, 0, st>>>(S, nh, Lq, L, ldS, key_mask, mask_ld, temperature);
+    }
     ZVX_POST_LAUNCH();
 }
 

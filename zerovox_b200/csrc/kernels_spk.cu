@@ -36,42 +36,57 @@ void instance_norm_time(const float* ref_mel, int B, int T, int n_mels, float* o
     ZVX_POST_LAUNCH();
 }
 
-// stem Conv2d(1 -> C, 3x3, pad 1) + bias -> ReLU -> BN (ResNetSE34V2.py:184-186).  One thread per output
-// pixel-channel; C is the fastest index so stores are coalesced and the 9 input taps are warp-broadcast.
-__global__ void stem_conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                    const float* __restrict__ bias, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, int H, int W, int C, long long total,
-                                    float* __restrict__ out) {
+// stem Conv2d(1 -> C, 3x3, pad 1) + bias -> ReLU -> BN (ResNetSE34V2.py:184-186).  Lane = output channel (coalesced
+// 128-byte stores per pixel); each thread produces XT consecutive pixels of one row so that its 9 weights stay in
+// registers and the 3 x (XT+2) input window is loaded once (warp-broadcast loads).
+constexpr int STEM_XT = 8;
+__global__ void __launch_bounds__(256) stem_conv3x3_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, int H, int W, int C, int xtiles,
+                                                           long long total, float* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = (int)(i % C);
     long long p = i / C;
-    const int x = (int)(p % W);
-    p /= W;
+    const int xt = (int)(p % xtiles);
+    p /= xtiles;
     const int y = (int)(p % H);
     const int b = (int)(p / H);
+    const int x0 = xt * STEM_XT;
     const float* ib = in + (long long)b * H * W;
-    float acc = 0.f;
+    float wv[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) wv[j] = __ldg(w + j * C + c);
+    float win[3][STEM_XT + 2];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
         const int yi = y + dy - 1;
-        if (yi < 0 || yi >= H) continue;
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const int xi = x + dx - 1;
-            if (xi < 0 || xi >= W) continue;
-            acc = fmaf(__ldg(ib + (long long)yi * W + xi), __ldg(w + (dy * 3 + dx) * C + c), acc);
+        for (int dx = 0; dx < STEM_XT + 2; ++dx) {
+            const int xi = x0 + dx - 1;
+            win[dy][dx] = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? __ldg(ib + (long long)yi * W + xi) : 0.f;
         }
     }
-    float v = fmaxf(acc + __ldg(bias + c), 0.f);
-    out[i] = fmaf(v, __ldg(scale + c), __ldg(shift + c));
+    const float bc = __ldg(bias + c), sc = __ldg(scale + c), sh = __ldg(shift + c);
+    float* op = out + (((long long)b * H + y) * W + x0) * C + c;
+#pragma unroll
+    for (int px = 0; px < STEM_XT; ++px) {
+        if (x0 + px >= W) break;
+        float acc = 0.f;   // same tap order as before: dy-major, dx-minor
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) acc = fmaf(win[dy][px + dx], wv[dy * 3 + dx], acc);
+        op[(long long)px * C] = fmaf(fmaxf(acc + bc, 0.f), sc, sh);
+    }
 }
 
 void stem_conv3x3(const float* in, const float* w, const float* bias, const float* scale, const float* shift, int B,
                   int H, int W, int C, float* out, cudaStream_t st) {
-    const long long total = (long long)B * H * W * C;
+    const int xtiles = cdiv(W, STEM_XT);
+    const long long total = (long long)B * H * xtiles * C;
     if (total == 0) return;
-    stem_conv3x3_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, w, bias, scale, shift, H, W, C, total, out);
+    stem_conv3x3_kernel<<<cdiv(total, 256), 256, 0, st>>>(in, w, bias, scale, shift, H, W, C, xtiles, total, out);
     ZVX_POST_LAUNCH();
 }
 
