@@ -1,0 +1,92 @@
+// Micro-benchmark: cycles per tcgen05.mma.kind::tf32 (M = 128, K = 8, both operands from shared memory) as a function
+// of N and of the operand layout.  One CTA per SM, one issuing thread, `reps` back-to-back MMAs into one accumulator.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench_mma tools/ubench_mma.cu && ./ubench_mma
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include "../zerovox_b200/csrc/tc_ptx.cuh"
+
+using namespace zvx;
+
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo16) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo16 & 0x3FFFu) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// mode 0: no-swizzle, every MMA reads a different row offset of A (the vocoder pattern); 1: 128B swizzle (GEMM pattern)
+__global__ void __launch_bounds__(128) bench(int N, int mode, int reps, int same_a, long long* out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sb = smem_u32(smem);
+    const uint32_t bar = sb + 200 * 1024, slot = bar + 8;
+    volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + 200 * 1024 + 8);
+    for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.f;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc(slot, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot_ptr;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (threadIdx.x == 0) {
+        const uint32_t sA = sb, sW = sb + 128 * 1024;
+        const int Rp = 1024;
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            uint64_t da, db;
+            if (mode == 0) {
+                const int row = same_a ? 0 : (r * 5) % 512;
+                da = desc_nosw(sA + row * 16, Rp);
+                db = desc_nosw(sW, N);
+            } else {
+                da = desc_sw128(sA + (same_a ? 0 : ((r & 3) * 16384))) + (uint64_t)(2 * (r & 3));
+                db = desc_sw128(sW) + (uint64_t)(2 * (r & 3));
+            }
+            umma_tf32(tmem, da, db, idesc, r ? 1u : 0u);
+        }
+        umma_commit(bar);
+        mbar_wait(bar, 0);
+        long long t1 = clock64();
+        if (blockIdx.x == 0) out[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+int main() {
+    long long* d;
+    cudaMalloc(&d, 8);
+    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const int reps = 4096;
+    printf("tcgen05.mma kind::tf32 M=128 K=8, SS operands, %d back-to-back MMAs, cycles per MMA (148 CTAs running)\n", reps);
+    for (int mode = 0; mode < 2; ++mode)
+        for (int same = 0; same < 2; ++same)
+            for (int N : {16, 32, 64, 128, 176, 256}) {
+                long long best = 1LL << 60;
+                for (int it = 0; it < 3; ++it) {
+                    bench<<<148, 128, 202 * 1024 + 1024>>>(N, mode, reps, same, d);
+                    long long h = 0;
+                    cudaError_t e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+                    if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+                    if (h < best) best = h;
+                }
+                printf("layout=%s a=%s N=%3d : %.1f cycles/MMA  (math floor N/2 = %d)\n", mode ? "sw128" : "nosw", same ? "same" : "moving",
+                       N, (double)best / reps, N / 2);
+            }
+    return 0;
+}
