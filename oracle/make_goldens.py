@@ -16,6 +16,7 @@ Usage:  python oracle/make_goldens.py   (from the repo root)
 """
 from __future__ import annotations
 
+import dataclasses
 import os
 import sys
 import types
@@ -114,6 +115,9 @@ CASES = [
     ("tiny_longform", zo.ZeroVoxConfig.tiny(), 3, 1, 30, 16, False, True, (2, 4)),  # T>max_txt_len, L>max_mel_len
     ("medium_forced", zo.ZeroVoxConfig(), 0, 2, 12, 48, True, True, (2, 7)),
     ("medium_predicted", zo.ZeroVoxConfig(), 0, 2, 10, 40, False, False, (2, 7)),
+    # decoder_kind="styletts" (configs/tts_medium_styledec.yaml: the shipped default models, BASELINE config 1)
+    ("tiny_styledec", dataclasses.replace(zo.ZeroVoxConfig.tiny(), decoder_kind="styletts"), 4, 3, 10, 24, True, True, (1, 5)),
+    ("medium_styledec", dataclasses.replace(zo.ZeroVoxConfig(), decoder_kind="styletts"), 0, 2, 11, 40, True, False, (2, 7)),
 ]
 
 

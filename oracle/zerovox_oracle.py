@@ -19,6 +19,8 @@ the restatement against those fixtures on any machine.
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -315,6 +317,65 @@ def hifigan_generator(h: HifiGanConfig, w: dict, mel: torch.Tensor, prefix: str 
     return torch.tanh(x)
 
 
+
+# ----------------------------------------------------------------------------
+# StyleTTS mel decoder (alternative decoder_kind, the shipped default models)
+# ----------------------------------------------------------------------------
+def _wn(w, p):
+    """torch.nn.utils.weight_norm with dim=0: w = g * v / ||v|| per output channel (styletts.py:28-34)."""
+    v, g = w[f"{p}.weight_v"], w[f"{p}.weight_g"]
+    return g * v / v.flatten(1).norm(dim=1).view(-1, 1, 1)
+
+
+def _wn_conv(w, p, x, padding):
+    return F.conv1d(x, _wn(w, p), w.get(f"{p}.bias"), padding=padding)
+
+
+def _adain(w, p, x, s):
+    """AdaIN1d.forward, styletts.py:87-92."""
+    h = F.linear(s, w[f"{p}.fc.weight"], w[f"{p}.fc.bias"]).unsqueeze(-1)
+    gamma, beta = torch.chunk(h, 2, dim=1)
+    return (1 + gamma) * F.instance_norm(x, eps=1e-5) + beta
+
+
+def styletts_decoder(cfg, w, enc_seq, mask, spk_emb, prefix="_mel_decoder"):
+    """StyleTTSDecoder.forward, styletts.py:181-205 (ResBlk1d 55-69, AdainResBlk1d 124-139); dropout is identity in
+    eval, `mask` is ignored by the reference.  enc_seq [B,L,H], spk_emb [B,1,H] -> mel [B,L,n_mels]."""
+    d = prefix
+    x0 = enc_seq.transpose(1, 2)
+    s = spk_emb.squeeze(1)
+    x = x0
+    for i in range(2):   # encode: ResBlk1d(normalize=True, downsample='none')
+        p = f"{d}.encode.{i}"
+        sc = _wn_conv(w, f"{p}.conv1x1", x, 0) if f"{p}.conv1x1.weight_v" in w else x
+        r = F.instance_norm(x, weight=w[f"{p}.norm1.weight"], bias=w[f"{p}.norm1.bias"], eps=1e-5)
+        r = _wn_conv(w, f"{p}.conv1", F.leaky_relu(r, 0.2), 1)
+        r = F.instance_norm(r, weight=w[f"{p}.norm2.weight"], bias=w[f"{p}.norm2.bias"], eps=1e-5)
+        r = _wn_conv(w, f"{p}.conv2", F.leaky_relu(r, 0.2), 1)
+        x = (sc + r) / math.sqrt(2)
+    asr = F.instance_norm(_wn_conv(w, f"{d}.asr_res.0", x0, 0), weight=w[f"{d}.asr_res.1.weight"],
+                          bias=w[f"{d}.asr_res.1.bias"], eps=1e-5)
+    res = True
+    for i in range(5):   # decode: AdainResBlk1d; block 2 is the (non-)upsampling one after which the residual stops
+        p = f"{d}.decode.{i}"
+        if res:
+            x = torch.cat([x, asr], dim=1)
+        r = _wn_conv(w, f"{p}.conv1", F.leaky_relu(_adain(w, f"{p}.norm1", x, s), 0.2), 1)
+        r = _wn_conv(w, f"{p}.conv2", F.leaky_relu(_adain(w, f"{p}.norm2", r, s), 0.2), 1)
+        sc = _wn_conv(w, f"{p}.conv1x1", x, 0) if f"{p}.conv1x1.weight_v" in w else x
+        x = (r + sc) / math.sqrt(2)
+        if i == 2:
+            res = False
+    x = _wn_conv(w, f"{d}.to_out.0", x, 0)
+    return x.transpose(1, 2)
+
+
+def mel_decoder(cfg, w, features, dec_mask, spk_emb):
+    """Dispatch on decoder_kind (model.py:225-244)."""
+    if cfg.decoder_kind == "styletts":
+        return styletts_decoder(cfg, w, features, dec_mask, spk_emb)
+    return fs2_decoder(cfg, w, features, dec_mask, spk_emb)
+
 # ----------------------------------------------------------------------------
 # model container
 # ----------------------------------------------------------------------------
@@ -335,7 +396,7 @@ def zerovox_forward(cfg, w, x, force_duration=False, style_embed=None):
         dec_mask = ~(torch.arange(L).expand(len(pred["mel_len"]), L) < pred["mel_len"].unsqueeze(1))
     else:
         dec_mask = masks[:, :, 0]
-    mel = fs2_decoder(cfg, w, pred["features"], dec_mask, se)
+    mel = mel_decoder(cfg, w, pred["features"], dec_mask, se)
     if masks is not None and mel.size(0) > 1:  # model.py:283-285
         mel = mel.masked_fill(masks[:, :, : mel.shape[-1]], 0)
     mel_t = mel.transpose(1, 2)
@@ -352,7 +413,7 @@ def zerovox_inference_ex(cfg, w, x, style_embed, force_duration=False, min_mel_l
     pred = fs2_encoder(cfg, w, x, style_embed, force_duration=force_duration)
     L = pred["features"].shape[1]
     dec_mask = ~(torch.arange(L).expand(1, L) < pred["mel_len"].unsqueeze(1))
-    mel = fs2_decoder(cfg, w, pred["features"], dec_mask, style_embed)
+    mel = mel_decoder(cfg, w, pred["features"], dec_mask, style_embed)
     mel_len = int(pred["mel_len"][0])
     mel = mel[0]
     if mel_len < min_mel_len:

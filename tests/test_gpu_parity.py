@@ -16,6 +16,7 @@ Tolerances (stated per stage, fp32 unless marked):
     (a) check the engine's style vector against the reference's within the TF32 tolerance and (b) compare everything
     downstream with the oracle fed that same style vector (stage-wise parity, SURVEY.md §7 "hard parts").
 """
+import dataclasses
 import os
 
 import numpy as np
@@ -188,6 +189,28 @@ def test_decoder(tiny, medium, which, B, L, policy):
 
 
 @pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("which,B,L", [("tiny", 3, 35), ("tiny", 1, 7), ("medium", 2, 59), ("medium", 3, 130)])
+def test_styletts_decoder(which, B, L, policy):
+    """StyleTTSDecoder.forward (styletts.py:181-205) stand-alone: the mirror module with reference-keyed weight-norm
+    parameters against the oracle restatement (pinned to the reference module by the *_styledec goldens)."""
+    from zerovox_b200.tts.styletts import StyleTTSDecoder
+    cfg = golden_cfg(which + "_st")
+    w = zo.make_weights(cfg, seed=3)
+    g = torch.Generator().manual_seed(17)
+    feats = torch.randn(B, L, cfg.hidden, generator=g)
+    style = torch.nn.functional.normalize(torch.randn(B, 1, cfg.hidden, generator=g), dim=-1)
+    dec = StyleTTSDecoder(dim_in=cfg.hidden, style_dim=cfg.hidden, residual_dim=64, dim_out=cfg.n_mels)
+    dec.load_state_dict({k[len("_mel_decoder."):]: v for k, v in w.items() if k.startswith("_mel_decoder.")})
+    dec._ctx.tensor_core_policy = policy
+    dec = dec.eval().to(DEV)
+    with torch.no_grad():
+        ref = zo.styletts_decoder(cfg, w, feats, None, style)
+        got, none = dec(feats.to(DEV), None, style.to(DEV))
+    assert none is None and got.shape == ref.shape == (B, L, cfg.n_mels)
+    check("styletts mel", got, ref, **tol(policy, "mel"))
+
+
+@pytest.mark.parametrize("policy", [0, 1])
 @pytest.mark.parametrize("v,B,L", [("v2", 2, 9), ("v1", 1, 7), ("v3", 2, 5), ("v2", 3, 70), ("v2", 1, 1),
                                    ("v1", 2, 40), ("v3", 3, 33), ("v2", 1, 300)])
 def test_vocoder_variants(golden_dir, v, B, L, policy):
@@ -215,14 +238,19 @@ def test_vocoder_variants(golden_dir, v, B, L, policy):
 
 # ---------------------------------------------------------------------------------------------- end to end
 GOLDEN_CASES = {"tiny_forced": "tiny", "tiny_predicted": "tiny", "tiny_longform": "tiny", "medium_forced": "medium",
-                "medium_predicted": "medium"}
+                "medium_predicted": "medium", "tiny_styledec": "tiny_st", "medium_styledec": "medium_st"}
+
+
+def golden_cfg(kind):
+    cfg = zo.ZeroVoxConfig.tiny() if kind.startswith("tiny") else zo.ZeroVoxConfig()
+    return dataclasses.replace(cfg, decoder_kind="styletts") if kind.endswith("_st") else cfg
 
 
 @pytest.mark.parametrize("policy", [0, 1])
 @pytest.mark.parametrize("name", list(GOLDEN_CASES))
 def test_forward_against_reference_goldens(golden_dir, name, policy):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    cfg = zo.ZeroVoxConfig.tiny() if GOLDEN_CASES[name] == "tiny" else zo.ZeroVoxConfig()
+    cfg = golden_cfg(GOLDEN_CASES[name])
     w = zo.make_weights(cfg, seed=int(g["seed_w"]), dur_bias=float(g["dur_bias"]))
     x = zo.make_inputs(cfg, int(g["B"]), int(g["T"]), int(g["T_ref"]), seed=int(g["seed_x"]), ragged=bool(g["ragged"]),
                        dur_lo=int(g["dur_lo"]), dur_hi=int(g["dur_hi"]))

@@ -21,13 +21,20 @@ REFERENCE_CTOR = ["symbols", "meldec_model", "sampling_rate", "hop_length", "n_m
 
 def test_constructor_and_method_signatures_match_reference():
     assert list(inspect.signature(ZeroVox.__init__).parameters)[1:] == REFERENCE_CTOR
-    assert list(inspect.signature(ZeroVox.forward).parameters) == ["self", "x", "force_duration", "normalize_before"]
+    fwd = inspect.signature(ZeroVox.forward).parameters
+    positional = [n for n, p in fwd.items() if p.kind is not inspect.Parameter.KEYWORD_ONLY]
+    assert positional == ["self", "x", "force_duration", "normalize_before"]   # extensions are keyword-only
     assert list(inspect.signature(ZeroVox.inference_ex).parameters) == ["self", "x", "style_embed", "normalize_before",
                                                                          "force_duration"]
     assert list(inspect.signature(ZeroVox.inference).parameters) == ["self", "x", "style_embed", "normalize_before"]
 
 
-@pytest.mark.parametrize("cfgf", [zo.ZeroVoxConfig.tiny, zo.ZeroVoxConfig])
+def _styledec_tiny():
+    import dataclasses
+    return dataclasses.replace(zo.ZeroVoxConfig.tiny(), decoder_kind="styletts")
+
+
+@pytest.mark.parametrize("cfgf", [zo.ZeroVoxConfig.tiny, zo.ZeroVoxConfig, _styledec_tiny])
 def test_state_dict_keys_match_reference(cfgf):
     cfg = cfgf()
     w = zo.make_weights(cfg, seed=0)  # keyed like the reference state_dict (validated by oracle/make_goldens.py)

@@ -1,5 +1,6 @@
 """CPU: the oracle restatement against the committed golden fixtures (which oracle/make_goldens.py produced by
 running the reference's own modules — see that script) plus the invariants the reference asserts."""
+import dataclasses
 import os
 
 import numpy as np
@@ -14,6 +15,8 @@ CASES = {
     "tiny_longform": zo.ZeroVoxConfig.tiny,
     "medium_forced": zo.ZeroVoxConfig,
     "medium_predicted": zo.ZeroVoxConfig,
+    "tiny_styledec": lambda: dataclasses.replace(zo.ZeroVoxConfig.tiny(), decoder_kind="styletts"),
+    "medium_styledec": lambda: dataclasses.replace(zo.ZeroVoxConfig(), decoder_kind="styletts"),
 }
 
 
@@ -49,7 +52,7 @@ def test_forward_matches_reference_golden(golden_dir, name):
     np.testing.assert_allclose(st["style_embed"].norm(dim=-1).numpy(), 1.0, atol=1e-5)  # ResNetSE34V2.py:207-208
 
 
-@pytest.mark.parametrize("name", ["tiny_forced", "medium_predicted"])
+@pytest.mark.parametrize("name", ["tiny_forced", "medium_predicted", "tiny_styledec"])
 def test_inference_ex_matches_reference_golden(golden_dir, name):
     cfg, w, x, g = load_case(golden_dir, name)
     x1 = {k: v[:1] for k, v in x.items() if k != "phoneme_mask"}

@@ -70,7 +70,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // invalid rows contribute zero (the convolutions' zero padding).
 //
 // epilogue: v = acc + bias[n]; if relu_first v = max(v,0); if scale v = v*scale[n] + shift[n];
-//           if R v += R[m, n]; if relu_last v = max(v,0).
+//           if R v += R[m, n]; if relu_last v = max(v,0); v *= post_scale.
 // batching: z in [0, nz); zb = z / nzh, zh = z % nzh; pointer offsets zb*s?_b + zh*s?_h.
 // ---------------------------------------------------------------------------------------------
 enum RowMode { ROW_PLAIN = 0, ROW_CONV1D = 1, ROW_CONV2D = 2 };
@@ -90,6 +90,7 @@ struct GemmArgs {
     int Lout = 0, Lin = 0, stride = 1, pad = 0, dil = 1;
     int Ho = 0, Wo = 0, Hi = 0, Wi = 0, ksize = 1;
     int relu_first = 0, relu_last = 0;
+    float post_scale = 1.f;
     int b_kn = 0;
     int nz = 1, nzh = 1;
     long long sA_b = 0, sA_h = 0, sW_b = 0, sW_h = 0, sC_b = 0, sC_h = 0;

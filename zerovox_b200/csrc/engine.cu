@@ -97,6 +97,14 @@ struct SEBlock {
     float *wd = nullptr, *bnd_s = nullptr, *bnd_b = nullptr;  // downsample (nullable)
 };
 
+struct STConv { float* w = nullptr; float* b = nullptr; int cin = 0, cout = 0, k = 1; };   // weight-norm folded, tap-major
+struct STBlock {                  // ResBlk1d (affine InstanceNorm) or AdainResBlk1d (styletts.py:11-69, 95-139)
+    STConv c1, c2, sc;            // sc.w == nullptr: identity shortcut
+    float *n1_g = nullptr, *n1_b = nullptr, *n2_g = nullptr, *n2_b = nullptr;   // affine IN weight / bias
+    float *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr, *fc2_b = nullptr;   // AdaIN fc (2C x style)
+    int cin = 0, cout = 0, cmid = 0;   // cmid: channels between conv1 and conv2
+};
+
 struct HGConv { float* w = nullptr; float* b = nullptr; int cin = 0, cout = 0, k = 1, dil = 1; };
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline numbers).
@@ -382,8 +390,66 @@ class Engine {
         energy_emb = upload(W(va + ".energy_embedding.weight", {cfg.ve_n_bins, H}));
     }
 
+    // weight_norm(dim=0): w = g * v / ||v|| per output channel (styletts.py:28-34), then tap-major [k][N][C]
+    STConv pack_wn_conv(const std::string& p, int cout, int cin, int k, bool bias) {
+        const HostTensor& v = W(p + ".weight_v", {cout, cin, k});
+        const HostTensor& g = W(p + ".weight_g", {cout, 1, 1});
+        HostTensor t;
+        t.shape = v.shape;
+        t.data.resize(v.data.size());
+        const size_t per = (size_t)cin * k;
+        for (int n = 0; n < cout; ++n) {
+            double ss = 0.0;
+            for (size_t i = 0; i < per; ++i) ss += (double)v.data[n * per + i] * v.data[n * per + i];
+            const float scale = g.data[(size_t)n] / (float)std::sqrt(ss);
+            for (size_t i = 0; i < per; ++i) t.data[n * per + i] = v.data[n * per + i] * scale;
+        }
+        STConv c;
+        c.w = upload(tap_major(t));
+        c.b = bias ? upload(W(p + ".bias", {cout})) : nullptr;
+        c.cin = cin; c.cout = cout; c.k = k;
+        return c;
+    }
+
+    void pack_decoder_styletts() {
+        const std::string d = "_mel_decoder";
+        const int RD = 64, BN = 2 * H;   // residual_dim, bottleneck (model.py:238-242; styletts.py:148)
+        st_enc.clear();
+        st_dec.clear();
+        const int enc_dims[2][2] = {{H, BN}, {BN, BN}};
+        for (int i = 0; i < 2; ++i) {
+            const std::string p = d + ".encode." + std::to_string(i);
+            const int ci = enc_dims[i][0], co = enc_dims[i][1];
+            STBlock b;
+            b.cin = ci; b.cout = co; b.cmid = ci;
+            b.c1 = pack_wn_conv(p + ".conv1", ci, ci, 3, true);
+            b.c2 = pack_wn_conv(p + ".conv2", co, ci, 3, true);
+            b.n1_g = upload(W(p + ".norm1.weight", {ci})); b.n1_b = upload(W(p + ".norm1.bias", {ci}));
+            b.n2_g = upload(W(p + ".norm2.weight", {ci})); b.n2_b = upload(W(p + ".norm2.bias", {ci}));
+            if (ci != co) b.sc = pack_wn_conv(p + ".conv1x1", co, ci, 1, false);
+            st_enc.push_back(b);
+        }
+        const int dec_dims[5][2] = {{BN + RD, BN}, {BN + RD, BN}, {BN + RD, H}, {H, H}, {H, H}};
+        for (int i = 0; i < 5; ++i) {
+            const std::string p = d + ".decode." + std::to_string(i);
+            const int ci = dec_dims[i][0], co = dec_dims[i][1];
+            STBlock b;
+            b.cin = ci; b.cout = co; b.cmid = co;
+            b.c1 = pack_wn_conv(p + ".conv1", co, ci, 3, true);
+            b.c2 = pack_wn_conv(p + ".conv2", co, co, 3, true);
+            b.fc1_w = upload(W(p + ".norm1.fc.weight", {2 * ci, H})); b.fc1_b = upload(W(p + ".norm1.fc.bias", {2 * ci}));
+            b.fc2_w = upload(W(p + ".norm2.fc.weight", {2 * co, H})); b.fc2_b = upload(W(p + ".norm2.fc.bias", {2 * co}));
+            if (ci != co) b.sc = pack_wn_conv(p + ".conv1x1", co, ci, 1, false);
+            st_dec.push_back(b);
+        }
+        st_asr = pack_wn_conv(d + ".asr_res.0", RD, H, 1, true);
+        st_asr_g = upload(W(d + ".asr_res.1.weight", {RD}));
+        st_asr_b = upload(W(d + ".asr_res.1.bias", {RD}));
+        st_out = pack_wn_conv(d + ".to_out.0", cfg.n_mels, H, 1, true);
+    }
+
     void pack_decoder() {
-        ZVX_REQUIRE(cfg.decoder_kind == 0, "decoder_kind=styletts has no CUDA path yet (SURVEY.md 8f row 1)");
+        if (cfg.decoder_kind == 1) return pack_decoder_styletts();
         const std::string d = "_mel_decoder";
         dec_pos_param = upload(W(d + ".position_enc", {1, cfg.max_mel_len + 1, H}));
         std::vector<float> scln_stack;
@@ -931,6 +997,7 @@ class Engine {
         ZVX_REQUIRE(B >= 1 && L >= 1, "zvx_decode: empty batch");
         ZVX_REQUIRE(mask || mel_len, "zvx_decode: need mask or mel_len");
         ws.reset();
+        if (cfg.decoder_kind == 1) return decode_styletts(features, mask, mel_len, style, B, L, zero_padded_mel, mel_BLC, mel_BCL, st);
         const int tc = P_TF32;
         if (!mask) {
             uint8_t* m = ws.get<uint8_t>((long long)B * L);
@@ -953,6 +1020,81 @@ class Engine {
         }
         float* mel = mel_BLC ? mel_BLC : ws.get<float>((long long)B * L * cfg.n_mels);
         linear(x, B * L, H, mel_w, mel_b, cfg.n_mels, mel, tc, st);
+        if (mel_BCL || zero_padded_mel)
+            transpose_mel(mel, mask, zero_padded_mel, B, L, cfg.n_mels, mel_BCL, zero_padded_mel ? mel : nullptr, st);
+        return 0;
+    }
+
+    // Conv1d over channel-last [B, L, *] with explicit leading dimensions (StyleTTS blocks write into concat buffers).
+    void st_conv(const float* x, int ldx, const STConv& c, float* y, int ldy, int B, int L, const float* R, int ldr,
+                 float post_scale, cudaStream_t st) {
+        GemmArgs a;
+        a.A = x; a.lda = ldx; a.W = c.w; a.ldw = c.cin; a.w_tap_stride = (long long)c.cout * c.cin; a.C = y; a.ldc = ldy;
+        a.bias = c.b; a.M = B * L; a.N = c.cout; a.K = c.cin; a.taps = c.k; a.R = R; a.ldr = ldr; a.post_scale = post_scale;
+        if (c.k > 1) { a.mode = ROW_CONV1D; a.Lout = L; a.Lin = L; a.stride = 1; a.pad = (c.k - 1) / 2; a.dil = 1; }
+        gemm(a, P_TF32, st);
+    }
+
+    // StyleTTSDecoder.forward (styletts.py:181-205).  `mask` is ignored by the reference decoder (InstanceNorm statistics
+    // run over all L frames, padded ones included); it only drives the mel zero-fill of ZeroVox.forward (model.py:283-285).
+    int decode_styletts(const float* features, const uint8_t* mask, const int64_t* mel_len, const float* style, int B, int L,
+                        int zero_padded_mel, float* mel_BLC, float* mel_BCL, cudaStream_t st) {
+        const int RD = 64, BN = 2 * H, CC = BN + RD;
+        const long long rows = (long long)B * L;
+        const float inv_sqrt2 = (float)(1.0 / std::sqrt(2.0));
+        if (!mask && (mel_BCL || zero_padded_mel)) {
+            uint8_t* m = ws.get<uint8_t>(rows);
+            mask_from_lengths(mel_len, B, L, m, st);
+            mask = m;
+        }
+        float* catA = ws.get<float>(rows * CC);   // [x | asr_res] concat buffers (ld = CC), ping-pong
+        float* catB = ws.get<float>(rows * CC);
+        float* t1 = ws.get<float>(rows * CC);     // normalised + activated conv operand
+        float* t2 = ws.get<float>(rows * BN);     // conv1 output
+        float* scb = ws.get<float>(rows * BN);    // learned shortcut
+        float* mean = ws.get<float>((long long)B * CC);
+        float* rstd = ws.get<float>((long long)B * CC);
+        float* hbuf = ws.get<float>((long long)B * 2 * CC);
+        float* xa = ws.get<float>(rows * H);
+        float* xb = ws.get<float>(rows * H);
+
+        auto block = [&](const STBlock& bl, const float* x, int ldx, float* y, int ldy, bool adain) {
+            auto norm_act = [&](const float* src, int lds, int C, const float* g, const float* b, const float* fw, const float* fb) {
+                instnorm_stats(src, B, L, C, lds, 1e-5f, mean, rstd, st);
+                if (adain) {
+                    linear(style, B, H, fw, fb, 2 * C, hbuf, P_EXACT, st);
+                    instnorm_apply(src, lds, mean, rstd, hbuf, hbuf + C, 2 * C, 1.f, 0.2f, B, L, C, t1, C, st);
+                } else {
+                    instnorm_apply(src, lds, mean, rstd, g, b, 0, 0.f, 0.2f, B, L, C, t1, C, st);
+                }
+            };
+            norm_act(x, ldx, bl.cin, bl.n1_g, bl.n1_b, bl.fc1_w, bl.fc1_b);
+            st_conv(t1, bl.cin, bl.c1, t2, bl.cmid, B, L, nullptr, 0, 1.f, st);
+            norm_act(t2, bl.cmid, bl.cmid, bl.n2_g, bl.n2_b, bl.fc2_w, bl.fc2_b);
+            const float* R = x;
+            int ldr = ldx;
+            if (bl.sc.w) {
+                st_conv(x, ldx, bl.sc, scb, bl.cout, B, L, nullptr, 0, 1.f, st);
+                R = scb; ldr = bl.cout;
+            }
+            st_conv(t1, bl.cmid, bl.c2, y, ldy, B, L, R, ldr, inv_sqrt2, st);   // (residual + shortcut) / sqrt(2)
+        };
+
+        block(st_enc[0], features, H, catA, CC, false);
+        block(st_enc[1], catA, CC, catB, CC, false);
+        {   // asr_res = InstanceNorm_affine(conv1x1(enc_seq)) -> tail columns of both concat buffers
+            st_conv(features, H, st_asr, t2, RD, B, L, nullptr, 0, 1.f, st);
+            instnorm_stats(t2, B, L, RD, RD, 1e-5f, mean, rstd, st);
+            instnorm_apply(t2, RD, mean, rstd, st_asr_g, st_asr_b, 0, 0.f, 1.f, B, L, RD, catA + BN, CC, st);
+            instnorm_apply(t2, RD, mean, rstd, st_asr_g, st_asr_b, 0, 0.f, 1.f, B, L, RD, catB + BN, CC, st);
+        }
+        block(st_dec[0], catB, CC, catA, CC, true);
+        block(st_dec[1], catA, CC, catB, CC, true);
+        block(st_dec[2], catB, CC, xa, H, true);      // the "upsample" block: the residual concat stops after it
+        block(st_dec[3], xa, H, xb, H, true);
+        block(st_dec[4], xb, H, xa, H, true);
+        float* mel = mel_BLC ? mel_BLC : ws.get<float>(rows * cfg.n_mels);
+        st_conv(xa, H, st_out, mel, cfg.n_mels, B, L, nullptr, 0, 1.f, st);
         if (mel_BCL || zero_padded_mel)
             transpose_mel(mel, mask, zero_padded_mel, B, L, cfg.n_mels, mel_BCL, zero_padded_mel ? mel : nullptr, st);
         return 0;
@@ -1176,6 +1318,9 @@ class Engine {
     int spk_D = 0;
     float *att_w0 = nullptr, *att_b0 = nullptr, *att_bn_s = nullptr, *att_bn_b = nullptr, *att_w3 = nullptr,
           *att_b3 = nullptr, *spk_fc_w = nullptr, *spk_fc_b = nullptr;
+    std::vector<STBlock> st_enc, st_dec;
+    STConv st_asr, st_out;
+    float *st_asr_g = nullptr, *st_asr_b = nullptr;
     HGConv hg_pre, hg_post;
     std::vector<HGConv> hg_ups, hg_c1, hg_c2;
     bool hg_tc_ok = false;

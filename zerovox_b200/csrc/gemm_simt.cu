@@ -231,6 +231,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmArgs a, const i
 #pragma unroll
                     for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] *= a.post_scale;
                 *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
 #pragma unroll
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmArgs a, const i
                         float x = v[j];
                         if (rp) x += rp[j];
                         if (a.relu_last) x = fmaxf(x, 0.f);
-                        cp[j] = x;
+                        cp[j] = x * a.post_scale;
                     }
                 }
             }
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmArgs a) {
         if (a.scale) x = fmaf(x, __ldg(a.scale + n), __ldg(a.shift + n));
         if (a.R) x += a.R[(long long)m * a.ldr + n];
         if (a.relu_last) x = fmaxf(x, 0.f);
-        a.C[(long long)m * a.ldc + n] = x;
+        a.C[(long long)m * a.ldc + n] = x * a.post_scale;
     }
 }
 

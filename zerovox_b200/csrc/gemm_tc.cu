@@ -525,6 +525,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     ZVX_REQUIRE(gemm_tc_supported(a), "gemm_tc: operand layout not supported by the TMA path");
     const bool split = a.A_lo != nullptr || a.W_lo != nullptr;
     ZVX_REQUIRE(!split || (a.A_lo && a.W_lo && aligned16(a.A_lo) && aligned16(a.W_lo)), "gemm_tc: split mode needs both lo operands");
+    ZVX_REQUIRE(!split || (!a.acc_mode && a.act_slope == 1.f && !a.C2), "gemm_tc: split mode has the plain epilogue only");
     TcParams p{};
     // tile shape: TH x TW = 128 positions, least padding first, wider rows on ties
     long long best = -1;
@@ -608,7 +609,8 @@ bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* o) {
     a.A = g.A; a.K = g.K; a.W = g.W; a.N = g.N; a.w_sn = g.ldw; a.Z1 = g.taps; a.w_s1 = g.w_tap_stride; a.Z2 = 1;
     a.C = g.C; a.R = g.R; a.bias = g.bias; a.scale = g.scale; a.shift = g.shift;
     a.relu_first = g.relu_first; a.relu_last = g.relu_last; a.c_sn = 1;
-    if (g.R && g.ldr != g.ldc) return false;
+    if (g.post_scale != 1.f) { a.acc_mode = 1; a.acc_init = 1; a.acc_scale = g.post_scale; }
+    if (g.R) a.r_sx = g.ldr;
     if (g.mode == ROW_PLAIN) {
         if (g.taps != 1) return false;
         a.Wi = a.Wo = g.M; a.a_sx = g.lda; a.c_sx = g.ldc;
@@ -616,7 +618,7 @@ bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* o) {
         if (g.Lin != g.Lout || g.M % g.Lout != 0 || g.stride != 1) return false;
         a.Wi = a.Wo = g.Lout; a.Hi = a.Ho = g.M / g.Lout;
         a.a_sx = g.lda; a.a_sy = (long long)g.Lin * g.lda;
-        a.c_sx = g.ldc; a.c_sy = (long long)g.Lout * g.ldc;
+        a.c_sx = g.ldc; a.c_sy = (long long)g.Lout * g.ldc; a.r_sy = (long long)g.Lout * g.ldr;
         a.ksx = g.taps; a.ksy = 1; a.dil = g.dil; a.pad_x = g.pad; a.pad_y = 0;
     } else {
         if (g.taps != g.ksize * g.ksize || g.stride < 1 || g.stride > 2) return false;
@@ -624,6 +626,7 @@ bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* o) {
         a.Wi = g.Wi; a.Wo = g.Wo; a.Hi = g.Hi; a.Ho = g.Ho; a.IMG = g.M / (g.Ho * g.Wo); a.stride = g.stride;
         a.a_sx = g.lda; a.a_sy = (long long)g.Wi * g.lda; a.a_simg = (long long)g.Hi * g.Wi * g.lda;
         a.c_sx = g.ldc; a.c_sy = (long long)g.Wo * g.ldc; a.c_simg = (long long)g.Ho * g.Wo * g.ldc;
+        a.r_sy = (long long)g.Wo * g.ldr; a.r_simg = (long long)g.Ho * g.Wo * g.ldr;
         a.ksx = a.ksy = g.ksize; a.dil = 1; a.pad_x = a.pad_y = g.pad;
     }
     *o = a;

@@ -64,6 +64,13 @@ void mask_from_lengths(const int64_t* mel_len, int B, int L, uint8_t* mask, cuda
 void transpose_mel(const float* mel_BLC, const uint8_t* mask, int zero_masked, int B, int L, int C, float* mel_BCL,
                    float* mel_BLC_inplace /*nullable*/, cudaStream_t st);
 
+// ---- StyleTTS decoder (styletts.py): InstanceNorm1d over time, channel-last [B, L, ld] ---------------
+void instnorm_stats(const float* x, int B, int L, int C, int ld, float eps, float* mean, float* rstd, cudaStream_t st);
+// y = lrelu( (g_add + g[b*g_bs + c]) * (x - mean) * rstd + bt[b*g_bs + c], slope )   (affine IN: g_bs = 0, g_add = 0;
+// AdaIN: g = h, bt = h + C, g_bs = 2C, g_add = 1)
+void instnorm_apply(const float* x, int ld, const float* mean, const float* rstd, const float* g, const float* bt,
+                    int g_bs, float g_add, float slope, int B, int L, int C, float* y, int ldy, cudaStream_t st);
+
 // ---- HiFi-GAN (kernels_hifigan.cu), channel-first [B, C, T] ------------------------------------------
 struct Conv1dArgs {
     const float* x = nullptr;   // [B, Cin, T]

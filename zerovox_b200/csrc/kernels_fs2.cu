@@ -471,3 +471,94 @@ void transpose_mel(const float* mel_BLC, const uint8_t* mask, int zero_masked, i
 }
 
 }  // namespace zvx
+
+namespace zvx {
+
+// ------------------------------------------------------------------------------------------------
+// StyleTTS decoder helpers (styletts.py): InstanceNorm1d over time on channel-last activations
+// ------------------------------------------------------------------------------------------------
+// mean / 1/sqrt(biased var + eps) per (utterance, channel) over the L rows of x[b] ([L, ld], channels [0, C)).
+// One block per (32-channel group, utterance): 32 channels x 8 row lanes; two passes (mean, then centred squares) like
+// ATen's instance_norm.
+__global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __restrict__ x, int L, int C, int ld,
+                                                             float eps, float* __restrict__ mean, float* __restrict__ rstd) {
+    __shared__ float red[8][33];
+    __shared__ float mu_s[32];
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const bool ok = c < C;
+    const float* p = x + (long long)b * L * ld + c;
+    float s = 0.f;
+    if (ok)
+        for (int l = threadIdx.y; l < L; l += 8) s += p[(long long)l * ld];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        mu_s[threadIdx.x] = t / (float)L;
+    }
+    __syncthreads();
+    const float mu = mu_s[threadIdx.x];
+    float q = 0.f;
+    if (ok)
+        for (int l = threadIdx.y; l < L; l += 8) {
+            const float d = p[(long long)l * ld] - mu;
+            q = fmaf(d, d, q);
+        }
+    __syncthreads();
+    red[threadIdx.y][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y == 0 && ok) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        mean[(long long)b * C + c] = mu;
+        rstd[(long long)b * C + c] = rsqrtf(t / (float)L + eps);
+    }
+}
+
+void instnorm_stats(const float* x, int B, int L, int C, int ld, float eps, float* mean, float* rstd, cudaStream_t st) {
+    if (B == 0 || C == 0) return;
+    instnorm_stats_kernel<<<dim3(cdiv(C, 32), B), dim3(32, 8), 0, st>>>(x, L, C, ld, eps, mean, rstd);
+    ZVX_POST_LAUNCH();
+}
+
+// y[b,l,c] = act( (x - mean) * rstd * gamma + beta ),  act = leaky-ReLU(slope) (slope 1 = identity)
+//   affine InstanceNorm1d : gamma = g[c], beta = bt[c]                        (g_bs = 0)
+//   AdaIN1d               : gamma = 1 + h[b, c], beta = h[b, C + c]           (styletts.py:87-92; g = h, bt = h + C, g_bs = 2C)
+__global__ void instnorm_apply_kernel(const float4* __restrict__ x, int ld4, const float* __restrict__ mean,
+                                      const float* __restrict__ rstd, const float* __restrict__ g,
+                                      const float* __restrict__ bt, int g_bs, float g_add, float slope, int L, int C4,
+                                      long long total, float4* __restrict__ y, int ldy4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c4 = (int)(i % C4);
+    const long long row = i / C4;
+    const int b = (int)(row / L);
+    const float4 v = __ldg(x + row * ld4 + c4);
+    const float4 mu = __ldg(reinterpret_cast<const float4*>(mean + (long long)b * C4 * 4) + c4);
+    const float4 rs = __ldg(reinterpret_cast<const float4*>(rstd + (long long)b * C4 * 4) + c4);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(g + (long long)b * g_bs) + c4);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(bt + (long long)b * g_bs) + c4);
+    auto f = [&](float xv, float m, float r, float gg, float bb) {
+        const float o = (g_add + gg) * ((xv - m) * r) + bb;
+        return o > 0.f ? o : o * slope;
+    };
+    y[row * ldy4 + c4] = make_float4(f(v.x, mu.x, rs.x, ga.x, be.x), f(v.y, mu.y, rs.y, ga.y, be.y),
+                                     f(v.z, mu.z, rs.z, ga.z, be.z), f(v.w, mu.w, rs.w, ga.w, be.w));
+}
+
+void instnorm_apply(const float* x, int ld, const float* mean, const float* rstd, const float* g, const float* bt,
+                    int g_bs, float g_add, float slope, int B, int L, int C, float* y, int ldy, cudaStream_t st) {
+    ZVX_REQUIRE(C % 4 == 0 && ld % 4 == 0 && ldy % 4 == 0 && g_bs % 4 == 0, "instnorm_apply: sizes must be multiples of 4");
+    const long long total = (long long)B * L * (C / 4);
+    if (total == 0) return;
+    instnorm_apply_kernel<<<cdiv(total, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), ld / 4, mean, rstd, g, bt,
+                                                             g_bs, g_add, slope, L, C / 4, total,
+                                                             reinterpret_cast<float4*>(y), ldy / 4);
+    ZVX_POST_LAUNCH();
+}
+
+}  // namespace zvx

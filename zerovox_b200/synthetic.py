@@ -219,6 +219,42 @@ def make_weights(cfg: ZeroVoxConfig, seed: int = 0, dur_bias: float | None = Non
         fft_stack(d, cfg.dec_layers, scln=cfg.dec_scln)
         w[f"{d}.mel_linear.weight"] = _fan_in_normal(g, (cfg.n_mels, H), H, 2.0)
         w[f"{d}.mel_linear.bias"] = 0.5 * torch.randn((cfg.n_mels,), generator=g)
+    elif cfg.decoder_kind == "styletts":
+        # StyleTTSDecoder(dim_in=H, style_dim=H, residual_dim=64, dim_out=n_mels) (model.py:238-242; styletts.py:144-179);
+        # conv weights stay in weight-norm form (weight_g / weight_v: styletts.py never removes it)
+        RD, BN_ = 64, 2 * H
+
+        def wn_conv(prefix, cout, cin, k, bias=True, gain=1.0):
+            w[f"{prefix}.weight_v"] = _fan_in_normal(g, (cout, cin, k), cin * k, 1.0)
+            w[f"{prefix}.weight_g"] = gain * (0.8 + 0.4 * torch.rand((cout, 1, 1), generator=g))
+            if bias:
+                w[f"{prefix}.bias"] = 0.1 * torch.randn((cout,), generator=g)
+
+        def inorm(prefix, c):
+            w[f"{prefix}.weight"] = 1.0 + 0.1 * torch.randn((c,), generator=g)
+            w[f"{prefix}.bias"] = 0.1 * torch.randn((c,), generator=g)
+
+        for i, (ci, co) in enumerate(((H, BN_), (BN_, BN_))):           # encode: ResBlk1d(normalize=True)
+            p = f"{d}.encode.{i}"
+            wn_conv(f"{p}.conv1", ci, ci, 3, gain=1.4)
+            wn_conv(f"{p}.conv2", co, ci, 3, gain=1.4)
+            inorm(f"{p}.norm1", ci)
+            inorm(f"{p}.norm2", ci)
+            if ci != co:
+                wn_conv(f"{p}.conv1x1", co, ci, 1, bias=False)
+        dims = ((BN_ + RD, BN_), (BN_ + RD, BN_), (BN_ + RD, H), (H, H), (H, H))
+        for i, (ci, co) in enumerate(dims):                              # decode: AdainResBlk1d
+            p = f"{d}.decode.{i}"
+            wn_conv(f"{p}.conv1", co, ci, 3, gain=1.4)
+            wn_conv(f"{p}.conv2", co, co, 3, gain=1.4)
+            for nm, c in (("norm1", ci), ("norm2", co)):
+                w[f"{p}.{nm}.fc.weight"] = 0.5 * torch.randn((2 * c, H), generator=g)   # |style| = 1 -> O(0.5) gamma / beta
+                w[f"{p}.{nm}.fc.bias"] = 0.1 * torch.randn((2 * c,), generator=g)
+            if ci != co:
+                wn_conv(f"{p}.conv1x1", co, ci, 1, bias=False)
+        wn_conv(f"{d}.asr_res.0", RD, H, 1)
+        inorm(f"{d}.asr_res.1", RD)
+        wn_conv(f"{d}.to_out.0", cfg.n_mels, H, 1, gain=2.0)
     else:
         raise NotImplementedError("oracle weights for decoder_kind=%r" % cfg.decoder_kind)
 

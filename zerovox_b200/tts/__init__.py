@@ -4,3 +4,4 @@ from .model import ZeroVox, get_meldec, AttrDict  # noqa: F401
 from .fs2 import FS2Encoder, FS2Decoder  # noqa: F401
 from .hifigan import Generator  # noqa: F401
 from .ResNetSE34V2 import ResNetSE34V2  # noqa: F401
+from .styletts import StyleTTSDecoder  # noqa: F401

@@ -19,6 +19,7 @@ import torch.nn as nn
 from ._context import EngineContext
 from .fs2 import FS2Decoder, FS2Encoder
 from .hifigan import Generator
+from .styletts import StyleTTSDecoder
 from .ResNetSE34V2 import ResNetSE34V2
 from .symbols import Symbols
 
@@ -99,7 +100,7 @@ class ZeroVox(nn.Module):
                 dec_conv_kernel_size=decoder_conv_kernel_size, dec_dropout=decoder_dropout, dec_scln=decoder_scln,
                 n_mel_channels=n_mels, spk_emb_size=emb_size)
         elif decoder_kind == "styletts":
-            raise NotImplementedError("zerovox_b200: decoder_kind='styletts' has no CUDA path yet (SURVEY.md 8f)")
+            self._mel_decoder = StyleTTSDecoder(dim_in=emb_size, style_dim=emb_size, residual_dim=64, dim_out=n_mels)
         else:
             raise Exception(f"unknown decoder kind: '{decoder_kind}'")
         self._meldec = get_meldec(modelspec=meldec_model, verbose=verbose) if meldec_model else None
@@ -138,8 +139,8 @@ class ZeroVox(nn.Module):
         return model
 
     # forward -------------------------------------------------------------------------------------------
-    def forward(self, x, force_duration=False, normalize_before=True, pad_to=None):
-        """Batched eval forward (model.py:260-306).  ``pad_to`` (extension, used by zerovox_b200.parallel): an int or a
+    def forward(self, x, force_duration=False, normalize_before=True, *, pad_to=None):
+        """Batched eval forward (model.py:260-306).  ``pad_to`` (keyword-only extension, used by zerovox_b200.parallel): an int or a
         callable ``local_L_max -> L`` giving the frame count to pad the batch to (>= the batch's own maximum), so that a
         shard reproduces the tail behaviour of the unsharded batch.  Returns (wav [B, L_max*hop], mel [B, n_mels, L_max],
         mel_len int64 [B], log_duration [B, T]) — the tuple utils/export_hifigan.py:109-151 consumes.  The
