@@ -121,6 +121,11 @@ int zvx_encode(zvx_handle* h, const int32_t* phoneme, const int32_t* puncts,
 int zvx_length_regulate(zvx_handle* h, const float* xprime, const int32_t* dur, int B, int T,
                         int L_max, float* features, int32_t* src_index, void* stream);
 
+/* The same gather restricted to the frames [frame0, frame0 + n_frames) (long-form inputs: the features of one chunk
+ * without materialising the whole sequence): features [B, n_frames, hidden], src_index [B, n_frames]. */
+int zvx_length_regulate_chunk(zvx_handle* h, const float* xprime, const int32_t* dur, int B, int T,
+                              int frame0, int n_frames, float* features, int32_t* src_index, void* stream);
+
 /* FS2Decoder.forward (fs2.py:281-315) + the mel masking of ZeroVox.forward (model.py:283-285).
  * features [B,L,hidden]; mask uint8 [B,L] (1 = padding) or NULL to derive it from mel_len
  * (model.py:269-273); style [B,hidden]; zero_padded_mel != 0 applies masked_fill(mask, 0) to the

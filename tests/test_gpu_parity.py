@@ -342,3 +342,78 @@ def test_launches_are_counted_and_native(tiny):
         model(dict(x), force_duration=True)
     assert eng.launch_count() - before > 50
     assert eng.workspace_bytes() > 0
+
+
+# ---------------------------------------------------------------------------------------------- long-form (config 5)
+def test_length_regulator_chunks_equal_full(medium):
+    """zvx_length_regulate_chunk: the frames [f0, f0+n) of the full gather, indices bit-exact."""
+    cfg = medium.cfg
+    g = torch.Generator().manual_seed(4)
+    B, T = 2, 300
+    x = torch.randn(B, T, cfg.hidden, generator=g).to(DEV)
+    dur = torch.randint(0, 9, (B, T), generator=g, dtype=torch.int32).to(DEV)
+    eng = medium.model(1)._shared_ctx.get(torch.device(DEV))
+    L = int(dur.sum(1).max())
+    full, idx = eng.length_regulate(x, dur, L, want_index=True)
+    for f0, n in ((0, 100), (100, 333), (433, L - 433), (L - 5, 40)):
+        part, pidx = eng.length_regulate(x, dur, n, want_index=True, frame0=f0)
+        m = min(n, L - f0)
+        assert torch.equal(part[:, :m], full[:, f0:f0 + m]) and torch.equal(pidx[:, :m], idx[:, f0:f0 + m])
+        if m < n:   # frames past every utterance's end: zero rows, index -1
+            assert float(part[:, m:].abs().max()) == 0.0 and bool((pidx[:, m:] == -1).all())
+
+
+@pytest.mark.parametrize("v", ["v1", "v2", "v3"])
+def test_vocoder_chunked_equals_full(v):
+    """Overlap-discard chunking with a 14-frame halo reproduces the unchunked waveform (receptive field < 14 frames)."""
+    h = {"v1": zo.HifiGanConfig.v1, "v2": zo.HifiGanConfig.v2, "v3": zo.HifiGanConfig.v3}[v]()
+    g = torch.Generator().manual_seed(5)
+    hw = zo.make_hifigan_weights(h, g)
+    mel = torch.randn((2, 80, 150), generator=g).to(DEV)
+    gen = build_generator(h, {"_meldec." + k: t for k, t in hw.items()}).to(DEV)
+    with torch.no_grad():
+        full = gen(mel)
+        for chunk in (37, 64):
+            part = gen.forward_chunked(mel, chunk_frames=chunk, halo_frames=14)
+            assert part.shape == full.shape
+            check(f"chunked({chunk}) vs full {v}", part, full, rtol=0.0, atol=2e-6)
+
+
+def test_longform_decoder_attention_chunks(medium, monkeypatch):
+    """L > max_mel_len (position table recomputed, fs2.py:287-294) with the attention score budget forced small so that
+    query rows are processed in several chunks: same mel as the oracle, and as the unchunked engine."""
+    import zerovox_b200.engine as engine_mod
+    cfg = medium.cfg
+    g = torch.Generator().manual_seed(6)
+    B, L = 1, 1900
+    feats = torch.randn(B, L, cfg.hidden, generator=g)
+    style = torch.nn.functional.normalize(torch.randn(B, 1, cfg.hidden, generator=g), dim=-1)
+    mask = torch.zeros(B, L, dtype=torch.bool)
+    with torch.no_grad():
+        ref = zo.fs2_decoder(cfg, medium.w, feats, mask, style)
+    eng = medium.model(1)._shared_ctx.get(torch.device(DEV))
+    full, _ = eng.decode(feats.to(DEV), style.to(DEV), mask=mask.to(DEV), want_bcl=False)
+    check("long-form mel vs oracle", full, ref, **TC_MEL)
+    monkeypatch.setenv("ZVX_SCORE_BYTES", str(2 * 2 * 500 * 1900 * 4))   # ~500 query rows per chunk
+    eng2 = engine_mod.Engine(eng.cfg, torch.device(DEV))
+    eng2.load_weights({k: v for k, v in medium.w.items() if k.startswith("_mel_decoder.")})
+    part, _ = eng2.decode(feats.to(DEV), style.to(DEV), mask=mask.to(DEV), want_bcl=False)
+    check("chunked attention vs unchunked", part, full, rtol=0.0, atol=1e-5)
+
+
+def test_longform_config5_properties(medium):
+    """BASELINE config 5 at full size: one 4096-phoneme utterance, forced durations U{2..10} (L ~ 24.5k frames > every
+    table), chunked vocoder.  Size-independent properties + the chunked vocoder against the unchunked one."""
+    cfg = medium.cfg
+    x = zo.make_inputs(cfg, 1, 4096, 64, seed=11)
+    model = medium.model(1)
+    with torch.no_grad():
+        style = model._spkemb(x["ref_mel"].to(DEV))
+        x1 = {k: v.to(DEV) for k, v in x.items() if k != "ref_mel"}
+        wav, mel_len, logd, mel = model.inference_ex(x1, style_embed=style, force_duration=True, vocoder_chunk_frames=512)
+        wav_full, mel_len2, _, _ = model.inference_ex(x1, style_embed=style, force_duration=True)
+    model._min_mel_len = 689   # inference_ex grows it to the longest utterance seen (model.py:331-335); restore for other tests
+    assert mel_len == mel_len2 == int(x["duration"].sum())                      # export_hifigan.py:125-128
+    assert wav.shape == (mel_len * cfg.hop_length,) and mel.shape == (cfg.n_mels, mel_len)
+    assert torch.isfinite(wav).all() and float(wav.abs().max()) <= 1.0
+    check("config5 chunked vs full vocoder", wav, wav_full, rtol=0.0, atol=2e-6)

@@ -24,8 +24,9 @@ def test_constructor_and_method_signatures_match_reference():
     fwd = inspect.signature(ZeroVox.forward).parameters
     positional = [n for n, p in fwd.items() if p.kind is not inspect.Parameter.KEYWORD_ONLY]
     assert positional == ["self", "x", "force_duration", "normalize_before"]   # extensions are keyword-only
-    assert list(inspect.signature(ZeroVox.inference_ex).parameters) == ["self", "x", "style_embed", "normalize_before",
-                                                                         "force_duration"]
+    iex = inspect.signature(ZeroVox.inference_ex).parameters
+    assert [n for n, p in iex.items() if p.kind is not inspect.Parameter.KEYWORD_ONLY] == [
+        "self", "x", "style_embed", "normalize_before", "force_duration"]
     assert list(inspect.signature(ZeroVox.inference).parameters) == ["self", "x", "style_embed", "normalize_before"]
 
 

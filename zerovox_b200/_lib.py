@@ -77,6 +77,7 @@ SYMBOLS = {
     "zvx_encode": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P,
                              C.POINTER(C.c_int), _P]),
     "zvx_length_regulate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "zvx_length_regulate_chunk": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "zvx_decode": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "zvx_vocode": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "zvx_debug_gemm": (C.c_int, [_P, C.POINTER(ZvxGemmDesc), C.c_int, _P]),

@@ -774,11 +774,12 @@ class Engine {
         static const int tc_mask = getenv("ZVX_TC_MASK") ? atoi(getenv("ZVX_TC_MASK")) : 15;   // bit0: tensor-core attention
         const bool split = (tc == P_EXACT);
         const float* wqkv_lo = split ? lo_of(ly.wqkv) : nullptr;
-        const bool tc_attn = tc_enabled(tc) && (tc_mask & 1) && (dk % 4 == 0) && rows >= 64 && Lq_max == L &&
+        const bool tc_attn = tc_enabled(tc) && (tc_mask & 1) && (dk % 4 == 0) && rows >= 64 &&
                              (!split || (wqkv_lo && sc.lo_qkv && lo_buf && rows * H <= lo_cap));
         if (tc_attn) {
             // tcgen05 path: [Q|K] row-major [rows, 2H]; V written transposed per utterance, Vt[b][c][t] (row pitch Lp),
-            // so that both attention contractions read K-major operands through TMA.
+            // so that both attention contractions read K-major operands through TMA.  Query rows are processed in
+            // chunks of Lq_max so that the score matrix stays inside the workspace budget (long-form inputs).
             const int Lp = (int)round_up(L, 4);
             float* qk = qkv;
             float* vt = qkv + rows * 2 * H;
@@ -793,24 +794,27 @@ class Engine {
             }
             gemm_tc_prof(v, st);
             if (split) tf32_split_lo(qkv, sc.lo_qkv, rows * 2 * H + (long long)B * H * Lp, st);
-            TcGemmArgs sq;   // S[b,h,q,j] = <Q[b,q,h,:], K[b,j,h,:]>
-            sq.A = qk; sq.K = dk; sq.Wi = sq.Wo = L; sq.Hi = sq.Ho = n_head; sq.IMG = B;
-            sq.a_sx = 2 * H; sq.a_sy = dk; sq.a_simg = (long long)L * 2 * H;
-            sq.W = qk + H; sq.N = L; sq.Z1 = n_head; sq.Z2 = B; sq.w_sn = 2 * H; sq.w_s1 = dk; sq.w_s2 = (long long)L * 2 * H;
-            sq.b_batched = 1;
-            sq.C = S; sq.c_simg = (long long)n_head * L * ldS; sq.c_sy = (long long)L * ldS; sq.c_sx = ldS; sq.c_sn = 1;
-            if (split) { sq.A_lo = sc.lo_qkv; sq.W_lo = sc.lo_qkv + H; }
-            gemm_tc_prof(sq, st);
-            attn_softmax(S, nz, n_head, L, L, ldS, mask, L, temperature, st);
-            if (split) tf32_split_lo(S, sc.lo_S, (long long)nz * L * ldS, st);
-            TcGemmArgs pv;   // att[b,q,h*dk + c] = sum_j P[b,h,q,j] * Vt[b, h*dk + c, j]
-            pv.A = S; pv.K = L; pv.Wi = pv.Wo = L; pv.Hi = pv.Ho = n_head; pv.IMG = B;
-            pv.a_sx = ldS; pv.a_sy = (long long)L * ldS; pv.a_simg = (long long)n_head * L * ldS;
-            pv.W = vt; pv.N = dk; pv.Z1 = n_head; pv.Z2 = B; pv.w_sn = Lp; pv.w_s1 = (long long)dk * Lp; pv.w_s2 = (long long)H * Lp;
-            pv.b_batched = 1;
-            pv.C = att; pv.c_simg = (long long)L * H; pv.c_sy = dk; pv.c_sx = H; pv.c_sn = 1;
-            if (split) { pv.A_lo = sc.lo_S; pv.W_lo = sc.lo_qkv + rows * 2 * H; }
-            gemm_tc_prof(pv, st);
+            for (int q0 = 0; q0 < L; q0 += Lq_max) {
+                const int Lq = std::min(Lq_max, L - q0);
+                TcGemmArgs sq;   // S[b,h,q,j] = <Q[b,q0+q,h,:], K[b,j,h,:]>
+                sq.A = qk + (long long)q0 * 2 * H; sq.K = dk; sq.Wi = sq.Wo = Lq; sq.Hi = sq.Ho = n_head; sq.IMG = B;
+                sq.a_sx = 2 * H; sq.a_sy = dk; sq.a_simg = (long long)L * 2 * H;
+                sq.W = qk + H; sq.N = L; sq.Z1 = n_head; sq.Z2 = B; sq.w_sn = 2 * H; sq.w_s1 = dk; sq.w_s2 = (long long)L * 2 * H;
+                sq.b_batched = 1;
+                sq.C = S; sq.c_simg = (long long)n_head * Lq * ldS; sq.c_sy = (long long)Lq * ldS; sq.c_sx = ldS; sq.c_sn = 1;
+                if (split) { sq.A_lo = sc.lo_qkv + (long long)q0 * 2 * H; sq.W_lo = sc.lo_qkv + H; }
+                gemm_tc_prof(sq, st);
+                attn_softmax(S, nz, n_head, Lq, L, ldS, mask, L, temperature, st);
+                if (split) tf32_split_lo(S, sc.lo_S, (long long)nz * Lq * ldS, st);
+                TcGemmArgs pv;   // att[b,q0+q,h*dk + c] = sum_j P[b,h,q,j] * Vt[b, h*dk + c, j]
+                pv.A = S; pv.K = L; pv.Wi = pv.Wo = Lq; pv.Hi = pv.Ho = n_head; pv.IMG = B;
+                pv.a_sx = ldS; pv.a_sy = (long long)Lq * ldS; pv.a_simg = (long long)n_head * Lq * ldS;
+                pv.W = vt; pv.N = dk; pv.Z1 = n_head; pv.Z2 = B; pv.w_sn = Lp; pv.w_s1 = (long long)dk * Lp; pv.w_s2 = (long long)H * Lp;
+                pv.b_batched = 1;
+                pv.C = att + (long long)q0 * H; pv.c_simg = (long long)L * H; pv.c_sy = dk; pv.c_sx = H; pv.c_sn = 1;
+                if (split) { pv.A_lo = sc.lo_S; pv.W_lo = sc.lo_qkv + rows * 2 * H; }
+                gemm_tc_prof(pv, st);
+            }
         } else {
         linear(x, (int)rows, H, ly.wqkv, ly.bqkv, 3 * H, qkv, tc, st);
         for (int q0 = 0; q0 < L; q0 += Lq_max) {
@@ -980,14 +984,14 @@ class Engine {
         return 0;
     }
 
-    int length_regulate(const float* xprime, const int32_t* dur, int B, int T, int L_max, float* features,
+    int length_regulate(const float* xprime, const int32_t* dur, int B, int T, int frame0, int L_max, float* features,
                         int32_t* src_index, cudaStream_t st) {
         ZVX_CUDA_CHECK(cudaSetDevice(dev));
-        ZVX_REQUIRE(B >= 1 && T >= 1 && L_max >= 0 && B <= 65535, "zvx_length_regulate: bad sizes");
+        ZVX_REQUIRE(B >= 1 && T >= 1 && L_max >= 0 && frame0 >= 0 && B <= 65535, "zvx_length_regulate: bad sizes");
         ws.reset();
         int32_t* cum = ws.get<int32_t>((long long)B * T);
         duration_scan(dur, B, T, cum, nullptr, st);
-        length_regulate_gather(xprime, cum, B, T, H, L_max, features, src_index, st);
+        length_regulate_gather(xprime, cum, B, T, H, frame0, L_max, features, src_index, st);
         return 0;
     }
 
@@ -1286,7 +1290,8 @@ class Engine {
     }
 
     static constexpr int kMaxBatch = 65536;
-    static constexpr long long kScoreBytes = 1LL << 30;  // attention-score chunk budget
+    // attention-score workspace budget: longer sequences are processed in chunks of query rows (exact)
+    long long kScoreBytes = getenv("ZVX_SCORE_BYTES") ? atoll(getenv("ZVX_SCORE_BYTES")) : (4LL << 30);
 
     zvx_config cfg;
     int dev = 0;
@@ -1399,7 +1404,13 @@ int zvx_encode(zvx_handle* h, const int32_t* phoneme, const int32_t* puncts, con
 
 int zvx_length_regulate(zvx_handle* h, const float* xprime, const int32_t* dur, int B, int T, int L_max,
                         float* features, int32_t* src_index, void* stream) {
-    ZVX_GUARD(h, return h->eng->length_regulate(xprime, dur, B, T, L_max, features, src_index, (cudaStream_t)stream));
+    ZVX_GUARD(h, return h->eng->length_regulate(xprime, dur, B, T, 0, L_max, features, src_index, (cudaStream_t)stream));
+}
+
+int zvx_length_regulate_chunk(zvx_handle* h, const float* xprime, const int32_t* dur, int B, int T, int frame0,
+                              int n_frames, float* features, int32_t* src_index, void* stream) {
+    ZVX_GUARD(h, return h->eng->length_regulate(xprime, dur, B, T, frame0, n_frames, features, src_index,
+                                                (cudaStream_t)stream));
 }
 
 int zvx_decode(zvx_handle* h, const float* features, const uint8_t* mask, const int64_t* mel_len,

@@ -49,9 +49,10 @@ void duration_round(const float* log_d, const int32_t* forced, int32_t* dur, int
 // K11a: inclusive scan of max(dur,0) along T; total -> mel_len (int64).      (fs2.py:447-455)
 void duration_scan(const int32_t* dur, int B, int T, int32_t* cum, int64_t* mel_len, cudaStream_t st);
 
-// K11b: gather. features[b,f,:] = x[b, idx, :], idx = upper_bound(cum[b], f); zero rows past mel_len. (fs2.py:403-459)
-void length_regulate_gather(const float* x, const int32_t* cum, int B, int T, int C, int L_max, float* features,
-                            int32_t* src_index /*nullable*/, cudaStream_t st);
+// K11b: gather of the frames [frame0, frame0 + L_max): features[b,f-frame0,:] = x[b, idx, :], idx = upper_bound(cum[b], f);
+// zero rows past mel_len. (fs2.py:403-459)
+void length_regulate_gather(const float* x, const int32_t* cum, int B, int T, int C, int frame0, int L_max,
+                            float* features, int32_t* src_index /*nullable*/, cudaStream_t st);
 
 // K12: out[b,l,:] = x[b,l,:] + pos[l,:]      (fs2.py:287-304)
 void add_posenc(const float* x, const float* pos, int B, int L, int C, float* out, cudaStream_t st);

@@ -370,18 +370,19 @@ void duration_scan(const int32_t* dur, int B, int T, int32_t* cum, int64_t* mel_
 // one warp per output frame: binary search of the run that covers it, then a coalesced 128-bit row copy
 __global__ void __launch_bounds__(256) length_regulate_gather_kernel(const float* __restrict__ x,
                                                                      const int32_t* __restrict__ cum, int T, int C4,
-                                                                     int L_max, float* __restrict__ features,
+                                                                     int frame0, int L_max, float* __restrict__ features,
                                                                      int32_t* __restrict__ src_index) {
     const int b = blockIdx.y;
-    const int f = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int fo = blockIdx.x * 8 + (threadIdx.x >> 5);   // frame within the chunk [frame0, frame0 + L_max)
     const int lane = threadIdx.x & 31;
-    if (f >= L_max) return;
+    if (fo >= L_max) return;
+    const int f = frame0 + fo;
     const int32_t* c = cum + (long long)b * T;
     const int total = T > 0 ? c[T - 1] : 0;
-    float4* o = reinterpret_cast<float4*>(features) + ((long long)b * L_max + f) * C4;
+    float4* o = reinterpret_cast<float4*>(features) + ((long long)b * L_max + fo) * C4;
     if (f >= total) {
         for (int c4 = lane; c4 < C4; c4 += 32) o[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src_index && lane == 0) src_index[(long long)b * L_max + f] = -1;
+        if (src_index && lane == 0) src_index[(long long)b * L_max + fo] = -1;
         return;
     }
     int lo = 0, hi = T - 1;  // first i with cum[i] > f
@@ -391,15 +392,15 @@ __global__ void __launch_bounds__(256) length_regulate_gather_kernel(const float
     }
     const float4* src = reinterpret_cast<const float4*>(x) + ((long long)b * T + lo) * C4;
     for (int c4 = lane; c4 < C4; c4 += 32) o[c4] = __ldg(src + c4);
-    if (src_index && lane == 0) src_index[(long long)b * L_max + f] = lo;
+    if (src_index && lane == 0) src_index[(long long)b * L_max + fo] = lo;
 }
 
-void length_regulate_gather(const float* x, const int32_t* cum, int B, int T, int C, int L_max, float* features,
-                            int32_t* src_index, cudaStream_t st) {
+void length_regulate_gather(const float* x, const int32_t* cum, int B, int T, int C, int frame0, int L_max,
+                            float* features, int32_t* src_index, cudaStream_t st) {
     ZVX_REQUIRE(C % 4 == 0, "length_regulate: C % 4");
     if (B == 0 || L_max == 0) return;
     dim3 grid(cdiv(L_max, 8), B);
-    length_regulate_gather_kernel<<<grid, 256, 0, st>>>(x, cum, T, C / 4, L_max, features, src_index);
+    length_regulate_gather_kernel<<<grid, 256, 0, st>>>(x, cum, T, C / 4, frame0, L_max, features, src_index);
     ZVX_POST_LAUNCH();
 }
 

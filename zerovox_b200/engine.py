@@ -218,17 +218,39 @@ class Engine:
             out["mel_len_host"] = list(host)
         return out
 
-    def length_regulate(self, xprime, duration, L_max: int, want_index=False):
-        """LengthRegulator.forward + pad: ([B,T,H], int32 [B,T]) -> features [B,L_max,H] (, src_index)."""
+    def length_regulate(self, xprime, duration, L_max: int, want_index=False, frame0: int = 0):
+        """LengthRegulator.forward + pad: ([B,T,H], int32 [B,T]) -> features [B,L_max,H] (, src_index).  With ``frame0``
+        only the frames [frame0, frame0 + L_max) are produced (chunked long-form processing)."""
         x = self._dev(xprime, torch.float32, "xprime")
         d = self._dev(duration, torch.int32, "duration")
         B, T, H = x.shape
         feats = torch.empty((B, L_max, H), device=self.device, dtype=torch.float32)
         idx = torch.empty((B, L_max), device=self.device, dtype=torch.int32) if want_index else None
         with torch.cuda.device(self.device):
-            self._check(self.lib.zvx_length_regulate(self._h, _ptr(x), _ptr(d), B, T, L_max, _ptr(feats), _ptr(idx),
-                                                     self._stream()), "zvx_length_regulate")
+            if frame0:
+                self._check(self.lib.zvx_length_regulate_chunk(self._h, _ptr(x), _ptr(d), B, T, int(frame0), L_max,
+                                                               _ptr(feats), _ptr(idx), self._stream()),
+                            "zvx_length_regulate_chunk")
+            else:
+                self._check(self.lib.zvx_length_regulate(self._h, _ptr(x), _ptr(d), B, T, L_max, _ptr(feats), _ptr(idx),
+                                                         self._stream()), "zvx_length_regulate")
         return (feats, idx) if want_index else feats
+
+    def vocode_chunked(self, mel_bcl: torch.Tensor, chunk_frames: int = 512, halo_frames: int = 14) -> torch.Tensor:
+        """hifigan.Generator.forward over a long mel in chunks of ``chunk_frames`` with ``halo_frames`` of context on
+        each side, keeping only the samples of the chunk proper (overlap-discard): exact, because the generator's
+        receptive field is < 14 mel frames per side for every upstream HiFi-GAN topology, while
+        the workspace stays bounded by the chunk size.  [B, n_mels, L] -> [B, 1, L*hop]."""
+        m = self._dev(mel_bcl, torch.float32, "mel")
+        B, Cm, L = m.shape
+        hop = self.cfg.hop_length
+        wav = torch.empty((B, 1, L * hop), device=self.device, dtype=torch.float32)
+        for c0 in range(0, L, chunk_frames):
+            c1 = min(L, c0 + chunk_frames)
+            a, b = max(0, c0 - halo_frames), min(L, c1 + halo_frames)
+            part = self.vocode(m[:, :, a:b].contiguous())
+            wav[:, :, c0 * hop:c1 * hop] = part[:, :, (c0 - a) * hop:(c1 - a) * hop]
+        return wav
 
     def decode(self, features, style, mask=None, mel_len=None, zero_padded_mel=False, want_blc=True, want_bcl=True):
         """FS2Decoder.forward (+ model.py:283-285 masking).  Returns (mel [B,L,n_mels] | None, mel [B,n_mels,L] | None)."""

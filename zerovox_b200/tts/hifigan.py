@@ -78,3 +78,11 @@ class Generator(EngineModuleMixin, nn.Module):
         unbatched = x.dim() == 2
         wav = eng.vocode((x.unsqueeze(0) if unbatched else x).to(eng.device))
         return wav.squeeze(0) if unbatched else wav
+
+    def forward_chunked(self, x, chunk_frames=512, halo_frames=14):
+        """Long-form vocoding (BASELINE config 5): same result as ``forward`` computed chunk by chunk with a
+        ``halo_frames`` context on each side that is discarded afterwards (exact overlap-discard, bounded workspace)."""
+        eng = self._engine()
+        unbatched = x.dim() == 2
+        wav = eng.vocode_chunked((x.unsqueeze(0) if unbatched else x).to(eng.device), chunk_frames, halo_frames)
+        return wav.squeeze(0) if unbatched else wav

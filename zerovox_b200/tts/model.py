@@ -168,9 +168,11 @@ class ZeroVox(nn.Module):
         wav = eng.vocode(mel).squeeze(1)
         return wav, mel, r["mel_len"], r["log_duration"]
 
-    def inference_ex(self, x, style_embed, normalize_before=True, force_duration=False):
+    def inference_ex(self, x, style_embed, normalize_before=True, force_duration=False, *, vocoder_chunk_frames=None):
         """Batch-1 path (model.py:308-347): zero-pads the mel to the stateful ``_min_mel_len`` before vocoding and
-        trims the waveform to mel_len*hop.  Returns (wav, mel_len, log_duration, mel [n_mels, mel_len])."""
+        trims the waveform to mel_len*hop.  Returns (wav, mel_len, log_duration, mel [n_mels, mel_len]).
+        ``vocoder_chunk_frames`` (keyword-only extension, long-form inputs): vocode in chunks of that many mel frames
+        with a 14-frame discarded halo — same waveform, bounded workspace."""
         start_time = time.time()
         eng = self._shared_ctx.get(next(self.parameters()).device)
         dev = eng.device
@@ -190,7 +192,10 @@ class ZeroVox(nn.Module):
         else:
             self._min_mel_len = max(self._min_mel_len, mel_len)
             padded = mel
-        wav = eng.vocode(padded)[0, 0]
+        if vocoder_chunk_frames:
+            wav = eng.vocode_chunked(padded, int(vocoder_chunk_frames), 14)[0, 0]
+        else:
+            wav = eng.vocode(padded)[0, 0]
         if self._verbose:
             torch.cuda.synchronize(dev)
             now = time.time()
