@@ -1,0 +1,147 @@
+#!/usr/bin/env python
+"""Measurements for the BASELINE.json configs that are not the bench.py headline (configs[1]):
+
+    python tools/bench_configs.py --config 3            # HiFi-GAN Generator only: mel length x batch sweep (V1, V2)
+    python tools/bench_configs.py --config 5            # long-form: one 4096-phoneme utterance, chunked vocoder
+    torchrun --nproc-per-node N tools/bench_configs.py --config 4   # B=256 ragged batch sharded over N GPUs (NCCL)
+
+CUDA-event timing on the device, 3 warm-ups, median of --iters runs; one JSON object per measurement on stdout.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from zerovox_b200 import synthetic as syn  # noqa: E402
+from zerovox_b200.testing import build_generator, build_model  # noqa: E402
+
+MFLOP_PER_FRAME = {"v1": 614.1, "v2": 38.5, "v3": 45.0}
+
+
+def timed(fn, iters, dev):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def config3(args, dev):
+    for v in ("v2", "v1"):
+        h = getattr(syn.HifiGanConfig, v)()
+        hw = syn.make_hifigan_weights(h, torch.Generator().manual_seed(11))
+        gen = build_generator(h, {"_meldec." + k: t for k, t in hw.items()}).to(dev)
+        for L in (128, 512, 2048, 4096):
+            for B in (1, 8, 32, 128):
+                if B * L > (131072 if v == "v2" else 32768):
+                    continue
+                mel = torch.randn((B, 80, L), generator=torch.Generator().manual_seed(1)).to(dev)
+                with torch.no_grad():
+                    ms = timed(lambda: gen(mel), args.iters, dev)
+                frames = B * L
+                print(json.dumps({"config": 3, "vocoder": v, "B": B, "L": L, "ms": round(ms, 4),
+                                  "mel_frames_per_sec": frames / ms * 1e3, "audio_sec_per_sec": frames * 256 / 22050 / ms * 1e3,
+                                  "tflops": frames * MFLOP_PER_FRAME[v] * 1e6 / (ms * 1e-3) / 1e12}), flush=True)
+
+
+def config5(args, dev):
+    cfg = syn.ZeroVoxConfig()
+    w = syn.make_weights(cfg, seed=0)
+    model = build_model(cfg, w, device=dev)
+    x = syn.make_inputs(cfg, 1, 4096, 440, seed=11)
+    with torch.no_grad():
+        style = model._spkemb(x["ref_mel"].to(dev))
+        x1 = {k: v.to(dev) for k, v in x.items() if k != "ref_mel"}
+        out = {}
+
+        def run():
+            out["r"] = model.inference_ex(x1, style_embed=style, force_duration=True, vocoder_chunk_frames=args.chunk)
+        ms = timed(run, args.iters, dev)
+    mel_len = out["r"][1]
+    print(json.dumps({"config": 5, "phonemes": 4096, "mel_frames": mel_len, "vocoder_chunk_frames": args.chunk, "ms": round(ms, 3),
+                      "audio_sec": mel_len * 256 / 22050, "audio_sec_per_sec": mel_len * 256 / 22050 / ms * 1e3,
+                      "mel_frames_per_sec": mel_len / ms * 1e3}), flush=True)
+
+
+def config4(args, dev, rank, world):
+    import torch.distributed as dist
+    from zerovox_b200.parallel import sharded_forward
+    cfg = syn.ZeroVoxConfig()
+    w = syn.make_weights(cfg, seed=0)
+    model = build_model(cfg, w, device=dev)
+    x = None
+    if rank == 0:
+        g = torch.Generator().manual_seed(3)
+        B, T = args.batch, 192
+        x = syn.make_inputs(cfg, B, T, 440, seed=13)
+        lens = torch.randint(64, 193, (B,), generator=g)     # T_i ~ U{64..192}, padded to 192 with phoneme_mask
+        mask = torch.arange(T)[None, :] >= lens[:, None]
+        x["phoneme_mask"] = mask
+        for k in ("phoneme", "puncts", "duration"):
+            x[k] = x[k].masked_fill(mask, 0)
+    out = {}
+
+    def run():
+        with torch.no_grad():
+            out["r"] = sharded_forward(model, x, force_duration=True, device=dev)
+    for _ in range(2):
+        run()
+    ts = []
+    for _ in range(args.iters):
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run()
+        b.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ts.append(float(t))
+    if rank == 0:
+        ms = statistics.median(ts)
+        wav, mel, mel_len, _ = out["r"]
+        frames = int(mel_len.sum())
+        print(json.dumps({"config": 4, "n_gpus": world, "B": args.batch, "ms_incl_scatter_gather": round(ms, 3),
+                          "mel_frames": frames, "audio_sec_per_sec": frames * 256 / 22050 / ms * 1e3,
+                          "mel_frames_per_sec": frames / ms * 1e3, "wav_shape": list(wav.shape)}), flush=True)
+
+
+def main():
+    p = argparse.ArgumentParser()
+    p.add_argument("--config", type=int, required=True, choices=[3, 4, 5])
+    p.add_argument("--iters", type=int, default=5)
+    p.add_argument("--chunk", type=int, default=2048)
+    p.add_argument("--batch", type=int, default=256)
+    args = p.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if args.config == 3:
+        config3(args, dev)
+    elif args.config == 5:
+        config5(args, dev)
+    else:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        config4(args, dev, rank, world)
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

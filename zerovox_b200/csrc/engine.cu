@@ -570,6 +570,7 @@ class Engine {
     void pack_vocoder_tc() {
         hg_tc_ok = false;
         hg_stage_kind.clear(); hg_ups_tc_w.clear(); hg_ups_tc_b.clear(); hg_c1_tc.clear(); hg_c2_tc.clear();
+        hg_c1_poly.clear(); hg_c2_poly.clear();
         const int C0 = cfg.hg_upsample_initial_channel, nk = cfg.hg_num_kernels, nd = cfg.hg_num_dilations;
         if (C0 % 4 != 0 || C0 < 8 || cfg.n_mels % 4 != 0) return;
         for (int i = 0; i < cfg.hg_num_upsamples; ++i) {
@@ -619,16 +620,18 @@ class Engine {
                 const std::string p = "resblocks." + std::to_string(i * nk + j);
                 const int rk = cfg.hg_resblock_kernel_sizes[j];
                 for (int di = 0; di < nd; ++di, ++ci) {
-                    auto pack = [&](const std::string& key) {
+                    const int dl = cfg.hg_resblock_dilation_sizes[j][di];
+                    auto pack = [&](const std::string& key, int dil, std::vector<float*>& poly) {
                         const HostTensor& t = W("_meldec." + key + ".weight", {cout, cout, rk});
-                        return hg_stage_kind[(size_t)i] == 1 ? upload(voc_pack_weight(t.data.data(), cout, cout, rk))
-                                                              : upload(tap_major(t));
+                        if (hg_stage_kind[(size_t)i] != 1) { poly.push_back(nullptr); return upload(tap_major(t)); }
+                        poly.push_back(upload(voc_poly_pack_weight(t.data.data(), cout, rk, dil)));
+                        return upload(voc_pack_weight(t.data.data(), cout, cout, rk));
                     };
                     if (cfg.hg_resblock == 1) {
-                        hg_c1_tc.push_back(pack(p + ".convs1." + std::to_string(di)));
-                        hg_c2_tc.push_back(pack(p + ".convs2." + std::to_string(di)));
+                        hg_c1_tc.push_back(pack(p + ".convs1." + std::to_string(di), dl, hg_c1_poly));
+                        hg_c2_tc.push_back(pack(p + ".convs2." + std::to_string(di), 1, hg_c2_poly));
                     } else {
-                        hg_c1_tc.push_back(pack(p + ".convs." + std::to_string(di)));
+                        hg_c1_tc.push_back(pack(p + ".convs." + std::to_string(di), dl, hg_c1_poly));
                     }
                 }
             }
@@ -1164,13 +1167,13 @@ class Engine {
                     for (int di = 0; di < nd; ++di, ++ci) {
                         const int dl = cfg.hg_resblock_dilation_sizes[j][di];
                         if (pair) {
-                            a.steps[a.nsteps].w = hg_c1_tc[ci]; a.steps[a.nsteps].b = hg_c1[ci].b;
-                            a.steps[a.nsteps].dil = dl; a.steps[a.nsteps++].kind = 0;
-                            a.steps[a.nsteps].w = hg_c2_tc[ci]; a.steps[a.nsteps].b = hg_c2[ci].b;
-                            a.steps[a.nsteps].dil = 1; a.steps[a.nsteps++].kind = 1;
+                            a.steps[a.nsteps].w = hg_c1_tc[ci]; a.steps[a.nsteps].w_poly = hg_c1_poly[ci];
+                            a.steps[a.nsteps].b = hg_c1[ci].b; a.steps[a.nsteps].dil = dl; a.steps[a.nsteps++].kind = 0;
+                            a.steps[a.nsteps].w = hg_c2_tc[ci]; a.steps[a.nsteps].w_poly = hg_c2_poly[ci];
+                            a.steps[a.nsteps].b = hg_c2[ci].b; a.steps[a.nsteps].dil = 1; a.steps[a.nsteps++].kind = 1;
                         } else {
-                            a.steps[a.nsteps].w = hg_c1_tc[ci]; a.steps[a.nsteps].b = hg_c1[ci].b;
-                            a.steps[a.nsteps].dil = dl; a.steps[a.nsteps++].kind = 1;
+                            a.steps[a.nsteps].w = hg_c1_tc[ci]; a.steps[a.nsteps].w_poly = hg_c1_poly[ci];
+                            a.steps[a.nsteps].b = hg_c1[ci].b; a.steps[a.nsteps].dil = dl; a.steps[a.nsteps++].kind = 1;
                         }
                     }
                     if (j > 0) { a.acc_in = bX; a.acc_in_bs = bs; }
@@ -1178,8 +1181,22 @@ class Engine {
                     const bool emit_act = (j == nk - 1) && more;
                     a.out = emit_act ? bXA : bX; a.out_bs = bs; a.out_slope = emit_act ? 0.1f : 1.f;
                     prof.begin(ZVX_PROF_VOC_TC, 2.0 * B * T * ch * ch * rk * a.nsteps, 4.0 * B * T * ch * (j > 0 ? 3.0 : 2.0), st);
-                    voc_resblock_tc(a, st);
+                    static const bool no_poly = getenv("ZVX_NO_POLY") != nullptr;   // A/B switch: voc_res.cu only
+                    static const bool dbg_times = getenv("ZVX_VOC_DBG") != nullptr;  // print one CTA's phase timestamps
+                    long long* dbg = nullptr;
+                    if (dbg_times) { dbg = ws.get<long long>(64); ZVX_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 64 * 8, st)); a.dbg = dbg; }
+                    if (no_poly || !voc_poly_tc(a, st)) voc_resblock_tc(a, st);
                     prof.end(st);
+                    if (dbg) {
+                        long long h[64];
+                        ZVX_CUDA_CHECK(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+                        ZVX_CUDA_CHECK(cudaStreamSynchronize(st));
+                        fprintf(stderr, "[voc dbg] C=%d k=%d T=%d:", ch, rk, T);
+                        for (int i = 1; i < 32 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+                        fprintf(stderr, " | issuer:");
+                        for (int i = 32; i < 64 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - h[0]);
+                        fprintf(stderr, "\n");
+                    }
                     continue;
                 }
                 View r = y, ra = ya;
@@ -1331,7 +1348,7 @@ class Engine {
     bool hg_tc_ok = false;
     std::vector<int> hg_stage_kind;   // per upsample stage: 1 = fused pair kernel, 2 = generic tcgen05 implicit GEMM
     float *hg_pre_tc = nullptr, *hg_post_tc = nullptr;
-    std::vector<float*> hg_ups_tc_w, hg_ups_tc_b, hg_c1_tc, hg_c2_tc;
+    std::vector<float*> hg_ups_tc_w, hg_ups_tc_b, hg_c1_tc, hg_c2_tc, hg_c1_poly, hg_c2_poly;
 };
 
 }  // namespace zvx

@@ -117,7 +117,11 @@ std::vector<float> voc_pack_weight(const float* w, int cout, int cin, int k);
 //   out = lrelu( resblock(x) * out_scale + (acc_in ? acc_in : 0), out_slope )      (acc_in may alias out)
 struct VocResArgs {
     static constexpr int MAX_STEPS = 8;
-    struct Step { const float* w = nullptr; const float* b = nullptr; int dil = 1; int kind = 1; };
+    struct Step {
+        const float* w = nullptr;        // packed image of voc_pack_weight (voc_res.cu)
+        const float* w_poly = nullptr;   // packed image of voc_poly_pack_weight (voc_poly.cu), optional
+        const float* b = nullptr; int dil = 1; int kind = 1;
+    };
     const float* x = nullptr; long long x_bs = 0;      // raw input [B][T][C], batch stride in elements
     int B = 0, T = 0, C = 0, k = 1, nsteps = 0;
     Step steps[MAX_STEPS];                             // weights in the packed image of voc_pack_weight
@@ -125,9 +129,16 @@ struct VocResArgs {
     const float* acc_in = nullptr; long long acc_in_bs = 0;
     float out_scale = 1.f, out_slope = 1.f;
     float* out = nullptr; long long out_bs = 0;
+    const void* sched = nullptr;                       // voc_poly.cu: device copy of the MMA schedule (set by voc_poly_tc)
+    long long* dbg = nullptr;                          // optional: clock64 checkpoints of one CTA (tools/voc_phase_times.py)
 };
 bool voc_resblock_supported(int C, int k, const int* dils, int nd, bool pair);
 void voc_resblock_tc(const VocResArgs& a, cudaStream_t st);
+// Polyphase formulation (voc_poly.cu): P = 128/C output samples per accumulator row, Toeplitz-expanded weights.
+// voc_poly_tc returns false (nothing launched) when the shape is outside its plan; callers then use voc_resblock_tc.
+bool voc_poly_supported(int C, int k, const int* dils, int nd, bool pair);
+bool voc_poly_tc(const VocResArgs& a, cudaStream_t st);
+std::vector<float> voc_poly_pack_weight(const float* w, int C, int k, int dil);
 
 // conv_post on channel-last input: wav[b,t] = tanh(bias + sum_{j,c} w[j][c] * lrelu(x[b, t+j-(k-1)/2, c], slope))
 void conv_post_cl(const float* x, long long x_bs, const float* w /*[k][C]*/, const float* bias, int B, int T, int C,
