@@ -107,6 +107,32 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# engine profiling class -> kernel names in profiles/*_ncu_summary.json (tools/ncu_summary.py)
+NCU_KERNELS = {"gemm_tf32_tcgen05": ("gemm_tc_kernel<0, 0>", "gemm_tc_kernel<1, 0>"),
+               "gemm_3xtf32_tcgen05": ("gemm_tc_kernel<1, 1>",),
+               "vocoder_pair_tcgen05": ("voc_poly_kernel<32>", "voc_poly_kernel<16>", "voc_poly_kernel<8>")}
+
+
+def ncu_traffic(cls):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the class's kernels from the committed
+    `ncu --set full` capture of tools/prof_step.py (same workload); None when there is no capture."""
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")))
+    if not paths or cls not in NCU_KERNELS:
+        return None, None
+    with open(paths[-1]) as f:
+        summ = json.load(f)
+    tot, n = 0.0, 0
+    for k in NCU_KERNELS[cls]:
+        e = summ.get(k)
+        if e and "avg_dram_traffic_bytes" in e:
+            tot += e["avg_dram_traffic_bytes"] * e["launches_captured"]
+            n += e["launches_captured"]
+    if n == 0:
+        return None, None
+    return tot / n, {"file": os.path.relpath(paths[-1], ROOT), "launches_captured": n}
+
+
 def audio_seconds(mel_len_total, cfg):
     return mel_len_total * cfg.hop_length / cfg.sampling_rate
 
@@ -273,8 +299,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32 (tcgen05, fp32 accumulate) decoder/vocoder/speaker-net; f32 encoder + variance predictors"
-                 if args.policy else "f32",
+        "dtype": "tf32 (tcgen05, fp32 accumulate) decoder/vocoder/speaker-net; 3xTF32 split (fp32-grade) encoder + "
+                 "variance predictors" if args.policy else "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "phonemes": args.phonemes,
                    "mel_frames_per_step": frames_total, "L_max": L_max, "mel_frames_per_sec": frames_total / (ms / 1e3),
@@ -300,9 +326,11 @@ def main():
         ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
         # TF32 tensor peak is half the dense bf16 rate; the measured denominators are bf16 (MEASURED_PEAKS.json)
         peak = peaks["bf16_tflops_sustained"]
+        traffic, traffic_src = ncu_traffic(dom)
         line["roofline"] = {
             "bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": None, "peak_source": f"bf16 dense, sustained, {peaks['source']} (MEASURED_PEAKS.json); "
+            "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": d["bytes"] / d["launches"], "peak_source": f"bf16 dense, sustained, {peaks['source']} (MEASURED_PEAKS.json); "
                                             "TF32 runs at half the bf16 rate, fp32 FMA kernels at ~1/20",
             "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
             "algorithmic_flops_per_launch": d["flops"] / d["launches"], "share_of_step": d["ms"] / ms,
