@@ -197,6 +197,9 @@ __global__ void __launch_bounds__(256) attn_softmax_warp_kernel(float* __restric
     float4* s4 = reinterpret_cast<float4*>(S + rowid * ldS);
     const uint8_t* km = key_mask ? key_mask + (long long)b * mask_ld : nullptr;
     const int n4 = ldS >> 2;
+    // exp(x/T - m) = exp2((x - max) * log2(e) / T): one multiply per element, ex2.approx (2 ulp) instead of a division
+    // and a full-precision expf; the final 1/sum is one reciprocal per row
+    const float sc = 1.4426950408889634f / temperature;
     float v[NV][4];
     float m = -INFINITY;
 #pragma unroll
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(256) attn_softmax_warp_kernel(float* __restric
         for (int e = 0; e < 4; ++e) {
             const int j = idx * 4 + e;
             float x = -INFINITY;
-            if (j < L && !(km && km[j])) x = in[e] / temperature;
+            if (j < L && !(km && km[j])) x = in[e];
             v[i][e] = x;
             m = fmaxf(m, x);
         }
@@ -220,17 +223,18 @@ __global__ void __launch_bounds__(256) attn_softmax_warp_kernel(float* __restric
     for (int i = 0; i < NV; ++i)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            v[i][e] = expf(v[i][e] - m);
+            v[i][e] = exp2f((v[i][e] - m) * sc);
             sum += v[i][e];
         }
     sum = warp_sum(sum);
+    const float inv = 1.f / sum;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int idx = lane + 32 * i;
         if (idx < n4) {
             float o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = (idx * 4 + e < L) ? v[i][e] / sum : 0.f;
+            for (int e = 0; e < 4; ++e) o[e] = (idx * 4 + e < L) ? v[i][e] * inv : 0.f;
             s4[idx] = make_float4(o[0], o[1], o[2], o[3]);
         }
     }

@@ -8,12 +8,13 @@
 namespace zvx {
 
 // InstanceNorm1d(n_mels) over time, no affine (ResNetSE34V2.py:123, 182); also performs the
-// transpose(1,2) of line 178: in [B,T,M] -> out [B,M,T].  One block per utterance; each warp owns
-// mel channels m = warp, warp+nw, ...; two passes (mean, then biased variance) like ATen.
+// transpose(1,2) of line 178: in [B,T,M] -> out [B,M,T].  One warp per (utterance, mel channel); two passes (mean,
+// then biased variance) like ATen.
 __global__ void __launch_bounds__(256) instance_norm_time_kernel(const float* __restrict__ in, int T, int M,
                                                                  float* __restrict__ out) {
     const int b = blockIdx.x;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, nw = (blockDim.x >> 5) * gridDim.y;
+    const int wid = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);   // warp index across the blocks of this utterance
     const float* x = in + (long long)b * T * M;
     float* o = out + (long long)b * M * T;
     for (int m = wid; m < M; m += nw) {
@@ -32,7 +33,7 @@ __global__ void __launch_bounds__(256) instance_norm_time_kernel(const float* __
 
 void instance_norm_time(const float* ref_mel, int B, int T, int n_mels, float* out, cudaStream_t st) {
     if (B == 0) return;
-    instance_norm_time_kernel<<<B, 256, 0, st>>>(ref_mel, T, n_mels, out);
+    instance_norm_time_kernel<<<dim3(B, cdiv(n_mels, 8)), 256, 0, st>>>(ref_mel, T, n_mels, out);
     ZVX_POST_LAUNCH();
 }
 
