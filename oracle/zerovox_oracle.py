@@ -108,7 +108,7 @@ def fft_block(w, p, x, spk, mask, slf_attn_mask, n_head, kernel_size, scln_on):
 def _pos_table(w, key, L, H, max_len):
     """fs2.py:287-304 / 383-392 — parameter rows when L <= max, recomputed table otherwise (eval)."""
     if L > max_len:
-        return get_sinusoid_encoding_table(L, H)[:L, :]
+        return get_sinusoid_encoding_table(L, H)[:L, :].to(w[key].device)
     return w[key][0, :L, :]
 
 
@@ -172,11 +172,11 @@ def length_regulator_indices(duration: np.ndarray, max_len: int | None = None):
 
 def length_regulate(x, duration, max_len=None):
     idx, mel_len = length_regulator_indices(duration.detach().cpu().numpy(), max_len)
-    idx_t = torch.from_numpy(idx).long()
+    idx_t = torch.from_numpy(idx).long().to(x.device)
     B, L = idx_t.shape
     g = torch.gather(x, 1, idx_t.clamp(min=0).unsqueeze(-1).expand(B, L, x.shape[-1]))
     g = g.masked_fill((idx_t < 0).unsqueeze(-1), 0.0)
-    return g, torch.from_numpy(mel_len), idx
+    return g, torch.from_numpy(mel_len).to(x.device), idx
 
 
 def fs2_encoder(cfg, w, x, style_embed, force_duration=False):
@@ -202,7 +202,7 @@ def fs2_encoder(cfg, w, x, style_embed, force_duration=False):
         dur = duration_round(log_d)
         out, mel_len, idx = length_regulate(feats, dur)
         L = out.shape[1]
-        mel_mask = torch.arange(L)[None, :] >= mel_len[:, None]  # fs2.py:565-573
+        mel_mask = torch.arange(L, device=mel_len.device)[None, :] >= mel_len[:, None]  # fs2.py:565-573
         masks = mel_mask.unsqueeze(2).expand(-1, -1, out.shape[2])
     return {"pitch": pitch, "energy": energy, "log_duration": log_d, "mel_len": mel_len,
             "features": out, "masks": masks,
@@ -393,7 +393,7 @@ def zerovox_forward(cfg, w, x, force_duration=False, style_embed=None):
     masks = pred["masks"]
     L = pred["features"].shape[1]
     if masks is None:  # model.py:269-273
-        dec_mask = ~(torch.arange(L).expand(len(pred["mel_len"]), L) < pred["mel_len"].unsqueeze(1))
+        dec_mask = ~(torch.arange(L, device=pred["mel_len"].device).expand(len(pred["mel_len"]), L) < pred["mel_len"].unsqueeze(1))
     else:
         dec_mask = masks[:, :, 0]
     mel = mel_decoder(cfg, w, pred["features"], dec_mask, se)
@@ -412,7 +412,7 @@ def zerovox_inference_ex(cfg, w, x, style_embed, force_duration=False, min_mel_l
     updated ``_min_mel_len`` (the reference mutates self._min_mel_len, model.py:331-335)."""
     pred = fs2_encoder(cfg, w, x, style_embed, force_duration=force_duration)
     L = pred["features"].shape[1]
-    dec_mask = ~(torch.arange(L).expand(1, L) < pred["mel_len"].unsqueeze(1))
+    dec_mask = ~(torch.arange(L, device=pred["mel_len"].device).expand(1, L) < pred["mel_len"].unsqueeze(1))
     mel = mel_decoder(cfg, w, pred["features"], dec_mask, style_embed)
     mel_len = int(pred["mel_len"][0])
     mel = mel[0]
