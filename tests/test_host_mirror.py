@@ -1,6 +1,7 @@
 """CPU: the host-side mirror keeps the reference's constructor signature, attribute names and state_dict keys,
 and refuses (loudly) to run anywhere but on the CUDA engine."""
 import inspect
+import os
 
 import pytest
 import torch
@@ -94,3 +95,39 @@ def test_symbols_table():
     assert s.num_phones == 5 and s.num_puncts == 4
     assert s.encode_phone("'") == 0 and s.decode_phone(2) == "a"
     assert s.encode_punct(Symbols.NO_PUNCT) == 0 and s.encode_punct(",") == 2 and s.is_punct(".") and not s.is_phone(".")
+
+
+def test_checkpoint_ingestion_like_synthesize(tmp_path, monkeypatch):
+    """The on-disk formats ZeroVoxTTS.__init__ / get_meldec read (synthesize.py:78-88, model.py:86-118): a Lightning
+    .ckpt ({'hyper_parameters', 'state_dict'}) loaded with strict=False + extra kwargs, and a vocoder directory with
+    config.json + generator.ckpt['generator'] in weight-norm form under $CACHED_PATH_ZEROVOX/model_repo/<name>/."""
+    import json
+    from zerovox_b200.tts import Generator, AttrDict, get_meldec
+    cfg = zo.ZeroVoxConfig.tiny()
+    w = zo.make_weights(cfg, seed=0)
+    # vocoder repo in the HF-cache layout of model.py:66-82
+    name = "zerovox-hifigan-test"
+    repo = tmp_path / "model_repo" / name
+    repo.mkdir(parents=True)
+    (repo / "config.json").write_text(json.dumps(cfg.hifigan.as_json_dict()))
+    raw_gen = Generator(AttrDict(cfg.hifigan.as_json_dict()))          # still weight-normed, like upstream checkpoints
+    torch.save({"generator": raw_gen.state_dict()}, repo / "generator.ckpt")
+    monkeypatch.setenv("CACHED_PATH_ZEROVOX", str(tmp_path))
+    gen = get_meldec(name)
+    assert "conv_pre.weight" in gen.state_dict() and not gen.training
+    torch.testing.assert_close(gen.state_dict()["conv_pre.weight"], raw_gen._engine_state_dict()["conv_pre.weight"])
+    assert os.path.isdir(repo) and get_meldec(str(repo)).state_dict().keys() == gen.state_dict().keys()   # directory form
+    # Lightning checkpoint: hyper-parameters minus the ignored ones, acoustic-model weights only (no _meldec.* keys)
+    kw = zerovox_kwargs(cfg)
+    hp = {k: v for k, v in kw.items() if k not in ("meldec_model",)}
+    sd = {k: v for k, v in w.items() if not k.startswith("_meldec.")}
+    ckpt = tmp_path / "epoch=0001.ckpt"
+    torch.save({"hyper_parameters": hp, "state_dict": sd}, ckpt)
+    zv = ZeroVox.load_from_checkpoint(lang="en", meldec_model=name, sampling_rate=cfg.sampling_rate, hop_length=cfg.hop_length,
+                                      checkpoint_path=str(ckpt), infer_device="cpu", map_location="cpu", strict=False,
+                                      verbose=False, betas=(0.0, 0.99), eps=1e-9)
+    assert isinstance(zv._meldec, Generator)
+    for k, v in sd.items():
+        torch.testing.assert_close(zv.state_dict()[k], v)
+    with pytest.raises(FileNotFoundError):
+        get_meldec("no-such-model")

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Measurements for the BASELINE.json configs that are not the bench.py headline (configs[1]):
 
+    python tools/bench_configs.py --config 1 --cpu      # one utterance, styledec model, GPU latency vs CPU oracle
     python tools/bench_configs.py --config 3            # HiFi-GAN Generator only: mel length x batch sweep (V1, V2)
     python tools/bench_configs.py --config 5            # long-form: one 4096-phoneme utterance, chunked vocoder
     torchrun --nproc-per-node N tools/bench_configs.py --config 4   # B=256 ragged batch sharded over N GPUs (NCCL)
@@ -39,6 +40,46 @@ def timed(fn, iters, dev):
         torch.cuda.synchronize(dev)
         ts.append(a.elapsed_time(b))
     return statistics.median(ts)
+
+
+def config1(args, dev):
+    """configs[0]: one utterance through inference_ex, tts_medium_styledec + HiFi-GAN V2 (the shipped default model shape),
+    precomputed speaker embedding as in zerovox/demo.py; GPU latency next to the CPU oracle on this box's cores."""
+    import dataclasses
+    import time
+    cfg = dataclasses.replace(syn.ZeroVoxConfig(), decoder_kind="styletts")
+    w = syn.make_weights(cfg, seed=0)
+    model = build_model(cfg, w, device=dev)
+    x = syn.make_inputs(cfg, 1, 128, 440, seed=7)
+    with torch.no_grad():
+        style = model._spkemb(x["ref_mel"].to(dev))
+        x1 = {k: v.to(dev) for k, v in x.items() if k != "ref_mel"}
+        out = {}
+
+        def run():
+            out["r"] = model.inference_ex(x1, style_embed=style, force_duration=True)
+        ms = timed(run, max(args.iters, 20), dev)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            run()
+        torch.cuda.synchronize(dev)
+        wall_ms = (time.perf_counter() - t0) / 20 * 1e3
+    mel_len = out["r"][1]
+    rec = {"config": 1, "decoder": "styletts", "vocoder": "v2", "B": 1, "phonemes": 128, "mel_frames": mel_len,
+           "gpu_ms_events": round(ms, 3), "gpu_ms_wall_incl_launch": round(wall_ms, 3), "audio_sec": mel_len * 256 / 22050,
+           "rtf_inverse_gpu": mel_len * 256 / 22050 / (wall_ms * 1e-3)}
+    if args.cpu:
+        from oracle import zerovox_oracle as zo   # measurement tool: CPU baseline leg
+        torch.set_num_threads(os.cpu_count() or 1)
+        xs = {k: v for k, v in x.items() if k != "ref_mel"}
+        with torch.no_grad():
+            zo.zerovox_inference_ex(cfg, w, dict(xs), style.cpu(), force_duration=True)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                zo.zerovox_inference_ex(cfg, w, dict(xs), style.cpu(), force_duration=True)
+            cpu_s = (time.perf_counter() - t0) / 3
+        rec.update({"cpu_ms": round(cpu_s * 1e3, 1), "cpu_threads": os.cpu_count(), "rtf_inverse_cpu": mel_len * 256 / 22050 / cpu_s})
+    print(json.dumps(rec), flush=True)
 
 
 def config3(args, dev):
@@ -124,7 +165,8 @@ def config4(args, dev, rank, world):
 
 def main():
     p = argparse.ArgumentParser()
-    p.add_argument("--config", type=int, required=True, choices=[3, 4, 5])
+    p.add_argument("--config", type=int, required=True, choices=[1, 3, 4, 5])
+    p.add_argument("--cpu", action="store_true", help="config 1: also time the CPU oracle")
     p.add_argument("--iters", type=int, default=5)
     p.add_argument("--chunk", type=int, default=2048)
     p.add_argument("--batch", type=int, default=256)
@@ -132,7 +174,9 @@ def main():
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    if args.config == 3:
+    if args.config == 1:
+        config1(args, dev)
+    elif args.config == 3:
         config3(args, dev)
     elif args.config == 5:
         config5(args, dev)
