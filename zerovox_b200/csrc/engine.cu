@@ -95,6 +95,7 @@ struct SEBlock {
     float *w2 = nullptr, *bn2_s = nullptr, *bn2_b = nullptr;
     float *se_w1 = nullptr, *se_b1 = nullptr, *se_w2 = nullptr, *se_b2 = nullptr;
     float *wd = nullptr, *bnd_s = nullptr, *bnd_b = nullptr;  // downsample (nullable)
+    float *w1_rs = nullptr, *w2_rs = nullptr;   // row-shift kernel images (conv_rs.cu) when the channel counts allow
 };
 
 struct STConv { float* w = nullptr; float* b = nullptr; int cin = 0, cout = 0, k = 1; };   // weight-norm folded, tap-major
@@ -486,6 +487,11 @@ class Engine {
                 b.w1 = upload(tap_major(W(p + ".conv1.weight", {planes, inpl, 3, 3})));
                 bn_fold(p + ".bn1", planes, &b.bn1_s, &b.bn1_b);
                 b.w2 = upload(tap_major(W(p + ".conv2.weight", {planes, planes, 3, 3})));
+                auto rs_ok = [](int c) { return c == 32 || c == 64; };
+                if (b.stride == 1 && rs_ok(inpl) && rs_ok(planes))
+                    b.w1_rs = upload(voc_pack_weight(W(p + ".conv1.weight", {planes, inpl, 3, 3}).data.data(), planes, inpl, 9));
+                if (rs_ok(planes))
+                    b.w2_rs = upload(voc_pack_weight(W(p + ".conv2.weight", {planes, planes, 3, 3}).data.data(), planes, planes, 9));
                 bn_fold(p + ".bn2", planes, &b.bn2_s, &b.bn2_b);
                 b.se_w1 = upload(W(p + ".se.fc.0.weight", {b.red, planes}));
                 b.se_b1 = upload(W(p + ".se.fc.0.bias", {b.red}));
@@ -623,7 +629,11 @@ class Engine {
                     const int dl = cfg.hg_resblock_dilation_sizes[j][di];
                     auto pack = [&](const std::string& key, int dil, std::vector<float*>& poly) {
                         const HostTensor& t = W("_meldec." + key + ".weight", {cout, cout, rk});
-                        if (hg_stage_kind[(size_t)i] != 1) { poly.push_back(nullptr); return upload(tap_major(t)); }
+                        if (hg_stage_kind[(size_t)i] != 1) {
+                            // 64-channel stages: image for the row-shift kernel in the `poly` slot, TMA image as before
+                            poly.push_back(cout == 64 ? upload(voc_pack_weight(t.data.data(), cout, cout, rk)) : nullptr);
+                            return upload(tap_major(t));
+                        }
                         poly.push_back(upload(voc_poly_pack_weight(t.data.data(), cout, rk, dil)));
                         return upload(voc_pack_weight(t.data.data(), cout, cout, rk));
                     };
@@ -904,13 +914,24 @@ class Engine {
             c.C = t1; c.ldc = b.planes; c.M = B * Ho * Wo; c.N = b.planes; c.K = b.inpl; c.taps = 9;
             c.mode = ROW_CONV2D; c.Ho = Ho; c.Wo = Wo; c.Hi = Hh; c.Wi = Ww; c.ksize = 3; c.stride = b.stride; c.pad = 1;
             c.relu_first = 1; c.scale = b.bn1_s; c.shift = b.bn1_b;
-            gemm(c, tc, st);
+            auto rs_conv = [&](const float* in, int cin, const float* wrs, const float* sc_, const float* sh_, int relu, float* out) {
+                ConvRsArgs r;
+                r.mode = 1; r.x = in; r.x_bs = (long long)Ho * Wo * cin; r.B = B; r.H = Ho; r.W = Wo; r.C = cin; r.N = b.planes;
+                r.w = wrs; r.scale = sc_; r.shift = sh_; r.relu_first = relu; r.y = out; r.y_bs = (long long)Ho * Wo * b.planes;
+                if (!rs_on || cfg.tensor_core_policy == 0 || !wrs || !conv_rs_supported(r)) return false;
+                prof.begin(ZVX_PROF_GEMM_TC, 2.0 * B * Ho * Wo * (double)cin * b.planes * 9,
+                           4.0 * B * Ho * Wo * (double)(cin + b.planes), st);
+                conv_rs(r, st);
+                prof.end(st);
+                return true;
+            };
+            if (!(b.stride == 1 && rs_conv(x, b.inpl, b.w1_rs, b.bn1_s, b.bn1_b, 1, t1))) gemm(c, tc, st);
             GemmArgs c2;
             c2.A = t1; c2.lda = b.planes; c2.W = b.w2; c2.ldw = b.planes; c2.w_tap_stride = (long long)b.planes * b.planes;
             c2.C = t2; c2.ldc = b.planes; c2.M = B * Ho * Wo; c2.N = b.planes; c2.K = b.planes; c2.taps = 9;
             c2.mode = ROW_CONV2D; c2.Ho = Ho; c2.Wo = Wo; c2.Hi = Ho; c2.Wi = Wo; c2.ksize = 3; c2.stride = 1; c2.pad = 1;
             c2.scale = b.bn2_s; c2.shift = b.bn2_b;
-            gemm(c2, tc, st);
+            if (!rs_conv(t1, b.planes, b.w2_rs, b.bn2_s, b.bn2_b, 0, t2)) gemm(c2, tc, st);
             const int S = hw_mean_splits(B, Ho * Wo);
             float* pooled = ws.get<float>((long long)B * S * b.planes);
             hw_sum_partial(t2, B, Ho * Wo, b.planes, S, pooled, st);
@@ -1205,7 +1226,32 @@ class Engine {
                     const bool first_buf = (r.p != bRA);
                     const View rn{first_buf ? bRA : bRB, bs}, rna{first_buf ? bRAa : bRBa, bs};
                     const int dl = cfg.hg_resblock_dilation_sizes[j][di];
-                    {
+                    const bool rs = rs_on && ch == 64 && hg_c1_poly[ci] && (!pair || hg_c2_poly[ci]);
+                    if (rs) {
+                        // row-shift kernel: reads the RAW tensors and applies the leaky ReLU on the way in
+                        ConvRsArgs c;
+                        c.mode = 0; c.B = B; c.T = T; c.C = ch; c.N = ch; c.k = rk; c.in_slope = 0.1f;
+                        auto run = [&](ConvRsArgs& cc) {
+                            prof.begin(ZVX_PROF_GEMM_TC, 2.0 * B * T * (double)ch * ch * rk, 4.0 * B * T * (double)(2 * ch), st);
+                            conv_rs(cc, st);
+                            prof.end(st);
+                        };
+                        if (pair) {
+                            c.x = r.p; c.x_bs = r.bs; c.w = hg_c1_poly[ci]; c.bias = hg_c1[ci].b; c.dil = dl; c.y = bT; c.y_bs = bs;
+                            run(c);
+                            c.x = bT; c.x_bs = bs; c.w = hg_c2_poly[ci]; c.bias = hg_c2[ci].b; c.dil = 1;
+                        } else {
+                            c.x = r.p; c.x_bs = r.bs; c.w = hg_c1_poly[ci]; c.bias = hg_c1[ci].b; c.dil = dl;
+                        }
+                        c.R = r.p; c.r_bs = r.bs;
+                        if (last) {
+                            c.y = bX; c.y_bs = bs; c.acc_mode = 1; c.acc_init = (j == 0); c.acc_scale = 1.f / (float)nk;
+                            if (j == nk - 1 && more) { c.y2 = bXA; c.slope2 = 0.1f; }
+                        } else {
+                            c.y = rn.p; c.y_bs = rn.bs;
+                        }
+                        run(c);
+                    } else {
                         TcGemmArgs g;   // conv over the leaky-ReLU'd copy
                         g.K = ch; g.Wi = g.Wo = T; g.Hi = g.Ho = B; g.a_sx = ch; g.N = ch; g.w_sn = ch; g.Z1 = rk;
                         g.w_s1 = (long long)ch * ch; g.ksx = rk; g.c_sx = ch;
@@ -1323,6 +1369,9 @@ class Engine {
     std::string sec_err[4];
     Workspace ws;
     Profiler prof;
+    // row-shift conv kernel (conv_rs.cu) for 32/64-channel convs: correct but measured slower than / on par with the TMA
+    // implicit GEMM at this size (profiles/r01_conv_rs_experiment.txt) -> opt-in until its phases are pipelined
+    bool rs_on = getenv("ZVX_RS") != nullptr;
     bool split_on = getenv("ZVX_NO_SPLIT") == nullptr;   // 3xTF32 for P_EXACT contractions (debug switch)
     std::map<const float*, const float*> w_lo;
     float* lo_buf = nullptr;
