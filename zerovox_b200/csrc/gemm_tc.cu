@@ -41,6 +41,8 @@ struct TcParams {
     int ksx, taps, kchunks, dil, pad_x, pad_y, stride, stride_y;
     int b_batched;
     int stages, stage_bytes, b_tile_bytes, b_tile_stride;
+    // x-tap reuse (xr): one activation tile of 128 + (ksx-1)*dil positions per (dy, k-chunk) serves all ksx taps of the row
+    int xr, xr_na, xr_a_bytes, xr_a_tx, xr_halo;
     uint32_t idesc;
     int Wo, Ho, N;
     float* C;
@@ -65,6 +67,13 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
     d |= (uint64_t)1 << 46;                     // descriptor version (Blackwell)               bits [46,48)
     d |= (uint64_t)2 << 61;                     // layout type: SWIZZLE_128B                    bits [61,64)
     return d;
+}
+
+// The same tile entered `rows` rows (128 B each) further down.  Measured on B200: the 128-byte swizzle is a function of
+// the absolute shared-memory address bits, so a start address that is not aligned to the 1024-byte atom needs NO
+// base-offset field (setting it to (addr >> 7) & 7 produces wrong operands).
+__device__ __forceinline__ uint64_t sw128_desc_rows(uint32_t saddr, int rows) {
+    return sw128_desc(saddr + (uint32_t)rows * 128u);
 }
 
 struct Tile { int n0, x0, y0, img; };
@@ -96,7 +105,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const __grid_constant__ CUtensorMap mapAlo, const __grid_constant__ CUtensorMap mapBlo, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t smem_a_ring = smem_u32(smem);                               // xr mode: activation ring first
+    const uint32_t smem_base = smem_a_ring + (uint32_t)(p.xr_na * p.xr_a_bytes);   // operand stages
     const uint32_t bars = smem_base + (uint32_t)(p.stages * p.stage_bytes);
     // barrier i at bars + 8*i : full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | tmem base slot
     auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
@@ -105,7 +115,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     auto tempty_bar = [&](int b) { return bars + 8u * (uint32_t)(2 * p.stages + 2 + b); };
     const uint32_t tmem_slot = bars + 8u * (uint32_t)(2 * p.stages + 4);
     volatile uint32_t* tmem_slot_ptr =
-        reinterpret_cast<volatile uint32_t*>(smem + p.stages * p.stage_bytes + 8 * (2 * p.stages + 4));
+        reinterpret_cast<volatile uint32_t*>(smem + p.xr_na * p.xr_a_bytes + p.stages * p.stage_bytes + 8 * (2 * p.stages + 4));
+    auto afull_bar = [&](int s) { return bars + 8u * (uint32_t)(2 * p.stages + 5 + s); };
+    auto aempty_bar = [&](int s) { return bars + 8u * (uint32_t)(2 * p.stages + 5 + p.xr_na + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -123,6 +135,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), 8);
+        }
+        for (int s = 0; s < p.xr_na; ++s) {
+            mbar_init(afull_bar(s), 1);
+            mbar_init(aempty_bar(s), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -147,6 +163,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = (uint32_t)(A_TILE_BYTES + p.b_tile_bytes) * (SPLIT ? 2u : 1u);
+            if (!SPLIT && p.xr) {
+                // x-tap reuse: per (dy, k-chunk) ONE activation tile of 128 + halo positions, then the ksx weight tiles
+                int sa = 0;
+                uint32_t pa = 0;
+                const int ksy = p.taps / p.ksx;
+                for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                    const Tile c = decode_tile(p, t);
+                    for (int dy = 0; dy < ksy; ++dy)
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            mbar_wait(aempty_bar(sa), pa ^ 1u);
+                            mbar_arrive_expect_tx(afull_bar(sa), (uint32_t)p.xr_a_tx);
+                            tma_load_4d(&mapA, afull_bar(sa), smem_a_ring + (uint32_t)(sa * p.xr_a_bytes), kc * BK, c.x0 - p.pad_x,
+                                        c.y0 + dy * p.dil - p.pad_y, c.img);
+                            if (++sa == p.xr_na) { sa = 0; pa ^= 1u; }
+                            for (int dx = 0; dx < p.ksx; ++dx) {
+                                mbar_wait(empty_bar(stage), phase ^ 1u);
+                                mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.b_tile_bytes);
+                                tma_load_4d(&mapB, full_bar(stage), smem_base + (uint32_t)(stage * p.stage_bytes), kc * BK, c.n0,
+                                            dy * p.ksx + dx, 0);
+                                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                            }
+                        }
+                }
+            } else
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const Tile c = decode_tile(p, t);
                 for (int s = 0; s < ksteps; ++s) {
@@ -177,6 +217,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             uint32_t cnt = 0;   // accumulation phases issued so far (one per tile unless SPLIT)
+            if (!SPLIT && p.xr) {
+                int sa = 0;
+                uint32_t pa = 0;
+                const int ksy = p.taps / p.ksx;
+                for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++cnt) {
+                    const int buf = (int)(cnt & 1u);
+                    mbar_wait(tempty_bar(buf), ((cnt >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
+                    uint32_t accum = 0u;
+                    for (int dy = 0; dy < ksy; ++dy)
+                        for (int kc = 0; kc < p.kchunks; ++kc) {
+                            mbar_wait(afull_bar(sa), pa);
+                            tc_fence_after();
+                            const uint32_t a_addr = smem_a_ring + (uint32_t)(sa * p.xr_a_bytes);
+                            for (int dx = 0; dx < p.ksx; ++dx) {
+                                mbar_wait(full_bar(stage), phase);
+                                tc_fence_after();
+                                const uint64_t da = sw128_desc_rows(a_addr, dx * p.dil);
+                                const uint64_t db = sw128_desc(smem_base + (uint32_t)(stage * p.stage_bytes));
+#pragma unroll
+                                for (int k = 0; k < BK / 8; ++k) {
+                                    umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, accum);
+                                    accum = 1u;
+                                }
+                                umma_commit(empty_bar(stage));
+                                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                            }
+                            umma_commit(aempty_bar(sa));
+                            if (++sa == p.xr_na) { sa = 0; pa ^= 1u; }
+                        }
+                    umma_commit(tfull_bar(buf));
+                }
+            } else
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 for (int s0 = 0; s0 < ksteps; s0 += phase_len, ++cnt) {
                     const int buf = (int)(cnt & 1u);
@@ -527,9 +601,16 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     ZVX_REQUIRE(!split || (a.A_lo && a.W_lo && aligned16(a.A_lo) && aligned16(a.W_lo)), "gemm_tc: split mode needs both lo operands");
     ZVX_REQUIRE(!split || (!a.acc_mode && a.act_slope == 1.f && !a.C2), "gemm_tc: split mode has the plain epilogue only");
     TcParams p{};
+    // x-tap reuse: the ksx taps of a filter row read one activation tile of 128 + (ksx-1)*dil positions through
+    // row-shifted descriptors instead of ksx separate TMA loads (the activation re-fetch is what bounds small-N convs)
+    static const bool no_xr = getenv("ZVX_NO_XR") != nullptr;
+    const int halo = (a.ksx - 1) * a.dil;
+    // (measured: pays off for filter rows of >= 5 taps — FFN k = 9, HiFi-GAN k = 7 / 11; for 3-tap rows the forced
+    // 128 x 1 tile shape costs more in padding than the saved fetches)
+    const bool xr = !no_xr && !split && a.ksx >= 5 && a.stride == 1 && !a.b_batched && halo <= 120;
     // tile shape: TH x TW = 128 positions, least padding first, wider rows on ties
     long long best = -1;
-    for (int tw = 128; tw >= (a.b_batched ? 128 : 8); tw >>= 1) {   // per-(y,img) W operands: one y per tile
+    for (int tw = 128; tw >= ((a.b_batched || xr) ? 128 : 8); tw >>= 1) {   // per-(y,img) W operands / xr: one y per tile
         const int th = BM / tw;
         const long long padded = round_up(a.Wo, tw) * round_up(a.Ho, th);
         if (best < 0 || padded < best) { best = padded; p.TW = tw; p.TH = th; }
@@ -557,6 +638,13 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.b_tile_stride = (int)round_up(p.b_tile_bytes, 1024);
     p.stage_bytes = (A_TILE_BYTES + p.b_tile_stride) * (split ? 2 : 1);
     p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes);
+    if (xr) {
+        p.xr = 1; p.xr_na = 3; p.xr_halo = halo;
+        p.xr_a_tx = (BM + halo) * BK * 4;
+        p.xr_a_bytes = (int)round_up(p.xr_a_tx, 1024);
+        p.stage_bytes = p.b_tile_stride;   // the operand stages hold weight tiles only
+        p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048 - p.xr_na * p.xr_a_bytes) / p.stage_bytes);
+    }
     // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3, M >> 4
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     p.Wo = a.Wo; p.Ho = a.Ho; p.N = a.N;
@@ -573,7 +661,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
 
     const long long adims[4] = {a.K, a.Wi, a.Hi, a.IMG};
     const long long astr[3] = {a.a_sx, a.a_sy, a.a_simg};
-    const int abox[4] = {BK, p.TW, p.TH, 1};
+    const int abox[4] = {BK, xr ? BM + halo : p.TW, p.TH, 1};
     const long long wdims[4] = {a.K, a.N, a.Z1, a.Z2};
     const long long wstr[3] = {a.w_sn, a.w_s1, a.w_s2};
     const int wbox[4] = {BK, p.BN, 1, 1};
@@ -585,7 +673,8 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     const CUtensorMap mapAlo = split ? make_map(a.A_lo, adims, astr, abox, false, a.stride, sy) : mapA;
     const CUtensorMap mapBlo = split ? make_map(a.W_lo, wdims, wstr, wbox) : mapB;
 
-    const int smem = p.stages * p.stage_bytes + 8 * (2 * p.stages + 4) + 16 + 1024;
+    int smem = p.xr_na * p.xr_a_bytes + p.stages * p.stage_bytes + 8 * (2 * p.stages + 5 + 2 * p.xr_na) + 16 + 1024;
+    smem = std::max(smem, 117 * 1024);   // one CTA per SM: every CTA allocates all 512 TMEM columns
     static bool attr = false;
     if (!attr) {
         ZVX_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
