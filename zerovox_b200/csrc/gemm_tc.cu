@@ -30,7 +30,7 @@ constexpr int A_TILE_BYTES = BM * BK * 4;
 constexpr int NUM_THREADS = 320;          // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;          // TMEM columns between the two accumulators
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 16;          // small-N problems are bound by bytes in flight: more, smaller stages
 constexpr int SPLIT_PHASE = 8;           // k-steps per accumulation phase of the 3xTF32 mode (32 hi*hi MMAs per chain)
 constexpr int LO_OFFSET = 128;           // TMEM column offset of the cross-term accumulator (split mode, BN <= 128)
 constexpr int SMEM_LIMIT = 227 * 1024;
@@ -56,6 +56,7 @@ struct TcParams {
     float act_slope;          // leaky-ReLU slope applied to the value stored in C (1 = identity)
     float* C2; float slope2;  // optional second output lrelu(v, slope2), same addressing as C
     int acc_mode, acc_init; float acc_scale;   // C = (acc_init ? 0 : C) + v * acc_scale
+    long long* dbg;           // optional clock64 trace of CTA 0 (ZVX_GEMM_DBG): [role][event]
 };
 
 // K-major, 128-byte-swizzled operand tile (rows of 32 fp32 = 128 B, 8-row atoms of 1024 B): matrix descriptor.
@@ -172,13 +173,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const Tile c = decode_tile(p, t);
                     for (int dy = 0; dy < ksy; ++dy)
                         for (int kc = 0; kc < p.kchunks; ++kc) {
-                            mbar_wait(aempty_bar(sa), pa ^ 1u);
+                            mbar_wait_spin(aempty_bar(sa), pa ^ 1u);
                             mbar_arrive_expect_tx(afull_bar(sa), (uint32_t)p.xr_a_tx);
                             tma_load_4d(&mapA, afull_bar(sa), smem_a_ring + (uint32_t)(sa * p.xr_a_bytes), kc * BK, c.x0 - p.pad_x,
                                         c.y0 + dy * p.dil - p.pad_y, c.img);
                             if (++sa == p.xr_na) { sa = 0; pa ^= 1u; }
                             for (int dx = 0; dx < p.ksx; ++dx) {
-                                mbar_wait(empty_bar(stage), phase ^ 1u);
+                                mbar_wait_spin(empty_bar(stage), phase ^ 1u);
                                 mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.b_tile_bytes);
                                 tma_load_4d(&mapB, full_bar(stage), smem_base + (uint32_t)(stage * p.stage_bytes), kc * BK, c.n0,
                                             dy * p.ksx + dx, 0);
@@ -189,10 +190,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             } else
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const Tile c = decode_tile(p, t);
+                if (p.dbg && blockIdx.x == 0 && t / (int)gridDim.x < 16) p.dbg[t / gridDim.x] = clock64();
                 for (int s = 0; s < ksteps; ++s) {
                     const int tap = s / p.kchunks, kc = s - tap * p.kchunks;
                     const int dy = tap / p.ksx, dx = tap - dy * p.ksx;
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_wait_spin(empty_bar(stage), phase ^ 1u);
                     mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
                     const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
                     tma_load_4d(&mapA, full_bar(stage), sa, kc * BK, c.x0 * p.stride + dx * p.dil - p.pad_x,
@@ -223,17 +225,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int ksy = p.taps / p.ksx;
                 for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++cnt) {
                     const int buf = (int)(cnt & 1u);
-                    mbar_wait(tempty_bar(buf), ((cnt >> 1) & 1u) ^ 1u);
+                    mbar_wait_spin(tempty_bar(buf), ((cnt >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
                     uint32_t accum = 0u;
                     for (int dy = 0; dy < ksy; ++dy)
                         for (int kc = 0; kc < p.kchunks; ++kc) {
-                            mbar_wait(afull_bar(sa), pa);
+                            mbar_wait_spin(afull_bar(sa), pa);
                             tc_fence_after();
                             const uint32_t a_addr = smem_a_ring + (uint32_t)(sa * p.xr_a_bytes);
                             for (int dx = 0; dx < p.ksx; ++dx) {
-                                mbar_wait(full_bar(stage), phase);
+                                mbar_wait_spin(full_bar(stage), phase);
                                 tc_fence_after();
                                 const uint64_t da = sw128_desc_rows(a_addr, dx * p.dil);
                                 const uint64_t db = sw128_desc(smem_base + (uint32_t)(stage * p.stage_bytes));
@@ -255,12 +257,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int s0 = 0; s0 < ksteps; s0 += phase_len, ++cnt) {
                     const int buf = (int)(cnt & 1u);
                     const uint32_t par = (cnt >> 1) & 1u;
-                    mbar_wait(tempty_bar(buf), par ^ 1u);
+                    mbar_wait_spin(tempty_bar(buf), par ^ 1u);
                     tc_fence_after();
+                    if (p.dbg && blockIdx.x == 0 && cnt < 16) p.dbg[16 + cnt] = clock64();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
                     const int s1 = min(ksteps, s0 + phase_len);
+                    long long waited = 0;
                     for (int s = s0; s < s1; ++s) {
-                        mbar_wait(full_bar(stage), phase);
+                        const long long w0 = p.dbg ? clock64() : 0;
+                        mbar_wait_spin(full_bar(stage), phase);
+                        if (p.dbg) waited += clock64() - w0;
                         tc_fence_after();
                         const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
                         const uint64_t da = sw128_desc(sa), db = sw128_desc(sa + A_TILE_BYTES);
@@ -285,6 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
                     umma_commit(tfull_bar(buf));
+                    if (p.dbg && blockIdx.x == 0 && cnt < 16) { p.dbg[32 + cnt] = clock64(); p.dbg[64 + cnt] = p.dbg[0] + waited; }
                 }
             }
         }
@@ -369,6 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             ++cnt;
             mbar_wait(tfull_bar(buf), par);
             tc_fence_after();
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && cnt <= 16) p.dbg[48 + cnt - 1] = clock64();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
             for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
                 uint32_t v[16];
@@ -684,12 +692,32 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     }
     // > 116 KB keeps the kernel at one CTA per SM (each CTA allocates all 512 TMEM columns)
     ZVX_REQUIRE(p.stages >= 2 && smem <= SMEM_LIMIT && smem > 116 * 1024, "gemm_tc: shared-memory plan out of range");
+    static const char* dbg_env = getenv("ZVX_GEMM_DBG");   // "N": trace launches whose N equals that value
+    static long long* dbg_buf = nullptr;
+    const bool dbg = dbg_env && atoi(dbg_env) == a.N && !split;
+    if (dbg) {
+        if (!dbg_buf) ZVX_CUDA_CHECK(cudaMalloc(&dbg_buf, 80 * sizeof(long long)));
+        ZVX_CUDA_CHECK(cudaMemsetAsync(dbg_buf, 0, 80 * sizeof(long long), st));
+        p.dbg = dbg_buf;
+    }
     const int grid = std::min(p.num_tiles, num_sms());
     const bool general = a.scale || a.acc_mode || a.act_slope != 1.f || a.C2;
     if (split) gemm_tc_kernel<true, true><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
     else if (general) gemm_tc_kernel<true, false><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
     else gemm_tc_kernel<false, false><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
     ZVX_POST_LAUNCH();
+    if (dbg) {
+        long long h[80];
+        ZVX_CUDA_CHECK(cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
+        ZVX_CUDA_CHECK(cudaStreamSynchronize(st));
+        fprintf(stderr, "[gemm dbg] N=%d K=%d taps=%d BN=%d tiles=%d stages=%d xr=%d\n", a.N, a.K, p.taps, p.BN, p.num_tiles, p.stages, p.xr);
+        const char* names[5] = {"producer tile start", "mma tile start", "mma tile committed", "epi tfull seen", "mma wait on TMA data"};
+        for (int r = 0; r < 5; ++r) {
+            fprintf(stderr, "  %-20s:", names[r]);
+            for (int i = 0; i < 10 && h[16 * r + i]; ++i) fprintf(stderr, " %lld", h[16 * r + i] - h[0]);
+            fprintf(stderr, "\n");
+        }
+    }
 }
 
 bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* o) {
