@@ -43,6 +43,7 @@ struct TcParams {
     int stages, stage_bytes, b_tile_bytes, b_tile_stride;
     // x-tap reuse (xr): one activation tile of 128 + (ksx-1)*dil positions per (dy, k-chunk) serves all ksx taps of the row
     int xr, xr_na, xr_a_bytes, xr_a_tx, xr_halo;
+    int ug, unit_bytes;       // k-steps grouped per pipeline stage (small-N problems: fewer barrier round trips / commits)
     uint32_t idesc;
     int Wo, Ho, N;
     float* C;
@@ -57,6 +58,7 @@ struct TcParams {
     float* C2; float slope2;  // optional second output lrelu(v, slope2), same addressing as C
     int acc_mode, acc_init; float acc_scale;   // C = (acc_init ? 0 : C) + v * acc_scale
     long long* dbg;           // optional clock64 trace of CTA 0 (ZVX_GEMM_DBG): [role][event]
+    int dbg_skip;             // experiment: 1 = issue no MMA (data movement only), 2 = issue no TMA (MMAs on stale tiles)
 };
 
 // K-major, 128-byte-swizzled operand tile (rows of 32 fp32 = 128 B, 8-row atoms of 1024 B): matrix descriptor.
@@ -154,6 +156,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int ksteps = p.taps * p.kchunks;
+    // shared-memory descriptor of the first operand stage: low word (address | LBO), and the word common to all (SBO = 1024 B,
+    // version 1, SWIZZLE_128B)
+    const uint32_t desc_lo0 = (uint32_t)(sw128_desc(smem_base) & 0xFFFFFFFFull);
+    const uint32_t DESC_HI = (uint32_t)(sw128_desc(0) >> 32);
     // SPLIT: the tensor core's fp32 accumulate truncates, a bias that grows with the accumulation chain; the chain is
     // cut every SPLIT_PHASE k-steps and the partial sums are added in registers (round-to-nearest) by the epilogue warps.
     const int phase_len = SPLIT ? SPLIT_PHASE : ksteps;
@@ -191,25 +197,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const Tile c = decode_tile(p, t);
                 if (p.dbg && blockIdx.x == 0 && t / (int)gridDim.x < 16) p.dbg[t / gridDim.x] = clock64();
-                for (int s = 0; s < ksteps; ++s) {
-                    const int tap = s / p.kchunks, kc = s - tap * p.kchunks;
-                    const int dy = tap / p.ksx, dx = tap - dy * p.ksx;
+                long long pwait = 0;
+                // (single-thread loop: its instruction latency bounds small tiles -> counters instead of divisions)
+                const int cx = c.x0 * p.stride - p.pad_x, cy = c.y0 * p.stride_y - p.pad_y;
+                const int bz1 = p.b_batched ? c.y0 : 0, bz2 = p.b_batched ? c.img : 0;
+                int kc = 0, dx = 0, dy = 0, tap = 0;
+                const int ug = SPLIT ? 1 : p.ug;
+                for (int s = 0; s < ksteps; s += ug) {
+                    const int ng = SPLIT ? 1 : min(ug, ksteps - s);   // k-steps in this stage
+                    const long long w0 = p.dbg ? clock64() : 0;
                     mbar_wait_spin(empty_bar(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-                    const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
-                    tma_load_4d(&mapA, full_bar(stage), sa, kc * BK, c.x0 * p.stride + dx * p.dil - p.pad_x,
-                                c.y0 * p.stride_y + dy * p.dil - p.pad_y, c.img);
-                    tma_load_4d(&mapB, full_bar(stage), sa + A_TILE_BYTES, kc * BK, c.n0, p.b_batched ? c.y0 : tap,
-                                p.b_batched ? c.img : 0);
-                    if (SPLIT) {
-                        const uint32_t sl = sa + (uint32_t)(A_TILE_BYTES + p.b_tile_stride);
-                        tma_load_4d(&mapAlo, full_bar(stage), sl, kc * BK, c.x0 * p.stride + dx * p.dil - p.pad_x,
-                                    c.y0 * p.stride_y + dy * p.dil - p.pad_y, c.img);
-                        tma_load_4d(&mapBlo, full_bar(stage), sl + A_TILE_BYTES, kc * BK, c.n0, p.b_batched ? c.y0 : tap,
-                                    p.b_batched ? c.img : 0);
+                    if (p.dbg) pwait += clock64() - w0;
+                    if (p.dbg_skip == 2) { mbar_arrive(full_bar(stage)); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
+                    const uint32_t fb = full_bar(stage);
+                    mbar_arrive_expect_tx(fb, tx_bytes * (uint32_t)ng);
+                    uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
+                    for (int j = 0; j < ng; ++j, sa += (uint32_t)p.unit_bytes) {
+                        const int xk = kc * BK, xa = cx + dx * p.dil, ya = cy + dy * p.dil;
+                        const int z1 = p.b_batched ? bz1 : tap;
+                        tma_load_4d(&mapA, fb, sa, xk, xa, ya, c.img);
+                        tma_load_4d(&mapB, fb, sa + A_TILE_BYTES, xk, c.n0, z1, bz2);
+                        if (SPLIT) {
+                            const uint32_t sl = sa + (uint32_t)(A_TILE_BYTES + p.b_tile_stride);
+                            tma_load_4d(&mapAlo, fb, sl, xk, xa, ya, c.img);
+                            tma_load_4d(&mapBlo, fb, sl + A_TILE_BYTES, xk, c.n0, z1, bz2);
+                        }
+                        if (++kc == p.kchunks) {
+                            kc = 0; ++tap;
+                            if (++dx == p.ksx) { dx = 0; ++dy; }
+                        }
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
+                if (p.dbg && blockIdx.x == 0 && t / (int)gridDim.x < 16) p.dbg[48 + t / gridDim.x] = p.dbg[0] + pwait;
             }
         }
         __syncwarp();
@@ -233,15 +253,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait_spin(afull_bar(sa), pa);
                             tc_fence_after();
-                            const uint32_t a_addr = smem_a_ring + (uint32_t)(sa * p.xr_a_bytes);
+                            const uint32_t a_lo = (uint32_t)(sw128_desc(smem_a_ring + (uint32_t)(sa * p.xr_a_bytes)) & 0xFFFFFFFFull);
                             for (int dx = 0; dx < p.ksx; ++dx) {
                                 mbar_wait_spin(full_bar(stage), phase);
                                 tc_fence_after();
-                                const uint64_t da = sw128_desc_rows(a_addr, dx * p.dil);
-                                const uint64_t db = sw128_desc(smem_base + (uint32_t)(stage * p.stage_bytes));
+                                const uint32_t alo = a_lo + (uint32_t)(dx * p.dil * 8);   // one row = 128 B = 8 descriptor units
+                                const uint32_t blo = desc_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);
 #pragma unroll
                                 for (int k = 0; k < BK / 8; ++k) {
-                                    umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, accum);
+                                    umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, accum);
                                     accum = 1u;
                                 }
                                 umma_commit(empty_bar(stage));
@@ -263,29 +283,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
                     const int s1 = min(ksteps, s0 + phase_len);
                     long long waited = 0;
-                    for (int s = s0; s < s1; ++s) {
+                    const int ug = SPLIT ? 1 : p.ug;
+                    for (int s = s0; s < s1; s += ug) {
+                        const int ng = SPLIT ? 1 : min(ug, s1 - s);
                         const long long w0 = p.dbg ? clock64() : 0;
                         mbar_wait_spin(full_bar(stage), phase);
                         if (p.dbg) waited += clock64() - w0;
-                        tc_fence_after();
-                        const uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
-                        const uint64_t da = sw128_desc(sa), db = sw128_desc(sa + A_TILE_BYTES);
-                        const int first = (s == s0);
-                        if (SPLIT) {
-                            const uint32_t sl = sa + (uint32_t)(A_TILE_BYTES + p.b_tile_stride);
-                            const uint64_t la = sw128_desc(sl), lb = sw128_desc(sl + A_TILE_BYTES);
+                        // no tcgen05 fence here: the operands were written by the async proxy (TMA) and the mbarrier
+                        // completion orders them before the MMA's own async-proxy reads
+                        uint32_t alo = desc_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);   // low descriptor words
+                        for (int j = 0; j < ng; ++j, alo += (uint32_t)(p.unit_bytes >> 4)) {
+                            const uint32_t blo = alo + (uint32_t)(A_TILE_BYTES >> 4);
+                            const uint32_t acc0 = (s + j == s0) ? 0u : 1u;
+                            if (SPLIT) {
+                                const uint32_t la = alo + (uint32_t)((A_TILE_BYTES + p.b_tile_stride) >> 4);
+                                const uint32_t lb = la + (uint32_t)(A_TILE_BYTES >> 4);
 #pragma unroll
-                            for (int k = 0; k < BK / 8; ++k) {
-                                const uint32_t accum = (first && k == 0) ? 0u : 1u;
-                                umma_tf32(d_tmem + LO_OFFSET, la + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, accum);
-                                umma_tf32(d_tmem + LO_OFFSET, da + (uint64_t)(2 * k), lb + (uint64_t)(2 * k), p.idesc, 1u);
-                                umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, accum);
+                                for (int k = 0; k < BK / 8; ++k) {
+                                    const uint32_t accum = k == 0 ? acc0 : 1u;
+                                    umma_tf32_lo(d_tmem + LO_OFFSET, la + 2 * k, blo + 2 * k, DESC_HI, p.idesc, accum);
+                                    umma_tf32_lo(d_tmem + LO_OFFSET, alo + 2 * k, lb + 2 * k, DESC_HI, p.idesc, 1u);
+                                    umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, accum);
+                                }
+                            } else if (p.dbg_skip != 1) {
+#pragma unroll
+                                for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes = 2 descriptor units per MMA
+                                    umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, k == 0 ? acc0 : 1u);
                             }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes = 2 descriptor units per MMA
-                                umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc,
-                                          (first && k == 0) ? 0u : 1u);
                         }
                         umma_commit(empty_bar(stage));
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -376,7 +400,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             ++cnt;
             mbar_wait(tfull_bar(buf), par);
             tc_fence_after();
-            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64 && cnt <= 16) p.dbg[48 + cnt - 1] = clock64();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
             for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
                 uint32_t v[16];
@@ -645,6 +668,17 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.b_tile_bytes = p.BN * BK * 4;
     p.b_tile_stride = (int)round_up(p.b_tile_bytes, 1024);
     p.stage_bytes = (A_TILE_BYTES + p.b_tile_stride) * (split ? 2 : 1);
+    p.unit_bytes = p.stage_bytes;
+    p.ug = 1;
+    {   // small stages: group k-steps so that one barrier round trip / commit covers ~40 KB of operands
+        static const int ug_env = getenv("ZVX_GEMM_UG") ? atoi(getenv("ZVX_GEMM_UG")) : 0;
+        const int ksteps = a.ksx * a.ksy * cdiv(a.K, BK);
+        // measured: two k-steps per stage is the sweet spot (22.5 -> 21.4 ms per configs[1] step) as long as >= 3 stages remain
+        int ug = ug_env > 0 ? ug_env : 2;
+        ug = std::min(ug, std::min(4, ksteps));
+        while (ug > 1 && (SMEM_LIMIT - 2048) / (ug * p.unit_bytes) < 3) --ug;
+        if (!split && !xr && ug > 1) { p.ug = ug; p.stage_bytes = ug * p.unit_bytes; }
+    }
     p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes);
     if (xr) {
         p.xr = 1; p.xr_na = 3; p.xr_halo = halo;
@@ -699,6 +733,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
         if (!dbg_buf) ZVX_CUDA_CHECK(cudaMalloc(&dbg_buf, 80 * sizeof(long long)));
         ZVX_CUDA_CHECK(cudaMemsetAsync(dbg_buf, 0, 80 * sizeof(long long), st));
         p.dbg = dbg_buf;
+        p.dbg_skip = getenv("ZVX_GEMM_SKIP") ? atoi(getenv("ZVX_GEMM_SKIP")) : 0;
     }
     const int grid = std::min(p.num_tiles, num_sms());
     const bool general = a.scale || a.acc_mode || a.act_slope != 1.f || a.C2;
@@ -711,7 +746,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
         ZVX_CUDA_CHECK(cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
         ZVX_CUDA_CHECK(cudaStreamSynchronize(st));
         fprintf(stderr, "[gemm dbg] N=%d K=%d taps=%d BN=%d tiles=%d stages=%d xr=%d\n", a.N, a.K, p.taps, p.BN, p.num_tiles, p.stages, p.xr);
-        const char* names[5] = {"producer tile start", "mma tile start", "mma tile committed", "epi tfull seen", "mma wait on TMA data"};
+        const char* names[5] = {"producer tile start", "mma tile start", "mma tile committed", "producer wait empty", "mma wait on TMA data"};
         for (int r = 0; r < 5; ++r) {
             fprintf(stderr, "  %-20s:", names[r]);
             for (int i = 0; i < 10 && h[16 * r + i]; ++i) fprintf(stderr, " %lld", h[16 * r + i] - h[0]);
