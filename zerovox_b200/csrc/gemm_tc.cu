@@ -58,7 +58,7 @@ struct TcParams {
     float* C2; float slope2;  // optional second output lrelu(v, slope2), same addressing as C
     int acc_mode, acc_init; float acc_scale;   // C = (acc_init ? 0 : C) + v * acc_scale
     long long* dbg;           // optional clock64 trace of CTA 0 (ZVX_GEMM_DBG): [role][event]
-    int dbg_skip;             // experiment: 1 = issue no MMA (data movement only), 2 = issue no TMA (MMAs on stale tiles)
+    int dbg_skip;             // experiment bits: 1 = issue no MMA, 2 = issue no TMA (MMAs on stale tiles), 4 = empty epilogue
 };
 
 // K-major, 128-byte-swizzled operand tile (rows of 32 fp32 = 128 B, 8-row atoms of 1024 B): matrix descriptor.
@@ -208,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const long long w0 = p.dbg ? clock64() : 0;
                     mbar_wait_spin(empty_bar(stage), phase ^ 1u);
                     if (p.dbg) pwait += clock64() - w0;
-                    if (p.dbg_skip == 2) { mbar_arrive(full_bar(stage)); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
+                    if (p.dbg_skip & 2) { mbar_arrive(full_bar(stage)); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
                     const uint32_t fb = full_bar(stage);
                     mbar_arrive_expect_tx(fb, tx_bytes * (uint32_t)ng);
                     uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
@@ -305,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                     umma_tf32_lo(d_tmem + LO_OFFSET, alo + 2 * k, lb + 2 * k, DESC_HI, p.idesc, 1u);
                                     umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, accum);
                                 }
-                            } else if (p.dbg_skip != 1) {
+                            } else if (!(p.dbg_skip & 1)) {
 #pragma unroll
                                 for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes = 2 descriptor units per MMA
                                     umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, k == 0 ? acc0 : 1u);
@@ -401,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait(tfull_bar(buf), par);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
-            for (int c0 = half * 16; c0 < p.BN; c0 += 32) {
+            for (int c0 = half * 16; c0 < ((p.dbg_skip & 4) ? 0 : p.BN); c0 += 32) {
                 uint32_t v[16];
                 __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
                 tmem_ld16(trow + (uint32_t)c0, v);
@@ -673,8 +673,9 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     {   // small stages: group k-steps so that one barrier round trip / commit covers ~40 KB of operands
         static const int ug_env = getenv("ZVX_GEMM_UG") ? atoi(getenv("ZVX_GEMM_UG")) : 0;
         const int ksteps = a.ksx * a.ksy * cdiv(a.K, BK);
-        // measured: two k-steps per stage is the sweet spot (22.5 -> 21.4 ms per configs[1] step) as long as >= 3 stages remain
-        int ug = ug_env > 0 ? ug_env : 2;
+        // measured per configs[1] step: 1 k-step per stage 22.5 ms, 2: 21.3, 3: 20.9, 4: 21.0 (>= 3 stages must remain); an
+        // ablated run (no TMA, no MMA, empty epilogue) still costs ~650 cycles per stage hand-shake, tcgen05.commit included
+        int ug = ug_env > 0 ? ug_env : 3;
         ug = std::min(ug, std::min(4, ksteps));
         while (ug > 1 && (SMEM_LIMIT - 2048) / (ug * p.unit_bytes) < 3) --ug;
         if (!split && !xr && ug > 1) { p.ug = ug; p.stage_bytes = ug * p.unit_bytes; }
