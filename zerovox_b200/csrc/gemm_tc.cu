@@ -184,11 +184,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             tma_load_4d(&mapA, afull_bar(sa), smem_a_ring + (uint32_t)(sa * p.xr_a_bytes), kc * BK, c.x0 - p.pad_x,
                                         c.y0 + dy * p.dil - p.pad_y, c.img);
                             if (++sa == p.xr_na) { sa = 0; pa ^= 1u; }
-                            for (int dx = 0; dx < p.ksx; ++dx) {
+                            for (int dx = 0; dx < p.ksx; dx += p.ug) {   // p.ug weight tiles (taps) per stage
+                                const int ng = min(p.ug, p.ksx - dx);
                                 mbar_wait_spin(empty_bar(stage), phase ^ 1u);
-                                mbar_arrive_expect_tx(full_bar(stage), (uint32_t)p.b_tile_bytes);
-                                tma_load_4d(&mapB, full_bar(stage), smem_base + (uint32_t)(stage * p.stage_bytes), kc * BK, c.n0,
-                                            dy * p.ksx + dx, 0);
+                                const uint32_t fb = full_bar(stage);
+                                mbar_arrive_expect_tx(fb, (uint32_t)(p.b_tile_bytes * ng));
+                                for (int j = 0; j < ng; ++j)
+                                    tma_load_4d(&mapB, fb, smem_base + (uint32_t)(stage * p.stage_bytes + j * p.b_tile_stride), kc * BK,
+                                                c.n0, dy * p.ksx + dx + j, 0);
                                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                             }
                         }
@@ -254,15 +257,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             mbar_wait_spin(afull_bar(sa), pa);
                             tc_fence_after();
                             const uint32_t a_lo = (uint32_t)(sw128_desc(smem_a_ring + (uint32_t)(sa * p.xr_a_bytes)) & 0xFFFFFFFFull);
-                            for (int dx = 0; dx < p.ksx; ++dx) {
+                            for (int dx = 0; dx < p.ksx; dx += p.ug) {
+                                const int ng = min(p.ug, p.ksx - dx);
                                 mbar_wait_spin(full_bar(stage), phase);
-                                tc_fence_after();
-                                const uint32_t alo = a_lo + (uint32_t)(dx * p.dil * 8);   // one row = 128 B = 8 descriptor units
-                                const uint32_t blo = desc_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);
+                                uint32_t alo = a_lo + (uint32_t)(dx * p.dil * 8);   // one row = 128 B = 8 descriptor units
+                                uint32_t blo = desc_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);
+                                for (int j = 0; j < ng; ++j, alo += (uint32_t)(p.dil * 8), blo += (uint32_t)(p.b_tile_stride >> 4)) {
 #pragma unroll
-                                for (int k = 0; k < BK / 8; ++k) {
-                                    umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, accum);
-                                    accum = 1u;
+                                    for (int k = 0; k < BK / 8; ++k) {
+                                        umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, accum);
+                                        accum = 1u;
+                                    }
                                 }
                                 umma_commit(empty_bar(stage));
                                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -685,7 +690,9 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
         p.xr = 1; p.xr_na = 3; p.xr_halo = halo;
         p.xr_a_tx = (BM + halo) * BK * 4;
         p.xr_a_bytes = (int)round_up(p.xr_a_tx, 1024);
-        p.stage_bytes = p.b_tile_stride;   // the operand stages hold weight tiles only
+        // the operand stages hold weight tiles only, several taps per stage when they are small (stage hand-shakes are costly)
+        p.ug = std::max(1, std::min(a.ksx, (48 * 1024) / p.b_tile_stride));
+        p.stage_bytes = p.ug * p.b_tile_stride;
         p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048 - p.xr_na * p.xr_a_bytes) / p.stage_bytes);
     }
     // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3, M >> 4
