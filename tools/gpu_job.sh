@@ -21,10 +21,14 @@ rm -f gpurun_out/voc_all.ncu-rep
 # one launch with source (C = 8, k = 11)
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:voc_poly_kernel \
     -s 8 -c 1 -o gpurun_out/voc_poly_c8k11 python tools/prof_step.py > gpurun_out/ncu_voc_src.log 2>&1
-# decoder layer 0 GEMMs (after 31 speaker-net + 34 encoder launches of the same kernel family)
-timeout 900 ncu --set full --clock-control none --profile-from-start off -k regex:gemm_tc_kernel \
-    -s 71 -c 9 -o gpurun_out/gemm_tc_dec python tools/prof_step.py > gpurun_out/ncu_gemm.log 2>&1
-ncu -i gpurun_out/gemm_tc_dec.ncu-rep --page raw --csv > gpurun_out/gemm_tc_dec_raw.csv 2>/dev/null
-rm -f gpurun_out/gemm_tc_dec.ncu-rep
+# every launch of the TMA GEMM family (speaker net, encoder 3xTF32, decoder, vocoder): raw metrics only
+timeout 1500 ncu --set full --clock-control none --profile-from-start off -k regex:gemm_tc_kernel \
+    -o gpurun_out/gemm_tc_all python tools/prof_step.py > gpurun_out/ncu_gemm.log 2>&1
+ncu -i gpurun_out/gemm_tc_all.ncu-rep --page raw --csv > gpurun_out/gemm_tc_all_raw.csv 2>/dev/null
+rm -f gpurun_out/gemm_tc_all.ncu-rep
+# the FFN k = 9 conv of decoder layer 0 with source (largest single kernel)
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_tc_kernel \
+    -s 76 -c 1 -o gpurun_out/gemm_tc_ffn_conv python tools/prof_step.py > gpurun_out/ncu_gemm_src.log 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 ls -la gpurun_out
 du -sh gpurun_out
