@@ -144,7 +144,7 @@ int zvx_vocode(zvx_handle* h, const float* mel_BCL, int B, int L, float* wav, vo
 #define ZVX_PROF_GEMM_TC      1   /* tcgen05 TF32 GEMM / implicit conv */
 #define ZVX_PROF_VOC_CONV     2   /* HiFi-GAN dilated Conv1d (+ fused lrelu / residual / MRF mean / tanh) */
 #define ZVX_PROF_VOC_UPSAMPLE 3   /* HiFi-GAN polyphase ConvTranspose1d */
-#define ZVX_PROF_VOC_TC       4   /* HiFi-GAN fused ResBlock conv pair on tcgen05 (C = 8/16/32) */
+#define ZVX_PROF_VOC_TC       4   /* HiFi-GAN fused ResBlock (+ MRF mean) on tcgen05, C = 8/16/32 */
 #define ZVX_PROF_GEMM_TC3     5   /* tcgen05 3xTF32 split GEMM (fp32-grade products: encoder, variance predictors) */
 #define ZVX_PROF_NUM_CLASSES  6
 int zvx_profile_enable(zvx_handle* h, int on);

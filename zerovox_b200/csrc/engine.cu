@@ -571,7 +571,7 @@ class Engine {
     }
 
     // Tensor-core (channel-last) image of the vocoder weights, used when tensor_core_policy != 0 and every stage has a
-    // channel count one of the tcgen05 kernels covers: C in {8,16,32} -> fused pair kernel (voc_tc.cu); C >= 64 (and a
+    // channel count one of the tcgen05 kernels covers: C in {8,16,32} -> fused resblock kernels (voc_poly.cu, voc_res.cu); C >= 64 (and a
     // multiple of 4) -> generic TMA-fed implicit GEMM (gemm_tc.cu).
     void pack_vocoder_tc() {
         hg_tc_ok = false;
@@ -1130,7 +1130,7 @@ class Engine {
 
     struct View { float* p; long long bs; };
 
-    // Channel-last tensor-core vocoder (gemm_tc.cu + voc_tc.cu); same arithmetic graph as vocode_simt below.
+    // Channel-last tensor-core vocoder (gemm_tc.cu + voc_poly.cu / voc_res.cu); same arithmetic graph as vocode_simt below.
     int vocode_tc(const float* mel_BCL, int B, int L, float* wav, cudaStream_t st) {
         const int C0 = cfg.hg_upsample_initial_channel, M = cfg.n_mels;
         const int nk = cfg.hg_num_kernels, nd = cfg.hg_num_dilations, nu = cfg.hg_num_upsamples;

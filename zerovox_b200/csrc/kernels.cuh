@@ -93,23 +93,8 @@ void conv1d_cf(const Conv1dArgs& a, cudaStream_t st);
 void conv_transpose1d_cf(const float* x, const float* w, const float* bias, int B, int Cin, int Cout, int T, int k,
                          int u, float in_slope, float* out, cudaStream_t st);
 
-// ---- HiFi-GAN on the tensor cores (voc_tc.cu), channel-last [B, T, C] ---------------------------------
-// Fused ResBlock1 pair  x + conv_{k,1}(lrelu(conv_{k,d1}(lrelu(x))))  (w2 != null) or single ResBlock2 conv
-// x + conv_{k,d1}(lrelu(x))  (w2 == null), C in {8, 16, 32}.  Weights in the packed image of voc_pack_weight.
-struct VocPairArgs {
-    const float* x = nullptr; long long x_bs = 0;      // raw input [B][T][C], batch stride in elements
-    const float* w1 = nullptr; const float* b1 = nullptr;
-    const float* w2 = nullptr; const float* b2 = nullptr;
-    int B = 0, T = 0, C = 0, k = 1, d1 = 1;
-    float in_slope = 0.1f, mid_slope = 0.1f;
-    int residual = 1;
-    float* out = nullptr; long long out_bs = 0;        // plain result
-    float* acc = nullptr; long long acc_bs = 0;        // acc = (acc_init ? 0 : acc) + result * acc_scale
-    int acc_init = 0; float acc_scale = 1.f;
-    float* act_out = nullptr; long long act_bs = 0; float act_slope = 0.1f;  // lrelu(acc or result) copy
-};
-bool voc_pair_supported(int C, int k, int dil);
-void voc_pair_tc(const VocPairArgs& a, cudaStream_t st);
+// ---- HiFi-GAN on the tensor cores, channel-last [B, T, C] (voc_res.cu, voc_poly.cu, conv_rs.cu) ---------------------
+// [Cout][Cin][k] (PyTorch Conv1d / flattened Conv2d) -> shared-memory image [k][Cin/4][max(Cout,16)][4], TF32-rounded
 std::vector<float> voc_pack_weight(const float* w, int cout, int cin, int k);
 
 // Whole MRF residual block fused (voc_res.cu): ResBlock1 = [conv_{k,d} (kind 0), conv_{k,1} (kind 1)] per dilation,

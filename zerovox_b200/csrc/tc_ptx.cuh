@@ -1,4 +1,4 @@
-// Inline-PTX wrappers shared by the tcgen05 kernels (gemm_tc.cu, voc_tc.cu): mbarrier, TMA, tcgen05 MMA / TMEM.
+// Inline-PTX wrappers shared by the tcgen05 kernels (gemm_tc.cu, voc_poly.cu, voc_res.cu, conv_rs.cu): mbarrier, TMA, tcgen05 MMA / TMEM.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>

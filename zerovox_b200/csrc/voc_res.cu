@@ -20,6 +20,8 @@
 #include "tc_ptx.cuh"
 
 #include <algorithm>
+#include <cstring>
+#include <vector>
 
 namespace zvx {
 
@@ -338,5 +340,23 @@ void voc_resblock_tc(const VocResArgs& a, cudaStream_t st) {
         default: launch<32>(a, p, st); break;
     }
 }
+
+// [Cout][Cin][k] (PyTorch Conv1d) -> the kernel's shared-memory image [k][Cin/4][Np][4], TF32-rounded (nearest even)
+std::vector<float> voc_pack_weight(const float* w, int cout, int cin, int k) {
+    const int Np = std::max(cout, 16), CQ = cin / 4;
+    std::vector<float> o((size_t)k * CQ * Np * 4, 0.f);
+    for (int n = 0; n < cout; ++n)
+        for (int ci = 0; ci < cin; ++ci)
+            for (int j = 0; j < k; ++j) {
+                float v = w[((size_t)n * cin + ci) * k + j];
+                uint32_t u;
+                memcpy(&u, &v, 4);
+                u = (u + 0x0FFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
+                memcpy(&v, &u, 4);
+                o[(((size_t)j * CQ + ci / 4) * Np + n) * 4 + (ci & 3)] = v;
+            }
+    return o;
+}
+
 
 }  // namespace zvx
