@@ -43,6 +43,7 @@ struct TcParams {
     int stages, stage_bytes, b_tile_bytes, b_tile_stride;
     // x-tap reuse (xr): one activation tile of 128 + (ksx-1)*dil positions per (dy, k-chunk) serves all ksx taps of the row
     int xr, xr_na, xr_a_bytes, xr_a_tx, xr_halo;
+    int spin;                 // single-thread roles spin on their barriers (small tiles)
     int ug, unit_bytes;       // k-steps grouped per pipeline stage (small-N problems: fewer barrier round trips / commits)
     uint32_t idesc;
     int Wo, Ho, N;
@@ -77,6 +78,12 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
 // base-offset field (setting it to (addr >> 7) & 7 produces wrong operands).
 __device__ __forceinline__ uint64_t sw128_desc_rows(uint32_t saddr, int rows) {
     return sw128_desc(saddr + (uint32_t)rows * 128u);
+}
+
+// Waits of the two single-thread roles: small tiles are bound by hand-shake latency (spin on test_wait); with large tiles the
+// waits are long and a spinning thread steals issue slots from the epilogue warps on its scheduler (suspending try_wait).
+__device__ __forceinline__ void mbar_wait_sel(int spin, uint32_t bar, uint32_t parity) {
+    if (spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity);
 }
 
 struct Tile { int n0, x0, y0, img; };
@@ -179,14 +186,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const Tile c = decode_tile(p, t);
                     for (int dy = 0; dy < ksy; ++dy)
                         for (int kc = 0; kc < p.kchunks; ++kc) {
-                            mbar_wait_spin(aempty_bar(sa), pa ^ 1u);
+                            mbar_wait_sel(p.spin, aempty_bar(sa), pa ^ 1u);
                             mbar_arrive_expect_tx(afull_bar(sa), (uint32_t)p.xr_a_tx);
                             tma_load_4d(&mapA, afull_bar(sa), smem_a_ring + (uint32_t)(sa * p.xr_a_bytes), kc * BK, c.x0 - p.pad_x,
                                         c.y0 + dy * p.dil - p.pad_y, c.img);
                             if (++sa == p.xr_na) { sa = 0; pa ^= 1u; }
                             for (int dx = 0; dx < p.ksx; dx += p.ug) {   // p.ug weight tiles (taps) per stage
                                 const int ng = min(p.ug, p.ksx - dx);
-                                mbar_wait_spin(empty_bar(stage), phase ^ 1u);
+                                mbar_wait_sel(p.spin, empty_bar(stage), phase ^ 1u);
                                 const uint32_t fb = full_bar(stage);
                                 mbar_arrive_expect_tx(fb, (uint32_t)(p.b_tile_bytes * ng));
                                 for (int j = 0; j < ng; ++j)
@@ -209,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int s = 0; s < ksteps; s += ug) {
                     const int ng = SPLIT ? 1 : min(ug, ksteps - s);   // k-steps in this stage
                     const long long w0 = p.dbg ? clock64() : 0;
-                    mbar_wait_spin(empty_bar(stage), phase ^ 1u);
+                    mbar_wait_sel(p.spin, empty_bar(stage), phase ^ 1u);
                     if (p.dbg) pwait += clock64() - w0;
                     if (p.dbg_skip & 2) { mbar_arrive(full_bar(stage)); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
                     const uint32_t fb = full_bar(stage);
@@ -248,18 +255,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int ksy = p.taps / p.ksx;
                 for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++cnt) {
                     const int buf = (int)(cnt & 1u);
-                    mbar_wait_spin(tempty_bar(buf), ((cnt >> 1) & 1u) ^ 1u);
+                    mbar_wait_sel(p.spin, tempty_bar(buf), ((cnt >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
                     uint32_t accum = 0u;
                     for (int dy = 0; dy < ksy; ++dy)
                         for (int kc = 0; kc < p.kchunks; ++kc) {
-                            mbar_wait_spin(afull_bar(sa), pa);
+                            mbar_wait_sel(p.spin, afull_bar(sa), pa);
                             tc_fence_after();
                             const uint32_t a_lo = (uint32_t)(sw128_desc(smem_a_ring + (uint32_t)(sa * p.xr_a_bytes)) & 0xFFFFFFFFull);
                             for (int dx = 0; dx < p.ksx; dx += p.ug) {
                                 const int ng = min(p.ug, p.ksx - dx);
-                                mbar_wait_spin(full_bar(stage), phase);
+                                mbar_wait_sel(p.spin, full_bar(stage), phase);
                                 uint32_t alo = a_lo + (uint32_t)(dx * p.dil * 8);   // one row = 128 B = 8 descriptor units
                                 uint32_t blo = desc_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);
                                 for (int j = 0; j < ng; ++j, alo += (uint32_t)(p.dil * 8), blo += (uint32_t)(p.b_tile_stride >> 4)) {
@@ -282,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int s0 = 0; s0 < ksteps; s0 += phase_len, ++cnt) {
                     const int buf = (int)(cnt & 1u);
                     const uint32_t par = (cnt >> 1) & 1u;
-                    mbar_wait_spin(tempty_bar(buf), par ^ 1u);
+                    mbar_wait_sel(p.spin, tempty_bar(buf), par ^ 1u);
                     tc_fence_after();
                     if (p.dbg && blockIdx.x == 0 && cnt < 16) p.dbg[16 + cnt] = clock64();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
@@ -292,7 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int s = s0; s < s1; s += ug) {
                         const int ng = SPLIT ? 1 : min(ug, s1 - s);
                         const long long w0 = p.dbg ? clock64() : 0;
-                        mbar_wait_spin(full_bar(stage), phase);
+                        mbar_wait_sel(p.spin, full_bar(stage), phase);
                         if (p.dbg) waited += clock64() - w0;
                         // no tcgen05 fence here: the operands were written by the async proxy (TMA) and the mbarrier
                         // completion orders them before the MMA's own async-proxy reads
@@ -675,6 +682,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.stage_bytes = (A_TILE_BYTES + p.b_tile_stride) * (split ? 2 : 1);
     p.unit_bytes = p.stage_bytes;
     p.ug = 1;
+    p.spin = (p.BN <= 64) ? 1 : 0;
     {   // small stages: group k-steps so that one barrier round trip / commit covers ~40 KB of operands
         static const int ug_env = getenv("ZVX_GEMM_UG") ? atoi(getenv("ZVX_GEMM_UG")) : 0;
         const int ksteps = a.ksx * a.ksy * cdiv(a.K, BK);
