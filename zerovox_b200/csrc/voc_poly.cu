@@ -35,7 +35,7 @@ namespace {
 constexpr int EPI_THREADS = 256;   // 8 loader / epilogue warps
 constexpr int NT = EPI_THREADS + 32;   // + 1 warp: MMA issuer and weight streamer
 constexpr int MAX_STEPS = VocResArgs::MAX_STEPS;
-constexpr int kRounds = 2;   // operand hand-over rounds per conv step (4 measured slower: each round costs a proxy fence)
+constexpr int kRounds = 2;   // operand hand-over rounds per conv step (4 measured slower twice: 6.7 vs 6.5 ms; each round costs a proxy fence)
 
 struct PolyPlan {
     int nsteps, P, H, TT, R;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(NT) voc_poly_kernel(const VocResArgs a, const 
     const uint32_t sb = smem_u32(smem);
     const uint32_t sA = sb + p.offA;
     constexpr int CQ = C / 4, P = 128 / C, NPH = P / 2;
-    constexpr int NR = kRounds, RPH = NPH / NR;   // operand hand-over in NR rounds of RPH phases per warp group
+    constexpr int NR = kRounds < NPH ? kRounds : NPH, RPH = NPH / NR;   // operand hand-over in NR rounds of RPH phases per warp group
     // barriers: mma_done[2] (one per accumulator buffer) | w_full[2] (weight buffers) | round[NPH] (operand phases ready)
     const uint32_t bars = sb + p.offBar;
     auto mma_bar = [&](int i) { return bars + 8u * (uint32_t)i; };
@@ -378,7 +378,7 @@ bool make_plan(const VocResArgs& a, PolyPlan* out) {
     o = (uint32_t)round_up(o, 16);
     // MMA schedule: round rd of step s hands over the input phases {rd*RPH .. rd*RPH + RPH - 1} + {0, NPH}
     {
-        const int NPH = P / 2, NR = kRounds, RPH = NPH / NR;
+        const int NPH = P / 2, NR = std::min(kRounds, NPH), RPH = NPH / NR;
         int n = 0;
         for (int s = 0; s < ns; ++s) {
             const int cd = p.cd[s];
@@ -412,7 +412,7 @@ bool make_plan(const VocResArgs& a, PolyPlan* out) {
 // The tcgen05.mma list of one block shape in issue order (see the kernel): x = A offset | B offset << 16 (16-byte units
 // relative to the operand bases), y = accumulator column | accumulate flag << 8.
 std::vector<uint2> build_schedule(const VocResArgs& a, const PolyPlan& p) {
-    const int C = a.C, CQ = C / 4, P = p.P, NPH = P / 2, NR = kRounds, RPH = NPH / NR, k = a.k;
+    const int C = a.C, CQ = C / 4, P = p.P, NPH = P / 2, NR = std::min(kRounds, NPH), RPH = NPH / NR, k = a.k;
     auto fdiv = [](int x, int y) { return (x >= 0) ? x / y : -((-x + y - 1) / y); };
     std::vector<uint2> t;
     for (int s = 0; s < p.nsteps; ++s) {
