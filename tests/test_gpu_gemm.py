@@ -130,7 +130,8 @@ def test_conv2d_stride2(eng, B, Hh, Ww, Cin, Cout, ksize, use_tc):
     check(got, ref.reshape(-1, Cout).float(), use_tc, 1.0)
 
 
-@pytest.mark.parametrize("M,N,K", [(32, 528, 5120), (5, 1056, 528), (64, 100, 300), (1, 528, 5120), (33, 8, 256)])
+@pytest.mark.parametrize("M,N,K", [(32, 528, 5120), (5, 1056, 528), (64, 100, 300), (1, 528, 5120), (33, 8, 256),
+                                   (32, 12672, 528), (7, 4230, 300), (40, 8192, 256)])
 def test_skinny_gemm(eng, M, N, K):
     """M <= 64 rows (speaker-net fc 5120 -> 528, SCLN affine stack): the fp32 FMA path switches to the skinny kernel."""
     A, W = rnd(M, K, seed=21), rnd(1, N, K, seed=22)

@@ -7,6 +7,8 @@
 // shared memory with register-staged global loads (one __syncthreads per k-step).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace zvx {
 
 namespace {
@@ -249,12 +251,61 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(const GemmArgs a, const i
     }
 }
 
-// Skinny GEMM (M <= 32 rows, any K): every warp owns one output column and strides over K, so the weight matrix is
-// streamed exactly once by the whole grid (the tiled kernel above would run such a problem on a handful of blocks).
-// Block = 8 warps = 8 columns sharing a [32 x 128] slab of A through shared memory.  fp32 FMA throughout.
-constexpr int SK_KC = 128;
+// Skinny GEMM (M <= 32 rows per pass, any K): lane = output row, warp = 8 output columns, block = 64 columns.  A [32 x 128]
+// and W [64 x 128] slabs go through shared memory once per block (A reads conflict-free across lanes, W reads are warp
+// broadcasts), so the weight matrix is streamed exactly once by the whole grid.  Used when N gives enough 64-column blocks
+// (SCLN / AdaIN affine stacks); narrow outputs (speaker-net fc, N = 528) use the one-warp-per-column kernel below.
+// fp32 FMA throughout, deterministic summation order.
+constexpr int SK_KC = 64, SK_NB = 64;
 __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmArgs a) {
     __shared__ float As[32][SK_KC + 1];
+    __shared__ float Ws[SK_NB][SK_KC + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n0 = blockIdx.x * SK_NB, m0 = blockIdx.y * 32;
+    const int mrows = min(32, a.M - m0);
+    const int kc0 = 0, kc1 = (a.K + SK_KC - 1) / SK_KC;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int kc = kc0; kc < kc1; ++kc) {
+        const int k0 = kc * SK_KC;
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * SK_KC; i += 256) {
+            const int m = i / SK_KC, k = i - m * SK_KC;
+            As[m][k] = (m < mrows && k0 + k < a.K) ? __ldg(a.A + (long long)(m0 + m) * a.lda + k0 + k) : 0.f;
+        }
+        for (int i = threadIdx.x; i < SK_NB * SK_KC; i += 256) {
+            const int n = i / SK_KC, k = i - n * SK_KC;
+            Ws[n][k] = (n0 + n < a.N && k0 + k < a.K) ? __ldg(a.W + (long long)(n0 + n) * a.ldw + k0 + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < SK_KC; ++k) {
+            const float av = As[lane][k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(av, Ws[wid * 8 + j][k], acc[j]);
+        }
+    }
+    if (lane >= mrows) return;
+    const int m = m0 + lane;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = n0 + wid * 8 + j;
+        if (n >= a.N) continue;
+        float x = acc[j];
+        if (a.bias) x += __ldg(a.bias + n);
+        if (a.relu_first) x = fmaxf(x, 0.f);
+        if (a.scale) x = fmaf(x, __ldg(a.scale + n), __ldg(a.shift + n));
+        if (a.R) x += a.R[(long long)m * a.ldr + n];
+        if (a.relu_last) x = fmaxf(x, 0.f);
+        a.C[(long long)m * a.ldc + n] = x * a.post_scale;
+    }
+}
+
+// one warp per output column, lanes stride over K (narrow outputs)
+constexpr int SKC_KC = 128;
+__global__ void __launch_bounds__(256) gemm_skinny_col_kernel(const GemmArgs a) {
+    __shared__ float As[32][SKC_KC + 1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int n = blockIdx.x * 8 + wid;
     const int m0 = blockIdx.y * 32;
@@ -263,15 +314,15 @@ __global__ void __launch_bounds__(256) gemm_skinny_kernel(const GemmArgs a) {
 #pragma unroll
     for (int m = 0; m < 32; ++m) acc[m] = 0.f;
     const float* wrow = a.W + (long long)min(n, a.N - 1) * a.ldw;
-    for (int k0 = 0; k0 < a.K; k0 += SK_KC) {
+    for (int k0 = 0; k0 < a.K; k0 += SKC_KC) {
         __syncthreads();
-        for (int i = threadIdx.x; i < 32 * SK_KC; i += 256) {
-            const int m = i / SK_KC, k = i - m * SK_KC;
+        for (int i = threadIdx.x; i < 32 * SKC_KC; i += 256) {
+            const int m = i / SKC_KC, k = i - m * SKC_KC;
             As[m][k] = (m < mrows && k0 + k < a.K) ? __ldg(a.A + (long long)(m0 + m) * a.lda + k0 + k) : 0.f;
         }
         __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < SK_KC; kk += 32) {
+        for (int kk = 0; kk < SKC_KC; kk += 32) {
             const int k = k0 + kk + lane;
             const float w = (k < a.K) ? __ldg(wrow + k) : 0.f;
 #pragma unroll
@@ -305,8 +356,11 @@ bool gemm_skinny_supported(const GemmArgs& a) {
 
 void gemm_skinny(const GemmArgs& a, cudaStream_t st) {
     ZVX_REQUIRE(gemm_skinny_supported(a), "gemm_skinny: unsupported problem");
-    dim3 grid(cdiv(a.N, 8), cdiv(a.M, 32));
-    gemm_skinny_kernel<<<grid, 256, 0, st>>>(a);
+    if (cdiv(a.N, SK_NB) >= 64) {
+        gemm_skinny_kernel<<<dim3(cdiv(a.N, SK_NB), cdiv(a.M, 32)), 256, 0, st>>>(a);
+    } else {
+        gemm_skinny_col_kernel<<<dim3(cdiv(a.N, 8), cdiv(a.M, 32)), 256, 0, st>>>(a);
+    }
     ZVX_POST_LAUNCH();
 }
 
