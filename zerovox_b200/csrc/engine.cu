@@ -595,14 +595,6 @@ class Engine {
             if (kind == 0) return;
             hg_stage_kind.push_back(kind);
         }
-        auto rn_tf32 = [](float v) {
-            uint32_t u;
-            std::memcpy(&u, &v, 4);
-            u = (u + 0x0FFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
-            std::memcpy(&v, &u, 4);
-            return v;
-        };
-        (void)rn_tf32;
         hg_pre_tc = upload(tap_major(W("_meldec.conv_pre.weight", {C0, cfg.n_mels, 7})));
         size_t ci = 0;
         for (int i = 0; i < cfg.hg_num_upsamples; ++i) {

@@ -73,12 +73,10 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
     return d;
 }
 
-// The same tile entered `rows` rows (128 B each) further down.  Measured on B200: the 128-byte swizzle is a function of
-// the absolute shared-memory address bits, so a start address that is not aligned to the 1024-byte atom needs NO
-// base-offset field (setting it to (addr >> 7) & 7 produces wrong operands).
-__device__ __forceinline__ uint64_t sw128_desc_rows(uint32_t saddr, int rows) {
-    return sw128_desc(saddr + (uint32_t)rows * 128u);
-}
+// A 128-byte-swizzled tile can be entered `rows` rows (128 B each) further down by adding rows * 8 to the descriptor's
+// address field.  Measured on B200: the swizzle is a function of the absolute shared-memory address bits, so a start
+// address that is not aligned to the 1024-byte atom needs NO base-offset field (setting it to (addr >> 7) & 7 produces
+// wrong operands).  The x-tap-reuse path below relies on this.
 
 // Waits of the two single-thread roles: small tiles are bound by hand-shake latency (spin on test_wait); with large tiles the
 // waits are long and a spinning thread steals issue slots from the epilogue warps on its scheduler (suspending try_wait).

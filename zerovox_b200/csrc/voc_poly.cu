@@ -60,23 +60,6 @@ __device__ __forceinline__ float lrelu(float v, float s) { return fmaxf(v, v * s
 // instructions; the cvt runs on the quarter-rate conversion pipe and would dominate the epilogue
 __device__ __forceinline__ float rna_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
-__device__ __forceinline__ uint64_t nosw_desc(uint32_t saddr, uint32_t lbo16) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(lbo16 & 0x3FFFu) << 16;
-    d |= (uint64_t)(128 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    return d;
-}
-
-template <int C>
-__device__ __forceinline__ void tmem_ld_c(uint32_t taddr, uint32_t* v) {
-    if constexpr (C == 8) tmem_ld8(taddr, v);
-    else if constexpr (C == 16) tmem_ld16(taddr, v);
-    else { tmem_ld16(taddr, v); tmem_ld16(taddr + 16, v + 16); }
-}
-
-
 template <int C>
 __global__ void __launch_bounds__(NT) voc_poly_kernel(const VocResArgs a, const PolyPlan p) {
     extern __shared__ uint8_t smem_raw[];
@@ -148,7 +131,6 @@ __global__ void __launch_bounds__(NT) voc_poly_kernel(const VocResArgs a, const 
             };
             load_w(0);
             for (int s = 0; s < p.nsteps; ++s) {
-                const uint32_t sW = sb + p.offW + (uint32_t)((s & 1) * p.wbuf_bytes);
                 const uint32_t d_tmem = tmem_base + (uint32_t)((s & 1) * 128);
                 const uint32_t rpar = (uint32_t)(s & 1);            // round barriers complete once per step (load = step -1)
                 // every MMA of the step comes from the precomputed schedule: {A offset | B offset << 16, D column | flags};

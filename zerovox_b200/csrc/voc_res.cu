@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(NT) voc_resblock_kernel(const VocResArgs a, co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const uint32_t sb = smem_u32(smem);
-    const uint32_t sX = sb + p.offX, sA = sb + p.offA, sW = sb + p.offW;
+    const uint32_t sA = sb + p.offA, sW = sb + p.offW;
     const uint32_t bar = sb + p.offBar, slot = bar + 8;
     volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + p.offBar + 8);
     float4* Xs = reinterpret_cast<float4*>(smem + p.offX);
