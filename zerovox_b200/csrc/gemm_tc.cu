@@ -43,6 +43,7 @@ struct TcParams {
     int stages, stage_bytes, b_tile_bytes, b_tile_stride;
     // x-tap reuse (xr): one activation tile of 128 + (ksx-1)*dil positions per (dy, k-chunk) serves all ksx taps of the row
     int xr, xr_na, xr_a_bytes, xr_a_tx, xr_halo;
+    int mt, a_bytes;          // MMA M tiles (128 positions each) per CTA tile, bytes of the activation tile
     int spin;                 // single-thread roles spin on their barriers (small tiles)
     int ug, unit_bytes;       // k-steps grouped per pipeline stage (small-N problems: fewer barrier round trips / commits)
     uint32_t idesc;
@@ -174,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const uint32_t tx_bytes = (uint32_t)(A_TILE_BYTES + p.b_tile_bytes) * (SPLIT ? 2u : 1u);
+            const uint32_t tx_bytes = (uint32_t)(p.a_bytes + p.b_tile_bytes) * (SPLIT ? 2u : 1u);
             if (!SPLIT && p.xr) {
                 // x-tap reuse: per (dy, k-chunk) ONE activation tile of 128 + halo positions, then the ksx weight tiles
                 int sa = 0;
@@ -224,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         const int xk = kc * BK, xa = cx + dx * p.dil, ya = cy + dy * p.dil;
                         const int z1 = p.b_batched ? bz1 : tap;
                         tma_load_4d(&mapA, fb, sa, xk, xa, ya, c.img);
-                        tma_load_4d(&mapB, fb, sa + A_TILE_BYTES, xk, c.n0, z1, bz2);
+                        tma_load_4d(&mapB, fb, sa + (uint32_t)p.a_bytes, xk, c.n0, z1, bz2);
                         if (SPLIT) {
                             const uint32_t sl = sa + (uint32_t)(A_TILE_BYTES + p.b_tile_stride);
                             tma_load_4d(&mapAlo, fb, sl, xk, xa, ya, c.img);
@@ -303,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         // completion orders them before the MMA's own async-proxy reads
                         uint32_t alo = desc_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);   // low descriptor words
                         for (int j = 0; j < ng; ++j, alo += (uint32_t)(p.unit_bytes >> 4)) {
-                            const uint32_t blo = alo + (uint32_t)(A_TILE_BYTES >> 4);
+                            const uint32_t blo = alo + (uint32_t)(p.a_bytes >> 4);
                             const uint32_t acc0 = (s + j == s0) ? 0u : 1u;
                             if (SPLIT) {
                                 const uint32_t la = alo + (uint32_t)((A_TILE_BYTES + p.b_tile_stride) >> 4);
@@ -316,9 +317,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                     umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, accum);
                                 }
                             } else if (!(p.dbg_skip & 1)) {
+                                for (int mi = 0; mi < p.mt; ++mi) {   // the M tiles of the CTA tile share the weight tile
+                                    const uint32_t am = alo + (uint32_t)(mi * (A_TILE_BYTES >> 4));
 #pragma unroll
-                                for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes = 2 descriptor units per MMA
-                                    umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, k == 0 ? acc0 : 1u);
+                                    for (int k = 0; k < BK / 8; ++k)   // 8 tf32 = 32 bytes = 2 descriptor units per MMA
+                                        umma_tf32_lo(d_tmem + (uint32_t)(mi * p.BN), am + 2 * k, blo + 2 * k, DESC_HI, p.idesc,
+                                                     k == 0 ? acc0 : 1u);
+                                }
                             }
                         }
                         umma_commit(empty_bar(stage));
@@ -335,14 +340,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // Two warps per TMEM lane quarter; they take alternate 16-column chunks of the accumulator.
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;
-        const int r = q * 32 + lane;            // position within the tile
-        const int ty = r / p.TW, tx = r - ty * p.TW;
         uint32_t cnt = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             const Tile c = decode_tile(p, t);
-            const int y = c.y0 + ty, x = c.x0 + tx;
-            const bool valid = (y < p.Ho) && (x < p.Wo);
-            const long long off = (long long)c.img * p.c_simg + (long long)y * p.c_sy + (long long)x * p.c_sx;
+            // position of this thread's accumulator row inside M tile mi of the CTA tile
+            int r = q * 32 + lane;
+            int ty = r / p.TW, tx = r - ty * p.TW;
+            int y = c.y0 + ty, x = c.x0 + tx;
+            bool valid = (y < p.Ho) && (x < p.Wo);
+            long long off = (long long)c.img * p.c_simg + (long long)y * p.c_sy + (long long)x * p.c_sx;
             float* __restrict__ cp = p.C + off;
             const float* __restrict__ rp =
                 p.R ? p.R + ((long long)c.img * p.r_simg + (long long)y * p.r_sy + (long long)x * p.r_sx) : nullptr;
@@ -410,7 +416,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             ++cnt;
             mbar_wait(tfull_bar(buf), par);
             tc_fence_after();
-            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
+            for (int mi = 0; mi < p.mt; ++mi) {
+            if (mi > 0) {
+                r = mi * BM + q * 32 + lane;
+                ty = r / p.TW; tx = r - ty * p.TW;
+                y = c.y0 + ty; x = c.x0 + tx;
+                valid = (y < p.Ho) && (x < p.Wo);
+                off = (long long)c.img * p.c_simg + (long long)y * p.c_sy + (long long)x * p.c_sx;
+                cp = p.C + off;
+                rp = p.R ? p.R + ((long long)c.img * p.r_simg + (long long)y * p.r_sy + (long long)x * p.r_sx) : nullptr;
+            }
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE + mi * p.BN);
             for (int c0 = half * 16; c0 < ((p.dbg_skip & 4) ? 0 : p.BN); c0 += 32) {
                 uint32_t v[16];
                 __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
@@ -519,6 +535,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     }
                 }
             }
+            }   // mi
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
@@ -649,12 +666,30 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     // (measured: pays off for filter rows of >= 5 taps — FFN k = 9, HiFi-GAN k = 7 / 11; for 3-tap rows the forced
     // 128 x 1 tile shape costs more in padding than the saved fetches)
     const bool xr = !no_xr && !split && a.ksx >= 5 && a.stride == 1 && !a.b_batched && halo <= 120;
-    // tile shape: TH x TW = 128 positions, least padding first, wider rows on ties
+    // tile shape: TH x TW = 128 * mt positions, least padding first, wider rows on ties.  Two M tiles per CTA tile for narrow
+    // outputs (N <= 64): they share every weight tile and, above all, every stage hand-shake and per-tile overhead.
+    static const bool no_mt2 = getenv("ZVX_NO_MT2") != nullptr;
+    const long long positions = (long long)a.IMG * a.Ho * a.Wo;
+    static const int mt2_n = getenv("ZVX_MT2_N") ? atoi(getenv("ZVX_MT2_N")) : 64;
+    p.mt = (!no_mt2 && !split && !xr && !a.b_batched && a.N <= mt2_n && positions >= 2LL * 256 * num_sms()) ? 2 : 1;
     long long best = -1;
-    for (int tw = 128; tw >= ((a.b_batched || xr) ? 128 : 8); tw >>= 1) {   // per-(y,img) W operands / xr: one y per tile
-        const int th = BM / tw;
-        const long long padded = round_up(a.Wo, tw) * round_up(a.Ho, th);
-        if (best < 0 || padded < best) { best = padded; p.TW = tw; p.TH = th; }
+    for (int pass = 0; pass < 2 && best < 0; ++pass) {
+        const int bm = BM * p.mt;
+        for (int tw = std::min(bm, 256); tw >= ((a.b_batched || xr) ? 128 : 8); tw >>= 1) {   // per-(y,img) W operands / xr: one y per tile
+            const int th = bm / tw;
+            if (th * a.stride > 256 || tw * a.stride > 256) continue;
+            const long long padded = round_up(a.Wo, tw) * round_up(a.Ho, th);
+            if (best < 0 || padded < best) { best = padded; p.TW = tw; p.TH = th; }
+        }
+        // two M tiles must not cost more than a few percent of extra padding
+        if (p.mt == 2) {
+            long long best1 = -1;
+            for (int tw = 128; tw >= 8; tw >>= 1) {
+                const long long padded = round_up(a.Wo, tw) * round_up(a.Ho, BM / tw);
+                if (best1 < 0 || padded < best1) best1 = padded;
+            }
+            if (best < 0 || best * 100 > best1 * 104) { p.mt = 1; best = -1; }
+        }
     }
     // column tile: multiple of 16, <= 256, least padding over a few tile counts
     {
@@ -677,7 +712,8 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.b_batched = a.b_batched;
     p.b_tile_bytes = p.BN * BK * 4;
     p.b_tile_stride = (int)round_up(p.b_tile_bytes, 1024);
-    p.stage_bytes = (A_TILE_BYTES + p.b_tile_stride) * (split ? 2 : 1);
+    p.a_bytes = p.mt * A_TILE_BYTES;
+    p.stage_bytes = (p.a_bytes + p.b_tile_stride) * (split ? 2 : 1);
     p.unit_bytes = p.stage_bytes;
     p.ug = 1;
     p.spin = (p.BN <= 64) ? 1 : 0;
