@@ -665,7 +665,8 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     const int halo = (a.ksx - 1) * a.dil;
     // (measured: pays off for filter rows of >= 5 taps — FFN k = 9, HiFi-GAN k = 7 / 11; for 3-tap rows the forced
     // 128 x 1 tile shape costs more in padding than the saved fetches)
-    const bool xr = !no_xr && !split && a.ksx >= 5 && a.stride == 1 && !a.b_batched && halo <= 120;
+    static const int xr_mink = getenv("ZVX_XR_MINK") ? atoi(getenv("ZVX_XR_MINK")) : 5;
+    const bool xr = !no_xr && !split && a.ksx >= xr_mink && a.stride == 1 && !a.b_batched && halo <= 120;
     // tile shape: TH x TW = 128 * mt positions, least padding first, wider rows on ties.  Two M tiles per CTA tile for narrow
     // outputs (N <= 64): they share every weight tile and, above all, every stage hand-shake and per-tile overhead.
     static const bool no_mt2 = getenv("ZVX_NO_MT2") != nullptr;
