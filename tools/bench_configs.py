@@ -82,6 +82,33 @@ def config1(args, dev):
     print(json.dumps(rec), flush=True)
 
 
+def config2(args, dev):
+    """configs[1] shape (B = 32 x T = 128, forced durations) for either decoder kind; stage split from CUDA events."""
+    import dataclasses
+    cfg = dataclasses.replace(syn.ZeroVoxConfig(), decoder_kind=args.decoder)
+    w = syn.make_weights(cfg, seed=0)
+    model = build_model(cfg, w, device=dev)
+    eng = model._shared_ctx.get(dev)
+    x = {k: v.to(dev) for k, v in syn.make_inputs(cfg, 32, 128, 440, seed=7).items()}
+    with torch.no_grad():
+        out = {}
+
+        def run():
+            out["r"] = model(x, force_duration=True)
+        ms = timed(run, args.iters, dev)
+        style = eng.spkemb(x["ref_mel"])
+        r = eng.encode(x["phoneme"], x["puncts"], style, None, x["duration"])
+        feats = eng.length_regulate(r["xprime"], r["duration_rounded"], r["L_max"])
+        mel = eng.decode(feats, style, mel_len=r["mel_len"], want_blc=False)[1]
+        stages = {"spkemb": timed(lambda: eng.spkemb(x["ref_mel"]), args.iters, dev),
+                  "encode": timed(lambda: eng.encode(x["phoneme"], x["puncts"], style, None, x["duration"]), args.iters, dev),
+                  "decode": timed(lambda: eng.decode(feats, style, mel_len=r["mel_len"], want_blc=False), args.iters, dev),
+                  "vocode": timed(lambda: eng.vocode(mel), args.iters, dev)}
+    frames = int(out["r"][2].sum())
+    print(json.dumps({"config": 2, "decoder": args.decoder, "ms": round(ms, 3), "stage_ms": {k: round(v, 3) for k, v in stages.items()},
+                      "mel_frames": frames, "audio_sec_per_sec": frames * 256 / 22050 / ms * 1e3}), flush=True)
+
+
 def config3(args, dev):
     for v in ("v2", "v1"):
         h = getattr(syn.HifiGanConfig, v)()
@@ -165,7 +192,8 @@ def config4(args, dev, rank, world):
 
 def main():
     p = argparse.ArgumentParser()
-    p.add_argument("--config", type=int, required=True, choices=[1, 3, 4, 5])
+    p.add_argument("--config", type=int, required=True, choices=[1, 2, 3, 4, 5])
+    p.add_argument("--decoder", default="fastspeech2", choices=["fastspeech2", "styletts"])
     p.add_argument("--cpu", action="store_true", help="config 1: also time the CPU oracle")
     p.add_argument("--iters", type=int, default=5)
     p.add_argument("--chunk", type=int, default=2048)
@@ -176,6 +204,8 @@ def main():
     torch.cuda.set_device(dev)
     if args.config == 1:
         config1(args, dev)
+    elif args.config == 2:
+        config2(args, dev)
     elif args.config == 3:
         config3(args, dev)
     elif args.config == 5:
