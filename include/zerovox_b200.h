@@ -168,6 +168,74 @@ typedef struct zvx_gemm_desc {
 } zvx_gemm_desc;
 int zvx_debug_gemm(zvx_handle* h, const zvx_gemm_desc* d, int use_tc, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Callers either side of the path.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Speaker-prompt front-end: what ZeroVoxTTS.speaker_embed (zerovox/tts/synthesize.py:123-143) does before `_spkemb`,
+ * i.e. librosa.effects.trim(top_db=40) and get_mel_from_wav (zerovox/tts/mels.py:356-394), on the GPU.  Independent of
+ * the model weights, hence its own handle.  Audio arguments of ZeroVoxTTS.__init__ (synthesize.py:48-60; values from
+ * configs/tts_medium.yaml:3-12). */
+typedef struct zvx_frontend zvx_frontend;
+typedef struct zvx_mel_config {
+    int32_t abi_version;    /* must be ZVX_ABI_VERSION */
+    int32_t sampling_rate;  /* 22050 */
+    int32_t fft_size;       /* 1024 (the only size built) */
+    int32_t hop_size;       /* 256 */
+    int32_t win_length;     /* 1024 (<= fft_size; centred, as librosa pads it) */
+    int32_t num_mels;       /* 80 */
+    float   fmin;           /* 0 */
+    float   fmax;           /* 8000 */
+    float   clip_val;       /* 1e-5 (dynamic_range_compression_numpy, mels.py:350); <= 0 selects 1e-5 */
+    int32_t reserved[7];
+} zvx_mel_config;
+
+int  zvx_frontend_create(const zvx_mel_config* cfg, int device, zvx_frontend** out);
+void zvx_frontend_destroy(zvx_frontend* h);
+const char* zvx_frontend_last_error(const zvx_frontend* h);   /* h may be NULL for create failures */
+
+/* Frames get_mel_from_wav yields for n_samples of audio: 1 + (n + 2*pad - fft_size) / hop with pad = (fft_size-hop)/2
+ * (reflect padding needs n > pad; 0 otherwise). */
+int64_t zvx_mel_num_frames(const zvx_frontend* h, int64_t n_samples);
+
+/* librosa.effects.trim(wav, top_db) with its defaults frame_length = 2048, hop_length = 512 (synthesize.py:126).
+ * wav fp32 [B, n_stride]; wav_len int64 [B] (device, NULL = n_stride each).  Writes the kept window per utterance to
+ * start / len (device int64 [B]: samples [start, start + len)).  If start_len_host != NULL (host int64 [2*B]: B starts
+ * then B lengths) the call synchronises `stream` once and returns them there, so the caller can size the mel. */
+int zvx_trim_silence(zvx_frontend* h, const float* wav, int B, int64_t n_stride, const int64_t* wav_len, float top_db,
+                     int frame_length, int hop_length, int64_t* start, int64_t* len, int64_t* start_len_host,
+                     void* stream);
+
+/* get_mel_from_wav (mels.py:356-394), fused: reflect pad, Hann STFT magnitude, Slaney mel filterbank, log(clip), energy.
+ * wav fp32 [B, n_stride]; wav_start / wav_len device int64 [B] select the window of each row (NULL = 0 / the rest of the
+ * row) — the outputs of zvx_trim_silence plug in directly.  mel_BTC fp32 [B, n_frames, num_mels] (the reference's `spec`
+ * transposed: exactly the `_spkemb` / zvx_spkemb input layout); energy fp32 [B, n_frames] or NULL.  Rows beyond an
+ * utterance's own frame count are zero-filled. */
+int zvx_mel_spectrogram(zvx_frontend* h, const float* wav, int B, int64_t n_stride, const int64_t* wav_start,
+                        const int64_t* wav_len, int n_frames, float* mel_BTC, float* energy, void* stream);
+
+/* Tokeniser + padding collator — host memory only, no device work.
+ * Symbols (zerovox/tts/symbols.py:2-49): vocabularies given as UTF-8 strings of single code points
+ * (configs/tts_medium.yaml:20-21); punct id 0 is the reserved '_NP_'. */
+typedef struct zvx_symbols zvx_symbols;
+int  zvx_symbols_create(const char* phones_utf8, const char* puncts_utf8, zvx_symbols** out);
+void zvx_symbols_destroy(zvx_symbols* s);
+const char* zvx_symbols_last_error(const zvx_symbols* s);
+int  zvx_symbols_num_phones(const zvx_symbols* s);   /* Symbols.num_phones */
+int  zvx_symbols_num_puncts(const zvx_symbols* s);   /* Symbols.num_puncts (includes '_NP_') */
+
+/* ZeroVoxTTS.transcript2phonemids (synthesize.py:145-190).  Returns the number of phones; at most `capacity` entries
+ * are written to phone_ids / punct_ids (host int32), so a return value > capacity means "call again with that much".
+ * Negative = error (-2: a blank met a vocabulary without ' ', where the reference raises KeyError). */
+int zvx_transcript2phonemids(zvx_symbols* s, const char* transcript_utf8, int32_t* phone_ids, int32_t* punct_ids,
+                             int capacity);
+
+/* collate_fn's padding (zerovox/tts/data.py:56-60, 82-83; get_mask_from_lengths fs2.py:565-573): B host sequences of
+ * lens[b] <= T ids -> phoneme / puncts int32 [B, T] zero-padded, phoneme_mask uint8 [B, T] (1 = padding; nullable):
+ * the zvx_encode inputs. */
+int zvx_collate(const int32_t* const* phone_seqs, const int32_t* const* punct_seqs, const int32_t* lens, int B, int T,
+                int32_t* phoneme, int32_t* puncts, uint8_t* phoneme_mask);
+
 /* Workspace control: bytes of engine-owned scratch currently reserved on the device. */
 int64_t zvx_workspace_bytes(const zvx_handle* h);
 

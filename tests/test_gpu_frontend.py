@@ -1,0 +1,153 @@
+"""GPU parity of the speaker-prompt front-end (csrc/frontend.cu) through the C ABI, against the
+oracle (oracle/frontend_oracle.py) and the goldens the reference's own get_mel_from_wav produced.
+
+Tolerances: the FFT runs in fp32 on the GPU and in float64 in librosa / the oracle, so a magnitude carries an absolute
+error of ~1e-6 x the frame's largest bin; on the log-mel that is <= 2e-3 absolute wherever the mel value is > 1e-3 x the
+frame's largest mel value (and the linear mel is compared everywhere, relative to the frame's largest);
+trim bounds (integers) are exact for signals whose frames are not within 0.01 dB of the threshold."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import frontend_oracle as fo
+from oracle import zerovox_oracle as zo
+from zerovox_b200.frontend import MelFrontend
+from zerovox_b200.synthetic import make_speech_like
+from zerovox_b200.testing import build_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def fe():
+    return MelFrontend(device=DEV)
+
+
+def check_mel(got_BTC, ref_spec, got_energy=None, ref_energy=None):
+    got = got_BTC.cpu().numpy().T                    # [80, frames] like the reference
+    assert got.shape == ref_spec.shape, (got.shape, ref_spec.shape)
+    lin_g, lin_r = np.exp(got.astype(np.float64)), np.exp(ref_spec.astype(np.float64))
+    fmax = lin_r.max(axis=0, keepdims=True)
+    e_lin = (np.abs(lin_g - lin_r) / fmax).max()
+    sig = lin_r > 1e-3 * fmax
+    e_log = np.abs(got - ref_spec)[sig].max()
+    print(f"  frames {got.shape[1]:5d}  linear mel err / frame max {e_lin:.2e}   log-mel err (significant bins) {e_log:.2e}")
+    assert e_lin < 2e-5 and e_log < 2e-3
+    if got_energy is not None:
+        e = np.abs(got_energy.cpu().numpy() - ref_energy).max() / ref_energy.max()
+        print(f"  energy rel err {e:.2e}")
+        assert e < 1e-5
+
+
+@pytest.mark.parametrize("name", ["short", "prompt"])
+def test_mel_matches_reference_golden(fe, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "melfront.npz"))
+    wav = make_speech_like(int(g[name + "_n"]), seed=int(g[name + "_seed"]))
+    mel, energy = fe.mel(torch.from_numpy(wav).to(DEV), with_energy=True)
+    check_mel(mel[0], g[name + "_spec"], energy[0], g[name + "_energy"])
+
+
+@pytest.mark.parametrize("n", [385, 1024, 1279, 1280, 22050 * 5 + 17])
+def test_mel_matches_oracle_edge_lengths(fe, n):
+    # 385 = shortest legal input (reflect padding needs n > 384); 1279/1280 straddle a frame boundary
+    wav = make_speech_like(n, seed=n % 97, lead=0.0, tail=0.0)
+    spec, energy = fo.get_mel_from_wav(wav)
+    assert fe.num_frames(n) == spec.shape[1] == n // 256
+    mel, en = fe.mel(torch.from_numpy(wav).to(DEV), with_energy=True)
+    check_mel(mel[0], spec, en[0], energy)
+
+
+def test_mel_too_short_gives_no_frames(fe):
+    assert fe.num_frames(384) == 0 and fe.num_frames(0) == 0
+    mel = fe.mel(torch.zeros(300, device=DEV))
+    assert mel.shape == (1, 0, 80)
+
+
+def test_mel_pure_tone_and_silence(fe):
+    n = 8192
+    t = np.arange(n) / 22050.0
+    tone = (0.5 * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)
+    spec, _ = fo.get_mel_from_wav(tone)
+    check_mel(fe.mel(torch.from_numpy(tone).to(DEV))[0], spec)
+    silent = fe.mel(torch.zeros(n, device=DEV))[0].cpu().numpy()
+    assert np.array_equal(silent, np.full_like(silent, np.log(np.float32(1e-5))))     # the clip floor, exactly
+
+
+def test_mel_batched_windows_match_per_item(fe):
+    """[B, n] rows with device-side (start, len) windows — rows are zero-filled beyond their own frame count."""
+    lens = [30000, 12345, 700, 22050]
+    starts = [0, 1000, 64, 3]
+    n = 32000
+    wavs = np.stack([make_speech_like(n, seed=10 + i, lead=0.0, tail=0.0) for i in range(len(lens))])
+    F = max(l // 256 for l in lens)
+    mel, en = fe.mel(torch.from_numpy(wavs).to(DEV), wav_start=torch.tensor(starts, device=DEV),
+                     wav_len=torch.tensor(lens, device=DEV), n_frames=F, with_energy=True)
+    for b, (s, l) in enumerate(zip(starts, lens)):
+        spec, energy = fo.get_mel_from_wav(wavs[b, s:s + l])
+        k = spec.shape[1]
+        check_mel(mel[b, :k], spec, en[b, :k], energy)
+        assert not mel[b, k:].any() and not en[b, k:].any()
+
+
+def test_trim_matches_oracle(fe):
+    n = 44223
+    wavs = np.stack([make_speech_like(n, seed=s, lead=l, tail=t) for s, l, t in ((2, .12, .10), (3, .0, .3), (4, .25, .0))]
+                    + [np.full(n, 0.3, dtype=np.float32), np.zeros(n, dtype=np.float32)])
+    lens = [n, n, 30000, n, 5000]
+    start, length, hs, hl = fe.trim(torch.from_numpy(wavs).to(DEV), wav_len=torch.tensor(lens, device=DEV))
+    for b in range(len(lens)):
+        _, (a, e) = fo.trim(wavs[b, :lens[b]])
+        assert (hs[b], hs[b] + hl[b]) == (a, e), (b, hs[b], hl[b], a, e)
+    assert start.tolist() == hs and length.tolist() == hl
+    # other trim parameters
+    _, _, hs, hl = fe.trim(torch.from_numpy(wavs[:1]).to(DEV), top_db=20.0, frame_length=1024, hop_length=256)
+    _, (a, e) = fo.trim(wavs[0], top_db=20.0, frame_length=1024, hop_length=256)
+    assert (hs[0], hs[0] + hl[0]) == (a, e)
+
+
+def test_speaker_prompt_mel_and_speaker_embed_mirror():
+    """ZeroVoxTTS.speaker_embed (synthesize.py:123-143) through the mirror: trim -> mel -> `_spkemb`, against the
+    oracle composition (speaker net in fp32 FMA, policy 0, so the only differences are the front-end's)."""
+    from zerovox_b200.tts.symbols import Symbols
+    from zerovox_b200.tts.synthesize import ZeroVoxTTS
+    cfg = zo.ZeroVoxConfig.tiny()
+    w = zo.make_weights(cfg, seed=0)
+    model = build_model(cfg, w, device=DEV, tensor_core_policy=0)
+    tts = ZeroVoxTTS(language="en", syms=Symbols(cfg.phones, cfg.puncts), checkpoint=None, meldec_model=None,
+                     hop_length=256, sampling_rate=22050, n_mel_channels=80, fft_size=1024, win_length=1024, mel_fmin=0,
+                     mel_fmax=8000, infer_device=DEV, model=model)
+    wav = make_speech_like(22050 * 2, seed=5)
+    ref_mel = fo.speaker_prompt_mel(wav)
+    got_mel = tts._frontend.speaker_prompt_mel(torch.from_numpy(wav).to(DEV))
+    check_mel(got_mel[0], ref_mel[0].T)
+    style = tts.speaker_embed(wav)                                  # numpy in, like the reference's caller
+    with torch.no_grad():
+        ref = zo.speaker_embed(cfg, w, torch.from_numpy(ref_mel))
+    assert style.shape == ref.shape
+    err = (style.cpu() - ref).abs().max().item()
+    print(f"  style |diff| {err:.2e}  (unit-norm vector of {ref.shape[-1]})")
+    assert err < 2e-4 and abs(style.norm().item() - 1.0) < 1e-5
+    assert tts.transcript2phonemids("this is a test.") == fo.transcript2phonemids(fo.Symbols(cfg.phones, cfg.puncts),
+                                                                                  "this is a test.")
+
+
+def test_get_mel_from_wav_mirror_signature():
+    from zerovox_b200.tts.mels import get_mel_from_wav
+    wav = make_speech_like(6000, seed=8)
+    spec, energy = get_mel_from_wav(audio=wav, sampling_rate=22050, fft_size=1024, hop_size=256, win_length=1024,
+                                    num_mels=80, fmin=0, fmax=8000)
+    ospec, oenergy = fo.get_mel_from_wav(wav)
+    assert isinstance(spec, np.ndarray) and spec.shape == ospec.shape and energy.shape == oenergy.shape
+    check_mel(torch.from_numpy(spec.T.copy()), ospec)
+
+
+def test_frontend_rejects_unsupported_config_and_cpu_tensors(fe):
+    with pytest.raises(RuntimeError, match="fft_size"):
+        MelFrontend(fft_size=2048, win_length=2048, device=DEV)
+    with pytest.raises(RuntimeError, match="fmax"):
+        MelFrontend(fmax=20000, device=DEV)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fe.mel(torch.zeros(4000))

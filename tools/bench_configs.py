@@ -5,6 +5,7 @@
     python tools/bench_configs.py --config 3            # HiFi-GAN Generator only: mel length x batch sweep (V1, V2)
     python tools/bench_configs.py --config 5            # long-form: one 4096-phoneme utterance, chunked vocoder
     torchrun --nproc-per-node N tools/bench_configs.py --config 4   # B=256 ragged batch sharded over N GPUs (NCCL)
+    python tools/bench_configs.py --config 6 --cpu      # speaker-prompt front-end (trim + log-mel) and tokeniser / collator
 
 CUDA-event timing on the device, 3 warm-ups, median of --iters runs; one JSON object per measurement on stdout.
 """
@@ -190,9 +191,60 @@ def config4(args, dev, rank, world):
                           "mel_frames_per_sec": frames / ms * 1e3, "wav_shape": list(wav.shape)}), flush=True)
 
 
+def config6(args, dev):
+    """SURVEY.md 8f rows 3 + 4: the speaker-prompt front-end (trim + log-mel, csrc/frontend.cu) on B prompts of 5 s, and the
+    native tokeniser / collator; CPU oracle beside both with --cpu (bounded samples)."""
+    import time
+    import numpy as np
+    from zerovox_b200.frontend import MelFrontend, Tokeniser
+    fe = MelFrontend(device=dev)
+    n = 22050 * 5
+    for B in (1, 32, 256):
+        wavs = torch.from_numpy(np.stack([syn.make_speech_like(n, seed=s) for s in range(min(B, 8))])).repeat((B + 7) // 8, 1)[:B]
+        wavs = wavs.contiguous().to(dev)
+        F = fe.num_frames(n)
+        ms_mel = timed(lambda: fe.mel(wavs, with_energy=True), max(args.iters, 20), dev)
+        ms_all = timed(lambda: fe.speaker_prompt_mel(wavs), max(args.iters, 20), dev)
+        alg_bytes = B * F * (256 * 4 + 80 * 4 + 4)           # one hop of samples in, one mel row + energy out
+        rec = {"config": 6, "what": "mel front-end", "B": B, "samples": n, "frames": B * F, "mel_ms": round(ms_mel, 4),
+               "trim_plus_mel_ms_incl_sync": round(ms_all, 4), "frames_per_sec": B * F / ms_mel * 1e3,
+               "audio_sec_per_sec": B * n / 22050 / ms_mel * 1e3, "algorithmic_GBps": alg_bytes / ms_mel / 1e6,
+               "fft_gflops": B * F * 5 * 1024 * 10 / ms_mel / 1e6}
+        if args.cpu and B == 32:
+            from oracle import frontend_oracle as fo      # measurement tool: CPU baseline leg
+            w1 = wavs[0].cpu().numpy()
+            fo.speaker_prompt_mel(w1)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                fo.speaker_prompt_mel(w1)
+            cpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+            rec.update({"cpu_ms_per_prompt_numpy_oracle": round(cpu_ms, 2), "cpu_audio_sec_per_sec": 5.0 / cpu_ms * 1e3})
+        print(json.dumps(rec), flush=True)
+    import random
+    rng = random.Random(1)
+    phones, puncts = "'-abcdefghijklmnopqrstuvwxyz", " ,.;:-!?\""
+    tok = Tokeniser(phones, puncts)
+    texts = ["".join(rng.choice(phones + puncts + "   ") for _ in range(160)) for _ in range(2048)]
+    t0 = time.perf_counter()
+    ids = [tok.transcript2phonemids(t) for t in texts]
+    t1 = time.perf_counter()
+    tok.collate([i[0] for i in ids], [i[1] for i in ids], pinned=True)
+    t2 = time.perf_counter()
+    rec = {"config": 6, "what": "tokeniser + collator (host C via ctypes)", "transcripts": len(texts), "chars": 160 * len(texts),
+           "tokenise_us_per_transcript": (t1 - t0) / len(texts) * 1e6, "collate_ms_batch_2048": (t2 - t1) * 1e3}
+    if args.cpu:
+        from oracle import frontend_oracle as fo
+        sym = fo.Symbols(phones, puncts)
+        t0 = time.perf_counter()
+        for t in texts:
+            fo.transcript2phonemids(sym, t)
+        rec["python_oracle_us_per_transcript"] = (time.perf_counter() - t0) / len(texts) * 1e6
+    print(json.dumps(rec), flush=True)
+
+
 def main():
     p = argparse.ArgumentParser()
-    p.add_argument("--config", type=int, required=True, choices=[1, 2, 3, 4, 5])
+    p.add_argument("--config", type=int, required=True, choices=[1, 2, 3, 4, 5, 6])
     p.add_argument("--decoder", default="fastspeech2", choices=["fastspeech2", "styletts"])
     p.add_argument("--cpu", action="store_true", help="config 1: also time the CPU oracle")
     p.add_argument("--iters", type=int, default=5)
@@ -210,6 +262,8 @@ def main():
         config3(args, dev)
     elif args.config == 5:
         config5(args, dev)
+    elif args.config == 6:
+        config6(args, dev)
     else:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)

@@ -57,6 +57,13 @@ class ZvxConfig(C.Structure):
     ]
 
 
+class ZvxMelConfig(C.Structure):
+    """Mirror of ``struct zvx_mel_config`` (speaker-prompt front-end)."""
+    _fields_ = [(n, C.c_int32) for n in ("abi_version", "sampling_rate", "fft_size", "hop_size", "win_length",
+                                         "num_mels")] + \
+               [(n, C.c_float) for n in ("fmin", "fmax", "clip_val")] + [("reserved", C.c_int32 * 7)]
+
+
 class ZvxGemmDesc(C.Structure):
     """Mirror of ``struct zvx_gemm_desc`` (kernel-level test hook)."""
     _fields_ = [(n, C.c_void_p) for n in ("A", "W", "C", "bias", "scale", "shift", "R")] + \
@@ -84,6 +91,19 @@ SYMBOLS = {
     "zvx_profile_enable": (C.c_int, [_P, C.c_int]),
     "zvx_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),
                                    C.POINTER(C.c_double)]),
+    "zvx_frontend_create": (C.c_int, [C.POINTER(ZvxMelConfig), C.c_int, C.POINTER(_P)]),
+    "zvx_frontend_destroy": (None, [_P]),
+    "zvx_frontend_last_error": (C.c_char_p, [_P]),
+    "zvx_mel_num_frames": (C.c_int64, [_P, C.c_int64]),
+    "zvx_trim_silence": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "zvx_mel_spectrogram": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, C.c_int, _P, _P, _P]),
+    "zvx_symbols_create": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(_P)]),
+    "zvx_symbols_destroy": (None, [_P]),
+    "zvx_symbols_last_error": (C.c_char_p, [_P]),
+    "zvx_symbols_num_phones": (C.c_int, [_P]),
+    "zvx_symbols_num_puncts": (C.c_int, [_P]),
+    "zvx_transcript2phonemids": (C.c_int, [_P, C.c_char_p, _P, _P, C.c_int]),
+    "zvx_collate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "zvx_workspace_bytes": (C.c_int64, [_P]),
     "zvx_launch_count": (C.c_int64, [_P]),
 }

@@ -309,3 +309,25 @@ def make_inputs(cfg: ZeroVoxConfig, B: int, T: int, T_ref: int, seed: int = 7,
     return x
 
 
+
+
+def make_speech_like(n: int, seed: int = 1, sr: int = 22050, lead: float = 0.12, tail: float = 0.10) -> np.ndarray:
+    """A seeded speech-shaped prompt for the mel front-end: a gliding harmonic stack under a
+    syllable-rate envelope plus a -50 dB noise floor, with near-silent (-80 dB) lead-in / tail so that
+    `librosa.effects.trim(top_db=40)` has something to cut.  float32 in (-1, 1); pure arithmetic, float64 inside."""
+    g = torch.Generator().manual_seed(seed)
+    t = np.arange(n, dtype=np.float64) / sr
+    f0 = 110.0 + 40.0 * np.sin(2 * np.pi * 0.7 * t + 0.3 * seed)
+    phase = 2 * np.pi * np.cumsum(f0) / sr
+    amps = torch.rand(24, generator=g, dtype=torch.float64).numpy()
+    y = np.zeros(n, dtype=np.float64)
+    for h in range(24):
+        y += amps[h] / (1.0 + 0.35 * h) * np.sin((h + 1) * phase + h)
+    env = 0.55 + 0.45 * np.sin(2 * np.pi * 3.1 * t + seed)
+    y = 0.25 * y / np.abs(y).max() * env
+    y += 10 ** (-50 / 20) * torch.randn(n, generator=g, dtype=torch.float64).numpy()
+    n0, n1 = int(lead * n), int(tail * n)
+    gate = np.ones(n)
+    gate[:n0] = 1e-4
+    gate[n - n1:] = 1e-4
+    return (y * gate).astype(np.float32)
