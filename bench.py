@@ -152,6 +152,27 @@ def cpu_reference_run(cfg, w, x, threads, runs):
     return statistics.median(times), frames
 
 
+def pipeline_roofline(prof, peaks, step_ms, sm_mhz):
+    """SURVEY.md 8d pipeline figure: T_roof = sum over kernel classes of max(FLOP / peak_class, bytes / HBM bandwidth),
+    with the ALGORITHMIC flops / bytes the engine recorded per class.  peak_class: TF32 tcgen05 = half the measured
+    sustained bf16 rate; 3xTF32 split = a third of that (three MMAs per product); fp32 FMA = 148 SMs x 128 lanes x 2 x
+    the SM clock sampled during the timed region.  Kernel classes without a flop model (norms, softmax, gathers:
+    ~9 % of the step) are outside both sums."""
+    tf32 = peaks["bf16_tflops_sustained"] / 2 * 1e12
+    fma = 148 * 128 * 2 * sm_mhz * 1e6
+    peak_of = {"gemm_tf32_tcgen05": tf32, "vocoder_pair_tcgen05": tf32, "gemm_3xtf32_tcgen05": tf32 / 3,
+               "gemm_fp32": fma, "vocoder_conv1d": fma, "vocoder_upsample": fma}
+    bw = peaks["hbm_gbs"] * 1e9
+    t_roof = t_meas = 0.0
+    for k, v in prof.items():
+        if v["launches"] <= 0:
+            continue
+        t_roof += max(v["flops"] / peak_of.get(k, fma), v["bytes"] / bw) * 1e3
+        t_meas += v["ms"]
+    return {"t_roof_ms": t_roof, "t_measured_ms_modelled_classes": t_meas, "frac": (t_roof / t_meas) if t_meas else None,
+            "share_of_step_modelled": t_meas / step_ms, "tf32_peak_tflops": tf32 / 1e12, "fp32_fma_peak_tflops": fma / 1e12}
+
+
 def run_reference(args, cfg, w, x_full, rank):
     if rank != 0:
         return
@@ -334,6 +355,7 @@ def main():
                                             "TF32 runs at half the bf16 rate, fp32 FMA kernels at ~1/20",
             "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
             "algorithmic_flops_per_launch": d["flops"] / d["launches"], "share_of_step": d["ms"] / ms,
+            "pipeline": pipeline_roofline(prof, peaks, ms, (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0),
             "classes": {k: {"ms": v["ms"], "launches": v["launches"],
                             "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None,
                             "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in prof.items()},

@@ -321,9 +321,9 @@ struct Frontend {
 
     void mel(const float* wav, int B, long long n_stride, const long long* wav_start, const long long* wav_len,
              int n_frames, float* mel_out, float* energy, cudaStream_t st) {
-        ZVX_REQUIRE(wav && mel_out, "zvx_mel_spectrogram: null pointer");
         ZVX_REQUIRE(B >= 1 && B <= 65535 && n_stride >= 1 && n_frames >= 0, "zvx_mel_spectrogram: bad sizes");
-        if (n_frames == 0) return;
+        if (n_frames == 0) return;                    // input shorter than one frame: nothing to write
+        ZVX_REQUIRE(wav && mel_out, "zvx_mel_spectrogram: null pointer");
         ZVX_CUDA_CHECK(cudaSetDevice(device));
         dim3 grid(cdiv(n_frames, FE_FPC), B);
         mel_spectrogram_kernel<<<grid, FE_TPF * FE_FPC, 0, st>>>(wav, n_stride, wav_start, wav_len, n_frames, p, mel_out, energy);
