@@ -151,3 +151,40 @@ def test_frontend_rejects_unsupported_config_and_cpu_tensors(fe):
         MelFrontend(fmax=20000, device=DEV)
     with pytest.raises(RuntimeError, match="no CPU path"):
         fe.mel(torch.zeros(4000))
+
+
+def test_tts_ex_mirror_end_to_end_text_to_waveform():
+    """ZeroVoxTTS.tts_ex (synthesize.py:215-239) through the mirror: normalised text -> native tokeniser -> inference_ex with
+    forced durations -> waveform, against the oracle fed the same ids (policy 0: fp32 FMA throughout)."""
+    from zerovox_b200.tts.symbols import Symbols
+    from zerovox_b200.tts.synthesize import ZeroVoxTTS
+
+    class Lower:                                     # stands in for ZeroVoxNormalizer.normalize (normalize.py, out of scope)
+        def normalize(self, text):
+            return text.lower(), None
+
+    cfg = zo.ZeroVoxConfig.tiny()
+    w = zo.make_weights(cfg, seed=0)
+    model = build_model(cfg, w, device=DEV, tensor_core_policy=0)
+    tts = ZeroVoxTTS(language="en", syms=Symbols(cfg.phones, cfg.puncts), checkpoint=None, meldec_model=None,
+                     hop_length=256, sampling_rate=22050, n_mel_channels=80, fft_size=1024, win_length=1024, mel_fmin=0,
+                     mel_fmax=8000, infer_device=DEV, model=model, normalizer=Lower())
+    text = "  Hello, World! This is it.  "
+    ph, pu = fo.transcript2phonemids(fo.Symbols(cfg.phones, cfg.puncts), text.strip().lower())
+    assert tts.text2phonemeids(text.strip()) == (ph, pu) and len(ph) == 18
+    dur = [(3 * i) % 5 + 1 for i in range(len(ph))]
+    style = tts.speaker_embed(make_speech_like(22050, seed=6))
+    wav, phoneme, length, mel = tts.tts_ex(text, style, duration=dur)
+    x = {"phoneme": torch.tensor([ph], dtype=torch.int32), "puncts": torch.tensor([pu], dtype=torch.int32),
+         "duration": torch.tensor([dur], dtype=torch.int32)}
+    with torch.no_grad():
+        owav, olen, _, omel, _ = zo.zerovox_inference_ex(cfg, w, x, style.cpu(), force_duration=True)
+    assert length == olen == sum(dur) and phoneme.cpu().tolist() == [ph]
+    assert wav.shape == (olen * 256,) and mel.shape == (80, olen)
+    e_mel = np.abs(mel - omel.numpy()).max() / np.abs(omel.numpy()).max()
+    e_wav = np.abs(wav - owav.numpy()).max()
+    print(f"  tts_ex: mel rel err {e_mel:.2e}, wav abs err {e_wav:.2e}")
+    assert e_mel < 5e-4 and e_wav < 5e-4
+    # empty text: the reference's early return (synthesize.py:221-222)
+    w0, p0, l0, m0 = tts.tts_ex("   ", style)
+    assert l0 == 0 and w0.shape == (1, 1) and p0.shape == (1, 1)
