@@ -799,26 +799,44 @@ class Engine {
             }
             gemm_tc_prof(v, st);
             if (split) tf32_split_lo(qkv, sc.lo_qkv, rows * 2 * H + (long long)B * H * Lp, st);
+            // Utterances are independent, so the three attention kernels run over slices of the batch whose score
+            // matrices (plus their Q / K / V rows) fit in L2: the softmax and the PV product then read what the kernel
+            // before them wrote from L2 instead of DRAM (the whole-batch score tensor is 172 MB at configs[1], moved
+            // four times).  ZVX_ATTN_SLICE_BYTES = 0 restores one slice.
+            static const long long slice_bytes =
+                getenv("ZVX_ATTN_SLICE_BYTES") ? atoll(getenv("ZVX_ATTN_SLICE_BYTES")) : kAttnSliceBytes;
+            int Bs = B;
+            if (slice_bytes > 0 && !split) {
+                const long long per_utt = (long long)n_head * std::min(Lq_max, L) * ldS * (long long)sizeof(float);
+                Bs = (int)std::max<long long>(1, std::min<long long>(B, slice_bytes / per_utt));
+                if (Bs * 2 > B) Bs = B;                       // a single uneven split gains nothing
+                else Bs = cdiv(B, cdiv(B, Bs));               // even slices
+            }
+            for (int b0 = 0; b0 < B; b0 += Bs) {
+            const int Bn = std::min(Bs, B - b0);
+            const long long r0 = (long long)b0 * L;          // first row of the slice in the [rows, .] buffers
+            const uint8_t* mask_s = mask ? mask + r0 : nullptr;
             for (int q0 = 0; q0 < L; q0 += Lq_max) {
                 const int Lq = std::min(Lq_max, L - q0);
                 TcGemmArgs sq;   // S[b,h,q,j] = <Q[b,q0+q,h,:], K[b,j,h,:]>
-                sq.A = qk + (long long)q0 * 2 * H; sq.K = dk; sq.Wi = sq.Wo = Lq; sq.Hi = sq.Ho = n_head; sq.IMG = B;
+                sq.A = qk + (r0 + q0) * 2 * H; sq.K = dk; sq.Wi = sq.Wo = Lq; sq.Hi = sq.Ho = n_head; sq.IMG = Bn;
                 sq.a_sx = 2 * H; sq.a_sy = dk; sq.a_simg = (long long)L * 2 * H;
-                sq.W = qk + H; sq.N = L; sq.Z1 = n_head; sq.Z2 = B; sq.w_sn = 2 * H; sq.w_s1 = dk; sq.w_s2 = (long long)L * 2 * H;
+                sq.W = qk + r0 * 2 * H + H; sq.N = L; sq.Z1 = n_head; sq.Z2 = Bn; sq.w_sn = 2 * H; sq.w_s1 = dk; sq.w_s2 = (long long)L * 2 * H;
                 sq.b_batched = 1;
                 sq.C = S; sq.c_simg = (long long)n_head * Lq * ldS; sq.c_sy = (long long)Lq * ldS; sq.c_sx = ldS; sq.c_sn = 1;
-                if (split) { sq.A_lo = sc.lo_qkv + (long long)q0 * 2 * H; sq.W_lo = sc.lo_qkv + H; }
+                if (split) { sq.A_lo = sc.lo_qkv + (r0 + q0) * 2 * H; sq.W_lo = sc.lo_qkv + r0 * 2 * H + H; }
                 gemm_tc_prof(sq, st);
-                attn_softmax(S, nz, n_head, Lq, L, ldS, mask, L, temperature, st);
-                if (split) tf32_split_lo(S, sc.lo_S, (long long)nz * Lq * ldS, st);
+                attn_softmax(S, Bn * n_head, n_head, Lq, L, ldS, mask_s, L, temperature, st);
+                if (split) tf32_split_lo(S, sc.lo_S, (long long)Bn * n_head * Lq * ldS, st);
                 TcGemmArgs pv;   // att[b,q0+q,h*dk + c] = sum_j P[b,h,q,j] * Vt[b, h*dk + c, j]
-                pv.A = S; pv.K = L; pv.Wi = pv.Wo = Lq; pv.Hi = pv.Ho = n_head; pv.IMG = B;
+                pv.A = S; pv.K = L; pv.Wi = pv.Wo = Lq; pv.Hi = pv.Ho = n_head; pv.IMG = Bn;
                 pv.a_sx = ldS; pv.a_sy = (long long)Lq * ldS; pv.a_simg = (long long)n_head * Lq * ldS;
-                pv.W = vt; pv.N = dk; pv.Z1 = n_head; pv.Z2 = B; pv.w_sn = Lp; pv.w_s1 = (long long)dk * Lp; pv.w_s2 = (long long)H * Lp;
+                pv.W = vt + (long long)b0 * H * Lp; pv.N = dk; pv.Z1 = n_head; pv.Z2 = Bn; pv.w_sn = Lp; pv.w_s1 = (long long)dk * Lp; pv.w_s2 = (long long)H * Lp;
                 pv.b_batched = 1;
-                pv.C = att + (long long)q0 * H; pv.c_simg = (long long)L * H; pv.c_sy = dk; pv.c_sx = H; pv.c_sn = 1;
-                if (split) { pv.A_lo = sc.lo_S; pv.W_lo = sc.lo_qkv + rows * 2 * H; }
+                pv.C = att + (r0 + q0) * H; pv.c_simg = (long long)L * H; pv.c_sy = dk; pv.c_sx = H; pv.c_sn = 1;
+                if (split) { pv.A_lo = sc.lo_S; pv.W_lo = sc.lo_qkv + rows * 2 * H + (long long)b0 * H * Lp; }
                 gemm_tc_prof(pv, st);
+            }
             }
         } else {
         linear(x, (int)rows, H, ly.wqkv, ly.bqkv, 3 * H, qkv, tc, st);
@@ -1347,6 +1365,8 @@ class Engine {
     static constexpr int kMaxBatch = 65536;
     // attention-score workspace budget: longer sequences are processed in chunks of query rows (exact)
     long long kScoreBytes = getenv("ZVX_SCORE_BYTES") ? atoll(getenv("ZVX_SCORE_BYTES")) : (4LL << 30);
+    // attention batch-slice budget (score bytes per slice); 0 = whole batch per launch.  Default set by measurement.
+    static constexpr long long kAttnSliceBytes = 0;
 
     zvx_config cfg;
     int dev = 0;
