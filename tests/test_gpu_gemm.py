@@ -100,7 +100,7 @@ def test_conv1d(eng, B, L, Cin, Cout, k, dil, use_tc):
 
 @pytest.mark.parametrize("use_tc", [0, 1, 2])
 @pytest.mark.parametrize("B,Hh,Ww,Cin,Cout", [(2, 80, 48, 32, 32), (1, 40, 33, 64, 64), (3, 10, 7, 256, 256),
-                                              (2, 20, 55, 128, 128)])
+                                              (2, 20, 55, 128, 128), (3, 80, 440, 32, 32), (5, 40, 220, 64, 64)])
 def test_conv2d_3x3(eng, B, Hh, Ww, Cin, Cout, use_tc):
     x, w = rnd(B, Hh, Ww, Cin, seed=8), rnd(Cout, Cin, 3, 3, seed=9) / (Cin * 9) ** 0.5
     scale, shift = rnd(Cout, seed=10).abs() + 0.5, rnd(Cout, seed=11)

@@ -43,6 +43,12 @@ struct TcParams {
     int stages, stage_bytes, b_tile_bytes, b_tile_stride;
     // x-tap reuse (xr): one activation tile of 128 + (ksx-1)*dil positions per (dy, k-chunk) serves all ksx taps of the row
     int xr, xr_na, xr_a_bytes, xr_a_tx, xr_halo;
+    // 2-D tap reuse (xr = 2): ONE activation tile of (TH + halo_y) x (TW + halo_x) positions per k-chunk serves every tap of the
+    // filter: accumulator row r <-> tile position (r / row_w, r % row_w) with row_w = TW + halo_x, a tap (dy, dx) is the row
+    // shift (dy * row_w + dx) * dil; the halo_x columns of every tile row are computed and discarded by the epilogue.
+    int xr_ky, xr_kx;         // activation loads per k-chunk (filter rows; 1 in 2-D mode) and taps served by each
+    int xr_wrap8;             // extra descriptor units when the tap index wraps to the next filter row (2-D mode)
+    int row_w;                // accumulator rows per tile row (= TW except in 2-D tap-reuse mode)
     int mt, a_bytes;          // MMA M tiles (128 positions each) per CTA tile, bytes of the activation tile
     int spin;                 // single-thread roles spin on their barriers (small tiles)
     int ug, unit_bytes;       // k-steps grouped per pipeline stage (small-N problems: fewer barrier round trips / commits)
@@ -180,24 +186,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 // x-tap reuse: per (dy, k-chunk) ONE activation tile of 128 + halo positions, then the ksx weight tiles
                 int sa = 0;
                 uint32_t pa = 0;
-                const int ksy = p.taps / p.ksx;
                 for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                     const Tile c = decode_tile(p, t);
-                    for (int dy = 0; dy < ksy; ++dy)
+                    for (int dy = 0; dy < p.xr_ky; ++dy)
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait_sel(p.spin, aempty_bar(sa), pa ^ 1u);
                             mbar_arrive_expect_tx(afull_bar(sa), (uint32_t)p.xr_a_tx);
                             tma_load_4d(&mapA, afull_bar(sa), smem_a_ring + (uint32_t)(sa * p.xr_a_bytes), kc * BK, c.x0 - p.pad_x,
                                         c.y0 + dy * p.dil - p.pad_y, c.img);
                             if (++sa == p.xr_na) { sa = 0; pa ^= 1u; }
-                            for (int dx = 0; dx < p.ksx; dx += p.ug) {   // p.ug weight tiles (taps) per stage
-                                const int ng = min(p.ug, p.ksx - dx);
+                            for (int dx = 0; dx < p.xr_kx; dx += p.ug) {   // p.ug weight tiles (taps) per stage
+                                const int ng = min(p.ug, p.xr_kx - dx);
                                 mbar_wait_sel(p.spin, empty_bar(stage), phase ^ 1u);
                                 const uint32_t fb = full_bar(stage);
                                 mbar_arrive_expect_tx(fb, (uint32_t)(p.b_tile_bytes * ng));
                                 for (int j = 0; j < ng; ++j)
                                     tma_load_4d(&mapB, fb, smem_base + (uint32_t)(stage * p.stage_bytes + j * p.b_tile_stride), kc * BK,
-                                                c.n0, dy * p.ksx + dx + j, 0);
+                                                c.n0, dy * p.xr_kx + dx + j, 0);
                                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                             }
                         }
@@ -251,29 +256,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (!SPLIT && p.xr) {
                 int sa = 0;
                 uint32_t pa = 0;
-                const int ksy = p.taps / p.ksx;
                 for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++cnt) {
                     const int buf = (int)(cnt & 1u);
                     mbar_wait_sel(p.spin, tempty_bar(buf), ((cnt >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
                     uint32_t accum = 0u;
-                    for (int dy = 0; dy < ksy; ++dy)
+                    for (int dy = 0; dy < p.xr_ky; ++dy)
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait_sel(p.spin, afull_bar(sa), pa);
                             tc_fence_after();
-                            const uint32_t a_lo = (uint32_t)(sw128_desc(smem_a_ring + (uint32_t)(sa * p.xr_a_bytes)) & 0xFFFFFFFFull);
-                            for (int dx = 0; dx < p.ksx; dx += p.ug) {
-                                const int ng = min(p.ug, p.ksx - dx);
+                            // the tap's operand = the tile entered (tap shift) rows further down: one row = 128 B = 8 descriptor units
+                            uint32_t alo = (uint32_t)(sw128_desc(smem_a_ring + (uint32_t)(sa * p.xr_a_bytes)) & 0xFFFFFFFFull);
+                            int tx = 0;   // tap column inside its filter row (2-D mode: the shift jumps a tile row when it wraps)
+                            for (int dx = 0; dx < p.xr_kx; dx += p.ug) {
+                                const int ng = min(p.ug, p.xr_kx - dx);
                                 mbar_wait_sel(p.spin, full_bar(stage), phase);
-                                uint32_t alo = a_lo + (uint32_t)(dx * p.dil * 8);   // one row = 128 B = 8 descriptor units
                                 uint32_t blo = desc_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);
-                                for (int j = 0; j < ng; ++j, alo += (uint32_t)(p.dil * 8), blo += (uint32_t)(p.b_tile_stride >> 4)) {
+                                for (int j = 0; j < ng; ++j, blo += (uint32_t)(p.b_tile_stride >> 4)) {
 #pragma unroll
                                     for (int k = 0; k < BK / 8; ++k) {
                                         umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, accum);
                                         accum = 1u;
                                     }
+                                    alo += (uint32_t)(p.dil * 8);
+                                    if (++tx == p.ksx) { tx = 0; alo += (uint32_t)p.xr_wrap8; }
                                 }
                                 umma_commit(empty_bar(stage));
                                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -345,9 +352,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const Tile c = decode_tile(p, t);
             // position of this thread's accumulator row inside M tile mi of the CTA tile
             int r = q * 32 + lane;
-            int ty = r / p.TW, tx = r - ty * p.TW;
+            int ty = r / p.row_w, tx = r - ty * p.row_w;
             int y = c.y0 + ty, x = c.x0 + tx;
-            bool valid = (y < p.Ho) && (x < p.Wo);
+            bool valid = (y < p.Ho) && (x < p.Wo) && (tx < p.TW);
             long long off = (long long)c.img * p.c_simg + (long long)y * p.c_sy + (long long)x * p.c_sx;
             float* __restrict__ cp = p.C + off;
             const float* __restrict__ rp =
@@ -419,9 +426,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int mi = 0; mi < p.mt; ++mi) {
             if (mi > 0) {
                 r = mi * BM + q * 32 + lane;
-                ty = r / p.TW; tx = r - ty * p.TW;
+                ty = r / p.row_w; tx = r - ty * p.row_w;
                 y = c.y0 + ty; x = c.x0 + tx;
-                valid = (y < p.Ho) && (x < p.Wo);
+                valid = (y < p.Ho) && (x < p.Wo) && (tx < p.TW);
                 off = (long long)c.img * p.c_simg + (long long)y * p.c_sy + (long long)x * p.c_sx;
                 cp = p.C + off;
                 rp = p.R ? p.R + ((long long)c.img * p.r_simg + (long long)y * p.r_sy + (long long)x * p.r_sx) : nullptr;
@@ -659,6 +666,18 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     ZVX_REQUIRE(!split || (a.A_lo && a.W_lo && aligned16(a.A_lo) && aligned16(a.W_lo)), "gemm_tc: split mode needs both lo operands");
     ZVX_REQUIRE(!split || (!a.acc_mode && a.act_slope == 1.f && !a.C2), "gemm_tc: split mode has the plain epilogue only");
     TcParams p{};
+    // column tile: multiple of 16, <= 256, least padding over a few tile counts
+    {
+        const int bn_max = split ? 128 : 256;   // split stages hold four operand tiles
+        const int t0 = cdiv(a.N, bn_max);
+        long long bw = -1;
+        for (int tn = t0; tn <= t0 + 4; ++tn) {
+            const int bn = (int)std::min<long long>(bn_max, round_up(cdiv(a.N, tn), 16));
+            const int tiles = cdiv(a.N, bn);
+            const long long waste = (long long)tiles * bn - a.N;
+            if (bw < 0 || waste < bw) { bw = waste; p.BN = bn; p.tiles_n = tiles; }
+        }
+    }
     // x-tap reuse: the ksx taps of a filter row read one activation tile of 128 + (ksx-1)*dil positions through
     // row-shifted descriptors instead of ksx separate TMA loads (the activation re-fetch is what bounds small-N convs)
     static const bool no_xr = getenv("ZVX_NO_XR") != nullptr;
@@ -667,13 +686,38 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     // 128 x 1 tile shape costs more in padding than the saved fetches)
     static const int xr_mink = getenv("ZVX_XR_MINK") ? atoi(getenv("ZVX_XR_MINK")) : 5;
     const bool xr = !no_xr && !split && a.ksx >= xr_mink && a.stride == 1 && !a.b_batched && halo <= 120;
+    // 2-D tap reuse (ksy > 1, unit stride): one (TH + halo_y) x (TW + halo_x) activation tile per k-chunk serves all taps; the
+    // activation fetch drops from taps x 16 KB to ~25 KB per k-chunk at the price of halo_x discarded columns per tile row.
+    // Measured on configs[1] (profiles/r01_ab_conv2d_tap_reuse.jsonl): speaker net 4.21 -> 3.81 ms with N <= 128 (32 / 64 / 128
+    // channel 3x3 convs); ZVX_XR2=0 switches it off, =2 forces it on problems below the size threshold (tests).
+    static const int xr2_env = getenv("ZVX_XR2") ? atoi(getenv("ZVX_XR2")) : 1;
+    static const int xr2_maxn = getenv("ZVX_XR2_MAXN") ? atoi(getenv("ZVX_XR2_MAXN")) : 128;
+    const int halo_y = (a.ksy - 1) * a.dil;
+    bool xr2 = xr2_env && !split && !xr && a.ksy > 1 && a.ksx > 1 && a.stride == 1 && !a.b_batched && a.N <= xr2_maxn;
+    int xr2_tw = 0, xr2_th = 0, xr2_roww = 0;
+    if (xr2) {
+        long long best2 = -1;
+        const int wstride = (int)round_up(p.BN * BK * 4, 1024);
+        const int wstage = std::max(1, std::min(a.ksx * a.ksy, (48 * 1024) / wstride)) * wstride;
+        for (int roww = 8; roww <= 128; roww <<= 1) {   // fewest tiles; on ties the narrower tile row (smaller halo buffer)
+            const int tw = roww - halo, th = BM / roww;
+            if (tw < 1 || th + halo_y > 256) continue;
+            const long long abytes = round_up((long long)(BM + halo_y * roww + halo) * BK * 4, 1024);
+            if ((SMEM_LIMIT - 2048 - 3 * abytes) / wstage < 3) continue;   // three activation buffers + >= 3 weight stages
+            const long long tiles = (long long)cdiv(a.Wo, tw) * cdiv(a.Ho, th);
+            if (best2 < 0 || tiles < best2) { best2 = tiles; xr2_tw = tw; xr2_th = th; xr2_roww = roww; }
+        }
+        // small problems keep the padding-free tiles of the general path
+        if (best2 < 0 || (xr2_env < 2 && best2 * a.IMG * cdiv(a.N, 256) < 2LL * num_sms())) xr2 = false;   // ZVX_XR2=2: always (tests)
+    }
     // tile shape: TH x TW = 128 * mt positions, least padding first, wider rows on ties.  Two M tiles per CTA tile for narrow
     // outputs (N <= 64): they share every weight tile and, above all, every stage hand-shake and per-tile overhead.
     static const bool no_mt2 = getenv("ZVX_NO_MT2") != nullptr;
     const long long positions = (long long)a.IMG * a.Ho * a.Wo;
     static const int mt2_n = getenv("ZVX_MT2_N") ? atoi(getenv("ZVX_MT2_N")) : 64;
-    p.mt = (!no_mt2 && !split && !xr && !a.b_batched && a.N <= mt2_n && positions >= 2LL * 256 * num_sms()) ? 2 : 1;
+    p.mt = (!no_mt2 && !split && !xr && !xr2 && !a.b_batched && a.N <= mt2_n && positions >= 2LL * 256 * num_sms()) ? 2 : 1;
     long long best = -1;
+    if (xr2) { p.TW = xr2_tw; p.TH = xr2_th; best = 0; }
     for (int pass = 0; pass < 2 && best < 0; ++pass) {
         const int bm = BM * p.mt;
         for (int tw = std::min(bm, 256); tw >= ((a.b_batched || xr) ? 128 : 8); tw >>= 1) {   // per-(y,img) W operands / xr: one y per tile
@@ -690,18 +734,6 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
                 if (best1 < 0 || padded < best1) best1 = padded;
             }
             if (best < 0 || best * 100 > best1 * 104) { p.mt = 1; best = -1; }
-        }
-    }
-    // column tile: multiple of 16, <= 256, least padding over a few tile counts
-    {
-        const int bn_max = split ? 128 : 256;   // split stages hold four operand tiles
-        const int t0 = cdiv(a.N, bn_max);
-        long long bw = -1;
-        for (int tn = t0; tn <= t0 + 4; ++tn) {
-            const int bn = (int)std::min<long long>(bn_max, round_up(cdiv(a.N, tn), 16));
-            const int tiles = cdiv(a.N, bn);
-            const long long waste = (long long)tiles * bn - a.N;
-            if (bw < 0 || waste < bw) { bw = waste; p.BN = bn; p.tiles_n = tiles; }
         }
     }
     p.tiles_x = cdiv(a.Wo, p.TW);
@@ -726,15 +758,25 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
         int ug = ug_env > 0 ? ug_env : 3;
         ug = std::min(ug, std::min(4, ksteps));
         while (ug > 1 && (SMEM_LIMIT - 2048) / (ug * p.unit_bytes) < 3) --ug;
-        if (!split && !xr && ug > 1) { p.ug = ug; p.stage_bytes = ug * p.unit_bytes; }
+        if (!split && !xr && !xr2 && ug > 1) { p.ug = ug; p.stage_bytes = ug * p.unit_bytes; }
     }
     p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes);
-    if (xr) {
-        p.xr = 1; p.xr_na = 3; p.xr_halo = halo;
-        p.xr_a_tx = (BM + halo) * BK * 4;
-        p.xr_a_bytes = (int)round_up(p.xr_a_tx, 1024);
+    p.row_w = p.TW;
+    if (xr || xr2) {
+        p.xr = xr ? 1 : 2; p.xr_na = 3; p.xr_halo = halo;
+        if (xr) {
+            p.xr_a_tx = (BM + halo) * BK * 4;
+            p.xr_a_bytes = (int)round_up(p.xr_a_tx, 1024);
+            p.xr_ky = a.ksy; p.xr_kx = a.ksx; p.xr_wrap8 = 0;
+        } else {
+            p.row_w = xr2_roww;
+            p.xr_a_tx = xr2_roww * (p.TH + halo_y) * BK * 4;                     // what the TMA box delivers
+            // + halo_x rows that only the discarded accumulator rows of the last taps read (never written: any bits will do)
+            p.xr_a_bytes = (int)round_up((BM + halo_y * xr2_roww + halo) * BK * 4, 1024);
+            p.xr_ky = 1; p.xr_kx = a.ksx * a.ksy; p.xr_wrap8 = (xr2_roww - a.ksx) * a.dil * 8;
+        }
         // the operand stages hold weight tiles only, several taps per stage when they are small (stage hand-shakes are costly)
-        p.ug = std::max(1, std::min(a.ksx, (48 * 1024) / p.b_tile_stride));
+        p.ug = std::max(1, std::min(p.xr_kx, (48 * 1024) / p.b_tile_stride));
         p.stage_bytes = p.ug * p.b_tile_stride;
         p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048 - p.xr_na * p.xr_a_bytes) / p.stage_bytes);
     }
@@ -754,7 +796,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
 
     const long long adims[4] = {a.K, a.Wi, a.Hi, a.IMG};
     const long long astr[3] = {a.a_sx, a.a_sy, a.a_simg};
-    const int abox[4] = {BK, xr ? BM + halo : p.TW, p.TH, 1};
+    const int abox[4] = {BK, xr ? BM + halo : (xr2 ? xr2_roww : p.TW), xr2 ? p.TH + halo_y : p.TH, 1};
     const long long wdims[4] = {a.K, a.N, a.Z1, a.Z2};
     const long long wstr[3] = {a.w_sn, a.w_s1, a.w_s2};
     const int wbox[4] = {BK, p.BN, 1, 1};
