@@ -112,6 +112,18 @@ def test_conv2d_3x3(eng, B, Hh, Ww, Cin, Cout, use_tc):
     check(got, ref.reshape(-1, Cout).float(), use_tc, 1.0)
 
 
+@pytest.mark.parametrize("B,Hh,Ww,Cin,Cout,ksize", [(2, 80, 440, 16, 16, 5), (2, 64, 300, 32, 48, 3), (1, 96, 410, 40, 24, 5)])
+def test_conv2d_tap_reuse_other_filters(eng, B, Hh, Ww, Cin, Cout, ksize):
+    """The 2-D tap-reuse path of gemm_tc (one haloed activation tile per k-chunk) on shapes large enough to select it:
+    5x5 filters (halo 4), channel counts that are not multiples of 32 (k-chunk tail), Cout that needs a column tail."""
+    x, w = rnd(B, Hh, Ww, Cin, seed=20), rnd(Cout, Cin, ksize, ksize, seed=21) / (Cin * ksize * ksize) ** 0.5
+    bias = rnd(Cout, seed=22)
+    Wt = w.permute(2, 3, 0, 1).reshape(ksize * ksize, Cout, Cin).contiguous()
+    got = run(eng, 2, x.reshape(-1, Cin), Wt, bias=bias, relu_last=1, use_tc=1, Hh=Hh, Ww=Ww, ksize=ksize, pad=ksize // 2)
+    ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=ksize // 2).relu()
+    check(got, ref.permute(0, 2, 3, 1).reshape(-1, Cout).float(), 1, 1.0)
+
+
 @pytest.mark.parametrize("use_tc", [0, 1])
 @pytest.mark.parametrize("B,Hh,Ww,Cin,Cout,ksize", [(2, 80, 48, 32, 64, 3), (3, 40, 55, 64, 128, 3), (2, 20, 27, 128, 256, 3),
                                                     (2, 80, 48, 32, 64, 1), (1, 21, 33, 64, 128, 1)])
