@@ -261,7 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_wait_sel(p.spin, tempty_bar(buf), ((cnt >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
-                    uint32_t accum = 0u;
+                    uint32_t acc_tap = 0u;   // 0 for the first tap of the tile (fresh accumulators), 1 afterwards
                     for (int dy = 0; dy < p.xr_ky; ++dy)
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait_sel(p.spin, afull_bar(sa), pa);
@@ -274,11 +274,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 mbar_wait_sel(p.spin, full_bar(stage), phase);
                                 uint32_t blo = desc_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);
                                 for (int j = 0; j < ng; ++j, blo += (uint32_t)(p.b_tile_stride >> 4)) {
+                                    for (int mi = 0; mi < p.mt; ++mi) {   // M tile mi = the same tile entered 128 rows further down
+                                        const uint32_t am = alo + (uint32_t)(mi * BM * 8);
 #pragma unroll
-                                    for (int k = 0; k < BK / 8; ++k) {
-                                        umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, accum);
-                                        accum = 1u;
+                                        for (int k = 0; k < BK / 8; ++k)
+                                            umma_tf32_lo(d_tmem + (uint32_t)(mi * p.BN), am + 2 * k, blo + 2 * k, DESC_HI, p.idesc,
+                                                         k == 0 ? acc_tap : 1u);
                                     }
+                                    acc_tap = 1u;
                                     alo += (uint32_t)(p.dil * 8);
                                     if (++tx == p.ksx) { tx = 0; alo += (uint32_t)p.xr_wrap8; }
                                 }
@@ -694,19 +697,39 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     static const int xr2_maxn = getenv("ZVX_XR2_MAXN") ? atoi(getenv("ZVX_XR2_MAXN")) : 128;
     const int halo_y = (a.ksy - 1) * a.dil;
     bool xr2 = xr2_env && !split && !xr && a.ksy > 1 && a.ksx > 1 && a.stride == 1 && !a.b_batched && a.N <= xr2_maxn;
-    int xr2_tw = 0, xr2_th = 0, xr2_roww = 0;
+    int xr2_tw = 0, xr2_th = 0, xr2_roww = 0, xr2_mt = 1, xr2_na = 3;
     if (xr2) {
-        long long best2 = -1;
+        // tile = mt * 128 accumulator rows = (mt * th) tile rows of roww positions, (roww - halo_x) of them kept.  Fewest tiles
+        // first (ties: the narrower tile row, smaller halo buffer); two M tiles per CTA tile (they share the weight stage, the
+        // activation load and every hand-shake) unless that pads the map by more than 4 %.  ZVX_XR2_MT=1 keeps one M tile.
+        // Measured (profiles/r01_ab_conv2d_tap_reuse_two_m_tiles.jsonl): speaker net 4.32 -> 3.79 ms with N <= 128.
+        static const int xr2_mtmax = getenv("ZVX_XR2_MT") ? atoi(getenv("ZVX_XR2_MT")) : 2;
         const int wstride = (int)round_up(p.BN * BK * 4, 1024);
         const int wstage = std::max(1, std::min(a.ksx * a.ksy, (48 * 1024) / wstride)) * wstride;
-        for (int roww = 8; roww <= 128; roww <<= 1) {   // fewest tiles; on ties the narrower tile row (smaller halo buffer)
-            const int tw = roww - halo, th = BM / roww;
-            if (tw < 1 || th + halo_y > 256) continue;
-            const long long abytes = round_up((long long)(BM + halo_y * roww + halo) * BK * 4, 1024);
-            if ((SMEM_LIMIT - 2048 - 3 * abytes) / wstage < 3) continue;   // three activation buffers + >= 3 weight stages
-            const long long tiles = (long long)cdiv(a.Wo, tw) * cdiv(a.Ho, th);
-            if (best2 < 0 || tiles < best2) { best2 = tiles; xr2_tw = tw; xr2_th = th; xr2_roww = roww; }
+        long long best_mt[3] = {-1, -1, -1};
+        int sel[3][4] = {};
+        static const int xr2_mt_maxn = getenv("ZVX_XR2_MT_MAXN") ? atoi(getenv("ZVX_XR2_MT_MAXN")) : 128;
+        for (int mt = 1; mt <= std::min(2, xr2_mtmax); ++mt) {
+            if (mt * p.BN > ACC_STRIDE || (mt > 1 && a.N > xr2_mt_maxn)) continue;
+            for (int roww = 8; roww <= 128; roww <<= 1) {
+                const int tw = roww - halo, th = BM / roww;
+                if (tw < 1 || mt * th + halo_y > 256) continue;
+                const long long abytes = round_up((long long)(mt * BM + halo_y * roww + halo) * BK * 4, 1024);
+                int na = 3;
+                if ((SMEM_LIMIT - 2048 - na * abytes) / wstage < 2) na = 2;
+                if ((SMEM_LIMIT - 2048 - na * abytes) / wstage < 2) continue;
+                const long long tiles = (long long)cdiv(a.Wo, tw) * cdiv(a.Ho, mt * th) * mt;   // in 128-row units
+                if (best_mt[mt] < 0 || tiles < best_mt[mt]) {
+                    best_mt[mt] = tiles; sel[mt][0] = tw; sel[mt][1] = th; sel[mt][2] = roww; sel[mt][3] = na;
+                }
+            }
         }
+        int mt = 1;
+        if (best_mt[2] >= 0 && (best_mt[1] < 0 || best_mt[2] * 100 <= best_mt[1] * 104) &&
+            best_mt[2] * a.IMG * p.tiles_n >= 4LL * num_sms())
+            mt = 2;
+        const long long best2 = best_mt[mt];
+        xr2_tw = sel[mt][0]; xr2_th = sel[mt][1]; xr2_roww = sel[mt][2]; xr2_na = sel[mt][3]; xr2_mt = mt;
         // small problems keep the padding-free tiles of the general path
         if (best2 < 0 || (xr2_env < 2 && best2 * a.IMG * cdiv(a.N, 256) < 2LL * num_sms())) xr2 = false;   // ZVX_XR2=2: always (tests)
     }
@@ -717,7 +740,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     static const int mt2_n = getenv("ZVX_MT2_N") ? atoi(getenv("ZVX_MT2_N")) : 64;
     p.mt = (!no_mt2 && !split && !xr && !xr2 && !a.b_batched && a.N <= mt2_n && positions >= 2LL * 256 * num_sms()) ? 2 : 1;
     long long best = -1;
-    if (xr2) { p.TW = xr2_tw; p.TH = xr2_th; best = 0; }
+    if (xr2) { p.TW = xr2_tw; p.TH = xr2_th * xr2_mt; p.mt = xr2_mt; best = 0; }
     for (int pass = 0; pass < 2 && best < 0; ++pass) {
         const int bm = BM * p.mt;
         for (int tw = std::min(bm, 256); tw >= ((a.b_batched || xr) ? 128 : 8); tw >>= 1) {   // per-(y,img) W operands / xr: one y per tile
@@ -763,7 +786,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes);
     p.row_w = p.TW;
     if (xr || xr2) {
-        p.xr = xr ? 1 : 2; p.xr_na = 3; p.xr_halo = halo;
+        p.xr = xr ? 1 : 2; p.xr_na = xr ? 3 : xr2_na; p.xr_halo = halo;
         if (xr) {
             p.xr_a_tx = (BM + halo) * BK * 4;
             p.xr_a_bytes = (int)round_up(p.xr_a_tx, 1024);
@@ -772,7 +795,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
             p.row_w = xr2_roww;
             p.xr_a_tx = xr2_roww * (p.TH + halo_y) * BK * 4;                     // what the TMA box delivers
             // + halo_x rows that only the discarded accumulator rows of the last taps read (never written: any bits will do)
-            p.xr_a_bytes = (int)round_up((BM + halo_y * xr2_roww + halo) * BK * 4, 1024);
+            p.xr_a_bytes = (int)round_up((p.mt * BM + halo_y * xr2_roww + halo) * BK * 4, 1024);
             p.xr_ky = 1; p.xr_kx = a.ksx * a.ksy; p.xr_wrap8 = (xr2_roww - a.ksx) * a.dil * 8;
         }
         // the operand stages hold weight tiles only, several taps per stage when they are small (stage hand-shakes are costly)
