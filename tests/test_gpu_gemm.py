@@ -98,6 +98,20 @@ def test_conv1d(eng, B, L, Cin, Cout, k, dil, use_tc):
     check(got, ref, use_tc, 1.0)
 
 
+@pytest.mark.parametrize("B,L,Cin,Cout,k,dil", [(12, 8192, 64, 64, 7, 3), (10, 8200, 80, 128, 7, 1), (16, 6568, 64, 64, 11, 5),
+                                                (9, 12001, 32, 16, 5, 1)])
+def test_conv1d_tap_reuse_two_m_tiles(eng, B, L, Cin, Cout, k, dil):
+    """Filter-row tap reuse with two M tiles per CTA tile (256 + halo positions behind one weight stage): shapes large
+    enough to select it — HiFi-GAN's 64-channel k = 7 / 11 dilated convs, conv_pre's 80 -> 128, a ragged row length."""
+    x, w = rnd(B, L, Cin, seed=30), rnd(Cout, Cin, k, seed=31) / (Cin * k) ** 0.5
+    bias = rnd(Cout, seed=32)
+    pad = dil * (k - 1) // 2
+    Wt = w.permute(2, 0, 1).contiguous()
+    got = run(eng, 1, x.reshape(B * L, Cin), Wt, bias=bias, relu_first=1, use_tc=1, L=L, pad=pad, dil=dil)
+    ref = torch.nn.functional.conv1d(x.double().transpose(1, 2), w.double(), bias.double(), padding=pad, dilation=dil)
+    check(got, ref.relu().transpose(1, 2).reshape(B * L, Cout).float(), 1, 1.0)
+
+
 @pytest.mark.parametrize("use_tc", [0, 1, 2])
 @pytest.mark.parametrize("B,Hh,Ww,Cin,Cout", [(2, 80, 48, 32, 32), (1, 40, 33, 64, 64), (3, 10, 7, 256, 256),
                                               (2, 20, 55, 128, 128), (3, 80, 440, 32, 32), (5, 40, 220, 64, 64)])

@@ -139,10 +139,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (threadIdx.x == 0) {
         prefetch_tmap(&mapA);
         prefetch_tmap(&mapB);
-        if (SPLIT) {
-            prefetch_tmap(&mapAlo);
-            prefetch_tmap(&mapBlo);
-        }
+        if (SPLIT || (p.xr == 1 && p.mt == 2)) prefetch_tmap(&mapAlo);
+        if (SPLIT) prefetch_tmap(&mapBlo);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -192,6 +190,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait_sel(p.spin, aempty_bar(sa), pa ^ 1u);
                             mbar_arrive_expect_tx(afull_bar(sa), (uint32_t)p.xr_a_tx);
+                            if (p.xr == 1 && p.mt == 2) {
+                                // 256 + halo positions exceed the 256-wide TMA box: the first 128 through the 128-wide map
+                                // (passed in mapAlo's slot), the other 128 + halo behind them
+                                tma_load_4d(&mapAlo, afull_bar(sa), smem_a_ring + (uint32_t)(sa * p.xr_a_bytes), kc * BK,
+                                            c.x0 - p.pad_x, c.y0 + dy * p.dil - p.pad_y, c.img);
+                                tma_load_4d(&mapA, afull_bar(sa), smem_a_ring + (uint32_t)(sa * p.xr_a_bytes + A_TILE_BYTES), kc * BK,
+                                            c.x0 - p.pad_x + BM, c.y0 + dy * p.dil - p.pad_y, c.img);
+                            } else
                             tma_load_4d(&mapA, afull_bar(sa), smem_a_ring + (uint32_t)(sa * p.xr_a_bytes), kc * BK, c.x0 - p.pad_x,
                                         c.y0 + dy * p.dil - p.pad_y, c.img);
                             if (++sa == p.xr_na) { sa = 0; pa ^= 1u; }
@@ -688,7 +694,11 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     // (measured: pays off for filter rows of >= 5 taps — FFN k = 9, HiFi-GAN k = 7 / 11; for 3-tap rows the forced
     // 128 x 1 tile shape costs more in padding than the saved fetches)
     static const int xr_mink = getenv("ZVX_XR_MINK") ? atoi(getenv("ZVX_XR_MINK")) : 5;
-    const bool xr = !no_xr && !split && a.ksx >= xr_mink && a.stride == 1 && !a.b_batched && halo <= 120;
+    // narrow 1-D convs are hand-shake bound: there even a 3-tap row gains from one activation load per k-chunk (A/B: ZVX_XR1_K3)
+    // (measured: vocoder stage 8.21 -> 8.18 ms, profiles/r01_ab_conv1d_tap_reuse_two_m_tiles_and_k3.jsonl)
+    static const int xr1_k3 = getenv("ZVX_XR1_K3") ? atoi(getenv("ZVX_XR1_K3")) : 1;
+    const bool xr_narrow = xr1_k3 && a.ksy == 1 && a.ksx >= 3 && a.N <= 128;
+    const bool xr = !no_xr && !split && (a.ksx >= xr_mink || xr_narrow) && a.stride == 1 && !a.b_batched && halo <= 120;
     // 2-D tap reuse (ksy > 1, unit stride): one (TH + halo_y) x (TW + halo_x) activation tile per k-chunk serves all taps; the
     // activation fetch drops from taps x 16 KB to ~25 KB per k-chunk at the price of halo_x discarded columns per tile row.
     // Measured on configs[1] (profiles/r01_ab_conv2d_tap_reuse.jsonl): speaker net 4.21 -> 3.81 ms with N <= 128 (32 / 64 / 128
@@ -740,6 +750,17 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     static const int mt2_n = getenv("ZVX_MT2_N") ? atoi(getenv("ZVX_MT2_N")) : 64;
     p.mt = (!no_mt2 && !split && !xr && !xr2 && !a.b_batched && a.N <= mt2_n && positions >= 2LL * 256 * num_sms()) ? 2 : 1;
     long long best = -1;
+    if (xr) {
+        // filter-row tap reuse: 128 x 1 tiles, or 256 x 1 (two M tiles behind one haloed activation buffer and one weight stage)
+        // for narrow outputs when the longer tiles pad the rows by < 4 % and still fill the GPU.  ZVX_XR1_MT=1: one M tile.
+        // (measured: vocoder stage 8.30 -> 8.19 ms)
+        static const int xr1_mtmax = getenv("ZVX_XR1_MT") ? atoi(getenv("ZVX_XR1_MT")) : 2;
+        const long long t1 = cdiv(a.Wo, BM), t2 = 2LL * cdiv(a.Wo, 2 * BM);
+        if (xr1_mtmax >= 2 && 2 * p.BN <= ACC_STRIDE && a.N <= 128 && t2 * 100 <= t1 * 104 &&
+            t2 * a.Ho * a.IMG * p.tiles_n >= 4LL * num_sms())
+            p.mt = 2;
+        p.TW = BM * p.mt; p.TH = 1; best = 0;
+    }
     if (xr2) { p.TW = xr2_tw; p.TH = xr2_th * xr2_mt; p.mt = xr2_mt; best = 0; }
     for (int pass = 0; pass < 2 && best < 0; ++pass) {
         const int bm = BM * p.mt;
@@ -788,7 +809,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     if (xr || xr2) {
         p.xr = xr ? 1 : 2; p.xr_na = xr ? 3 : xr2_na; p.xr_halo = halo;
         if (xr) {
-            p.xr_a_tx = (BM + halo) * BK * 4;
+            p.xr_a_tx = (p.mt * BM + halo) * BK * 4;
             p.xr_a_bytes = (int)round_up(p.xr_a_tx, 1024);
             p.xr_ky = a.ksy; p.xr_kx = a.ksx; p.xr_wrap8 = 0;
         } else {
@@ -802,6 +823,10 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
         p.ug = std::max(1, std::min(p.xr_kx, (48 * 1024) / p.b_tile_stride));
         p.stage_bytes = p.ug * p.b_tile_stride;
         p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048 - p.xr_na * p.xr_a_bytes) / p.stage_bytes);
+        if (p.stages < 2 && p.xr_na > 2) {
+            p.xr_na = 2;
+            p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048 - p.xr_na * p.xr_a_bytes) / p.stage_bytes);
+        }
     }
     // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3, M >> 4
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -828,7 +853,9 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.stride = a.stride; p.stride_y = sy;
     const CUtensorMap mapA = make_map(a.A, adims, astr, abox, split, a.stride, sy);
     const CUtensorMap mapB = make_map(a.W, wdims, wstr, wbox, split);
-    const CUtensorMap mapAlo = split ? make_map(a.A_lo, adims, astr, abox, false, a.stride, sy) : mapA;
+    const int abox128[4] = {BK, BM, 1, 1};   // xr + two M tiles: the first 128 positions of the activation buffer
+    const CUtensorMap mapAlo = split ? make_map(a.A_lo, adims, astr, abox, false, a.stride, sy)
+                               : ((xr && p.mt == 2) ? make_map(a.A, adims, astr, abox128, false, a.stride, sy) : mapA);
     const CUtensorMap mapBlo = split ? make_map(a.W_lo, wdims, wstr, wbox) : mapB;
 
     int smem = p.xr_na * p.xr_a_bytes + p.stages * p.stage_bytes + 8 * (2 * p.stages + 5 + 2 * p.xr_na) + 16 + 1024;
