@@ -50,7 +50,7 @@ typedef struct zvx_config {
     int32_t vp_filter_size;       /* 256 */
     int32_t vp_kernel_size;       /* 3 */
     int32_t ve_n_bins;            /* 256 */
-    int32_t decoder_kind;         /* 0 = fastspeech2 (FFT blocks + SCLN); 1 = styletts (not built yet) */
+    int32_t decoder_kind;         /* 0 = fastspeech2 (FFT blocks + SCLN); 1 = styletts (InstanceNorm / AdaIN conv stacks, styletts.py:181-205) */
     int32_t dec_layers;           /* 6 */
     int32_t dec_heads;            /* 2 */
     int32_t conv_filter_size;     /* 1024 */
