@@ -350,6 +350,7 @@ def main():
         traffic, traffic_src = ncu_traffic(dom)
         line["roofline"] = {
             "bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "frac_of_tf32_peak": ach / (peak / 2),   # the kernel computes in TF32: half the bf16 rate the measured peak is for
             "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": d["bytes"] / d["launches"], "peak_source": f"bf16 dense, sustained, {peaks['source']} (MEASURED_PEAKS.json); "
                                             "TF32 runs at half the bf16 rate, fp32 FMA kernels at ~1/20",

@@ -139,3 +139,24 @@ def test_collate_matches_oracle_and_pad_sequence():
     assert ph.shape == (2, 0) and mask.shape == (2, 0)
     with pytest.raises(ValueError):
         tok.collate([[1, 2]], [[1]])
+
+
+def test_native_tokeniser_property_any_unicode():
+    """Property test (hypothesis): for ANY string and ANY small vocabulary the native tokeniser equals the restatement of
+    the reference loop — code points, not bytes; invalid characters skipped; output lengths equal."""
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+    chars = st.characters(blacklist_categories=("Cs",), blacklist_characters="\x00")
+
+    @hyp.settings(max_examples=300, deadline=None)
+    @hyp.given(phones=st.text(chars, min_size=1, max_size=12), puncts=st.text(chars, min_size=0, max_size=6),
+               text=st.text(chars, max_size=80))
+    def prop(phones, puncts, text):
+        puncts = " " + puncts                      # every shipped config lists the blank; without it the reference raises
+        tok, sym = Tokeniser(phones, puncts), fo.Symbols(phones, puncts)
+        body = text + phones[:3] + puncts[:2] + text[::-1]
+        ph, pu = tok.transcript2phonemids(body)
+        assert (ph, pu) == fo.transcript2phonemids(sym, body)
+        assert len(ph) == len(pu) and tok.num_phones == sym.num_phones and tok.num_puncts == sym.num_puncts
+
+    prop()
