@@ -153,3 +153,68 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
         logd_g[idx] = f[:, W + n_mels * L:]
         len_g[idx] = gathered[r][: nb * 8].view(torch.int64)[:n]
     return wav_g, mel_g, len_g, logd_g
+
+
+def mixed_language_forward(models: Mapping[str, Callable], x: Mapping[str, torch.Tensor] | None, lang: Sequence[str] | None,
+                           force_duration: bool = False, sharded: bool = False, group=None,
+                           device: torch.device | str | None = None, hop_length: int = 256, n_mels: int = 80):
+    """BASELINE config 4's mixed EN/DE batch: utterance i is synthesised by ``models[lang[i]]``.
+
+    The reference ties one checkpoint to one language (``ZeroVoxTTS(language=...)``, synthesize.py:48-100), so a mixed
+    batch is one batch per weight set there too: utterances are grouped by the *model object* their tag maps to (two tags
+    may share one weight set), every group runs as a batch of its own — through :func:`sharded_forward` when ``sharded``
+    (rank 0 holds ``x`` and ``lang``; the other ranks pass ``None`` and learn the group plan from one small object
+    broadcast) — and the results are merged back in the original order, zero-padded to the longest group.
+
+    Returns ``(wav [B, L*hop], mel [B, n_mels, L], mel_len int64 [B], log_duration [B, T])`` (on rank 0 when sharded,
+    ``None`` elsewhere).
+    """
+    rank = dist.get_rank(group) if sharded else 0
+    plan = None
+    if rank == 0:
+        assert x is not None and lang is not None, "rank 0 must hold the batch and its language tags"
+        B = x["phoneme"].shape[0]
+        if len(lang) != B:
+            raise ValueError(f"{len(lang)} language tags for {B} utterances")
+        unknown = sorted({t for t in lang if t not in models})
+        if unknown:
+            raise KeyError(f"no model for language tag(s) {unknown}")
+        first_tag, members = {}, {}
+        for i, t in enumerate(lang):                      # group by weight set, in order of first appearance
+            key = first_tag.setdefault(id(models[t]), t)
+            members.setdefault(key, []).append(i)
+        plan = [(k, v) for k, v in members.items()]
+    if sharded:
+        box = [plan]
+        dist.broadcast_object_list(box, src=0, group=group)
+        plan = box[0]
+
+    results = []
+    for tag, idx in plan:
+        xg = None
+        if rank == 0:
+            sel = torch.as_tensor(idx, dtype=torch.long)
+            xg = {k: v[sel.to(v.device)] for k, v in x.items() if isinstance(v, torch.Tensor)}
+        if sharded:
+            out = sharded_forward(models[tag], xg, force_duration=force_duration, group=group, device=device,
+                                  hop_length=hop_length, n_mels=n_mels)
+        else:
+            out = models[tag](xg, force_duration=force_duration)
+        results.append(out)
+    if rank != 0:
+        return None
+
+    B, T = x["phoneme"].shape
+    L = max(r[1].shape[2] for r in results)
+    dev = results[0][0].device
+    wav = torch.zeros((B, L * hop_length), dtype=torch.float32, device=dev)
+    mel = torch.zeros((B, results[0][1].shape[1], L), dtype=torch.float32, device=dev)
+    mel_len = torch.zeros((B,), dtype=torch.int64, device=dev)
+    logd = torch.zeros((B, T), dtype=torch.float32, device=dev)
+    for (tag, idx), (w, m, ml, ld) in zip(plan, results):
+        sel = torch.as_tensor(idx, dtype=torch.long, device=dev)
+        wav[sel, : w.shape[1]] = w.to(torch.float32)
+        mel[sel, :, : m.shape[2]] = m.to(torch.float32)
+        mel_len[sel] = ml.to(torch.int64)
+        logd[sel] = ld.to(torch.float32)
+    return wav, mel, mel_len, logd
