@@ -188,3 +188,66 @@ def test_tts_ex_mirror_end_to_end_text_to_waveform():
     # empty text: the reference's early return (synthesize.py:221-222)
     w0, p0, l0, m0 = tts.tts_ex("   ", style)
     assert l0 == 0 and w0.shape == (1, 1) and p0.shape == (1, 1)
+
+
+def test_load_model_directory_then_speak(tmp_path, monkeypatch):
+    """ZeroVoxTTS.load_model on the reference's on-disk layout (synthesize.py:275-328): a model directory with modelcfg.yaml +
+    checkpoints/*.ckpt (Lightning format) and a vocoder repo in the cache layout with weight-normed generator.ckpt; then the
+    demo flow (zerovox/demo.py:103-115): speaker_embed(prompt) -> tts(text) -> waveform, against the oracle."""
+    import json
+    import yaml
+    from zerovox_b200.testing import zerovox_kwargs
+    from zerovox_b200.tts import AttrDict, Generator
+    from zerovox_b200.tts.synthesize import ZeroVoxTTS
+
+    class Lower:
+        def normalize(self, text):
+            return text.lower(), None
+
+    cfg = zo.ZeroVoxConfig.tiny()
+    w = zo.make_weights(cfg, seed=3)
+    name = "zerovox-hifigan-test"
+    repo = tmp_path / "model_repo" / name
+    repo.mkdir(parents=True)
+    (repo / "config.json").write_text(json.dumps(cfg.hifigan.as_json_dict()))
+    raw_gen = Generator(AttrDict(cfg.hifigan.as_json_dict()))          # weight-normed, like upstream generator.ckpt
+    torch.save({"generator": raw_gen.state_dict()}, repo / "generator.ckpt")
+    monkeypatch.setenv("CACHED_PATH_ZEROVOX", str(tmp_path))
+    mdir = tmp_path / "tts_en_test"
+    (mdir / "checkpoints").mkdir(parents=True)
+    (mdir / "modelcfg.yaml").write_text(yaml.safe_dump({
+        "lang": ["en"], "model": {"phones": cfg.phones, "puncts": cfg.puncts},
+        "audio": {"sampling_rate": 22050, "fft_size": 1024, "fmax": 8000, "fmin": 0, "win_length": 1024, "num_mels": 80,
+                  "hop_size": 256}}))
+    hp = {k: v for k, v in zerovox_kwargs(cfg).items() if k != "meldec_model"}
+    sd = {k: v for k, v in w.items() if not k.startswith("_meldec.")}
+    torch.save({"hyper_parameters": hp, "state_dict": sd}, mdir / "checkpoints" / "epoch=0003.ckpt")
+
+    modelcfg, tts = ZeroVoxTTS.load_model(str(mdir), meldec_model=name, infer_device=DEV, normalizer=Lower())
+    assert modelcfg["audio"]["hop_size"] == 256
+    tts._model._shared_ctx.tensor_core_policy = 0                      # fp32 FMA: tight comparison
+    tts._model._shared_ctx.mark_stale()
+    prompt = make_speech_like(22050, seed=9)
+    style = tts.speaker_embed(prompt)
+    wav_p, phoneme_p, length_p = tts.tts("Hello there, world.", style)          # the demo call (predicted durations)
+    assert wav_p.shape == (length_p * 256,) and phoneme_p.shape[1] == 15
+    # oracle with the same weights: vocoder = the folded (remove_weight_norm) form of the raw generator
+    wo = dict(sd)
+    wo.update({"_meldec." + k: v for k, v in raw_gen._engine_state_dict().items()})
+    ph, pu = fo.transcript2phonemids(fo.Symbols(cfg.phones, cfg.puncts), "hello there, world.")
+    assert len(ph) == 15
+    dur = [(5 * i) % 4 + 2 for i in range(len(ph))]                               # forced: no rounding boundary in the compare
+    wav, phoneme, length, mel = tts.tts_ex("Hello there, world.", style, duration=dur)
+    x = {"phoneme": torch.tensor([ph], dtype=torch.int32), "puncts": torch.tensor([pu], dtype=torch.int32),
+         "duration": torch.tensor([dur], dtype=torch.int32)}
+    with torch.no_grad():
+        ostyle = zo.speaker_embed(cfg, wo, torch.from_numpy(fo.speaker_prompt_mel(prompt)))
+        owav, olen, _, omel, _ = zo.zerovox_inference_ex(cfg, wo, x, style.cpu(), force_duration=True)
+    assert (style.cpu() - ostyle).abs().max().item() < 2e-4
+    assert length == olen == sum(dur) and phoneme.cpu().tolist() == [ph] and wav.shape == (olen * 256,)
+    e_wav = np.abs(wav - owav.numpy()).max()
+    e_mel = np.abs(mel - omel.numpy()).max() / np.abs(omel.numpy()).max()
+    print(f"  load_model -> tts_ex: {olen} frames, mel rel err {e_mel:.2e}, wav err {e_wav:.2e}")
+    assert e_wav < 5e-4 and e_mel < 5e-4
+    with pytest.raises(FileNotFoundError):
+        ZeroVoxTTS.load_model("no-such-model", meldec_model=name, infer_device=DEV)

@@ -4,7 +4,7 @@ the hot path — ``speaker_embed`` (synthesize.py:123-143), ``transcript2phonemi
 
 Not mirrored (outside the path, SURVEY.md §8f / DESIGN.md §9): audio file loading + resampling (librosa.load), the NeMo /
 uroman text normaliser (pass any callable with ``normalize(text) -> (transcript, _)`` as ``normalizer``), the HuggingFace
-download in ``load_model`` and the torchinfo ``summary``.
+download in ``load_model`` (local directory / cache layouts are read, nothing is fetched) and the torchinfo ``summary``.
 """
 from __future__ import annotations
 
@@ -101,6 +101,42 @@ class ZeroVoxTTS:
     def tts(self, text: str, spkemb):
         wav, phoneme, length, _ = self.tts_ex(text=text, spkemb=spkemb)
         return wav, phoneme, length
+
+    @classmethod
+    def load_model(cls, modelpath, meldec_model, infer_device: str = "cuda", num_threads: int = -1, verbose: bool = False,
+                   *, normalizer=None):
+        """synthesize.py:275-328: ``modelpath`` is a model directory (``modelcfg.yaml`` + ``checkpoints/*.ckpt``, newest
+        wins) or a model name resolved in the local cache layout ``$CACHED_PATH_ZEROVOX/model_repo/<name>/{modelcfg.yaml,
+        checkpoint.pkl}`` (model.py:66-82).  Nothing is downloaded: a missing file raises FileNotFoundError.
+        Returns ``(modelcfg, ZeroVoxTTS)`` like the reference."""
+        import glob
+        from pathlib import Path
+
+        import yaml
+
+        from .model import model_cache_path
+        if os.path.isdir(modelpath):
+            config_path = Path(modelpath) / "modelcfg.yaml"
+            list_of_files = glob.glob(os.path.join(modelpath, "checkpoints/*.ckpt"))
+            if not list_of_files:
+                raise FileNotFoundError(f"no checkpoints/*.ckpt under {modelpath}")
+            checkpoint = max(list_of_files, key=os.path.getctime)
+        else:
+            config_path = model_cache_path(str(modelpath), "modelcfg.yaml")
+            checkpoint = model_cache_path(str(modelpath), "checkpoint.pkl")
+        if verbose:
+            print("synthesize: using config    : ", config_path)
+            print("synthesize: using checkpoint: ", checkpoint)
+        with open(config_path) as modelcfgf:
+            modelcfg = yaml.load(modelcfgf, Loader=yaml.FullLoader)
+        synth = cls(language=modelcfg["lang"][0],
+                    syms=Symbols(phones=modelcfg["model"]["phones"], puncts=modelcfg["model"]["puncts"]),
+                    checkpoint=checkpoint, meldec_model=str(meldec_model), hop_length=modelcfg["audio"]["hop_size"],
+                    win_length=modelcfg["audio"]["win_length"], mel_fmin=modelcfg["audio"]["fmin"],
+                    mel_fmax=modelcfg["audio"]["fmax"], sampling_rate=modelcfg["audio"]["sampling_rate"],
+                    n_mel_channels=modelcfg["audio"]["num_mels"], fft_size=modelcfg["audio"]["fft_size"],
+                    infer_device=infer_device, num_threads=num_threads, verbose=verbose, normalizer=normalizer)
+        return modelcfg, synth
 
     @property
     def normalizer(self):
