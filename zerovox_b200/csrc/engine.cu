@@ -779,7 +779,7 @@ class Engine {
         static const int tc_mask = getenv("ZVX_TC_MASK") ? atoi(getenv("ZVX_TC_MASK")) : 15;   // bit0: tensor-core attention
         const bool split = (tc == P_EXACT);
         const float* wqkv_lo = split ? lo_of(ly.wqkv) : nullptr;
-        const bool tc_attn = tc_enabled(tc) && (tc_mask & 1) && (dk % 4 == 0) && rows >= 64 &&
+        const bool tc_attn = tc_enabled(tc) && (tc_mask & 1) && (dk % 4 == 0) && rows >= tc_min_rows() &&
                              (!split || (wqkv_lo && sc.lo_qkv && lo_buf && rows * H <= lo_cap));
         if (tc_attn) {
             // tcgen05 path: [Q|K] row-major [rows, 2H]; V written transposed per utterance, Vt[b][c][t] (row pitch Lp),

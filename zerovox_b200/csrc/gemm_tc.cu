@@ -898,6 +898,13 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     }
 }
 
+// Smallest row count that goes to the tensor-core kernel.  A single short utterance has M = T phonemes: on the fp32 FMA
+// kernel its few CTAs take 50 - 200 us per contraction, a (mostly empty) 128-row tensor-core tile a fraction of that.
+int tc_min_rows() {
+    static const int v = getenv("ZVX_TC_MIN_M") ? atoi(getenv("ZVX_TC_MIN_M")) : 64;
+    return v;
+}
+
 bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* o) {
     if (g.b_kn || g.nz != 1) return false;
     TcGemmArgs a;
@@ -925,7 +932,7 @@ bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* o) {
         a.ksx = a.ksy = g.ksize; a.dil = 1; a.pad_x = a.pad_y = g.pad;
     }
     *o = a;
-    if (g.M < 64) return false;   // tiny problems stay on the fp32 FMA kernel
+    if (g.M < tc_min_rows()) return false;   // tiny problems stay on the fp32 FMA kernel
     return gemm_tc_supported(a);
 }
 

@@ -56,5 +56,6 @@ void tf32_split_lo(const float* x, float* lo, long long n, cudaStream_t st);
 
 // Conversion from the SIMT kernel's argument block (ROW_PLAIN / ROW_CONV1D / ROW_CONV2D with stride 1, nz == 1).
 bool gemm_tc_from(const GemmArgs& g, TcGemmArgs* out);
+int tc_min_rows();   // smallest M that goes to the tensor-core kernel (ZVX_TC_MIN_M)
 
 }  // namespace zvx
