@@ -900,8 +900,10 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
 
 // Smallest row count that goes to the tensor-core kernel.  A single short utterance has M = T phonemes: on the fp32 FMA
 // kernel its few CTAs take 50 - 200 us per contraction, a (mostly empty) 128-row tensor-core tile a fraction of that.
+// Measured with the demo flow (46 phonemes, profiles/r01_demo_host_profile.log): threshold 64 -> 16 takes zvx_encode from
+// 3.56 to 1.48 ms and the whole sentence from 5.48 to 3.35 ms; all GPU parity tests pass with either value.
 int tc_min_rows() {
-    static const int v = getenv("ZVX_TC_MIN_M") ? atoi(getenv("ZVX_TC_MIN_M")) : 64;
+    static const int v = getenv("ZVX_TC_MIN_M") ? atoi(getenv("ZVX_TC_MIN_M")) : 16;
     return v;
 }
 
