@@ -210,7 +210,8 @@ int zvx_trim_silence(zvx_frontend* h, const float* wav, int B, int64_t n_stride,
  * wav fp32 [B, n_stride]; wav_start / wav_len device int64 [B] select the window of each row (NULL = 0 / the rest of the
  * row) — the outputs of zvx_trim_silence plug in directly.  mel_BTC fp32 [B, n_frames, num_mels] (the reference's `spec`
  * transposed: exactly the `_spkemb` / zvx_spkemb input layout); energy fp32 [B, n_frames] or NULL.  Rows beyond an
- * utterance's own frame count are zero-filled. */
+ * utterance's own frame count are zero-filled.  Windows are clamped to the row: a bad (start, len) pair shortens the
+ * output, it never reads outside the buffer. */
 int zvx_mel_spectrogram(zvx_frontend* h, const float* wav, int B, int64_t n_stride, const int64_t* wav_start,
                         const int64_t* wav_len, int n_frames, float* mel_BTC, float* energy, void* stream);
 

@@ -76,8 +76,9 @@ mel_spectrogram_kernel(const float* __restrict__ wav, long long n_stride, const 
     const int fl = threadIdx.x / FE_TPF, t = threadIdx.x % FE_TPF;
     const int b = blockIdx.y;
     const int f = blockIdx.x * FE_FPC + fl;
-    const long long start = wav_start ? wav_start[b] : 0;
-    const long long len = wav_len ? wav_len[b] : n_stride - start;
+    // the window is clamped to the row: a bad (start, len) pair can shorten the output but never read outside the buffer
+    const long long start = wav_start ? min(max(wav_start[b], 0LL), n_stride) : 0;
+    const long long len = wav_len ? min(max(wav_len[b], 0LL), n_stride - start) : n_stride - start;
     const bool valid = f < n_frames && f < fe_num_frames(len, p.hop, p.pad);
     float2* buf = bufs[fl];
     float* mag = mags[fl];
@@ -171,7 +172,7 @@ frame_rms_kernel(const float* __restrict__ wav, long long n_stride, const long l
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     const long long f = (long long)blockIdx.x * 8 + warp;
-    const long long len = wav_len ? wav_len[b] : n_stride;
+    const long long len = wav_len ? min(max(wav_len[b], 0LL), n_stride) : n_stride;
     if (f >= n_frames_max || f > len / hop) return;                  // 1 + len // hop frames
     const float* x = wav + (long long)b * n_stride;
     const long long lo = f * hop - frame_length / 2;
@@ -196,7 +197,7 @@ trim_bounds_kernel(const float* __restrict__ rms, const unsigned* __restrict__ r
                    long long* __restrict__ start_out, long long* __restrict__ len_out) {
     __shared__ int s_first, s_last;
     const int b = blockIdx.x;
-    const long long len = wav_len ? wav_len[b] : n_stride;
+    const long long len = wav_len ? min(max(wav_len[b], 0LL), n_stride) : n_stride;
     const long long nfr = min((long long)n_frames_max, 1 + len / hop);
     if (threadIdx.x == 0) { s_first = 0x7fffffff; s_last = -1; }
     __syncthreads();
