@@ -2,17 +2,24 @@
 """bench.py — audio-seconds/second (RTF^-1) of the ZeroVOX phoneme -> waveform forward on B200.
 
     python bench.py --gpus N --steps K --warmup W            # this engine (default)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own PyTorch modules on the host CPU cores
 
-Workload (BASELINE.json configs[1]): tts_medium (FS2/SCLN decoder) + HiFi-GAN V2, batch = 32 EN phoneme sequences of
-length 128, forced durations U{2..10} (L ~ 768 mel frames per utterance), ref_mel [32, 440, 80]; synthetic seeded
-weights and inputs (no network for checkpoints).  One "step" = one ZeroVox.forward over one batch: speaker net ->
-encoder + variance adaptor -> length regulator -> decoder -> vocoder.  N > 1: one process per GPU, every rank runs
-its own batch of 32 (weak scaling, utterances are independent; no data-path collective).
+Workload (BASELINE.json configs[1]): tts_medium (FS2/SCLN decoder) + HiFi-GAN V2, 32 EN phoneme sequences of length 128
+per GPU, forced durations U{2..10} (L ~ 768 mel frames per utterance), ref_mel [*, 440, 80]; synthetic seeded weights and
+inputs (no network for checkpoints).  One "step" = one ZeroVox.forward over one batch: speaker net -> encoder + variance
+adaptor -> length regulator -> decoder -> vocoder.
 
-The JSON line follows the driver contract; `value` is device-resident throughput (inputs already in HBM, CUDA-event
-time), `e2e` is the same metric through ZeroVox.forward with pinned HOST inputs and the waveform read back to the
-host inside the timed region.
+N = 1: `value` times ZeroVox.forward on device-resident inputs (CUDA events); `e2e` the same call with pinned HOST inputs
+and the waveform read back to the host inside the timed region.
+N > 1 (north_star's multi-GPU path, BASELINE config 4's mechanism): rank 0 holds the GLOBAL batch of 32*N utterances;
+one step = zerovox_b200.parallel.sharded_forward = ONE NCCL scatter of the packed inputs -> forward on every rank's block
+-> ONE NCCL gather-v of the valid waveforms / mels to rank 0.  `value`: global batch resident in rank 0's HBM, result in
+rank 0's HBM; `e2e`: global batch in rank 0's pinned host memory, gathered waveforms copied to rank 0's host.  Both are
+max-over-ranks.  `replicas` keeps the collective-free number (every rank its own batch of 32) beside it, and `config4`
+the ragged mixed-language variant (T_i ~ U{64..192}, two weight sets).
+
+Other workloads (one JSON line each, same contract): --workload config3 (HiFi-GAN only, L x B sweep, V1 and V2),
+--workload config5 (one 4096-phoneme utterance, chunked vocoder).
 """
 from __future__ import annotations
 
@@ -33,7 +40,8 @@ import torch  # noqa: E402
 
 METRIC = "audio-sec/sec (RTF^-1) @22.05kHz, phoneme->waveform"
 UNIT = "audio-s/s"
-WORKLOAD = "configs[1]: tts_medium + HiFi-GAN V2, B=32 x T=128 phonemes, forced durations U{2..10}, T_ref=440"
+WORKLOAD = "configs[1]: tts_medium + HiFi-GAN V2, B=32 x T=128 phonemes per GPU, forced durations U{2..10}, T_ref=440"
+MFLOP_PER_FRAME = {"v1": 614.1, "v2": 38.5, "v3": 45.0}
 
 
 def parse():
@@ -42,13 +50,16 @@ def parse():
     p.add_argument("--steps", type=int, default=10)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--batch", type=int, default=32)
+    p.add_argument("--workload", default="configs1", choices=["configs1", "config3", "config5"])
+    p.add_argument("--batch", type=int, default=32, help="utterances per GPU")
     p.add_argument("--phonemes", type=int, default=128)
     p.add_argument("--ref-frames", type=int, default=440)
     p.add_argument("--policy", type=int, default=1, help="0 = all fp32 FMA, 1 = TF32 tensor cores where allowed")
-    p.add_argument("--cpu-sample-batch", type=int, default=4, help="utterances in the bounded CPU sample")
+    p.add_argument("--cpu-sample-batch", type=int, default=0, help="utterances in the CPU sample (0 = the full batch)")
+    p.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: stop timing after this many seconds")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-config4", action="store_true")
     return p.parse_args()
 
 
@@ -58,8 +69,26 @@ def measured_peaks():
         with open(path) as f:
             d = json.load(f)
         return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
-                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "sm_max_mhz": d.get("sm_max_mhz"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0,
+            "source": "fallback"}
+
+
+def tf32_peak(peaks):
+    """TF32 tensor peak in TFLOP/s for the roofline denominators: the measured figures of tools/measure_tf32_peak.py
+    (profiles/*_tf32_peak.json: cuBLAS TF32 8192^3 burst / sustained, measured like MEASURED_PEAKS.json's bf16 pair, and the
+    tcgen05.mma.kind::tf32 issue-rate ceiling) when committed, else half the measured bf16 figures."""
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_tf32_peak.json")))
+    if paths:
+        with open(paths[-1]) as f:
+            d = json.load(f)
+        return {"burst": d["cublas_tf32_tflops_burst"], "sustained": d["cublas_tf32_tflops_sustained"],
+                "tcgen05_issue_ceiling": d.get("tcgen05_tf32_issue_tflops"),
+                "source": f"measured on B200: {os.path.relpath(paths[-1], ROOT)}"}
+    return {"burst": peaks["bf16_tflops"] / 2, "sustained": peaks["bf16_tflops_sustained"] / 2, "tcgen05_issue_ceiling": None,
+            "source": f"assumed: half the {peaks['source']} bf16 dense rate (MEASURED_PEAKS.json); no TF32 measurement committed"}
 
 
 class ClockSampler:
@@ -110,12 +139,13 @@ class ClockSampler:
 # engine profiling class -> kernel names in profiles/*_ncu_summary.json (tools/ncu_summary.py)
 NCU_KERNELS = {"gemm_tf32_tcgen05": ("gemm_tc_kernel<0, 0>", "gemm_tc_kernel<1, 0>"),
                "gemm_3xtf32_tcgen05": ("gemm_tc_kernel<1, 1>",),
-               "vocoder_pair_tcgen05": ("voc_poly_kernel<32>", "voc_poly_kernel<16>", "voc_poly_kernel<8>")}
+               "vocoder_pair_tcgen05": ("voc_poly_kernel<32>", "voc_poly_kernel<16>", "voc_poly_kernel<8>",
+                                        "voc_stage_kernel<32>", "voc_stage_kernel<16>", "voc_stage_kernel<8>")}
 
 
 def ncu_traffic(cls):
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the class's kernels from the committed
-    `ncu --set full` capture of tools/prof_step.py (same workload); None when there is no capture."""
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the class's kernels from the newest
+    committed `ncu --set full` capture of tools/prof_step.py (same workload); None when there is no capture."""
     import glob
     paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")))
     if not paths or cls not in NCU_KERNELS:
@@ -137,28 +167,100 @@ def audio_seconds(mel_len_total, cfg):
     return mel_len_total * cfg.hop_length / cfg.sampling_rate
 
 
-def cpu_reference_run(cfg, w, x, threads, runs):
-    """The reference algorithm (oracle port of the reference's PyTorch modules) on the host cores."""
-    from oracle import zerovox_oracle as zo  # the CPU-baseline leg is the one place bench.py may use the oracle
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU side: the reference's own modules (oracle/_ref, written by oracle/build_ref.py) — or, where that copy is absent, the
+# oracle port — on the host cores.  The one place bench.py executes anything under oracle/.
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_forward_fn(cfg, w):
+    """Returns (fn(x) -> total mel frames, kind).  kind "reference": the unmodified zerovox.tts modules composed as
+    model.py:260-290 + the intended HiFi-GAN tail; "port": oracle/zerovox_oracle.py."""
+    from oracle import reference_modules as rm
+    if rm.available():
+        zv = rm.build_reference_model(cfg, w)
+
+        def fn(x):
+            return int(rm.reference_forward(zv, dict(x), True)[2].sum())
+        return fn, "reference"
+    from oracle import zerovox_oracle as zo
+
+    def fn(x):
+        with torch.no_grad():
+            return int(zo.zerovox_forward(cfg, w, dict(x), force_duration=True)[2].sum())
+    return fn, "port"
+
+
+def cpu_baseline_block(cfg, w, x_full, sample_batch):
+    """Bounded CPU sample beside the GPU number: ONE run of the full batch on all host threads (10-30 s of CPU work), plus
+    a 2-utterance single-thread run (BASELINE.md section 3 asks for N = all cores and N = 1)."""
+    fn, kind = cpu_forward_fn(cfg, w)
+    threads = os.cpu_count() or 1
+    B = x_full["phoneme"].shape[0]
+    nb = B if sample_batch <= 0 else min(sample_batch, B)
+    xs = {k: v[:nb].clone() for k, v in x_full.items()}
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    frames = fn(xs)
+    t_all = time.perf_counter() - t0
+    out = {"value": audio_seconds(frames, cfg) / t_all, "unit": UNIT, "cores": threads, "kind": kind,
+           "sample": f"{nb} of the {B} utterances of the same batch (same seeds), one run, no warm-up, "
+                     f"torch.set_num_threads({threads})", "seconds_per_run": t_all, "mel_frames_per_sec": frames / t_all}
+    x2 = {k: v[:2].clone() for k, v in x_full.items()}
+    torch.set_num_threads(1)
+    t0 = time.perf_counter()
+    f2 = fn(x2)
+    t1 = time.perf_counter() - t0
+    torch.set_num_threads(threads)
+    out["single_thread"] = {"value": audio_seconds(f2, cfg) / t1, "unit": UNIT, "cores": 1,
+                            "sample": "2 utterances of the same batch, one run", "seconds_per_run": t1}
+    return out
+
+
+def run_reference(args, cfg, w, x_full):
+    """--impl reference: the reference's CPU implementation of the same workload (full batch per step, all host threads);
+    timing stops after --ref-budget-s seconds of timed steps so that a 20-step request still ends within minutes."""
+    fn, kind = cpu_forward_fn(cfg, w)
+    threads = os.cpu_count() or 1
+    B = x_full["phoneme"].shape[0]
+    nb = B if args.cpu_sample_batch <= 0 else min(args.cpu_sample_batch, B)
+    x = {k: v[:nb] for k, v in x_full.items()}
     torch.set_num_threads(threads)
     times, frames = [], 0
-    with torch.no_grad():
-        zo.zerovox_forward(cfg, w, dict(x), force_duration=True)  # warm-up
-        for _ in range(runs):
-            t0 = time.perf_counter()
-            _, _, mel_len, _, _ = zo.zerovox_forward(cfg, w, dict(x), force_duration=True)
-            times.append(time.perf_counter() - t0)
-            frames = int(mel_len.sum())
-    return statistics.median(times), frames
+    t_first = time.perf_counter()
+    frames = fn(x)                                     # warm-up (one is enough for a CPU path: no JIT, no autotuning)
+    t_first = time.perf_counter() - t_first
+    budget = args.ref_budget_s
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        frames = fn(x)
+        times.append(time.perf_counter() - t0)
+        if sum(times) + times[-1] > budget:
+            break
+    t = sum(times) / len(times)
+    val = audio_seconds(frames, cfg) / t
+    sample = (f"{nb} of the {B} utterances of the workload batch per step (same seeds), all host threads; "
+              f"{len(times)} of the requested {args.steps} steps timed (budget {budget:.0f} s), 1 warm-up of {t_first:.1f} s")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "phonemes": args.phonemes,
+                   "mel_frames_per_sec": frames / t, "steps_requested": args.steps,
+                   "note": ("the reference's own zerovox.tts modules (oracle/_ref copy of the unmodified sources; lightning "
+                            "stubbed), composed as model.py:260-290 + the intended HiFi-GAN tail — the reference's own eval "
+                            "tail raises with hifigan.Generator (BASELINE.md section 3)") if kind == "reference" else
+                           "oracle port of the reference's PyTorch CPU path (oracle/_ref absent on this box)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
 
 
-def pipeline_roofline(prof, peaks, step_ms, sm_mhz):
+def pipeline_roofline(prof, peaks, step_ms, sm_mhz, tf32_tflops=None):
     """SURVEY.md 8d pipeline figure: T_roof = sum over kernel classes of max(FLOP / peak_class, bytes / HBM bandwidth),
-    with the ALGORITHMIC flops / bytes the engine recorded per class.  peak_class: TF32 tcgen05 = half the measured
-    sustained bf16 rate; 3xTF32 split = a third of that (three MMAs per product); fp32 FMA = 148 SMs x 128 lanes x 2 x
-    the SM clock sampled during the timed region.  Kernel classes without a flop model (norms, softmax, gathers:
-    ~9 % of the step) are outside both sums."""
-    tf32 = peaks["bf16_tflops_sustained"] / 2 * 1e12
+    with the ALGORITHMIC flops / bytes the engine recorded per class.  peak_class: TF32 tcgen05 = the measured TF32 rate
+    (default: half the measured sustained bf16 rate); 3xTF32 split = a third of that (three MMAs per product); fp32 FMA =
+    148 SMs x 128 lanes x 2 x the SM clock sampled during the timed region.  Kernel classes without a flop model (norms,
+    softmax, gathers: ~9 % of the step) are outside both sums."""
+    tf32 = (tf32_tflops if tf32_tflops else peaks["bf16_tflops_sustained"] / 2) * 1e12
     fma = 148 * 128 * 2 * sm_mhz * 1e6
     peak_of = {"gemm_tf32_tcgen05": tf32, "vocoder_pair_tcgen05": tf32, "gemm_3xtf32_tcgen05": tf32 / 3,
                "gemm_fp32": fma, "vocoder_conv1d": fma, "vocoder_upsample": fma}
@@ -173,38 +275,65 @@ def pipeline_roofline(prof, peaks, step_ms, sm_mhz):
             "share_of_step_modelled": t_meas / step_ms, "tf32_peak_tflops": tf32 / 1e12, "fp32_fma_peak_tflops": fma / 1e12}
 
 
-def run_reference(args, cfg, w, x_full, rank):
-    if rank != 0:
-        return
-    threads = os.cpu_count() or 1
-    nb = min(args.cpu_sample_batch, args.batch)
-    x = {k: v[:nb] for k, v in x_full.items()}
-    times, frames = [], 0
-    from oracle import zerovox_oracle as zo
-    torch.set_num_threads(threads)
-    with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 1))):
-            zo.zerovox_forward(cfg, w, dict(x), force_duration=True)
-        for _ in range(args.steps):
-            t0 = time.perf_counter()
-            _, _, mel_len, _, _ = zo.zerovox_forward(cfg, w, dict(x), force_duration=True)
-            times.append(time.perf_counter() - t0)
-            frames = int(mel_len.sum())
-    t = sum(times) / len(times)
-    val = audio_seconds(frames, cfg) / t
-    sample = f"{nb} of the {args.batch} utterances of the workload batch per step (same seeds), all host threads"
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "mel_frames_per_sec": frames / t,
-                   "note": "reference = oracle port of the reference's PyTorch CPU path (pure-Python reference, "
-                           "nothing to compile); batched eval tail composed as in oracle/zerovox_oracle.py"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+def roofline_block(eng, run_step, peaks, step_ms, clocks):
+    """Dominant kernel class of one extra step, timed live with CUDA events around every launch of the class."""
+    eng.profile(True)
+    run_step()
+    prof = eng.profile_read()
+    eng.profile(False)
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    if d["launches"] <= 0 or d["ms"] <= 0:
+        return None
+    tp = tf32_peak(peaks)
+    ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+    peak = tp["sustained"]                             # a kernel timed inside a long step: the sustained figure
+    traffic, traffic_src = ncu_traffic(dom)
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    return {
+        "bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+        "peak_source": "TF32 dense, sustained; " + tp["source"], "peak_burst": tp["burst"],
+        "tcgen05_tf32_issue_ceiling": tp["tcgen05_issue_ceiling"],
+        "frac_of_half_bf16_sustained": ach / (peaks["bf16_tflops_sustained"] / 2),
+        "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_bytes_per_launch": d["bytes"] / d["launches"], "launches_per_step": d["launches"],
+        "avg_launch_ms": d["ms"] / d["launches"], "algorithmic_flops_per_launch": d["flops"] / d["launches"],
+        "share_of_step": d["ms"] / step_ms,
+        "pipeline": pipeline_roofline(prof, peaks, step_ms, sm_mhz, tp["sustained"]),
+        "classes": {k: {"ms": v["ms"], "launches": v["launches"],
+                        "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None,
+                        "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in prof.items()},
+    }
 
 
+def event_loop(fn, steps, flush, dev):
+    """steps x fn() with the L2 flushed in between; CUDA events on the launching (current) stream.  Returns ms list."""
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize(dev)
+    return [a.elapsed_time(b) for a, b in evs]
+
+
+def config4_inputs(syn, cfg, B, seed=13):
+    """BASELINE config 4's batch: T_i ~ U{64..192} phonemes padded to 192 with phoneme_mask, alternating EN/DE tags."""
+    g = torch.Generator().manual_seed(3)
+    T = 192
+    x = syn.make_inputs(cfg, B, T, 440, seed=seed)
+    lens = torch.randint(64, 193, (B,), generator=g)
+    mask = torch.arange(T)[None, :] >= lens[:, None]
+    x["phoneme_mask"] = mask
+    for k in ("phoneme", "puncts", "duration"):
+        x[k] = x[k].masked_fill(mask, 0)
+    return x, ["en" if i % 2 == 0 else "de" for i in range(B)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -217,11 +346,16 @@ def main():
         if rank == 0:
             w = syn.make_weights(cfg, seed=0)
             x = syn.make_inputs(cfg, args.batch, args.phonemes, args.ref_frames, seed=7)
-            run_reference(args, cfg, w, x, rank)
+            run_reference(args, cfg, w, x)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU path)"
+    if args.workload != "configs1":
+        import bench_workloads
+        return bench_workloads.run(args, rank, local_rank, world)
+
     from zerovox_b200.testing import build_model
+    from zerovox_b200.parallel import sharded_forward, mixed_language_forward
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     dist = None
@@ -229,26 +363,49 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
+    W = max(args.warmup, 3)
     w = syn.make_weights(cfg, seed=0)
-    x_host = syn.make_inputs(cfg, args.batch, args.phonemes, args.ref_frames, seed=7 + rank)
-    x_host = {k: v.pin_memory() for k, v in x_host.items()}
     model = build_model(cfg, w, device=dev, tensor_core_policy=args.policy)
     eng = model._shared_ctx.get(dev)
-    x_dev = {k: v.to(dev) for k, v in x_host.items()}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    keys = ("phoneme", "puncts", "duration", "ref_mel")
 
-    def step_device():
+    # per-rank batch (replica measurement; at N = 1 this IS the workload) and, for N > 1, the global batch on rank 0
+    x_host = {k: v.pin_memory() for k, v in syn.make_inputs(cfg, args.batch, args.phonemes, args.ref_frames, seed=7 + rank).items()}
+    x_dev = {k: v.to(dev) for k, v in x_host.items()}
+    Bg = args.batch * world
+    xg_host = xg_dev = spec = None
+    if world > 1:
+        xg = syn.make_inputs(cfg, Bg, args.phonemes, args.ref_frames, seed=7)   # every rank derives the header from it
+        Lh = int(xg["duration"].clamp(min=0).sum(1).max())
+        spec = [Bg, args.phonemes, args.ref_frames, cfg.n_mels, 0, 1, 0, Lh, 0, 0, 0, 0]
+        if rank == 0:
+            xg_host = {k: xg[k].pin_memory() for k in keys}
+            xg_dev = {k: v.to(dev) for k, v in xg_host.items()}
+        del xg
+
+    def step_replica():
         with torch.no_grad():
             return model(x_dev, force_duration=True)
 
-    for _ in range(max(args.warmup, 3)):
-        out = step_device()
-    torch.cuda.synchronize(dev)
-    mel_len = out[2]
-    frames = int(mel_len.sum())
-    L_max = int(mel_len.max())
+    last = {}
 
-    # ---- timed region: device-resident inputs, CUDA events per step, L2 flushed between steps ----------------
+    def step_sharded(x, events=None):
+        with torch.no_grad():
+            last["r"] = sharded_forward(model, x, force_duration=True, device=dev, hop_length=cfg.hop_length,
+                                        n_mels=cfg.n_mels, ragged=True, spec=spec, events=events)
+
+    step_device = step_replica if world == 1 else (lambda: step_sharded(xg_dev))
+    for _ in range(W):
+        out = step_replica()
+        if world > 1:
+            step_device()
+    torch.cuda.synchronize(dev)
+    frames_local = int(out[2].sum())
+    L_max = int(out[2].max())
+    frames = frames_local if world == 1 else (sum(last["r"].mel_len_host) if rank == 0 else 0)
+
+    # ---- timed region: inputs resident in HBM, CUDA events per step, L2 flushed between steps -----------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -256,38 +413,61 @@ def main():
         dist.barrier()
     torch.cuda.synchronize(dev)
     launches0 = eng.launch_count()
-    evs = []
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        step_device()
-        b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize(dev)
+    phase_events = []
+
+    def timed_step():
+        if world == 1:
+            step_replica()
+        else:
+            ev = {}
+            step_sharded(xg_dev, ev)
+            phase_events.append(ev)
+    ms_list = event_loop(timed_step, args.steps, flush, dev)
     if dist:
         dist.barrier()
     wall = time.perf_counter() - wall0
     launches = eng.launch_count() - launches0
-    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    ms = sum(ms_list) / len(ms_list)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: pinned host inputs -> H2D -> forward -> waveform D2H, all inside the timed region ---------------
+    # ---- replicas (N > 1): every rank its own batch, no collective — the number the sharded path is compared with ----
+    ms_rep = None
+    if world > 1:
+        dist.barrier()
+        ms_rep = sum(event_loop(step_replica, args.steps, flush, dev)) / args.steps
+
+    # ---- e2e: pinned host inputs -> H2D -> (scatter ->) forward (-> gather) -> waveform D2H, all inside the timed region --
     e2e = None
     if not args.no_e2e:
-        wav_host = torch.empty((args.batch, L_max * cfg.hop_length), dtype=torch.float32).pin_memory()
-        len_host = torch.empty((args.batch,), dtype=torch.int64).pin_memory()
-        keys = ("phoneme", "puncts", "duration", "ref_mel")
-        h2d = sum(x_host[k].numel() * x_host[k].element_size() for k in keys)
-        d2h = wav_host.numel() * 4 + len_host.numel() * 8
+        if world == 1:
+            wav_host = torch.empty((args.batch, L_max * cfg.hop_length), dtype=torch.float32).pin_memory()
+            len_host = torch.empty((args.batch,), dtype=torch.int64).pin_memory()
+            h2d = sum(x_host[k].numel() * x_host[k].element_size() for k in keys)
+            d2h = wav_host.numel() * 4 + len_host.numel() * 8
 
-        def step_e2e():
-            with torch.no_grad():
-                wav, _, ml, _ = model({k: x_host[k] for k in keys}, force_duration=True)  # forward() does the H2D
-                wav_host.copy_(wav, non_blocking=True)
-                len_host.copy_(ml, non_blocking=True)
-            torch.cuda.synchronize(dev)
+            def step_e2e():
+                with torch.no_grad():
+                    wav, _, ml, _ = model({k: x_host[k] for k in keys}, force_duration=True)  # forward() does the H2D
+                    wav_host.copy_(wav, non_blocking=True)
+                    len_host.copy_(ml, non_blocking=True)
+                torch.cuda.synchronize(dev)
+        else:
+            h2d = d2h = 0
+            wav_host = None
+            if rank == 0:
+                h2d = sum(xg_host[k].numel() * xg_host[k].element_size() for k in keys)
+                wav_host = torch.empty(sum(e - s for s, e in last["r"].wav_segments()), dtype=torch.float32).pin_memory()
+                d2h = wav_host.numel() * 4
+
+            def step_e2e():
+                step_sharded(xg_host if rank == 0 else None)
+                if rank == 0:
+                    o = 0
+                    for s, e in last["r"].wav_segments():   # the valid samples of every utterance; lengths are host-known
+                        wav_host[o:o + e - s].copy_(last["r"].buf[s:e], non_blocking=True)
+                        o += e - s
+                torch.cuda.synchronize(dev)
         for _ in range(2):
             step_e2e()
         if dist:
@@ -298,79 +478,96 @@ def main():
         t_e2e = (time.perf_counter() - t0) / args.steps
         e2e = {"ms": t_e2e * 1e3, "h2d": h2d, "d2h": d2h}
 
-    # ---- max over ranks -------------------------------------------------------------------------------------
-    if dist:
-        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, float(frames)], device=dev, dtype=torch.float64)
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, frames_total = float(tmax[0]), int(tsum[2])
-        if e2e:
-            e2e["ms"] = float(tmax[1])
-    else:
-        frames_total = frames
+    # ---- config 4 variant (N > 1): ragged T_i ~ U{64..192}, alternating EN / DE weight sets, sharded ------------------
+    c4 = None
+    if world > 1 and not args.no_config4:
+        model_de = build_model(cfg, syn.make_weights(cfg, seed=1), device=dev, tensor_core_policy=args.policy)
+        models = {"en": model, "de": model_de}
+        x4, lang = config4_inputs(syn, cfg, Bg) if rank == 0 else (None, None)
+        if rank == 0:
+            x4 = {k: v.to(dev) for k, v in x4.items()}
+        res4 = {}
 
+        def step_c4():
+            with torch.no_grad():
+                res4["r"] = mixed_language_forward(models, x4, lang, force_duration=True, sharded=True, device=dev,
+                                                   hop_length=cfg.hop_length, n_mels=cfg.n_mels)
+        for _ in range(2):
+            step_c4()
+        dist.barrier()
+        n4 = max(3, min(args.steps, 5))
+        ms4 = sum(event_loop(step_c4, n4, flush, dev)) / n4
+        c4 = {"ms": ms4, "frames": int(res4["r"][2].sum()) if rank == 0 else 0, "steps": n4}
+        del model_de, models
+
+    # ---- max over ranks -------------------------------------------------------------------------------------------------
+    if dist:
+        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, ms_rep or 0.0, c4["ms"] if c4 else 0.0], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_rep = float(t[0]), float(t[2])
+        if e2e:
+            e2e["ms"] = float(t[1])
+        if c4:
+            c4["ms"] = float(t[3])
+        fr = torch.tensor([float(frames_local)], device=dev, dtype=torch.float64)
+        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+        frames_replicas = int(fr[0])
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
-    value = audio_seconds(frames_total, cfg) / (ms / 1e3)
+    value = audio_seconds(frames, cfg) / (ms / 1e3)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "tf32 (tcgen05, fp32 accumulate) decoder/vocoder/speaker-net; 3xTF32 split (fp32-grade) encoder + "
                  "variance predictors" if args.policy else "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "phonemes": args.phonemes,
-                   "mel_frames_per_step": frames_total, "L_max": L_max, "mel_frames_per_sec": frames_total / (ms / 1e3),
-                   "audio_sec_per_step": audio_seconds(frames_total, cfg), "tensor_core_policy": args.policy,
+        "config": {"workload": WORKLOAD, "global_batch": Bg, "batch_per_gpu": args.batch, "phonemes": args.phonemes,
+                   "parallelism": "single GPU" if world == 1 else
+                                  f"batch-sharded x{world}: rank 0 holds the global batch; 1 NCCL scatter + 1 NCCL gather-v per step",
+                   "mel_frames_per_step": frames, "L_max": L_max, "mel_frames_per_sec": frames / (ms / 1e3),
+                   "audio_sec_per_step": audio_seconds(frames, cfg), "tensor_core_policy": args.policy,
                    "l2": "256 MiB buffer written between timed steps (L2 flush); activations per step also exceed L2",
                    "wall_s_timed_region": wall},
         "gpu_launches": launches,
         "clocks": clocks,
     }
     if e2e:
-        line["e2e"] = {"value": audio_seconds(frames_total, cfg) / (e2e["ms"] / 1e3), "unit": UNIT,
+        line["e2e"] = {"value": audio_seconds(frames, cfg) / (e2e["ms"] / 1e3), "unit": UNIT,
                        "ms_per_step": e2e["ms"], "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
+    if world > 1:
+        r = last["r"]
+        ph = {}
+        for a, b, name in (("packed", "scattered", "scatter_ms"), ("scattered", "forward", "forward_rank0_ms"),
+                           ("forward", "result_packed", "pack_valid_ms"), ("result_packed", "gathered", "gather_ms")):
+            ph[name] = statistics.mean(ev[a].elapsed_time(ev[b]) for ev in phase_events)
+        line["collective"] = {
+            "scatter": "NCCL scatter (torch.distributed.scatter) of one packed uint8 row per utterance, built on the GPU",
+            "gather": "NCCL gather-v: one grouped ncclSend/ncclRecv (batch_isend_irecv) of every rank's valid waveform + mel "
+                      "samples, received in place in rank 0's result buffer",
+            "control_plane": "none in the timed region (header known on every rank; forced durations give all lengths)",
+            "scatter_bytes_per_step": int(r.scatter_bytes), "gather_bytes_per_step": int(r.gather_bytes),
+            "phases_rank0_ms": ph}
+        line["replicas"] = {"value": audio_seconds(frames_replicas, cfg) / (ms_rep / 1e3), "unit": UNIT, "ms_per_step": ms_rep,
+                            "note": "every rank its own batch of 32, no collective (round-1 measurement)",
+                            "sharded_over_replicas": (value / (audio_seconds(frames_replicas, cfg) / (ms_rep / 1e3)))}
+        if c4:
+            line["config4"] = {"workload": f"config 4: B={Bg} utterances, T_i ~ U{{64..192}} padded to 192, alternating EN/DE weight "
+                                           "sets (two sharded forwards per step), forced durations",
+                               "value": audio_seconds(c4["frames"], cfg) / (c4["ms"] / 1e3), "unit": UNIT,
+                               "ms_per_step": c4["ms"], "mel_frames_per_step": c4["frames"], "steps": c4["steps"]}
 
-    # ---- roofline of the dominant kernel class (CUDA events around every launch of the class, one extra step) ----
     peaks = measured_peaks()
-    eng.profile(True)
-    step_device()
-    prof = eng.profile_read()
-    eng.profile(False)
-    dom = max(prof, key=lambda k: prof[k]["ms"])
-    d = prof[dom]
-    if d["launches"] > 0 and d["ms"] > 0:
-        ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-        # TF32 tensor peak is half the dense bf16 rate; the measured denominators are bf16 (MEASURED_PEAKS.json)
-        peak = peaks["bf16_tflops_sustained"]
-        traffic, traffic_src = ncu_traffic(dom)
-        line["roofline"] = {
-            "bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "frac_of_tf32_peak": ach / (peak / 2),   # the kernel computes in TF32: half the bf16 rate the measured peak is for
-            "traffic": traffic, "traffic_source": traffic_src,
-            "algorithmic_bytes_per_launch": d["bytes"] / d["launches"], "peak_source": f"bf16 dense, sustained, {peaks['source']} (MEASURED_PEAKS.json); "
-                                            "TF32 runs at half the bf16 rate, fp32 FMA kernels at ~1/20",
-            "launches_per_step": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
-            "algorithmic_flops_per_launch": d["flops"] / d["launches"], "share_of_step": d["ms"] / ms,
-            "pipeline": pipeline_roofline(prof, peaks, ms, (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0),
-            "classes": {k: {"ms": v["ms"], "launches": v["launches"],
-                            "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 else None,
-                            "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None} for k, v in prof.items()},
-        }
+    rf = roofline_block(eng, step_replica, peaks, ms if world == 1 else ms_rep, clocks)
+    if rf:
+        line["roofline"] = rf
 
-    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample, rank 0 at N = 1 only -----------
+    # ---- CPU baseline: the reference's modules on this box's host cores, bounded sample, rank 0 at N = 1 only ---------
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        nb = min(args.cpu_sample_batch, args.batch)
-        xs = {k: v[:nb].clone() for k, v in syn.make_inputs(cfg, args.batch, args.phonemes, args.ref_frames, seed=7).items()}
-        t_cpu, f_cpu = cpu_reference_run(cfg, w, xs, threads, runs=2)
-        line["cpu_baseline"] = {"value": audio_seconds(f_cpu, cfg) / t_cpu, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{nb} of the {args.batch} utterances of the same batch, median of 2 runs after "
-                                          f"1 warm-up, torch.set_num_threads({threads})", "seconds_per_run": t_cpu}
+        line["cpu_baseline"] = cpu_baseline_block(cfg, w, syn.make_inputs(cfg, args.batch, args.phonemes, args.ref_frames, seed=7),
+                                                  args.cpu_sample_batch)
     print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()

@@ -237,6 +237,24 @@ int zvx_transcript2phonemids(zvx_symbols* s, const char* transcript_utf8, int32_
 int zvx_collate(const int32_t* const* phone_seqs, const int32_t* const* punct_seqs, const int32_t* lens, int B, int T,
                 int32_t* phoneme, int32_t* puncts, uint8_t* phoneme_mask);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU boundary: ragged <-> padded copies around the single NCCL scatter / gather.
+ * ZeroVox.forward returns zero-padded batches (model.py:260-306) of which the consumer keeps wav[i][:mel_len[i]*hop]
+ * and mel[i][:, :mel_len[i]] (utils/export_hifigan.py:138-151): a shard packs only those valid parts before the gather.
+ * Utterance b occupies rows * lens[b] * unit elements of `packed` starting at element offs[b], laid out
+ * [rows][lens[b] * unit]; in `padded` its row r starts at b * b_stride + r * row_stride (elements).  lens / offs are
+ * DEVICE int64 [B]; lens are clamped to [0, max_units].  When unit % 4 == 0 the offsets must be multiples of 4 elements
+ * and the bases 16-byte aligned for the 128-bit path (else a scalar path runs).  Work is enqueued on `stream` of the
+ * CURRENT device; no handle is involved.  waveform: rows = 1, unit = hop; mel [B, n_mels, L]: rows = n_mels, unit = 1.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int zvx_ragged_pack(const float* padded, int64_t b_stride, int64_t row_stride, int rows, int unit, int B,
+                    int64_t max_units, const int64_t* lens, const int64_t* offs, float* packed, void* stream);
+/* The inverse; with zero_tail != 0 the elements [lens[b]*unit, max_units*unit) of every padded row are zero-filled. */
+int zvx_ragged_unpack(const float* packed, const int64_t* lens, const int64_t* offs, int rows, int unit, int B,
+                      int64_t max_units, float* padded, int64_t b_stride, int64_t row_stride, int zero_tail,
+                      void* stream);
+const char* zvx_ragged_last_error(void);
+
 /* Workspace control: bytes of engine-owned scratch currently reserved on the device. */
 int64_t zvx_workspace_bytes(const zvx_handle* h);
 

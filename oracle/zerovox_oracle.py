@@ -197,7 +197,8 @@ def fs2_encoder(cfg, w, x, style_embed, force_duration=False):
     if force_duration:
         dur = x["duration"]
         out, mel_len, idx = length_regulate(feats, dur)
-        masks = None
+        # fs2.py:748, 772: a collated batch carries 'mel_mask' (data.py:85-93) and it becomes the mask of the forced path
+        masks = x["mel_mask"].unsqueeze(2).expand(-1, -1, out.shape[2]) if "mel_mask" in x else None
     else:
         dur = duration_round(log_d)
         out, mel_len, idx = length_regulate(feats, dur)

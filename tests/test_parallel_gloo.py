@@ -21,8 +21,11 @@ from zerovox_b200.parallel import mixed_language_forward, partition, sharded_for
 HOP, NMEL = 4, 6
 
 
-def fake_model(x, force_duration=False, pad_to=None):
-    """Per-utterance deterministic function of the inputs (so sharding must not change it)."""
+def fake_model(x, force_duration=False, pad_to=None, zero_padded_mel=None):
+    """Per-utterance deterministic function of the inputs (so sharding must not change it).  Like the reference
+    (model.py:283-285) the padded frames are zero-filled only when a mel mask exists and the batch has more than one
+    utterance — otherwise they hold a length-dependent non-zero pattern, so a shard that decides this from its LOCAL batch
+    size, or pads to its local frame count, is caught."""
     ph, pu = x["phoneme"].long(), x["puncts"].long()
     n, T = ph.shape
     valid = ~x["phoneme_mask"] if "phoneme_mask" in x else torch.ones(n, T, dtype=torch.bool)
@@ -30,12 +33,16 @@ def fake_model(x, force_duration=False, pad_to=None):
     mel_len = dur.sum(1)
     L = int(mel_len.max())
     if pad_to is not None:
-        L = max(L, int(pad_to(L) if callable(pad_to) else pad_to))
+        L = max(L, int(pad_to(L, mel_len.tolist()) if callable(pad_to) else pad_to))
+    zero = zero_padded_mel if zero_padded_mel is not None else (((not force_duration) or "mel_mask" in x) and n > 1)
     base = x["ref_mel"].sum(dim=(1, 2))[:, None] + (ph * valid).float().sum(1, keepdim=True)
     t = torch.arange(L)[None, :].float()
-    mel = (base[:, :, None] + torch.arange(NMEL)[None, :, None].float() * 0.5 + t[:, None, :]) * (t < mel_len[:, None])[:, None, :]
+    inside = (t < mel_len[:, None])[:, None, :]
+    mel = base[:, :, None] + torch.arange(NMEL)[None, :, None].float() * 0.5 + t[:, None, :]
+    mel = torch.where(inside, mel, torch.zeros(()) if zero else (t[:, None, :] - L) * torch.ones(n, NMEL, 1))
     tw = torch.arange(L * HOP)[None, :].float()
-    wav = torch.sin(base + tw * 0.01) * (tw < (mel_len * HOP)[:, None])
+    inside_w = tw < (mel_len * HOP)[:, None]
+    wav = torch.where(inside_w, torch.sin(base + tw * 0.01), torch.zeros(()) if zero else torch.cos(tw - L * HOP) * torch.ones(n, 1))
     logd = torch.log1p(dur.float())
     return wav, mel, mel_len, logd
 
@@ -57,14 +64,31 @@ def make_batch(B, T, T_ref, seed, ragged, forced):
     return x
 
 
-def fake_model_de(x, force_duration=False, pad_to=None):
+def fake_model_de(x, force_duration=False, pad_to=None, zero_padded_mel=None):
     """A second 'weight set': same signature, different function of the inputs (and longer utterances)."""
-    wav, mel, mel_len, logd = fake_model(dict(x, puncts=x["puncts"] + 1), force_duration=force_duration, pad_to=pad_to)
+    wav, mel, mel_len, logd = fake_model(dict(x, puncts=x["puncts"] + 1), force_duration=force_duration, pad_to=pad_to,
+                                         zero_padded_mel=True)
     return -wav, mel + 100.0 * (mel != 0), mel_len, logd + 1.0
 
 
-def check_mixed(out, x, lang, models, forced):
-    """Every utterance must equal what its own model gives for the batch of its own weight set."""
+def assert_valid_equal(out, ref, exact_tails):
+    """out == ref on every utterance's own samples / frames; past them: equal when the tails were shipped, else zero."""
+    wav, mel, mel_len, logd = out
+    rw, rm, rl, rd = ref
+    assert torch.equal(mel_len, rl) and torch.equal(logd, rd)
+    assert wav.shape[1] == mel.shape[2] * HOP and mel.shape[2] >= rm.shape[2]
+    if exact_tails:
+        assert wav.shape == rw.shape and mel.shape == rm.shape
+        assert torch.equal(wav, rw) and torch.equal(mel, rm)
+        return
+    for i, n in enumerate(rl.tolist()):
+        assert torch.equal(mel[i, :, :n], rm[i, :, :n]) and not mel[i, :, n:].any()
+        assert torch.equal(wav[i, : n * HOP], rw[i, : n * HOP]) and not wav[i, n * HOP:].any()
+
+
+def check_mixed(out, x, lang, models, forced, sharded=False):
+    """Every utterance must equal what its own model gives for the batch of its own weight set (unsharded: tails included,
+    zeros past the group's own frame count; sharded: the valid parts, zeros past them)."""
     wav, mel, mel_len, logd = out
     B = x["phoneme"].shape[0]
     assert wav.shape[0] == mel.shape[0] == B and wav.shape[1] == mel.shape[2] * HOP
@@ -73,7 +97,11 @@ def check_mixed(out, x, lang, models, forced):
         groups.setdefault(id(models[t]), (models[t], []))[1].append(i)
     for model, idx in groups.values():
         sel = torch.tensor(idx)
-        rw, rm, rl, rd = model({k: v[sel] for k, v in x.items()}, force_duration=forced)
+        ref = model({k: v[sel] for k, v in x.items()}, force_duration=forced)
+        if sharded:
+            assert_valid_equal((wav[sel], mel[sel], mel_len[sel], logd[sel]), ref, exact_tails=False)
+            continue
+        rw, rm, rl, rd = ref
         L = rm.shape[2]
         assert torch.equal(mel_len[sel], rl) and torch.equal(logd[sel], rd)
         assert torch.equal(mel[sel][:, :, :L], rm) and not mel[sel][:, :, L:].any()
@@ -104,7 +132,7 @@ def _worker_mixed(rank, world, port, q):
             out = mixed_language_forward(models, x, lang, force_duration=forced, sharded=True, device="cpu",
                                          hop_length=HOP, n_mels=NMEL)
             if rank == 0:
-                check_mixed(out, x, lang, models, forced)
+                check_mixed(out, x, lang, models, forced, sharded=True)
             else:
                 assert out is None
         q.put((rank, "ok"))
@@ -133,16 +161,34 @@ def _worker(rank, world, port, cases, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        for (B, T, T_ref, seed, ragged, forced) in cases:
+        for (B, T, T_ref, seed, ragged, forced, mel_mask) in cases:
             x = make_batch(B, T, T_ref, seed, ragged, forced) if rank == 0 else None
-            out = sharded_forward(fake_model, x, force_duration=forced, device="cpu", hop_length=HOP, n_mels=NMEL)
+            if rank == 0 and mel_mask:
+                ml = x["duration"].long().clamp(min=0).sum(1)
+                x["mel_mask"] = torch.arange(int(ml.max()))[None, :] >= ml[:, None]
+            ref = fake_model(x, force_duration=forced) if rank == 0 else None
+            for tails in ("valid", "padded"):
+                out = sharded_forward(fake_model, x, force_duration=forced, device="cpu", hop_length=HOP, n_mels=NMEL,
+                                      tails=tails)
+                if rank == 0:
+                    assert_valid_equal(out, ref, exact_tails=(tails == "padded"))
+                else:
+                    assert out is None
+            # the ragged container itself, with the header known on every rank (no broadcast)
+            Lh = int(x["duration"].clamp(min=0).sum(1).max()) if (rank == 0 and forced) else -1
+            box = [[B, T, T_ref, NMEL, int(ragged), int(forced), int(mel_mask), Lh,
+                    x["mel_mask"].shape[1] if (rank == 0 and mel_mask) else 0,
+                    int(((not forced) or mel_mask) and B > 1), 0, 0]]
+            dist.broadcast_object_list(box, src=0)
+            rb = sharded_forward(fake_model, x, force_duration=forced, device="cpu", hop_length=HOP, n_mels=NMEL,
+                                 ragged=True, spec=box[0])
             if rank == 0:
-                ref = fake_model(x, force_duration=forced)
-                for name, a, b in zip(("wav", "mel", "mel_len", "log_duration"), out, ref):
-                    assert a.shape == b.shape, (name, a.shape, b.shape)
-                    assert torch.equal(a, b), f"{name} differs for case {(B, T, T_ref, seed, ragged, forced)}"
+                assert rb.B == B and len(rb.wav_segments()) <= world and rb.gather_bytes % 4 == 0
+                for i, n in enumerate(ref[2].tolist()):
+                    assert torch.equal(rb.wav(i), ref[0][i, : n * HOP]) and torch.equal(rb.mel(i), ref[1][i, :, :n])
+                assert torch.equal(rb.log_duration(), ref[3])
             else:
-                assert out is None
+                assert rb is None
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         q.put((rank, repr(e)))
@@ -151,17 +197,29 @@ def _worker(rank, world, port, cases, q):
         dist.destroy_process_group()
 
 
-def test_partition_balances_and_covers():
-    parts = partition([5, 9, 1, 7, 3, 8, 2], 3)
-    assert sorted(i for p in parts for i in p) == list(range(7))
-    assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
-    assert parts[0][0] == 1  # longest first
-    assert partition([], 2) == [[], []]
+def test_partition_consecutive_blocks():
+    parts = partition(7, 3)
+    assert [list(p) for p in parts] == [[0, 1, 2], [3, 4, 5], [6]]
+    assert [list(p) for p in partition(2, 4)] == [[0], [1], [], []]
+    assert [list(p) for p in partition(0, 2)] == [[], []]
+
+
+def test_sharded_forward_single_process_matches_model():
+    """world size 1, no process group: the same container API, nothing to scatter."""
+    for forced in (True, False):
+        x = make_batch(5, 7, 3, 11, True, forced)
+        ref = fake_model(x, force_duration=forced)
+        out = sharded_forward(fake_model, x, force_duration=forced, device="cpu", hop_length=HOP, n_mels=NMEL, tails="padded")
+        assert_valid_equal(out, ref, exact_tails=True)
 
 
 @pytest.mark.timeout(180)
 def test_sharded_forward_world2_gloo():
-    cases = [(8, 12, 5, 0, False, True), (7, 9, 4, 1, True, True), (5, 6, 3, 2, True, False), (1, 4, 2, 3, False, False)]
+    # (B, T, T_ref, seed, ragged, forced, mel_mask); B = 2 on 2 ranks: one utterance per shard, the zero-fill decision of
+    # model.py:283-285 must come from the global batch; B = 1: a rank without work
+    cases = [(8, 12, 5, 0, False, True, False), (7, 9, 4, 1, True, True, False), (5, 6, 3, 2, True, False, False),
+             (1, 4, 2, 3, False, False, False), (2, 6, 3, 4, True, False, False), (2, 5, 3, 5, False, True, False),
+             (2, 5, 3, 6, False, True, True), (6, 8, 3, 7, True, True, True)]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)

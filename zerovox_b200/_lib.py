@@ -104,6 +104,10 @@ SYMBOLS = {
     "zvx_symbols_num_puncts": (C.c_int, [_P]),
     "zvx_transcript2phonemids": (C.c_int, [_P, C.c_char_p, _P, _P, C.c_int]),
     "zvx_collate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "zvx_ragged_pack": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P]),
+    "zvx_ragged_unpack": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int,
+                                    _P]),
+    "zvx_ragged_last_error": (C.c_char_p, []),
     "zvx_workspace_bytes": (C.c_int64, [_P]),
     "zvx_launch_count": (C.c_int64, [_P]),
 }

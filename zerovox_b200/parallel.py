@@ -1,158 +1,351 @@
 """Batch sharding of one global batch across the GPUs of a box (BASELINE config 4).
 
-Utterances are independent in eval mode, so the data path needs no collective: rank 0 packs every rank's share of the
-inputs into ONE byte buffer per rank and scatters it; every rank runs ``ZeroVox.forward`` on its shard; the results are
-packed into one byte buffer per rank and gathered on rank 0.  ``torch.distributed`` is the plumbing (NCCL over
-NVLink/NVSwitch on GPUs; the same code runs over gloo with CPU tensors, which is how the host logic is tested).
+Utterances are independent in eval mode, so the data path needs exactly two collectives: rank 0 packs the inputs of the
+global batch into one row per utterance ON THE GPU and scatters equal row blocks (``scatter``); every rank runs
+``ZeroVox.forward`` on its block of consecutive utterances; every rank packs the VALID part of its results — the
+``mel_len[i] * hop`` samples and ``mel_len[i]`` frames per utterance that the consumer keeps
+(utils/export_hifigan.py:138-151) — into one contiguous buffer that rank 0 receives directly at its final offset in the
+gathered buffer (``gather-v``: one grouped ncclSend / ncclRecv, no staging copy, no re-ordering: blocks are consecutive).
+``torch.distributed`` is the plumbing (NCCL over NVLink / NVSwitch on GPUs; the same code runs over gloo with CPU tensors,
+which is how the host logic is tested — the ragged pack / unpack then use plain tensor slicing instead of the CUDA
+kernels of csrc/ragged.cu).
+
+Control plane: one broadcast of 12 int64 (shapes, flags, the global frame count when durations are forced) unless every
+rank passes ``spec``; with predicted durations one all-gather of the per-utterance frame counts, which also yields the
+global frame count.
 
 Exactness against an unsharded run.  The reference's batch-composition quirks make an utterance's tail
-depend on the batch's padded lengths: every shard therefore keeps the *global* phoneme length T (inputs are never
-trimmed) and decodes / vocodes at the *global* frame count ``L_pad`` (``pad_to``).  With forced durations rank 0 knows
-``L_pad`` up front and ships it in the header; with predicted durations it is one 8-byte MAX all-reduce — the only
-other collective, and control-plane only.
+depend on the batch's padded lengths: every shard keeps the *global* phoneme length T (inputs are never trimmed), decodes
+and vocodes at the *global* frame count ``L_pad`` (``pad_to``), and takes the reference's "zero-fill padded mel frames iff
+a mel mask exists and B > 1" decision (model.py:283-285) from the GLOBAL batch size (``zero_padded_mel``).  The valid
+samples / frames of every utterance are then those of the unsharded batch.  ``tails="valid"`` (default) returns zeros past
+an utterance's own length; ``tails="padded"`` also ships the padded tails, reproducing the unsharded tensors everywhere.
 """
 from __future__ import annotations
 
+import ctypes as C
+from dataclasses import dataclass, field
 from typing import Callable, Mapping, Sequence
 
 import torch
 import torch.distributed as dist
 
-_HEADER = 8                                            # int64 words
+_HEADER = 12                                           # int64 words
+_ALIGN = 64                                            # elements: every rank's segment of the gathered buffer starts 256-byte aligned
 
 
-def partition(lengths: Sequence[int], world: int) -> list[list[int]]:
-    """Longest-first round-robin deal (phoneme count is a proxy for frames ~ 6*T): rank r gets utterances
-    order[r::world]; every rank receives ceil(B/world) or floor(B/world) utterances with similar total length."""
-    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
-    return [order[r::world] for r in range(world)]
+def partition(n_utterances: int, world: int) -> list[range]:
+    """Blocks of consecutive utterances, ceil(B / world) per rank (the last ranks may get fewer or none).  Every shard is
+    padded to the global T and L_pad, so a shard's cost is proportional to its utterance COUNT whatever the utterance
+    lengths are: equal counts are balanced, and consecutive blocks let rank 0 receive every result in place."""
+    nb = -(-n_utterances // world) if n_utterances else 0
+    return [range(min(r * nb, n_utterances), min((r + 1) * nb, n_utterances)) for r in range(world)]
 
 
-def _pack_inputs(x: Mapping[str, torch.Tensor], idx: Sequence[int], nb: int, has_mask: bool, has_dur: bool):
-    """Byte image of one rank's shard, padded to nb utterances (padding rows repeat the shard's first utterance; they are
-    dropped again by the valid count)."""
-    sel = list(idx) + [idx[0] if idx else 0] * (nb - len(idx))
-    sel_t = torch.as_tensor(sel, dtype=torch.long)
-    parts = []
-    for k in ("phoneme", "puncts"):
-        parts.append(x[k].cpu().to(torch.int32)[sel_t].contiguous().view(torch.uint8).reshape(-1))
-    if has_dur:
-        parts.append(x["duration"].cpu().to(torch.int32)[sel_t].contiguous().view(torch.uint8).reshape(-1))
-    parts.append(x["ref_mel"].cpu().to(torch.float32)[sel_t].contiguous().view(torch.uint8).reshape(-1))
-    if has_mask:   # byte-sized rows last so that every wider view stays aligned
-        parts.append(x["phoneme_mask"].cpu().to(torch.uint8)[sel_t].contiguous().reshape(-1))
-    return torch.cat(parts)
+# ---------------------------------------------------------------------------------------------------------------------
+# ragged pack / unpack: CUDA kernels through the C ABI on the GPU, tensor slicing for the gloo / CPU plumbing tests
+# ---------------------------------------------------------------------------------------------------------------------
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
 
 
-def _unpack_inputs(buf: torch.Tensor, nb: int, T: int, T_ref: int, n_mels: int, has_mask: bool, has_dur: bool):
-    out, off = {}, 0
+def _ragged_copy(pack: bool, padded: torch.Tensor, packed: torch.Tensor, lens_dev: torch.Tensor, offs_dev: torch.Tensor,
+                 lens: Sequence[int], offs: Sequence[int], rows: int, unit: int, zero_tail: bool = True):
+    """padded [B, rows, max_units * unit] (or [B, max_units * unit] when rows == 1) <-> packed 1-D."""
+    B = padded.shape[0]
+    if B == 0:
+        return
+    p3 = padded.reshape(B, rows, -1)
+    max_units = p3.shape[2] // unit
+    if padded.is_cuda:
+        from . import _lib
+        lib = _lib.load()
+        assert padded.is_contiguous() and packed.is_contiguous() and padded.dtype == packed.dtype == torch.float32
+        st = C.c_void_p(torch.cuda.current_stream(padded.device).cuda_stream)
+        with torch.cuda.device(padded.device):
+            if pack:
+                rc = lib.zvx_ragged_pack(_ptr(p3), p3.stride(0), p3.stride(1), rows, unit, B, max_units, _ptr(lens_dev),
+                                         _ptr(offs_dev), _ptr(packed), st)
+            else:
+                rc = lib.zvx_ragged_unpack(_ptr(packed), _ptr(lens_dev), _ptr(offs_dev), rows, unit, B, max_units, _ptr(p3),
+                                           p3.stride(0), p3.stride(1), 1 if zero_tail else 0, st)
+        if rc != 0:
+            raise RuntimeError("zvx_ragged: " + lib.zvx_ragged_last_error().decode())
+        return
+    for b in range(B):                                 # gloo / CPU plumbing path (tests)
+        n = max(0, min(int(lens[b]), max_units)) * unit
+        seg = packed[offs[b]: offs[b] + rows * n].view(rows, n)
+        if pack:
+            seg.copy_(p3[b, :, :n])
+        else:
+            p3[b, :, :n] = seg
+            if zero_tail:
+                p3[b, :, n:] = 0
 
-    def take(nbytes):
-        nonlocal off
-        t = buf[off:off + nbytes]
-        off += nbytes
-        return t
 
-    out["phoneme"] = take(nb * T * 4).view(torch.int32).reshape(nb, T)
-    out["puncts"] = take(nb * T * 4).view(torch.int32).reshape(nb, T)
-    if has_dur:
-        out["duration"] = take(nb * T * 4).view(torch.int32).reshape(nb, T)
-    out["ref_mel"] = take(nb * T_ref * n_mels * 4).view(torch.float32).reshape(nb, T_ref, n_mels)
-    if has_mask:
-        out["phoneme_mask"] = take(nb * T).reshape(nb, T).to(torch.bool)
-    return out
+# ---------------------------------------------------------------------------------------------------------------------
+# the gathered result on rank 0
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class RaggedBatch:
+    """Rank 0's gathered results: ``buf`` holds, per rank in utterance order, [wav | mel | log_duration] of that rank's
+    block — the valid ``mel_len[i] * hop`` samples and ``[n_mels, mel_len[i]]`` frames of every utterance."""
+    buf: torch.Tensor                                  # float32 1-D
+    B: int
+    T: int
+    L: int                                             # global padded frame count
+    hop: int
+    n_mels: int
+    lens: list[int]                                    # frames shipped per utterance (mel_len, or L with tails="padded")
+    mel_len_host: list[int]
+    wav_off: list[int]                                 # element offsets into buf, per utterance
+    mel_off: list[int]
+    logd_off: list[int]
+    seg: list[tuple[int, int, int]]                    # per rank: (segment start, wav elements, segment elements)
+    gather_bytes: int = 0                              # bytes received from the other ranks
+    scatter_bytes: int = 0                             # bytes sent to the other ranks
+    events: dict = field(default_factory=dict)
+
+    def wav(self, i: int) -> torch.Tensor:
+        return self.buf[self.wav_off[i]: self.wav_off[i] + self.lens[i] * self.hop]
+
+    def mel(self, i: int) -> torch.Tensor:
+        return self.buf[self.mel_off[i]: self.mel_off[i] + self.lens[i] * self.n_mels].view(self.n_mels, self.lens[i])
+
+    def log_duration(self) -> torch.Tensor:
+        return torch.stack([self.buf[o: o + self.T] for o in self.logd_off]) if self.B else self.buf.new_zeros((0, self.T))
+
+    def wav_segments(self) -> list[tuple[int, int]]:
+        """(start, end) element ranges of buf that hold waveforms — one per rank (what an e2e caller copies to the host)."""
+        return [(s, s + w) for s, w, _ in self.seg if w]
+
+    def padded(self):
+        """The tuple of ``ZeroVox.forward`` for the whole batch: (wav [B, L*hop], mel [B, n_mels, L], mel_len int64 [B],
+        log_duration [B, T]); zeros past every utterance's shipped length."""
+        dev = self.buf.device
+        wav = torch.empty((self.B, self.L * self.hop), dtype=torch.float32, device=dev)
+        mel = torch.empty((self.B, self.n_mels, self.L), dtype=torch.float32, device=dev)
+        lens_d = torch.tensor(self.lens, dtype=torch.int64, device=dev)
+        _ragged_copy(False, wav, self.buf, lens_d, torch.tensor(self.wav_off, dtype=torch.int64, device=dev), self.lens,
+                     self.wav_off, 1, self.hop)
+        _ragged_copy(False, mel, self.buf, lens_d, torch.tensor(self.mel_off, dtype=torch.int64, device=dev), self.lens,
+                     self.mel_off, self.n_mels, 1)
+        return wav, mel, torch.tensor(self.mel_len_host, dtype=torch.int64, device=dev), self.log_duration()
 
 
-def _input_bytes(nb, T, T_ref, n_mels, has_mask, has_dur):
-    n = nb * T * 4 * (3 if has_dur else 2) + (nb * T if has_mask else 0) + nb * T_ref * n_mels * 4
-    return (n + 15) // 16 * 16
+def _layout(counts: Sequence[int], lens: Sequence[int], T: int, hop: int, n_mels: int):
+    """Offsets of every utterance / rank inside the gathered buffer.  lens: frames shipped per utterance, global order."""
+    wav_off, mel_off, logd_off, seg = [], [], [], []
+    base, i = 0, 0
+    for n in counts:
+        F = sum(lens[i:i + n])
+        w0, m0, d0 = base, base + F * hop, base + F * (hop + n_mels)
+        acc = 0
+        for j in range(n):
+            wav_off.append(w0 + acc * hop)
+            mel_off.append(m0 + acc * n_mels)
+            logd_off.append(d0 + j * T)
+            acc += lens[i + j]
+        size = -(-(F * (hop + n_mels) + n * T) // _ALIGN) * _ALIGN
+        seg.append((base, F * hop, size))
+        base += size
+        i += n
+    return wav_off, mel_off, logd_off, seg, base
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# scatter -> forward -> gather-v
+# ---------------------------------------------------------------------------------------------------------------------
+def _row_layout(T, T_ref, n_mels_in, has_mask, has_dur, Lm):
+    """Byte offsets of the fields of one utterance's input row (4-byte fields first, byte masks last, 16-byte rows)."""
+    o, f = 0, {}
+    for name, n in (("phoneme", 4 * T), ("puncts", 4 * T), ("duration", 4 * T if has_dur else 0),
+                    ("ref_mel", 4 * T_ref * n_mels_in), ("phoneme_mask", T if has_mask else 0), ("mel_mask", Lm)):
+        f[name] = (o, o + n)
+        o += n
+    return f, -(-o // 16) * 16
 
 
 def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force_duration: bool = False,
-                    group=None, device: torch.device | str | None = None, hop_length: int = 256, n_mels: int = 80):
-    """Run ``model(x_shard, force_duration=..., pad_to=L_pad)`` on every rank of ``group`` for the global batch ``x`` held
-    by rank 0 (other ranks pass ``x=None``).  ``model`` is a ``ZeroVox`` (or any callable with that signature returning
-    ``(wav [n, L*hop], mel [n, n_mels, L], mel_len int64 [n], log_duration [n, T])``).
+                    group=None, device: torch.device | str | None = None, hop_length: int = 256, n_mels: int = 80,
+                    tails: str = "valid", ragged: bool = False, spec: Sequence[int] | None = None,
+                    events: dict | None = None):
+    """Run ``model(x_shard, force_duration=..., pad_to=..., zero_padded_mel=...)`` on every rank of ``group`` for the
+    global batch ``x`` held by rank 0 (other ranks pass ``x=None``).  ``model`` is a ``ZeroVox`` (or any callable with
+    that signature returning ``(wav [n, L*hop], mel [n, n_mels, L], mel_len int64 [n], log_duration [n, T])``).
 
-    Returns on rank 0 the tuple of ``ZeroVox.forward`` for the whole batch in the original utterance order, padded to the
-    global L_pad; ``None`` on the other ranks.  Collectives: one scatter (inputs), one gather (results), plus a single
-    8-byte MAX all-reduce of the frame count when durations are predicted.
+    Returns on rank 0 the tuple of ``ZeroVox.forward`` for the whole batch in the original utterance order, padded to
+    the global L_pad (``ragged=True``: the :class:`RaggedBatch` itself, no expansion); ``None`` on the other ranks.
+    ``spec``: the 12-word header when every rank already knows it (skips the broadcast); ``events``: a dict that
+    receives CUDA events at the phase boundaries (bench.py).
     """
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    dev = torch.device(device) if device is not None else (
-        torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    if tails not in ("valid", "padded"):
+        raise ValueError("tails must be 'valid' or 'padded'")
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if multi else (0, 1)
+    if device is not None:
+        dev = torch.device(device)
+    elif multi and dist.get_backend(group) == "nccl" or (not multi and torch.cuda.is_available()):
+        dev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        dev = torch.device("cpu")
 
-    # ---- header: shapes + flags + L_pad hint, broadcast as 8 int64 ---------------------------------------------
-    hdr = torch.zeros(_HEADER, dtype=torch.int64)
-    parts = None
+    def mark(name):
+        if events is not None and dev.type == "cuda":
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            events[name] = e
+
+    # ---- header -------------------------------------------------------------------------------------------------
+    all_lens = None                                    # rank 0, forced durations: frames of every utterance
     if rank == 0:
         assert x is not None, "rank 0 must hold the global batch"
         B, T = x["phoneme"].shape
-        T_ref = x["ref_mel"].shape[1]
+        T_ref, n_mels_in = x["ref_mel"].shape[1], x["ref_mel"].shape[2]
         has_mask, has_dur = "phoneme_mask" in x, bool(force_duration) and "duration" in x
-        if has_mask:
-            lengths = (~x["phoneme_mask"].cpu().to(torch.bool)).sum(1).tolist()
-        else:
-            lengths = [T] * B
-        parts = partition(lengths, world)
-        nb = max(len(p) for p in parts)
-        L_hint = int(x["duration"].cpu().clamp(min=0).sum(1).max()) if has_dur else -1
-        hdr[:] = torch.tensor([B, T, T_ref, nb, int(has_mask), int(has_dur), L_hint, x["ref_mel"].shape[2]])
-    hdr = hdr.to(dev)
-    dist.broadcast(hdr, src=0, group=group)
-    B, T, T_ref, nb, has_mask, has_dur, L_hint, n_mels_in = (int(v) for v in hdr.cpu().tolist())
-    has_mask, has_dur = bool(has_mask), bool(has_dur)
+        has_mm = has_dur and "mel_mask" in x
+        L_hint, Lm = -1, 0
+        if has_dur:
+            all_lens = x["duration"].clamp(min=0).sum(1).tolist()
+            L_hint = int(max(all_lens)) if all_lens else 0
+        if has_mm:
+            Lm = x["mel_mask"].shape[1]
+        # model.py:283-285 on the GLOBAL batch: zero-fill iff a mel mask exists and B > 1
+        zero_pad = int(((not has_dur) or has_mm) and B > 1)
+        hdr_list = [B, T, T_ref, n_mels_in, int(has_mask), int(has_dur), int(has_mm), L_hint, Lm, zero_pad,
+                    int(tails == "padded"), 0]
+        if spec is not None and list(spec) != hdr_list:
+            raise ValueError(f"spec {list(spec)} does not describe the batch {hdr_list}")
+    if spec is not None:
+        hdr_list = [int(v) for v in spec]
+    elif multi:
+        hdr = torch.tensor(hdr_list if rank == 0 else [0] * _HEADER, dtype=torch.int64).to(dev)
+        dist.broadcast(hdr, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+        hdr_list = hdr.cpu().tolist()
+    B, T, T_ref, n_mels_in, has_mask, has_dur, has_mm, L_hint, Lm, zero_pad, tails_padded, _ = hdr_list
+    has_mask, has_dur, has_mm = bool(has_mask), bool(has_dur), bool(has_mm)
+    parts = partition(B, world)
+    counts = [len(p) for p in parts]
+    nb, n_mine = max(counts) if counts else 0, counts[rank]
 
-    # ---- ONE scatter of the packed inputs ---------------------------------------------------------------------
-    nbytes = _input_bytes(nb, T, T_ref, n_mels_in, has_mask, has_dur)
-    recv = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    send = None
-    if rank == 0:
-        send = []
-        for r in range(world):
-            b = _pack_inputs(x, parts[r], nb, has_mask, has_dur)
-            pad = torch.zeros(nbytes, dtype=torch.uint8)
-            pad[: b.numel()] = b
-            send.append(pad.to(dev))
-    dist.scatter(recv, send, src=0, group=group)
-    xs = _unpack_inputs(recv, nb, T, T_ref, n_mels_in, has_mask, has_dur)
+    # ---- ONE scatter of the inputs, packed on the device as one row per utterance --------------------------------------
+    fields, row_bytes = _row_layout(T, T_ref, n_mels_in, has_mask, has_dur, Lm if has_mm else 0)
+    scatter_bytes = 0
+    if multi:
+        recv = torch.empty((nb, row_bytes), dtype=torch.uint8, device=dev)
+        send = None
+        if rank == 0:
+            rows = torch.zeros((world * nb, row_bytes), dtype=torch.uint8, device=dev)
+            for name, dt in (("phoneme", torch.int32), ("puncts", torch.int32), ("duration", torch.int32),
+                             ("ref_mel", torch.float32), ("phoneme_mask", torch.uint8), ("mel_mask", torch.uint8)):
+                a, b = fields[name]
+                if b > a:
+                    t = x[name].to(dev, non_blocking=True).to(dt).contiguous()
+                    rows[:B, a:b] = t.view(torch.uint8).reshape(B, b - a)
+            send = list(rows.view(world, nb * row_bytes).unbind(0))
+            scatter_bytes = (world - 1) * nb * row_bytes
+        mark("packed")
+        dist.scatter(recv.view(-1), send, src=0 if group is None else dist.get_global_rank(group, 0), group=group)
+        xs = {}
+        for name, dt in (("phoneme", torch.int32), ("puncts", torch.int32), ("duration", torch.int32),
+                         ("ref_mel", torch.float32), ("phoneme_mask", torch.uint8), ("mel_mask", torch.uint8)):
+            a, b = fields[name]
+            if b > a:
+                t = recv[:n_mine, a:b].contiguous().view(dt)
+                xs[name] = t.reshape(n_mine, T_ref, n_mels_in) if name == "ref_mel" else (
+                    t.to(torch.bool) if dt == torch.uint8 else t)
+    else:
+        xs = {k: v for k, v in x.items() if isinstance(v, torch.Tensor)}
+    mark("scattered")
 
-    # ---- forward on the shard, at the global frame count ------------------------------------------------------
-    def l_pad(local_lmax: int) -> int:
-        if L_hint >= 0:
+    # ---- forward on the block, at the global frame count ---------------------------------------------------------------
+    lens_box = {}
+
+    def pad_to(local_lmax: int, mel_len_host: Sequence[int]) -> int:
+        lens_box["mine"] = [int(v) for v in mel_len_host]
+        if has_dur or not multi:
             return max(L_hint, local_lmax)
-        t = torch.tensor([local_lmax], dtype=torch.int64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        return int(t.item())
+        return _exchange_lengths(lens_box, nb, world, dev, group)
 
-    wav, mel, mel_len, logd = model(xs, force_duration=has_dur, pad_to=l_pad)
-    L = mel.shape[2]
+    if n_mine > 0:
+        wav, mel, mel_len, logd = model(xs, force_duration=has_dur, pad_to=pad_to, zero_padded_mel=bool(zero_pad))
+        L = mel.shape[2]
+    else:                                              # more ranks than utterances: still part of every collective
+        if not has_dur:
+            _exchange_lengths({"mine": []}, nb, world, dev, group)
+        wav = mel = mel_len = logd = None
+        L = 0
+    mark("forward")
+    my_true = lens_box.get("mine", [])
+    if n_mine > 0 and len(my_true) != n_mine:          # a model that never called pad_to (not ZeroVox): read the lengths
+        my_true = [int(v) for v in mel_len.cpu().tolist()]
+    if not multi and not has_dur:
+        lens_box["all"] = list(my_true)
 
-    # ---- ONE gather of the packed results ---------------------------------------------------------------------
-    f32 = torch.cat([wav.reshape(nb, -1), mel.reshape(nb, -1), logd.reshape(nb, -1)], dim=1).to(torch.float32).contiguous()
-    out = torch.cat([mel_len.to(torch.int64).contiguous().view(torch.uint8).reshape(-1), f32.view(torch.uint8).reshape(-1)])
-    gathered = [torch.empty_like(out) for _ in range(world)] if rank == 0 else None
-    dist.gather(out, gathered, dst=0, group=group)
+    # ---- ONE gather-v of the valid results, received in place ----------------------------------------------------------
+    my_ship = [L] * n_mine if tails_padded else my_true
+    F = sum(my_ship)
+    my_size = -(-(F * (hop_length + n_mels) + n_mine * T) // _ALIGN) * _ALIGN
+    out = None
+    if rank == 0:
+        true_all = [int(v) for v in (all_lens if has_dur else lens_box["all"])]
+        L_glob = max(L, max(true_all) if true_all else 0) if world > 1 else L
+        ship_all = [L_glob] * B if tails_padded else true_all
+        wav_off, mel_off, logd_off, seg, total = _layout(counts, ship_all, T, hop_length, n_mels)
+        buf = torch.empty(total, dtype=torch.float32, device=dev)
+        out = RaggedBatch(buf=buf, B=B, T=T, L=L_glob, hop=hop_length, n_mels=n_mels, lens=ship_all, mel_len_host=true_all,
+                          wav_off=wav_off, mel_off=mel_off, logd_off=logd_off, seg=seg,
+                          gather_bytes=4 * sum(s[2] for s in seg[1:]), events=events if events is not None else {})
+        mine = buf[:my_size]
+    else:
+        mine = torch.empty(my_size, dtype=torch.float32, device=dev)
+    if n_mine > 0:
+        lens_d = mel_len.to(torch.int64) if not tails_padded else torch.full((n_mine,), L, dtype=torch.int64, device=dev)
+        start = torch.cumsum(lens_d, 0) - lens_d
+        w_offs, m_offs = start * hop_length, start * n_mels + F * hop_length
+        acc, wl, ml = 0, [], []
+        for v in my_ship:
+            wl.append(acc * hop_length)
+            ml.append(F * hop_length + acc * n_mels)
+            acc += v
+        _ragged_copy(True, wav.to(torch.float32).contiguous(), mine, lens_d, w_offs, my_ship, wl, 1, hop_length)
+        _ragged_copy(True, mel.to(torch.float32).contiguous(), mine, lens_d, m_offs, my_ship, ml, n_mels, 1)
+        d0 = F * (hop_length + n_mels)
+        mine[d0: d0 + n_mine * T].view(n_mine, T).copy_(logd)
+    mark("result_packed")
+    if multi:
+        root = 0 if group is None else dist.get_global_rank(group, 0)
+        ops = []
+        if rank == 0:
+            for r in range(1, world):
+                s0, _, size = out.seg[r]
+                if size:
+                    ops.append(dist.P2POp(dist.irecv, out.buf[s0: s0 + size], r if group is None else dist.get_global_rank(group, r), group))
+        elif my_size:
+            ops.append(dist.P2POp(dist.isend, mine, root, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+    mark("gathered")
     if rank != 0:
         return None
+    out.scatter_bytes = scatter_bytes
+    return out if ragged else out.padded()
 
-    W = L * hop_length
-    wav_g = torch.empty((B, W), dtype=torch.float32, device=dev)
-    mel_g = torch.empty((B, n_mels, L), dtype=torch.float32, device=dev)
-    len_g = torch.empty((B,), dtype=torch.int64, device=dev)
-    logd_g = torch.empty((B, T), dtype=torch.float32, device=dev)
-    row = W + n_mels * L + T
-    for r in range(world):
-        idx = torch.as_tensor(parts[r], dtype=torch.long, device=dev)
-        n = len(parts[r])
-        if n == 0:
-            continue
-        f = gathered[r][nb * 8:].view(torch.float32).reshape(nb, row)[:n]
-        wav_g[idx] = f[:, :W]
-        mel_g[idx] = f[:, W:W + n_mels * L].reshape(n, n_mels, L)
-        logd_g[idx] = f[:, W + n_mels * L:]
-        len_g[idx] = gathered[r][: nb * 8].view(torch.int64)[:n]
-    return wav_g, mel_g, len_g, logd_g
+
+def _exchange_lengths(lens_box: dict, nb: int, world: int, dev, group) -> int:
+    """Predicted durations: one all-gather of the per-utterance frame counts (control plane) -> the global frame count;
+    rank 0 keeps all counts to size the gathered buffer."""
+    mine = lens_box["mine"]
+    t = torch.full((max(nb, 1),), -1, dtype=torch.int64)
+    if mine:
+        t[: len(mine)] = torch.tensor(mine, dtype=torch.int64)
+    t = t.to(dev)
+    allt = torch.empty((world * max(nb, 1),), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allt, t, group=group)
+    vals = allt.cpu().view(world, max(nb, 1)).tolist()
+    lens_box["all"] = [v for row in vals for v in row if v >= 0]
+    return max([0] + lens_box["all"])
 
 
 def mixed_language_forward(models: Mapping[str, Callable], x: Mapping[str, torch.Tensor] | None, lang: Sequence[str] | None,

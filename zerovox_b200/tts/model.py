@@ -139,15 +139,19 @@ class ZeroVox(nn.Module):
         return model
 
     # forward -------------------------------------------------------------------------------------------
-    def forward(self, x, force_duration=False, normalize_before=True, *, pad_to=None):
-        """Batched eval forward (model.py:260-306).  ``pad_to`` (keyword-only extension, used by zerovox_b200.parallel): an int or a
-        callable ``local_L_max -> L`` giving the frame count to pad the batch to (>= the batch's own maximum), so that a
-        shard reproduces the tail behaviour of the unsharded batch.  Returns (wav [B, L_max*hop], mel [B, n_mels, L_max],
-        mel_len int64 [B], log_duration [B, T]) — the tuple utils/export_hifigan.py:109-151 consumes.  The
-        reference's own eval tail (model.py:298-304) is ParallelWaveGAN leftover code that raises with
-        hifigan.Generator; the intended semantics ``wav = _meldec(mel.transpose(1,2)).squeeze(1)`` are built."""
+    def forward(self, x, force_duration=False, normalize_before=True, *, pad_to=None, zero_padded_mel=None):
+        """Batched eval forward (model.py:260-306).  Returns (wav [B, L_max*hop], mel [B, n_mels, L_max], mel_len int64 [B],
+        log_duration [B, T]) — the tuple utils/export_hifigan.py:109-151 consumes.  The reference's own eval tail
+        (model.py:298-304) is ParallelWaveGAN leftover code that raises with hifigan.Generator; the intended semantics
+        ``wav = _meldec(mel.transpose(1,2)).squeeze(1)`` are built.
+
+        Keyword-only extensions used by zerovox_b200.parallel so that a shard reproduces the unsharded batch: ``pad_to`` —
+        an int, or a callable ``(local_L_max, mel_len_host) -> L`` — is the frame count to pad the batch to (>= its own
+        maximum); ``zero_padded_mel`` overrides the reference's batch-size dependent zero-fill of padded mel frames
+        (model.py:283-285 applies it iff a mel mask exists and B > 1 — B being the GLOBAL batch there)."""
         if self.training:
-            raise NotImplementedError("ZeroVox.forward in training mode is outside the zerovox_b200 hot path")
+            raise NotImplementedError("ZeroVox.forward in training mode is outside the zerovox_b200 hot path; "
+                                      "zerovox_b200.patch() keeps training on the reference modules")
         if self._meldec is None:
             raise RuntimeError("ZeroVox.forward: no vocoder (_meldec is None)")
         eng = self._shared_ctx.get(next(self.parameters()).device)
@@ -159,12 +163,22 @@ class ZeroVox(nn.Module):
                        forced, need_lengths=True)
         L = r["L_max"]
         if pad_to is not None:
-            L = max(L, int(pad_to(L) if callable(pad_to) else pad_to))
+            L = max(L, int(pad_to(L, r["mel_len_host"]) if callable(pad_to) else pad_to))
         feats = eng.length_regulate(r["xprime"], r["duration_rounded"], L)
-        # model.py:283-285: the mel is zero-filled at padded frames only when the mel mask exists (predicted
-        # durations) and B > 1
-        zero_pad = (not force_duration) and feats.shape[0] > 1
-        _, mel = eng.decode(feats, style, mel_len=r["mel_len"], zero_padded_mel=zero_pad, want_blc=False)
+        # fs2.py:748, 772 + model.py:264-285: the mel mask is x['mel_mask'] when the collated batch carries one (the
+        # utils/export_hifigan.py flow, forced durations), else the one derived from predicted durations; with forced
+        # durations and no 'mel_mask' there is none.  The mel is zero-filled at padded frames iff a mask exists and B > 1.
+        dec_mask = None
+        if force_duration and "mel_mask" in x:
+            dec_mask = x["mel_mask"].to(dev, non_blocking=True)
+            if dec_mask.shape[1] != L:
+                raise RuntimeError(f"x['mel_mask'] covers {dec_mask.shape[1]} frames, the durations give {L} "
+                                   "(the reference fails on this batch too: fs2.py:772, model.py:279)")
+        zero_pad = zero_padded_mel
+        if zero_pad is None:
+            zero_pad = ((not force_duration) or "mel_mask" in x) and feats.shape[0] > 1
+        _, mel = eng.decode(feats, style, mask=dec_mask, mel_len=r["mel_len"], zero_padded_mel=bool(zero_pad),
+                            want_blc=False)
         wav = eng.vocode(mel).squeeze(1)
         return wav, mel, r["mel_len"], r["log_duration"]
 
