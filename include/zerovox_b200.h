@@ -255,6 +255,11 @@ int zvx_ragged_unpack(const float* packed, const int64_t* lens, const int64_t* o
                       void* stream);
 const char* zvx_ragged_last_error(void);
 
+/* Runtime options of a handle (the release library reads no environment variables).
+ *   "score_workspace_bytes": budget of the attention-score workspace; longer inputs are processed in chunks of query rows
+ *                            (exact: the softmax is per row).  Default 4 GiB. */
+int zvx_set_option(zvx_handle* h, const char* name, int64_t value);
+
 /* Workspace control: bytes of engine-owned scratch currently reserved on the device. */
 int64_t zvx_workspace_bytes(const zvx_handle* h);
 

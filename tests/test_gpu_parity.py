@@ -381,7 +381,7 @@ def test_vocoder_chunked_equals_full(v):
             check(f"chunked({chunk}) vs full {v}", part, full, rtol=0.0, atol=5e-4)
 
 
-def test_longform_decoder_attention_chunks(medium, monkeypatch):
+def test_longform_decoder_attention_chunks(medium):
     """L > max_mel_len (position table recomputed, fs2.py:287-294) with the attention score budget forced small so that
     query rows are processed in several chunks: same mel as the oracle, and as the unchunked engine."""
     import zerovox_b200.engine as engine_mod
@@ -396,8 +396,8 @@ def test_longform_decoder_attention_chunks(medium, monkeypatch):
     eng = medium.model(1)._shared_ctx.get(torch.device(DEV))
     full, _ = eng.decode(feats.to(DEV), style.to(DEV), mask=mask.to(DEV), want_bcl=False)
     check("long-form mel vs oracle", full, ref, **TC_MEL)
-    monkeypatch.setenv("ZVX_SCORE_BYTES", str(2 * 2 * 500 * 1900 * 4))   # ~500 query rows per chunk
     eng2 = engine_mod.Engine(eng.cfg, torch.device(DEV))
+    eng2.set_option("score_workspace_bytes", 2 * 2 * 500 * 1900 * 4)   # ~500 query rows per chunk
     eng2.load_weights({k: v for k, v in medium.w.items() if k.startswith("_mel_decoder.")})
     part, _ = eng2.decode(feats.to(DEV), style.to(DEV), mask=mask.to(DEV), want_bcl=False)
     check("chunked attention vs unchunked", part, full, rtol=0.0, atol=1e-5)

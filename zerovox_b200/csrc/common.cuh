@@ -5,6 +5,7 @@
 #include <stdexcept>
 #include <string>
 #include <cstdio>
+#include <cstdlib>
 
 namespace zvx {
 
@@ -31,6 +32,22 @@ struct Error : std::runtime_error {
             throw ::zvx::Error(_buf);                                                        \
         }                                                                                    \
     } while (0)
+
+// Tuning / ablation switches (ZVX_* environment variables) exist only in -DZVX_DEBUG builds (ZVX_BUILD_DEBUG=1 python
+// __graft_entry__.py; tools/gpu_ab_*.sh): the release library has the measured defaults baked in and reads no environment.
+#ifdef ZVX_DEBUG
+static inline int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+static inline long long env_ll(const char* name, long long dflt) { const char* v = getenv(name); return v ? atoll(v) : dflt; }
+static inline bool env_set(const char* name) { return getenv(name) != nullptr; }
+#define ZVX_DBG_PTR(p) ((p).dbg)
+#define ZVX_DBG_SKIP(p) ((p).dbg_skip)
+#else
+static inline constexpr int env_int(const char*, int dflt) { return dflt; }
+static inline constexpr long long env_ll(const char*, long long dflt) { return dflt; }
+static inline constexpr bool env_set(const char*) { return false; }
+#define ZVX_DBG_PTR(p) (static_cast<long long*>(nullptr))
+#define ZVX_DBG_SKIP(p) (0)
+#endif
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline long long round_up(long long a, long long b) { return (a + b - 1) / b * b; }

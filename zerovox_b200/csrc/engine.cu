@@ -37,7 +37,9 @@ struct HostTensor {
 };
 
 // Growable block workspace: pointers are stable within a call; the same call sequence re-uses the same blocks, so
-// steady state performs no cudaMalloc.
+// steady state performs no cudaMalloc.  A request that fits no remaining block first RELEASES every block behind the cursor
+// (they are too small for this call sequence and would otherwise be stranded until zvx_destroy: device memory of a
+// long-running server with growing shapes stays bounded by the live high-water mark) and then allocates one new block.
 class Workspace {
   public:
     ~Workspace() { release(); }
@@ -46,6 +48,13 @@ class Workspace {
     T* get(long long n) {
         size_t bytes = (size_t)round_up(std::max<long long>(n, 1) * (long long)sizeof(T), 256);
         while (cur_ < blocks_.size() && off_ + bytes > blocks_[cur_].size) {
+            if (off_ == 0) {
+                // an EMPTY block that is too small: nothing of this call lives in it -> free it instead of skipping it
+                ZVX_CUDA_CHECK(cudaDeviceSynchronize());   // earlier calls' kernels may still read it (rare path: shapes grew)
+                cudaFree(blocks_[cur_].p);
+                blocks_.erase(blocks_.begin() + (long)cur_);
+                continue;
+            }
             ++cur_;
             off_ = 0;
         }
@@ -95,7 +104,6 @@ struct SEBlock {
     float *w2 = nullptr, *bn2_s = nullptr, *bn2_b = nullptr;
     float *se_w1 = nullptr, *se_b1 = nullptr, *se_w2 = nullptr, *se_b2 = nullptr;
     float *wd = nullptr, *bnd_s = nullptr, *bnd_b = nullptr;  // downsample (nullable)
-    float *w1_rs = nullptr, *w2_rs = nullptr;   // row-shift kernel images (conv_rs.cu) when the channel counts allow
 };
 
 struct STConv { float* w = nullptr; float* b = nullptr; int cin = 0, cout = 0, k = 1; };   // weight-norm folded, tap-major
@@ -487,11 +495,6 @@ class Engine {
                 b.w1 = upload(tap_major(W(p + ".conv1.weight", {planes, inpl, 3, 3})));
                 bn_fold(p + ".bn1", planes, &b.bn1_s, &b.bn1_b);
                 b.w2 = upload(tap_major(W(p + ".conv2.weight", {planes, planes, 3, 3})));
-                auto rs_ok = [](int c) { return c == 32 || c == 64; };
-                if (b.stride == 1 && rs_ok(inpl) && rs_ok(planes))
-                    b.w1_rs = upload(voc_pack_weight(W(p + ".conv1.weight", {planes, inpl, 3, 3}).data.data(), planes, inpl, 9));
-                if (rs_ok(planes))
-                    b.w2_rs = upload(voc_pack_weight(W(p + ".conv2.weight", {planes, planes, 3, 3}).data.data(), planes, planes, 9));
                 bn_fold(p + ".bn2", planes, &b.bn2_s, &b.bn2_b);
                 b.se_w1 = upload(W(p + ".se.fc.0.weight", {b.red, planes}));
                 b.se_b1 = upload(W(p + ".se.fc.0.bias", {b.red}));
@@ -622,8 +625,7 @@ class Engine {
                     auto pack = [&](const std::string& key, int dil, std::vector<float*>& poly) {
                         const HostTensor& t = W("_meldec." + key + ".weight", {cout, cout, rk});
                         if (hg_stage_kind[(size_t)i] != 1) {
-                            // 64-channel stages: image for the row-shift kernel in the `poly` slot, TMA image as before
-                            poly.push_back(cout == 64 ? upload(voc_pack_weight(t.data.data(), cout, cout, rk)) : nullptr);
+                                poly.push_back(nullptr);
                             return upload(tap_major(t));
                         }
                         poly.push_back(upload(voc_poly_pack_weight(t.data.data(), cout, rk, dil)));
@@ -776,7 +778,7 @@ class Engine {
         const int ldS = sc.ldS, Lq_max = sc.Lq_max;
         const int nz = B * n_head;
         const float temperature = (float)std::pow((double)dk, 0.5);  // np.power(d_k, 0.5), fs2.py:122
-        static const int tc_mask = getenv("ZVX_TC_MASK") ? atoi(getenv("ZVX_TC_MASK")) : 15;   // bit0: tensor-core attention
+        static const int tc_mask = env_int("ZVX_TC_MASK", 15);   // bit0: tensor-core attention (debug builds only)
         const bool split = (tc == P_EXACT);
         const float* wqkv_lo = split ? lo_of(ly.wqkv) : nullptr;
         const bool tc_attn = tc_enabled(tc) && (tc_mask & 1) && (dk % 4 == 0) && rows >= tc_min_rows() &&
@@ -803,8 +805,7 @@ class Engine {
             // matrices (plus their Q / K / V rows) fit in L2: the softmax and the PV product then read what the kernel
             // before them wrote from L2 instead of DRAM (the whole-batch score tensor is 172 MB at configs[1], moved
             // four times).  ZVX_ATTN_SLICE_BYTES = 0 restores one slice.
-            static const long long slice_bytes =
-                getenv("ZVX_ATTN_SLICE_BYTES") ? atoll(getenv("ZVX_ATTN_SLICE_BYTES")) : kAttnSliceBytes;
+            static const long long slice_bytes = env_ll("ZVX_ATTN_SLICE_BYTES", kAttnSliceBytes);
             int Bs = B;
             if (slice_bytes > 0 && !split) {
                 const long long per_utt = (long long)n_head * std::min(Lq_max, L) * ldS * (long long)sizeof(float);
@@ -924,24 +925,13 @@ class Engine {
             c.C = t1; c.ldc = b.planes; c.M = B * Ho * Wo; c.N = b.planes; c.K = b.inpl; c.taps = 9;
             c.mode = ROW_CONV2D; c.Ho = Ho; c.Wo = Wo; c.Hi = Hh; c.Wi = Ww; c.ksize = 3; c.stride = b.stride; c.pad = 1;
             c.relu_first = 1; c.scale = b.bn1_s; c.shift = b.bn1_b;
-            auto rs_conv = [&](const float* in, int cin, const float* wrs, const float* sc_, const float* sh_, int relu, float* out) {
-                ConvRsArgs r;
-                r.mode = 1; r.x = in; r.x_bs = (long long)Ho * Wo * cin; r.B = B; r.H = Ho; r.W = Wo; r.C = cin; r.N = b.planes;
-                r.w = wrs; r.scale = sc_; r.shift = sh_; r.relu_first = relu; r.y = out; r.y_bs = (long long)Ho * Wo * b.planes;
-                if (!rs_on || cfg.tensor_core_policy == 0 || !wrs || !conv_rs_supported(r)) return false;
-                prof.begin(ZVX_PROF_GEMM_TC, 2.0 * B * Ho * Wo * (double)cin * b.planes * 9,
-                           4.0 * B * Ho * Wo * (double)(cin + b.planes), st);
-                conv_rs(r, st);
-                prof.end(st);
-                return true;
-            };
-            if (!(b.stride == 1 && rs_conv(x, b.inpl, b.w1_rs, b.bn1_s, b.bn1_b, 1, t1))) gemm(c, tc, st);
+            gemm(c, tc, st);
             GemmArgs c2;
             c2.A = t1; c2.lda = b.planes; c2.W = b.w2; c2.ldw = b.planes; c2.w_tap_stride = (long long)b.planes * b.planes;
             c2.C = t2; c2.ldc = b.planes; c2.M = B * Ho * Wo; c2.N = b.planes; c2.K = b.planes; c2.taps = 9;
             c2.mode = ROW_CONV2D; c2.Ho = Ho; c2.Wo = Wo; c2.Hi = Ho; c2.Wi = Wo; c2.ksize = 3; c2.stride = 1; c2.pad = 1;
             c2.scale = b.bn2_s; c2.shift = b.bn2_b;
-            if (!rs_conv(t1, b.planes, b.w2_rs, b.bn2_s, b.bn2_b, 0, t2)) gemm(c2, tc, st);
+            gemm(c2, tc, st);
             const int S = hw_mean_splits(B, Ho * Wo);
             float* pooled = ws.get<float>((long long)B * S * b.planes);
             hw_sum_partial(t2, B, Ho * Wo, b.planes, S, pooled, st);
@@ -1147,7 +1137,8 @@ class Engine {
         long long big = std::max((long long)B * L * C0, (long long)B * L * M), t = L;
         for (int i = 0; i < nu; ++i) {
             t *= cfg.hg_upsample_rates[i];
-            big = std::max(big, (long long)B * (t + 16) * (C0 >> (i + 1)));
+            // the transposed-conv GEMM writes (T_in + 1) * u = T_out + u rows per utterance
+            big = std::max(big, (long long)B * (t + cfg.hg_upsample_rates[i]) * (C0 >> (i + 1)));
         }
         float* bX = ws.get<float>(big);    // stage output (MRF accumulator), raw
         float* bXA = ws.get<float>(big);   // its leaky-ReLU'd copy (upsampler operand)
@@ -1212,8 +1203,8 @@ class Engine {
                     const bool emit_act = (j == nk - 1) && more;
                     a.out = emit_act ? bXA : bX; a.out_bs = bs; a.out_slope = emit_act ? 0.1f : 1.f;
                     prof.begin(ZVX_PROF_VOC_TC, 2.0 * B * T * ch * ch * rk * a.nsteps, 4.0 * B * T * ch * (j > 0 ? 3.0 : 2.0), st);
-                    static const bool no_poly = getenv("ZVX_NO_POLY") != nullptr;   // A/B switch: voc_res.cu only
-                    static const bool dbg_times = getenv("ZVX_VOC_DBG") != nullptr;  // print one CTA's phase timestamps
+                    static const bool no_poly = env_set("ZVX_NO_POLY");   // A/B switch (debug builds): voc_res.cu only
+                    static const bool dbg_times = env_set("ZVX_VOC_DBG");  // debug builds: print one CTA's phase timestamps
                     long long* dbg = nullptr;
                     if (dbg_times) { dbg = ws.get<long long>(64); ZVX_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 64 * 8, st)); a.dbg = dbg; }
                     if (no_poly || !voc_poly_tc(a, st)) voc_resblock_tc(a, st);
@@ -1236,32 +1227,7 @@ class Engine {
                     const bool first_buf = (r.p != bRA);
                     const View rn{first_buf ? bRA : bRB, bs}, rna{first_buf ? bRAa : bRBa, bs};
                     const int dl = cfg.hg_resblock_dilation_sizes[j][di];
-                    const bool rs = rs_on && ch == 64 && hg_c1_poly[ci] && (!pair || hg_c2_poly[ci]);
-                    if (rs) {
-                        // row-shift kernel: reads the RAW tensors and applies the leaky ReLU on the way in
-                        ConvRsArgs c;
-                        c.mode = 0; c.B = B; c.T = T; c.C = ch; c.N = ch; c.k = rk; c.in_slope = 0.1f;
-                        auto run = [&](ConvRsArgs& cc) {
-                            prof.begin(ZVX_PROF_GEMM_TC, 2.0 * B * T * (double)ch * ch * rk, 4.0 * B * T * (double)(2 * ch), st);
-                            conv_rs(cc, st);
-                            prof.end(st);
-                        };
-                        if (pair) {
-                            c.x = r.p; c.x_bs = r.bs; c.w = hg_c1_poly[ci]; c.bias = hg_c1[ci].b; c.dil = dl; c.y = bT; c.y_bs = bs;
-                            run(c);
-                            c.x = bT; c.x_bs = bs; c.w = hg_c2_poly[ci]; c.bias = hg_c2[ci].b; c.dil = 1;
-                        } else {
-                            c.x = r.p; c.x_bs = r.bs; c.w = hg_c1_poly[ci]; c.bias = hg_c1[ci].b; c.dil = dl;
-                        }
-                        c.R = r.p; c.r_bs = r.bs;
-                        if (last) {
-                            c.y = bX; c.y_bs = bs; c.acc_mode = 1; c.acc_init = (j == 0); c.acc_scale = 1.f / (float)nk;
-                            if (j == nk - 1 && more) { c.y2 = bXA; c.slope2 = 0.1f; }
-                        } else {
-                            c.y = rn.p; c.y_bs = rn.bs;
-                        }
-                        run(c);
-                    } else {
+                    {
                         TcGemmArgs g;   // conv over the leaky-ReLU'd copy
                         g.K = ch; g.Wi = g.Wo = T; g.Hi = g.Ho = B; g.a_sx = ch; g.N = ch; g.w_sn = ch; g.Z1 = rk;
                         g.w_s1 = (long long)ch * ch; g.ksx = rk; g.c_sx = ch;
@@ -1362,9 +1328,20 @@ class Engine {
         return 0;
     }
 
+    int set_option(const char* name, int64_t value) {
+        ZVX_REQUIRE(name, "zvx_set_option: null name");
+        const std::string n(name);
+        if (n == "score_workspace_bytes") {
+            ZVX_REQUIRE(value >= (1 << 20), "zvx_set_option: score_workspace_bytes must be >= 1 MiB");
+            kScoreBytes = value;
+            return 0;
+        }
+        throw Error("zvx_set_option: unknown option '" + n + "'");
+    }
+
     static constexpr int kMaxBatch = 65536;
     // attention-score workspace budget: longer sequences are processed in chunks of query rows (exact)
-    long long kScoreBytes = getenv("ZVX_SCORE_BYTES") ? atoll(getenv("ZVX_SCORE_BYTES")) : (4LL << 30);
+    long long kScoreBytes = 4LL << 30;   // zvx_set_option("score_workspace_bytes")
     // attention batch-slice budget (score bytes per slice); 0 = whole batch per launch.  Default set by measurement.
     static constexpr long long kAttnSliceBytes = 0;
 
@@ -1381,10 +1358,7 @@ class Engine {
     std::string sec_err[4];
     Workspace ws;
     Profiler prof;
-    // row-shift conv kernel (conv_rs.cu) for 32/64-channel convs: correct but measured slower than / on par with the TMA
-    // implicit GEMM at this size (profiles/r01_conv_rs_experiment.txt) -> opt-in until its phases are pipelined
-    bool rs_on = getenv("ZVX_RS") != nullptr;
-    bool split_on = getenv("ZVX_NO_SPLIT") == nullptr;   // 3xTF32 for P_EXACT contractions (debug switch)
+    bool split_on = !env_set("ZVX_NO_SPLIT");   // 3xTF32 for P_EXACT contractions (switchable in debug builds only)
     std::map<const float*, const float*> w_lo;
     float* lo_buf = nullptr;
     long long lo_cap = 0;
@@ -1554,6 +1528,8 @@ int zvx_debug_gemm(zvx_handle* h, const zvx_gemm_desc* d, int use_tc, void* stre
         return 0;
     });
 }
+
+int zvx_set_option(zvx_handle* h, const char* name, int64_t value) { ZVX_GUARD(h, return h->eng->set_option(name, value)); }
 
 int64_t zvx_workspace_bytes(const zvx_handle* h) { return (h && h->eng) ? h->eng->ws.bytes() : 0; }
 

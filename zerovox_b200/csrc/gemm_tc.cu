@@ -216,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             } else
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const Tile c = decode_tile(p, t);
-                if (p.dbg && blockIdx.x == 0 && t / (int)gridDim.x < 16) p.dbg[t / gridDim.x] = clock64();
+                if (ZVX_DBG_PTR(p) && blockIdx.x == 0 && t / (int)gridDim.x < 16) ZVX_DBG_PTR(p)[t / gridDim.x] = clock64();
                 long long pwait = 0;
                 // (single-thread loop: its instruction latency bounds small tiles -> counters instead of divisions)
                 const int cx = c.x0 * p.stride - p.pad_x, cy = c.y0 * p.stride_y - p.pad_y;
@@ -225,10 +225,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 const int ug = SPLIT ? 1 : p.ug;
                 for (int s = 0; s < ksteps; s += ug) {
                     const int ng = SPLIT ? 1 : min(ug, ksteps - s);   // k-steps in this stage
-                    const long long w0 = p.dbg ? clock64() : 0;
+                    const long long w0 = ZVX_DBG_PTR(p) ? clock64() : 0;
                     mbar_wait_sel(p.spin, empty_bar(stage), phase ^ 1u);
-                    if (p.dbg) pwait += clock64() - w0;
-                    if (p.dbg_skip & 2) { mbar_arrive(full_bar(stage)); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
+                    if (ZVX_DBG_PTR(p)) pwait += clock64() - w0;
+                    if (ZVX_DBG_SKIP(p) & 2) { mbar_arrive(full_bar(stage)); if (++stage == p.stages) { stage = 0; phase ^= 1u; } continue; }
                     const uint32_t fb = full_bar(stage);
                     mbar_arrive_expect_tx(fb, tx_bytes * (uint32_t)ng);
                     uint32_t sa = smem_base + (uint32_t)(stage * p.stage_bytes);
@@ -249,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                if (p.dbg && blockIdx.x == 0 && t / (int)gridDim.x < 16) p.dbg[48 + t / gridDim.x] = p.dbg[0] + pwait;
+                if (ZVX_DBG_PTR(p) && blockIdx.x == 0 && t / (int)gridDim.x < 16) ZVX_DBG_PTR(p)[48 + t / gridDim.x] = ZVX_DBG_PTR(p)[0] + pwait;
             }
         }
         __syncwarp();
@@ -306,16 +306,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const uint32_t par = (cnt >> 1) & 1u;
                     mbar_wait_sel(p.spin, tempty_bar(buf), par ^ 1u);
                     tc_fence_after();
-                    if (p.dbg && blockIdx.x == 0 && cnt < 16) p.dbg[16 + cnt] = clock64();
+                    if (ZVX_DBG_PTR(p) && blockIdx.x == 0 && cnt < 16) ZVX_DBG_PTR(p)[16 + cnt] = clock64();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
                     const int s1 = min(ksteps, s0 + phase_len);
                     long long waited = 0;
                     const int ug = SPLIT ? 1 : p.ug;
                     for (int s = s0; s < s1; s += ug) {
                         const int ng = SPLIT ? 1 : min(ug, s1 - s);
-                        const long long w0 = p.dbg ? clock64() : 0;
+                        const long long w0 = ZVX_DBG_PTR(p) ? clock64() : 0;
                         mbar_wait_sel(p.spin, full_bar(stage), phase);
-                        if (p.dbg) waited += clock64() - w0;
+                        if (ZVX_DBG_PTR(p)) waited += clock64() - w0;
                         // no tcgen05 fence here: the operands were written by the async proxy (TMA) and the mbarrier
                         // completion orders them before the MMA's own async-proxy reads
                         uint32_t alo = desc_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);   // low descriptor words
@@ -332,7 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                     umma_tf32_lo(d_tmem + LO_OFFSET, alo + 2 * k, lb + 2 * k, DESC_HI, p.idesc, 1u);
                                     umma_tf32_lo(d_tmem, alo + 2 * k, blo + 2 * k, DESC_HI, p.idesc, accum);
                                 }
-                            } else if (!(p.dbg_skip & 1)) {
+                            } else if (!(ZVX_DBG_SKIP(p) & 1)) {
                                 for (int mi = 0; mi < p.mt; ++mi) {   // the M tiles of the CTA tile share the weight tile
                                     const uint32_t am = alo + (uint32_t)(mi * (A_TILE_BYTES >> 4));
 #pragma unroll
@@ -346,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
                     umma_commit(tfull_bar(buf));
-                    if (p.dbg && blockIdx.x == 0 && cnt < 16) { p.dbg[32 + cnt] = clock64(); p.dbg[64 + cnt] = p.dbg[0] + waited; }
+                    if (ZVX_DBG_PTR(p) && blockIdx.x == 0 && cnt < 16) { ZVX_DBG_PTR(p)[32 + cnt] = clock64(); ZVX_DBG_PTR(p)[64 + cnt] = ZVX_DBG_PTR(p)[0] + waited; }
                 }
             }
         }
@@ -443,7 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 rp = p.R ? p.R + ((long long)c.img * p.r_simg + (long long)y * p.r_sy + (long long)x * p.r_sx) : nullptr;
             }
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE + mi * p.BN);
-            for (int c0 = half * 16; c0 < ((p.dbg_skip & 4) ? 0 : p.BN); c0 += 32) {
+            for (int c0 = half * 16; c0 < ((ZVX_DBG_SKIP(p) & 4) ? 0 : p.BN); c0 += 32) {
                 uint32_t v[16];
                 __syncwarp();   // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
                 tmem_ld16(trow + (uint32_t)c0, v);
@@ -609,7 +609,7 @@ CUtensorMap make_map(const float* base, const long long dims[4], const long long
     // TFLOAT32 element type: the TMA unit rounds fp32 -> tf32 (nearest) in flight.  With plain FLOAT32 the tensor core
     // truncates the low 13 mantissa bits, a systematic -7e-4 relative bias per contraction (measured, tools/diag_tf32.py;
     // ZVX_TMAP_F32=1 restores that behaviour for the experiment).
-    static const bool f32_env = getenv("ZVX_TMAP_F32") != nullptr;
+    static const bool f32_env = env_set("ZVX_TMAP_F32");
     const bool f32_type = f32_env || raw_f32;   // split mode: hi = the tensor core's own truncation of the raw bits
     const CUresult rc = encode_fn()(&m, f32_type ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), gd, gs, bx, es,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -689,22 +689,22 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     }
     // x-tap reuse: the ksx taps of a filter row read one activation tile of 128 + (ksx-1)*dil positions through
     // row-shifted descriptors instead of ksx separate TMA loads (the activation re-fetch is what bounds small-N convs)
-    static const bool no_xr = getenv("ZVX_NO_XR") != nullptr;
+    static const bool no_xr = env_set("ZVX_NO_XR");
     const int halo = (a.ksx - 1) * a.dil;
     // (measured: pays off for filter rows of >= 5 taps — FFN k = 9, HiFi-GAN k = 7 / 11; for 3-tap rows the forced
     // 128 x 1 tile shape costs more in padding than the saved fetches)
-    static const int xr_mink = getenv("ZVX_XR_MINK") ? atoi(getenv("ZVX_XR_MINK")) : 5;
+    static const int xr_mink = env_int("ZVX_XR_MINK", 5);
     // narrow 1-D convs are hand-shake bound: there even a 3-tap row gains from one activation load per k-chunk (A/B: ZVX_XR1_K3)
     // (measured: vocoder stage 8.21 -> 8.18 ms, profiles/r01_ab_conv1d_tap_reuse_two_m_tiles_and_k3.jsonl)
-    static const int xr1_k3 = getenv("ZVX_XR1_K3") ? atoi(getenv("ZVX_XR1_K3")) : 1;
+    static const int xr1_k3 = env_int("ZVX_XR1_K3", 1);
     const bool xr_narrow = xr1_k3 && a.ksy == 1 && a.ksx >= 3 && a.N <= 128;
     const bool xr = !no_xr && !split && (a.ksx >= xr_mink || xr_narrow) && a.stride == 1 && !a.b_batched && halo <= 120;
     // 2-D tap reuse (ksy > 1, unit stride): one (TH + halo_y) x (TW + halo_x) activation tile per k-chunk serves all taps; the
     // activation fetch drops from taps x 16 KB to ~25 KB per k-chunk at the price of halo_x discarded columns per tile row.
     // Measured on configs[1] (profiles/r01_ab_conv2d_tap_reuse.jsonl): speaker net 4.21 -> 3.81 ms with N <= 128 (32 / 64 / 128
     // channel 3x3 convs); ZVX_XR2=0 switches it off, =2 forces it on problems below the size threshold (tests).
-    static const int xr2_env = getenv("ZVX_XR2") ? atoi(getenv("ZVX_XR2")) : 1;
-    static const int xr2_maxn = getenv("ZVX_XR2_MAXN") ? atoi(getenv("ZVX_XR2_MAXN")) : 128;
+    static const int xr2_env = env_int("ZVX_XR2", 1);
+    static const int xr2_maxn = env_int("ZVX_XR2_MAXN", 128);
     const int halo_y = (a.ksy - 1) * a.dil;
     bool xr2 = xr2_env && !split && !xr && a.ksy > 1 && a.ksx > 1 && a.stride == 1 && !a.b_batched && a.N <= xr2_maxn;
     int xr2_tw = 0, xr2_th = 0, xr2_roww = 0, xr2_mt = 1, xr2_na = 3;
@@ -713,12 +713,12 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
         // first (ties: the narrower tile row, smaller halo buffer); two M tiles per CTA tile (they share the weight stage, the
         // activation load and every hand-shake) unless that pads the map by more than 4 %.  ZVX_XR2_MT=1 keeps one M tile.
         // Measured (profiles/r01_ab_conv2d_tap_reuse_two_m_tiles.jsonl): speaker net 4.32 -> 3.79 ms with N <= 128.
-        static const int xr2_mtmax = getenv("ZVX_XR2_MT") ? atoi(getenv("ZVX_XR2_MT")) : 2;
+        static const int xr2_mtmax = env_int("ZVX_XR2_MT", 2);
         const int wstride = (int)round_up(p.BN * BK * 4, 1024);
         const int wstage = std::max(1, std::min(a.ksx * a.ksy, (48 * 1024) / wstride)) * wstride;
         long long best_mt[3] = {-1, -1, -1};
         int sel[3][4] = {};
-        static const int xr2_mt_maxn = getenv("ZVX_XR2_MT_MAXN") ? atoi(getenv("ZVX_XR2_MT_MAXN")) : 128;
+        static const int xr2_mt_maxn = env_int("ZVX_XR2_MT_MAXN", 128);
         for (int mt = 1; mt <= std::min(2, xr2_mtmax); ++mt) {
             if (mt * p.BN > ACC_STRIDE || (mt > 1 && a.N > xr2_mt_maxn)) continue;
             for (int roww = 8; roww <= 128; roww <<= 1) {
@@ -745,16 +745,16 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     }
     // tile shape: TH x TW = 128 * mt positions, least padding first, wider rows on ties.  Two M tiles per CTA tile for narrow
     // outputs (N <= 64): they share every weight tile and, above all, every stage hand-shake and per-tile overhead.
-    static const bool no_mt2 = getenv("ZVX_NO_MT2") != nullptr;
+    static const bool no_mt2 = env_set("ZVX_NO_MT2");
     const long long positions = (long long)a.IMG * a.Ho * a.Wo;
-    static const int mt2_n = getenv("ZVX_MT2_N") ? atoi(getenv("ZVX_MT2_N")) : 64;
+    static const int mt2_n = env_int("ZVX_MT2_N", 64);
     p.mt = (!no_mt2 && !split && !xr && !xr2 && !a.b_batched && a.N <= mt2_n && positions >= 2LL * 256 * num_sms()) ? 2 : 1;
     long long best = -1;
     if (xr) {
         // filter-row tap reuse: 128 x 1 tiles, or 256 x 1 (two M tiles behind one haloed activation buffer and one weight stage)
         // for narrow outputs when the longer tiles pad the rows by < 4 % and still fill the GPU.  ZVX_XR1_MT=1: one M tile.
         // (measured: vocoder stage 8.30 -> 8.19 ms)
-        static const int xr1_mtmax = getenv("ZVX_XR1_MT") ? atoi(getenv("ZVX_XR1_MT")) : 2;
+        static const int xr1_mtmax = env_int("ZVX_XR1_MT", 2);
         const long long t1 = cdiv(a.Wo, BM), t2 = 2LL * cdiv(a.Wo, 2 * BM);
         if (xr1_mtmax >= 2 && 2 * p.BN <= ACC_STRIDE && a.N <= 128 && t2 * 100 <= t1 * 104 &&
             t2 * a.Ho * a.IMG * p.tiles_n >= 4LL * num_sms())
@@ -795,7 +795,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.ug = 1;
     p.spin = (p.BN <= 64) ? 1 : 0;
     {   // small stages: group k-steps so that one barrier round trip / commit covers ~40 KB of operands
-        static const int ug_env = getenv("ZVX_GEMM_UG") ? atoi(getenv("ZVX_GEMM_UG")) : 0;
+        static const int ug_env = env_int("ZVX_GEMM_UG", 0);
         const int ksteps = a.ksx * a.ksy * cdiv(a.K, BK);
         // measured per configs[1] step: 1 k-step per stage 22.5 ms, 2: 21.3, 3: 20.9, 4: 21.0 (>= 3 stages must remain); an
         // ablated run (no TMA, no MMA, empty epilogue) still costs ~650 cycles per stage hand-shake, tcgen05.commit included
@@ -869,6 +869,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     }
     // > 116 KB keeps the kernel at one CTA per SM (each CTA allocates all 512 TMEM columns)
     ZVX_REQUIRE(p.stages >= 2 && smem <= SMEM_LIMIT && smem > 116 * 1024, "gemm_tc: shared-memory plan out of range");
+#ifdef ZVX_DEBUG
     static const char* dbg_env = getenv("ZVX_GEMM_DBG");   // "N": trace launches whose N equals that value
     static long long* dbg_buf = nullptr;
     const bool dbg = dbg_env && atoi(dbg_env) == a.N && !split;
@@ -878,12 +879,14 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
         p.dbg = dbg_buf;
         p.dbg_skip = getenv("ZVX_GEMM_SKIP") ? atoi(getenv("ZVX_GEMM_SKIP")) : 0;
     }
+#endif
     const int grid = std::min(p.num_tiles, num_sms());
     const bool general = a.scale || a.acc_mode || a.act_slope != 1.f || a.C2;
     if (split) gemm_tc_kernel<true, true><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
     else if (general) gemm_tc_kernel<true, false><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
     else gemm_tc_kernel<false, false><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
     ZVX_POST_LAUNCH();
+#ifdef ZVX_DEBUG
     if (dbg) {
         long long h[80];
         ZVX_CUDA_CHECK(cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -896,6 +899,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
             fprintf(stderr, "\n");
         }
     }
+#endif
 }
 
 // Smallest row count that goes to the tensor-core kernel.  A single short utterance has M = T phonemes: on the fp32 FMA
@@ -903,7 +907,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
 // Measured with the demo flow (46 phonemes, profiles/r01_demo_host_profile.log): threshold 64 -> 16 takes zvx_encode from
 // 3.56 to 1.48 ms and the whole sentence from 5.48 to 3.35 ms; all GPU parity tests pass with either value.
 int tc_min_rows() {
-    static const int v = getenv("ZVX_TC_MIN_M") ? atoi(getenv("ZVX_TC_MIN_M")) : 16;
+    static const int v = env_int("ZVX_TC_MIN_M", 16);
     return v;
 }
 

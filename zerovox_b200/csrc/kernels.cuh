@@ -93,7 +93,7 @@ void conv1d_cf(const Conv1dArgs& a, cudaStream_t st);
 void conv_transpose1d_cf(const float* x, const float* w, const float* bias, int B, int Cin, int Cout, int T, int k,
                          int u, float in_slope, float* out, cudaStream_t st);
 
-// ---- HiFi-GAN on the tensor cores, channel-last [B, T, C] (voc_res.cu, voc_poly.cu, conv_rs.cu) ---------------------
+// ---- HiFi-GAN on the tensor cores, channel-last [B, T, C] (voc_res.cu, voc_poly.cu) ---------------------------------
 // [Cout][Cin][k] (PyTorch Conv1d / flattened Conv2d) -> shared-memory image [k][Cin/4][max(Cout,16)][4], TF32-rounded
 std::vector<float> voc_pack_weight(const float* w, int cout, int cin, int k);
 
@@ -124,27 +124,6 @@ void voc_resblock_tc(const VocResArgs& a, cudaStream_t st);
 bool voc_poly_supported(int C, int k, const int* dils, int nd, bool pair);
 bool voc_poly_tc(const VocResArgs& a, cudaStream_t st);
 std::vector<float> voc_poly_pack_weight(const float* w, int C, int k, int dil);
-
-// Row-shift convolution on tcgen05 (conv_rs.cu) for C_in, C_out in {32, 64}: the activation tile is staged once and every
-// filter tap is a row offset of the operand descriptor.  mode 0: Conv1d over [B][T][C] ('same' padding, dilation dil);
-// mode 1: Conv2d 3x3, pad 1, stride 1 over [B][H][W][C].  Weights in the image of voc_pack_weight ([tap][C/4][N][4]).
-//   v = conv(lrelu(x, in_slope)) + bias; relu_first; v*scale + shift; + R; acc: v = v*acc_scale + (acc_init ? 0 : y);
-//   y = v; y2 = lrelu(v, slope2) (optional)
-struct ConvRsArgs {
-    int mode = 0;
-    const float* x = nullptr; long long x_bs = 0;
-    int B = 0, T = 0, H = 0, W = 0, C = 0, N = 0, k = 1, dil = 1;
-    const float* w = nullptr;
-    const float* bias = nullptr; const float* scale = nullptr; const float* shift = nullptr;
-    int relu_first = 0;
-    float in_slope = 1.f;
-    const float* R = nullptr; long long r_bs = 0;
-    int acc_mode = 0, acc_init = 0; float acc_scale = 1.f;
-    float* y = nullptr; long long y_bs = 0;
-    float* y2 = nullptr; float slope2 = 1.f;
-};
-bool conv_rs_supported(const ConvRsArgs& a);
-void conv_rs(const ConvRsArgs& a, cudaStream_t st);
 
 // conv_post on channel-last input: wav[b,t] = tanh(bias + sum_{j,c} w[j][c] * lrelu(x[b, t+j-(k-1)/2, c], slope))
 void conv_post_cl(const float* x, long long x_bs, const float* w /*[k][C]*/, const float* bias, int B, int T, int C,

@@ -297,6 +297,10 @@ class Engine:
             out[name] = {"ms": ms.value, "launches": n.value, "flops": fl.value, "bytes": by.value}
         return out
 
+    def set_option(self, name: str, value: int):
+        """zvx_set_option: e.g. ``score_workspace_bytes`` (attention-score budget; long inputs are chunked over query rows)."""
+        self._check(self.lib.zvx_set_option(self._h, name.encode(), int(value)), "zvx_set_option")
+
     def workspace_bytes(self) -> int:
         return int(self.lib.zvx_workspace_bytes(self._h))
 

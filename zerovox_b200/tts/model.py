@@ -140,84 +140,99 @@ class ZeroVox(nn.Module):
 
     # forward -------------------------------------------------------------------------------------------
     def forward(self, x, force_duration=False, normalize_before=True, *, pad_to=None, zero_padded_mel=None):
-        """Batched eval forward (model.py:260-306).  Returns (wav [B, L_max*hop], mel [B, n_mels, L_max], mel_len int64 [B],
-        log_duration [B, T]) — the tuple utils/export_hifigan.py:109-151 consumes.  The reference's own eval tail
-        (model.py:298-304) is ParallelWaveGAN leftover code that raises with hifigan.Generator; the intended semantics
-        ``wav = _meldec(mel.transpose(1,2)).squeeze(1)`` are built.
-
-        Keyword-only extensions used by zerovox_b200.parallel so that a shard reproduces the unsharded batch: ``pad_to`` —
-        an int, or a callable ``(local_L_max, mel_len_host) -> L`` — is the frame count to pad the batch to (>= its own
-        maximum); ``zero_padded_mel`` overrides the reference's batch-size dependent zero-fill of padded mel frames
-        (model.py:283-285 applies it iff a mel mask exists and B > 1 — B being the GLOBAL batch there)."""
+        """Batched eval forward (model.py:260-306); see :func:`engine_forward` for the return tuple and the two
+        keyword-only extensions."""
         if self.training:
             raise NotImplementedError("ZeroVox.forward in training mode is outside the zerovox_b200 hot path; "
                                       "zerovox_b200.patch() keeps training on the reference modules")
         if self._meldec is None:
             raise RuntimeError("ZeroVox.forward: no vocoder (_meldec is None)")
         eng = self._shared_ctx.get(next(self.parameters()).device)
-        dev = eng.device
-        style = eng.spkemb(x["ref_mel"].to(dev, non_blocking=True))
-        mask = x["phoneme_mask"].to(dev, non_blocking=True) if "phoneme_mask" in x else None
-        forced = x["duration"].to(dev, non_blocking=True) if force_duration else None
-        r = eng.encode(x["phoneme"].to(dev, non_blocking=True), x["puncts"].to(dev, non_blocking=True), style, mask,
-                       forced, need_lengths=True)
-        L = r["L_max"]
-        if pad_to is not None:
-            L = max(L, int(pad_to(L, r["mel_len_host"]) if callable(pad_to) else pad_to))
-        feats = eng.length_regulate(r["xprime"], r["duration_rounded"], L)
-        # fs2.py:748, 772 + model.py:264-285: the mel mask is x['mel_mask'] when the collated batch carries one (the
-        # utils/export_hifigan.py flow, forced durations), else the one derived from predicted durations; with forced
-        # durations and no 'mel_mask' there is none.  The mel is zero-filled at padded frames iff a mask exists and B > 1.
-        dec_mask = None
-        if force_duration and "mel_mask" in x:
-            dec_mask = x["mel_mask"].to(dev, non_blocking=True)
-            if dec_mask.shape[1] != L:
-                raise RuntimeError(f"x['mel_mask'] covers {dec_mask.shape[1]} frames, the durations give {L} "
-                                   "(the reference fails on this batch too: fs2.py:772, model.py:279)")
-        zero_pad = zero_padded_mel
-        if zero_pad is None:
-            zero_pad = ((not force_duration) or "mel_mask" in x) and feats.shape[0] > 1
-        _, mel = eng.decode(feats, style, mask=dec_mask, mel_len=r["mel_len"], zero_padded_mel=bool(zero_pad),
-                            want_blc=False)
-        wav = eng.vocode(mel).squeeze(1)
-        return wav, mel, r["mel_len"], r["log_duration"]
+        return engine_forward(eng, x, force_duration=force_duration, pad_to=pad_to, zero_padded_mel=zero_padded_mel)
 
     def inference_ex(self, x, style_embed, normalize_before=True, force_duration=False, *, vocoder_chunk_frames=None):
-        """Batch-1 path (model.py:308-347): zero-pads the mel to the stateful ``_min_mel_len`` before vocoding and
-        trims the waveform to mel_len*hop.  Returns (wav, mel_len, log_duration, mel [n_mels, mel_len]).
-        ``vocoder_chunk_frames`` (keyword-only extension, long-form inputs): vocode in chunks of that many mel frames
-        with a 14-frame discarded halo — same waveform, bounded workspace."""
-        start_time = time.time()
+        """Batch-1 path (model.py:308-347); see :func:`engine_inference_ex`."""
         eng = self._shared_ctx.get(next(self.parameters()).device)
-        dev = eng.device
-        forced = x["duration"].to(dev) if force_duration else None
-        mask = x["phoneme_mask"].to(dev) if "phoneme_mask" in x else None
-        r = eng.encode(x["phoneme"].to(dev), x["puncts"].to(dev), style_embed.to(dev), mask, forced)
-        if len(r["mel_len_host"]) != 1:
-            raise RuntimeError("inference_ex is the batch-1 path (model.py:325); use forward() for batches")
-        mel_len = int(r["mel_len_host"][0])
-        feats = eng.length_regulate(r["xprime"], r["duration_rounded"], r["L_max"])
-        pe_time = time.time()
-        _, mel = eng.decode(feats, style_embed.to(dev), mel_len=r["mel_len"], want_blc=False)
-        dec_time = time.time()
-        if mel_len < self._min_mel_len:
-            padded = torch.zeros((1, mel.shape[1], self._min_mel_len), device=dev, dtype=mel.dtype)
-            padded[:, :, :mel_len] = mel
-        else:
-            self._min_mel_len = max(self._min_mel_len, mel_len)
-            padded = mel
-        if vocoder_chunk_frames:
-            wav = eng.vocode_chunked(padded, int(vocoder_chunk_frames), 14)[0, 0]
-        else:
-            wav = eng.vocode(padded)[0, 0]
-        if self._verbose:
-            torch.cuda.synchronize(dev)
-            now = time.time()
-            print(f"synthesis timing stats: pe={pe_time - start_time}s, dec={dec_time - pe_time}s, "
-                  f"meldec={now - dec_time}s")
-        return wav[: mel_len * self._hop_length], mel_len, r["log_duration"], mel[0, :, :mel_len]
+        return engine_inference_ex(self, eng, x, style_embed, force_duration=force_duration,
+                                   vocoder_chunk_frames=vocoder_chunk_frames)
 
     def inference(self, x, style_embed, normalize_before=True):
         wav, mel_len, log_duration, _ = self.inference_ex(x=x, style_embed=style_embed,
                                                            normalize_before=normalize_before)
         return wav, mel_len, log_duration
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the two eval-mode call sequences over the C ABI, shared by the mirror class above and by zerovox_b200.patch() (which
+# rebinds them on the reference's own ZeroVox class)
+# ---------------------------------------------------------------------------------------------------------------------
+def engine_forward(eng, x, force_duration=False, *, pad_to=None, zero_padded_mel=None):
+    """Batched eval forward (model.py:260-306).  Returns (wav [B, L_max*hop], mel [B, n_mels, L_max], mel_len int64 [B],
+    log_duration [B, T]) — the tuple utils/export_hifigan.py:109-151 consumes.  The reference's own eval tail
+    (model.py:298-304) is ParallelWaveGAN leftover code that raises with hifigan.Generator; the intended semantics
+    ``wav = _meldec(mel.transpose(1,2)).squeeze(1)`` are built.
+
+    Keyword-only extensions used by zerovox_b200.parallel so that a shard reproduces the unsharded batch: ``pad_to`` — an
+    int, or a callable ``(local_L_max, mel_len_host) -> L`` — is the frame count to pad the batch to (>= its own maximum);
+    ``zero_padded_mel`` overrides the reference's batch-size dependent zero-fill of padded mel frames (model.py:283-285
+    applies it iff a mel mask exists and B > 1 — B being the GLOBAL batch there)."""
+    dev = eng.device
+    style = eng.spkemb(x["ref_mel"].to(dev, non_blocking=True))
+    mask = x["phoneme_mask"].to(dev, non_blocking=True) if "phoneme_mask" in x else None
+    forced = x["duration"].to(dev, non_blocking=True) if force_duration else None
+    r = eng.encode(x["phoneme"].to(dev, non_blocking=True), x["puncts"].to(dev, non_blocking=True), style, mask,
+                   forced, need_lengths=True)
+    L = r["L_max"]
+    if pad_to is not None:
+        L = max(L, int(pad_to(L, r["mel_len_host"]) if callable(pad_to) else pad_to))
+    feats = eng.length_regulate(r["xprime"], r["duration_rounded"], L)
+    # fs2.py:748, 772 + model.py:264-285: the mel mask is x['mel_mask'] when the collated batch carries one (the
+    # utils/export_hifigan.py flow, forced durations), else the one derived from predicted durations; with forced
+    # durations and no 'mel_mask' there is none.  The mel is zero-filled at padded frames iff a mask exists and B > 1.
+    dec_mask = None
+    if force_duration and "mel_mask" in x:
+        dec_mask = x["mel_mask"].to(dev, non_blocking=True)
+        if dec_mask.shape[1] != L:
+            raise RuntimeError(f"x['mel_mask'] covers {dec_mask.shape[1]} frames, the durations give {L} "
+                               "(the reference fails on this batch too: fs2.py:772, model.py:279)")
+    zero_pad = zero_padded_mel
+    if zero_pad is None:
+        zero_pad = ((not force_duration) or "mel_mask" in x) and feats.shape[0] > 1
+    _, mel = eng.decode(feats, style, mask=dec_mask, mel_len=r["mel_len"], zero_padded_mel=bool(zero_pad), want_blc=False)
+    wav = eng.vocode(mel).squeeze(1)
+    return wav, mel, r["mel_len"], r["log_duration"]
+
+
+def engine_inference_ex(owner, eng, x, style_embed, force_duration=False, *, vocoder_chunk_frames=None):
+    """Batch-1 path (model.py:308-347): zero-pads the mel to the stateful ``owner._min_mel_len`` before vocoding and trims
+    the waveform to mel_len*hop.  Returns (wav, mel_len, log_duration, mel [n_mels, mel_len]).
+    ``vocoder_chunk_frames`` (keyword-only extension, long-form inputs): vocode in chunks of that many mel frames with a
+    14-frame discarded halo — same waveform, bounded workspace."""
+    start_time = time.time()
+    dev = eng.device
+    forced = x["duration"].to(dev) if force_duration else None
+    mask = x["phoneme_mask"].to(dev) if "phoneme_mask" in x else None
+    r = eng.encode(x["phoneme"].to(dev), x["puncts"].to(dev), style_embed.to(dev), mask, forced)
+    if len(r["mel_len_host"]) != 1:
+        raise RuntimeError("inference_ex is the batch-1 path (model.py:325); use forward() for batches")
+    mel_len = int(r["mel_len_host"][0])
+    feats = eng.length_regulate(r["xprime"], r["duration_rounded"], r["L_max"])
+    pe_time = time.time()
+    _, mel = eng.decode(feats, style_embed.to(dev), mel_len=r["mel_len"], want_blc=False)
+    dec_time = time.time()
+    if mel_len < owner._min_mel_len:
+        padded = torch.zeros((1, mel.shape[1], owner._min_mel_len), device=dev, dtype=mel.dtype)
+        padded[:, :, :mel_len] = mel
+    else:
+        owner._min_mel_len = max(owner._min_mel_len, mel_len)
+        padded = mel
+    if vocoder_chunk_frames:
+        wav = eng.vocode_chunked(padded, int(vocoder_chunk_frames), 14)[0, 0]
+    else:
+        wav = eng.vocode(padded)[0, 0]
+    if getattr(owner, "_verbose", False):
+        torch.cuda.synchronize(dev)
+        now = time.time()
+        print(f"synthesis timing stats: pe={pe_time - start_time}s, dec={dec_time - pe_time}s, "
+              f"meldec={now - dec_time}s")
+    return wav[: mel_len * owner._hop_length], mel_len, r["log_duration"], mel[0, :, :mel_len]
