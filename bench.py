@@ -60,6 +60,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-config4", action="store_true")
+    p.add_argument("--e2e-groups", type=int, default=4,
+                   help="N > 1 e2e: vocoder delivery groups per rank (gather + D2H of group i overlap the vocoding of group i+1)")
     return p.parse_args()
 
 
@@ -390,10 +392,11 @@ def main():
 
     last = {}
 
-    def step_sharded(x, events=None):
+    def step_sharded(x, events=None, groups=1, host_out=None):
         with torch.no_grad():
             last["r"] = sharded_forward(model, x, force_duration=True, device=dev, hop_length=cfg.hop_length,
-                                        n_mels=cfg.n_mels, ragged=True, spec=spec, events=events)
+                                        n_mels=cfg.n_mels, ragged=True, spec=spec, events=events, vocoder_groups=groups,
+                                        host_out=host_out)
 
     step_device = step_replica if world == 1 else (lambda: step_sharded(xg_dev))
     for _ in range(W):
@@ -460,13 +463,10 @@ def main():
                 wav_host = torch.empty(sum(e - s for s, e in last["r"].wav_segments()), dtype=torch.float32).pin_memory()
                 d2h = wav_host.numel() * 4
 
-            def step_e2e():
-                step_sharded(xg_host if rank == 0 else None)
-                if rank == 0:
-                    o = 0
-                    for s, e in last["r"].wav_segments():   # the valid samples of every utterance; lengths are host-known
-                        wav_host[o:o + e - s].copy_(last["r"].buf[s:e], non_blocking=True)
-                        o += e - s
+            def step_e2e(groups=args.e2e_groups):
+                # pinned host inputs in, the valid samples of every utterance out to pinned host memory (rank-major, back to
+                # back; lengths are host-known): the copies ride the side stream group by group
+                step_sharded(xg_host if rank == 0 else None, groups=groups, host_out=wav_host)
                 torch.cuda.synchronize(dev)
         for _ in range(2):
             step_e2e()
@@ -477,6 +477,14 @@ def main():
             step_e2e()
         t_e2e = (time.perf_counter() - t0) / args.steps
         e2e = {"ms": t_e2e * 1e3, "h2d": h2d, "d2h": d2h}
+        if world > 1 and args.e2e_groups > 1:            # the same path without the pipelined delivery, for comparison
+            for _ in range(2):
+                step_e2e(1)
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_e2e(1)
+            e2e["ms_unpipelined"] = (time.perf_counter() - t0) / args.steps * 1e3
 
     # ---- config 4 variant (N > 1): ragged T_i ~ U{64..192}, alternating EN / DE weight sets, sharded ------------------
     c4 = None
@@ -502,11 +510,14 @@ def main():
 
     # ---- max over ranks -------------------------------------------------------------------------------------------------
     if dist:
-        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, ms_rep or 0.0, c4["ms"] if c4 else 0.0], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, ms_rep or 0.0, c4["ms"] if c4 else 0.0,
+                          (e2e or {}).get("ms_unpipelined", 0.0)], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_rep = float(t[0]), float(t[2])
         if e2e:
             e2e["ms"] = float(t[1])
+            if "ms_unpipelined" in e2e:
+                e2e["ms_unpipelined"] = float(t[4])
         if c4:
             c4["ms"] = float(t[3])
         fr = torch.tensor([float(frames_local)], device=dev, dtype=torch.float64)
@@ -537,6 +548,10 @@ def main():
     if e2e:
         line["e2e"] = {"value": audio_seconds(frames, cfg) / (e2e["ms"] / 1e3), "unit": UNIT,
                        "ms_per_step": e2e["ms"], "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
+        if "ms_unpipelined" in e2e:
+            line["e2e"].update({"delivery_groups": args.e2e_groups, "ms_per_step_unpipelined": e2e["ms_unpipelined"],
+                                "note": "every rank vocodes in delivery_groups utterance groups; the gather-v and the D2H copy of a "
+                                        "group overlap the next group's kernels (sharded_forward(vocoder_groups=, host_out=))"})
     if world > 1:
         r = last["r"]
         ph = {}

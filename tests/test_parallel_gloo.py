@@ -21,7 +21,7 @@ from zerovox_b200.parallel import mixed_language_forward, partition, sharded_for
 HOP, NMEL = 4, 6
 
 
-def fake_model(x, force_duration=False, pad_to=None, zero_padded_mel=None):
+def fake_model(x, force_duration=False, pad_to=None, zero_padded_mel=None, vocoder_groups=None, on_group=None):
     """Per-utterance deterministic function of the inputs (so sharding must not change it).  Like the reference
     (model.py:283-285) the padded frames are zero-filled only when a mel mask exists and the batch has more than one
     utterance — otherwise they hold a length-dependent non-zero pattern, so a shard that decides this from its LOCAL batch
@@ -44,6 +44,10 @@ def fake_model(x, force_duration=False, pad_to=None, zero_padded_mel=None):
     inside_w = tw < (mel_len * HOP)[:, None]
     wav = torch.where(inside_w, torch.sin(base + tw * 0.01), torch.zeros(()) if zero else torch.cos(tw - L * HOP) * torch.ones(n, 1))
     logd = torch.log1p(dur.float())
+    if on_group is not None:
+        from zerovox_b200.tts.model import group_bounds
+        for i, (g0, g1) in enumerate(group_bounds(n, vocoder_groups)):
+            on_group(i, g0, g1, wav, mel, mel_len)
     return wav, mel, mel_len, logd
 
 
@@ -64,7 +68,7 @@ def make_batch(B, T, T_ref, seed, ragged, forced):
     return x
 
 
-def fake_model_de(x, force_duration=False, pad_to=None, zero_padded_mel=None):
+def fake_model_de(x, force_duration=False, pad_to=None, zero_padded_mel=None, **kw):
     """A second 'weight set': same signature, different function of the inputs (and longer utterances)."""
     wav, mel, mel_len, logd = fake_model(dict(x, puncts=x["puncts"] + 1), force_duration=force_duration, pad_to=pad_to,
                                          zero_padded_mel=True)
@@ -180,9 +184,14 @@ def _worker(rank, world, port, cases, q):
                     x["mel_mask"].shape[1] if (rank == 0 and mel_mask) else 0,
                     int(((not forced) or mel_mask) and B > 1), 0, 0]]
             dist.broadcast_object_list(box, src=0)
+            host = torch.zeros(B * T * 7 * HOP + 64) if rank == 0 else None
             rb = sharded_forward(fake_model, x, force_duration=forced, device="cpu", hop_length=HOP, n_mels=NMEL,
-                                 ragged=True, spec=box[0])
+                                 ragged=True, spec=box[0], vocoder_groups=3, host_out=host)
             if rank == 0:
+                o = 0
+                for i, n in enumerate(ref[2].tolist()):     # host_out: the valid waveforms back to back, utterance order
+                    assert torch.equal(host[o:o + n * HOP], ref[0][i, : n * HOP]), f"host_out utterance {i}"
+                    o += n * HOP
                 assert rb.B == B and len(rb.wav_segments()) <= world and rb.gather_bytes % 4 == 0
                 for i, n in enumerate(ref[2].tolist()):
                     assert torch.equal(rb.wav(i), ref[0][i, : n * HOP]) and torch.equal(rb.mel(i), ref[1][i, :, :n])

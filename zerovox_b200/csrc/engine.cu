@@ -579,7 +579,7 @@ class Engine {
     void pack_vocoder_tc() {
         hg_tc_ok = false;
         hg_stage_kind.clear(); hg_ups_tc_w.clear(); hg_ups_tc_b.clear(); hg_c1_tc.clear(); hg_c2_tc.clear();
-        hg_c1_poly.clear(); hg_c2_poly.clear();
+        hg_c1_poly.clear(); hg_c2_poly.clear(); hg_c1_pair.clear(); hg_c2_pair.clear();
         const int C0 = cfg.hg_upsample_initial_channel, nk = cfg.hg_num_kernels, nd = cfg.hg_num_dilations;
         if (C0 % 4 != 0 || C0 < 8 || cfg.n_mels % 4 != 0) return;
         for (int i = 0; i < cfg.hg_num_upsamples; ++i) {
@@ -622,20 +622,24 @@ class Engine {
                 const int rk = cfg.hg_resblock_kernel_sizes[j];
                 for (int di = 0; di < nd; ++di, ++ci) {
                     const int dl = cfg.hg_resblock_dilation_sizes[j][di];
-                    auto pack = [&](const std::string& key, int dil, std::vector<float*>& poly) {
+                    const bool pair_ok = cfg.hg_resblock == 1 && hg_stage_kind[(size_t)i] == 1 &&
+                                         voc_pair_supported(cout, rk, cfg.hg_resblock_dilation_sizes[j], nd);
+                    auto pack = [&](const std::string& key, int dil, std::vector<float*>& poly, std::vector<float*>& pairw) {
                         const HostTensor& t = W("_meldec." + key + ".weight", {cout, cout, rk});
                         if (hg_stage_kind[(size_t)i] != 1) {
-                                poly.push_back(nullptr);
+                            poly.push_back(nullptr);
+                            pairw.push_back(nullptr);
                             return upload(tap_major(t));
                         }
+                        pairw.push_back(pair_ok ? upload(voc_pair_pack_weight(t.data.data(), cout, rk)) : nullptr);
                         poly.push_back(upload(voc_poly_pack_weight(t.data.data(), cout, rk, dil)));
                         return upload(voc_pack_weight(t.data.data(), cout, cout, rk));
                     };
                     if (cfg.hg_resblock == 1) {
-                        hg_c1_tc.push_back(pack(p + ".convs1." + std::to_string(di), dl, hg_c1_poly));
-                        hg_c2_tc.push_back(pack(p + ".convs2." + std::to_string(di), 1, hg_c2_poly));
+                        hg_c1_tc.push_back(pack(p + ".convs1." + std::to_string(di), dl, hg_c1_poly, hg_c1_pair));
+                        hg_c2_tc.push_back(pack(p + ".convs2." + std::to_string(di), 1, hg_c2_poly, hg_c2_pair));
                     } else {
-                        hg_c1_tc.push_back(pack(p + ".convs." + std::to_string(di), dl, hg_c1_poly));
+                        hg_c1_tc.push_back(pack(p + ".convs." + std::to_string(di), dl, hg_c1_poly, hg_c1_pair));
                     }
                 }
             }
@@ -1190,8 +1194,10 @@ class Engine {
                         const int dl = cfg.hg_resblock_dilation_sizes[j][di];
                         if (pair) {
                             a.steps[a.nsteps].w = hg_c1_tc[ci]; a.steps[a.nsteps].w_poly = hg_c1_poly[ci];
+                            a.steps[a.nsteps].w_pair = hg_c1_pair[ci];
                             a.steps[a.nsteps].b = hg_c1[ci].b; a.steps[a.nsteps].dil = dl; a.steps[a.nsteps++].kind = 0;
                             a.steps[a.nsteps].w = hg_c2_tc[ci]; a.steps[a.nsteps].w_poly = hg_c2_poly[ci];
+                            a.steps[a.nsteps].w_pair = hg_c2_pair[ci];
                             a.steps[a.nsteps].b = hg_c2[ci].b; a.steps[a.nsteps].dil = 1; a.steps[a.nsteps++].kind = 1;
                         } else {
                             a.steps[a.nsteps].w = hg_c1_tc[ci]; a.steps[a.nsteps].w_poly = hg_c1_poly[ci];
@@ -1207,7 +1213,9 @@ class Engine {
                     static const bool dbg_times = env_set("ZVX_VOC_DBG");  // debug builds: print one CTA's phase timestamps
                     long long* dbg = nullptr;
                     if (dbg_times) { dbg = ws.get<long long>(64); ZVX_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 64 * 8, st)); a.dbg = dbg; }
-                    if (no_poly || !voc_poly_tc(a, st)) voc_resblock_tc(a, st);
+                    static const bool no_pair = env_set("ZVX_NO_PAIR");   // A/B switch (debug builds): skip voc_pair.cu
+                    if (no_pair || !pair || !voc_pair_tc(a, st))
+                        if (no_poly || !voc_poly_tc(a, st)) voc_resblock_tc(a, st);
                     prof.end(st);
                     if (dbg) {
                         long long h[64];
@@ -1383,7 +1391,7 @@ class Engine {
     bool hg_tc_ok = false;
     std::vector<int> hg_stage_kind;   // per upsample stage: 1 = fused pair kernel, 2 = generic tcgen05 implicit GEMM
     float *hg_pre_tc = nullptr, *hg_post_tc = nullptr;
-    std::vector<float*> hg_ups_tc_w, hg_ups_tc_b, hg_c1_tc, hg_c2_tc, hg_c1_poly, hg_c2_poly;
+    std::vector<float*> hg_ups_tc_w, hg_ups_tc_b, hg_c1_tc, hg_c2_tc, hg_c1_poly, hg_c2_poly, hg_c1_pair, hg_c2_pair;
 };
 
 }  // namespace zvx

@@ -105,6 +105,7 @@ struct VocResArgs {
     struct Step {
         const float* w = nullptr;        // packed image of voc_pack_weight (voc_res.cu)
         const float* w_poly = nullptr;   // packed image of voc_poly_pack_weight (voc_poly.cu), optional
+        const float* w_pair = nullptr;   // packed image of voc_pair_pack_weight (voc_pair.cu), optional
         const float* b = nullptr; int dil = 1; int kind = 1;
     };
     const float* x = nullptr; long long x_bs = 0;      // raw input [B][T][C], batch stride in elements
@@ -124,6 +125,11 @@ void voc_resblock_tc(const VocResArgs& a, cudaStream_t st);
 bool voc_poly_supported(int C, int k, const int* dils, int nd, bool pair);
 bool voc_poly_tc(const VocResArgs& a, cudaStream_t st);
 std::vector<float> voc_poly_pack_weight(const float* w, int C, int k, int dil);
+// ResBlock1 in the residue-major / trimmed-Toeplitz formulation, two CTAs per SM where they fit (voc_pair.cu): the first
+// choice for C in {8, 16, 32}; returns false (nothing launched) outside its plan, callers then fall back to voc_poly_tc.
+bool voc_pair_supported(int C, int k, const int* dils, int nd);
+bool voc_pair_tc(const VocResArgs& a, cudaStream_t st);
+std::vector<float> voc_pair_pack_weight(const float* w, int C, int k);
 
 // conv_post on channel-last input: wav[b,t] = tanh(bias + sum_{j,c} w[j][c] * lrelu(x[b, t+j-(k-1)/2, c], slope))
 void conv_post_cl(const float* x, long long x_bs, const float* w /*[k][C]*/, const float* bias, int B, int T, int C,

@@ -269,13 +269,20 @@ class Engine:
                         "zvx_decode")
         return blc, bcl
 
-    def vocode(self, mel_bcl: torch.Tensor) -> torch.Tensor:
-        """hifigan.Generator.forward: [B, n_mels, L] -> [B, 1, L*hop]."""
+    def vocode(self, mel_bcl: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """hifigan.Generator.forward: [B, n_mels, L] -> [B, 1, L*hop] (written into ``out`` when given: a contiguous
+        [B, 1, L*hop] or [B, L*hop] fp32 tensor, e.g. a batch slice of a larger result)."""
         m = self._dev(mel_bcl, torch.float32, "mel")
         B, Cm, L = m.shape
         if Cm != self.cfg.n_mels:
             raise RuntimeError(f"mel has {Cm} channels, vocoder expects {self.cfg.n_mels}")
-        wav = torch.empty((B, 1, L * self.cfg.hop_length), device=self.device, dtype=torch.float32)
+        if out is None:
+            wav = torch.empty((B, 1, L * self.cfg.hop_length), device=self.device, dtype=torch.float32)
+        else:
+            if out.device != self.device or out.dtype != torch.float32 or not out.is_contiguous() or \
+                    out.numel() != B * L * self.cfg.hop_length:
+                raise RuntimeError("vocode(out=): need a contiguous fp32 tensor of B * L * hop elements on the engine's device")
+            wav = out
         with torch.cuda.device(self.device):
             self._check(self.lib.zvx_vocode(self._h, _ptr(m), B, L, _ptr(wav), self._stream()), "zvx_vocode")
         return wav

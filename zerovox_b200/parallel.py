@@ -169,7 +169,7 @@ def _row_layout(T, T_ref, n_mels_in, has_mask, has_dur, Lm):
 def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force_duration: bool = False,
                     group=None, device: torch.device | str | None = None, hop_length: int = 256, n_mels: int = 80,
                     tails: str = "valid", ragged: bool = False, spec: Sequence[int] | None = None,
-                    events: dict | None = None):
+                    events: dict | None = None, vocoder_groups: int = 1, host_out: torch.Tensor | None = None):
     """Run ``model(x_shard, force_duration=..., pad_to=..., zero_padded_mel=...)`` on every rank of ``group`` for the
     global batch ``x`` held by rank 0 (other ranks pass ``x=None``).  ``model`` is a ``ZeroVox`` (or any callable with
     that signature returning ``(wav [n, L*hop], mel [n, n_mels, L], mel_len int64 [n], log_duration [n, T])``).
@@ -178,6 +178,12 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
     the global L_pad (``ragged=True``: the :class:`RaggedBatch` itself, no expansion); ``None`` on the other ranks.
     ``spec``: the 12-word header when every rank already knows it (skips the broadcast); ``events``: a dict that
     receives CUDA events at the phase boundaries (bench.py).
+
+    Pipelined delivery: with ``vocoder_groups`` = G > 1 every rank vocodes its block in G utterance groups and ships each
+    group's waveforms as soon as they are enqueued (the gather-v becomes G grouped ncclSend/ncclRecv exchanges on a side
+    stream, overlapping the next group's kernels); with ``host_out`` (rank 0: a pinned fp32 buffer) the gathered waveforms
+    are also copied to the host group by group — rank-major, utterance order, valid samples back to back — so that only the
+    last group's transfer is exposed.
     """
     if tails not in ("valid", "padded"):
         raise ValueError("tails must be 'valid' or 'padded'")
@@ -258,8 +264,13 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
         xs = {k: v for k, v in x.items() if isinstance(v, torch.Tensor)}
     mark("scattered")
 
-    # ---- forward on the block, at the global frame count ---------------------------------------------------------------
-    lens_box = {}
+    # ---- forward on the block, at the global frame count; results shipped group by group --------------------------------
+    from .tts.model import group_bounds
+    G = max(1, int(vocoder_groups or 1))
+    cuda = dev.type == "cuda"
+    side = torch.cuda.Stream(dev) if cuda and (G > 1 or host_out is not None) else None
+    root = 0 if (group is None or not multi) else dist.get_global_rank(group, 0)
+    lens_box, st = {}, {"groups_done": 0}
 
     def pad_to(local_lmax: int, mel_len_host: Sequence[int]) -> int:
         lens_box["mine"] = [int(v) for v in mel_len_host]
@@ -267,69 +278,149 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
             return max(L_hint, local_lmax)
         return _exchange_lengths(lens_box, nb, world, dev, group)
 
-    if n_mine > 0:
-        wav, mel, mel_len, logd = model(xs, force_duration=has_dur, pad_to=pad_to, zero_padded_mel=bool(zero_pad))
-        L = mel.shape[2]
-    else:                                              # more ranks than utterances: still part of every collective
-        if not has_dur:
-            _exchange_lengths({"mine": []}, nb, world, dev, group)
-        wav = mel = mel_len = logd = None
-        L = 0
-    mark("forward")
-    my_true = lens_box.get("mine", [])
-    if n_mine > 0 and len(my_true) != n_mine:          # a model that never called pad_to (not ZeroVox): read the lengths
-        my_true = [int(v) for v in mel_len.cpu().tolist()]
-    if not multi and not has_dur:
-        lens_box["all"] = list(my_true)
-
-    # ---- ONE gather-v of the valid results, received in place ----------------------------------------------------------
-    my_ship = [L] * n_mine if tails_padded else my_true
-    F = sum(my_ship)
-    my_size = -(-(F * (hop_length + n_mels) + n_mine * T) // _ALIGN) * _ALIGN
-    out = None
-    if rank == 0:
-        true_all = [int(v) for v in (all_lens if has_dur else lens_box["all"])]
-        L_glob = max(L, max(true_all) if true_all else 0) if world > 1 else L
-        ship_all = [L_glob] * B if tails_padded else true_all
-        wav_off, mel_off, logd_off, seg, total = _layout(counts, ship_all, T, hop_length, n_mels)
-        buf = torch.empty(total, dtype=torch.float32, device=dev)
-        out = RaggedBatch(buf=buf, B=B, T=T, L=L_glob, hop=hop_length, n_mels=n_mels, lens=ship_all, mel_len_host=true_all,
-                          wav_off=wav_off, mel_off=mel_off, logd_off=logd_off, seg=seg,
-                          gather_bytes=4 * sum(s[2] for s in seg[1:]), events=events if events is not None else {})
-        mine = buf[:my_size]
-    else:
-        mine = torch.empty(my_size, dtype=torch.float32, device=dev)
-    if n_mine > 0:
-        lens_d = mel_len.to(torch.int64) if not tails_padded else torch.full((n_mine,), L, dtype=torch.int64, device=dev)
-        start = torch.cumsum(lens_d, 0) - lens_d
-        w_offs, m_offs = start * hop_length, start * n_mels + F * hop_length
-        acc, wl, ml = 0, [], []
-        for v in my_ship:
-            wl.append(acc * hop_length)
-            ml.append(F * hop_length + acc * n_mels)
-            acc += v
-        _ragged_copy(True, wav.to(torch.float32).contiguous(), mine, lens_d, w_offs, my_ship, wl, 1, hop_length)
-        _ragged_copy(True, mel.to(torch.float32).contiguous(), mine, lens_d, m_offs, my_ship, ml, n_mels, 1)
-        d0 = F * (hop_length + n_mels)
-        mine[d0: d0 + n_mine * T].view(n_mine, T).copy_(logd)
-    mark("result_packed")
-    if multi:
-        root = 0 if group is None else dist.get_global_rank(group, 0)
-        ops = []
+    def prepare(L, mel_len):
+        """Everything that needs the frame counts: shipped lengths, offsets, rank 0's result buffer (lazily, at the first
+        finished group: predicted durations are only known after the encoder)."""
+        my_true = lens_box.get("mine", [])
+        if n_mine > 0 and len(my_true) != n_mine:      # a model that never called pad_to (not ZeroVox): read the lengths
+            my_true = [int(v) for v in mel_len.cpu().tolist()]
+        st["my_ship"] = [L] * n_mine if tails_padded else my_true
+        st["F"] = F = sum(st["my_ship"])
+        st["my_size"] = -(-(F * (hop_length + n_mels) + n_mine * T) // _ALIGN) * _ALIGN
+        st["L"] = L
         if rank == 0:
-            for r in range(1, world):
-                s0, _, size = out.seg[r]
-                if size:
-                    ops.append(dist.P2POp(dist.irecv, out.buf[s0: s0 + size], r if group is None else dist.get_global_rank(group, r), group))
-        elif my_size:
-            ops.append(dist.P2POp(dist.isend, mine, root, group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+            if has_dur:
+                true_all = [int(v) for v in all_lens]
+            elif multi:
+                true_all = [int(v) for v in lens_box["all"]]
+            else:
+                true_all = list(my_true)
+            ship_all = [L] * B if tails_padded else true_all
+            wav_off, mel_off, logd_off, seg, total = _layout(counts, ship_all, T, hop_length, n_mels)
+            buf = torch.empty(total, dtype=torch.float32, device=dev)
+            st["out"] = RaggedBatch(buf=buf, B=B, T=T, L=L, hop=hop_length, n_mels=n_mels, lens=ship_all, mel_len_host=true_all,
+                                    wav_off=wav_off, mel_off=mel_off, logd_off=logd_off, seg=seg,
+                                    gather_bytes=4 * sum(x_[2] for x_ in seg[1:]), scatter_bytes=scatter_bytes,
+                                    events=events if events is not None else {})
+            st["mine"] = buf[:st["my_size"]]
+            # host offsets of every rank's waveform segment (rank-major, contiguous)
+            ho, acc = [], 0
+            for (_, w, _) in seg:
+                ho.append(acc)
+                acc += w
+            st["host_seg"] = ho
+            if host_out is not None and host_out.numel() < acc:
+                raise ValueError(f"host_out holds {host_out.numel()} samples, the gathered waveforms need {acc}")
+        else:
+            st["mine"] = torch.empty(st["my_size"], dtype=torch.float32, device=dev)
+        if n_mine > 0:
+            lens_d = mel_len.to(torch.int64) if not tails_padded else torch.full((n_mine,), L, dtype=torch.int64, device=dev)
+            start = torch.cumsum(lens_d, 0) - lens_d
+            st["lens_d"], st["w_offs"], st["m_offs"] = lens_d, start * hop_length, start * n_mels + F * hop_length
+            acc, wl, ml = 0, [], []
+            for v in st["my_ship"]:
+                wl.append(acc * hop_length)
+                ml.append(F * hop_length + acc * n_mels)
+                acc += v
+            st["wl"], st["ml"], st["cum"] = wl, ml, wl + [acc * hop_length]
+
+    def ship(parts):
+        """One grouped NCCL exchange: rank 0 receives ``parts`` = [(rank, start, end)] element ranges of every peer's buffer
+        in place; a peer sends its own range.  Then (rank 0, host_out) the device-to-host copies of the waveform ranges.
+        Runs on the side stream when there is one, so the next group's kernels overlap it."""
+        def body():
+            ops = []
+            if multi:
+                for (r, a0, a1, is_wav) in parts:
+                    if a1 <= a0:
+                        continue
+                    if rank == 0 and r != 0:
+                        s0 = st["out"].seg[r][0]
+                        ops.append(dist.P2POp(dist.irecv, st["out"].buf[s0 + a0: s0 + a1],
+                                              r if group is None else dist.get_global_rank(group, r), group))
+                    elif rank == r and r != 0:
+                        ops.append(dist.P2POp(dist.isend, st["mine"][a0:a1], root, group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            if rank == 0 and host_out is not None:
+                for (r, a0, a1, is_wav) in parts:
+                    if is_wav and a1 > a0:
+                        s0, h0 = st["out"].seg[r][0], st["host_seg"][r]
+                        host_out[h0 + a0: h0 + a1].copy_(st["out"].buf[s0 + a0: s0 + a1], non_blocking=True)
+        if side is None:
+            body()
+        else:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                body()
+
+    def peer_wav_range(r, i):
+        """Element range (inside rank r's segment) of the waveforms of rank r's i-th vocoder group, from the lengths rank 0
+        holds; None when rank r has no such group."""
+        gb = group_bounds(counts[r], G) if counts[r] else []
+        if i >= len(gb):
+            return None
+        base = sum(counts[:r])
+        ship_all = st["out"].lens
+        a0 = sum(ship_all[base: base + gb[i][0]]) * hop_length
+        a1 = sum(ship_all[base: base + gb[i][1]]) * hop_length
+        return a0, a1
+
+    def on_group(i, g0, g1, wav, mel, mel_len):
+        if "mine" not in st:
+            prepare(mel.shape[2], mel_len)
+        if g1 > g0:
+            _ragged_copy(True, wav[g0:g1].to(torch.float32).contiguous(), st["mine"], st["lens_d"][g0:g1], st["w_offs"][g0:g1],
+                         st["my_ship"][g0:g1], st["wl"][g0:g1], 1, hop_length)
+        if rank == 0:
+            parts = []
+            for r in range(world):
+                rng = peer_wav_range(r, i)
+                if rng:
+                    parts.append((r, rng[0], rng[1], True))
+        else:
+            parts = [(rank, st["cum"][g0], st["cum"][g1], True)]
+        ship(parts)
+        st["groups_done"] += 1
+
+    kw = dict(vocoder_groups=G, on_group=on_group) if (G > 1) else {}
+    if n_mine > 0:
+        wav, mel, mel_len, logd = model(xs, force_duration=has_dur, pad_to=pad_to, zero_padded_mel=bool(zero_pad), **kw)
+        L = mel.shape[2]
+        mark("forward")
+        if st["groups_done"] == 0:                     # the model vocoded in one piece (or ignores the group protocol)
+            for i, (g0, g1) in enumerate(group_bounds(n_mine, G)):
+                on_group(i, g0, g1, wav, mel, mel_len)
+        # the small tail of the segment: valid mel frames + log-durations
+        F = st["F"]
+        _ragged_copy(True, mel.to(torch.float32).contiguous(), st["mine"], st["lens_d"], st["m_offs"], st["my_ship"], st["ml"],
+                     n_mels, 1)
+        d0 = F * (hop_length + n_mels)
+        st["mine"][d0: d0 + n_mine * T].view(n_mine, T).copy_(logd)
+    else:                                              # more ranks than utterances: still part of every collective
+        if not has_dur and multi:
+            _exchange_lengths({"mine": []}, nb, world, dev, group)
+        mark("forward")
+        prepare(0, None)
+    mark("result_packed")
+    if rank == 0:
+        # groups the other ranks have but rank 0's own loop did not reach (it has at least as many, so: none) + the tails
+        tails_parts = []
+        for r in range(world):
+            Fr = st["out"].seg[r][1]
+            tails_parts.append((r, Fr, st["out"].seg[r][2], False))
+        ship(tails_parts)
+    elif n_mine > 0:
+        ship([(rank, st["F"] * hop_length, st["my_size"], False)])
+    if side is not None:
+        torch.cuda.current_stream(dev).wait_stream(side)
     mark("gathered")
     if rank != 0:
         return None
-    out.scatter_bytes = scatter_bytes
+    out = st["out"]
     return out if ragged else out.padded()
 
 

@@ -139,16 +139,18 @@ class ZeroVox(nn.Module):
         return model
 
     # forward -------------------------------------------------------------------------------------------
-    def forward(self, x, force_duration=False, normalize_before=True, *, pad_to=None, zero_padded_mel=None):
-        """Batched eval forward (model.py:260-306); see :func:`engine_forward` for the return tuple and the two
-        keyword-only extensions."""
+    def forward(self, x, force_duration=False, normalize_before=True, *, pad_to=None, zero_padded_mel=None,
+                vocoder_groups=None, on_group=None):
+        """Batched eval forward (model.py:260-306); see :func:`engine_forward` for the return tuple and the keyword-only
+        extensions."""
         if self.training:
             raise NotImplementedError("ZeroVox.forward in training mode is outside the zerovox_b200 hot path; "
                                       "zerovox_b200.patch() keeps training on the reference modules")
         if self._meldec is None:
             raise RuntimeError("ZeroVox.forward: no vocoder (_meldec is None)")
         eng = self._shared_ctx.get(next(self.parameters()).device)
-        return engine_forward(eng, x, force_duration=force_duration, pad_to=pad_to, zero_padded_mel=zero_padded_mel)
+        return engine_forward(eng, x, force_duration=force_duration, pad_to=pad_to, zero_padded_mel=zero_padded_mel,
+                              vocoder_groups=vocoder_groups, on_group=on_group)
 
     def inference_ex(self, x, style_embed, normalize_before=True, force_duration=False, *, vocoder_chunk_frames=None):
         """Batch-1 path (model.py:308-347); see :func:`engine_inference_ex`."""
@@ -166,7 +168,13 @@ class ZeroVox(nn.Module):
 # the two eval-mode call sequences over the C ABI, shared by the mirror class above and by zerovox_b200.patch() (which
 # rebinds them on the reference's own ZeroVox class)
 # ---------------------------------------------------------------------------------------------------------------------
-def engine_forward(eng, x, force_duration=False, *, pad_to=None, zero_padded_mel=None):
+def group_bounds(n: int, groups: int) -> list[tuple[int, int]]:
+    """Consecutive, nearly equal utterance groups (the vocoder's delivery units): [(first, end), ...]."""
+    groups = max(1, min(int(groups or 1), n))
+    return [(n * i // groups, n * (i + 1) // groups) for i in range(groups)]
+
+
+def engine_forward(eng, x, force_duration=False, *, pad_to=None, zero_padded_mel=None, vocoder_groups=None, on_group=None):
     """Batched eval forward (model.py:260-306).  Returns (wav [B, L_max*hop], mel [B, n_mels, L_max], mel_len int64 [B],
     log_duration [B, T]) — the tuple utils/export_hifigan.py:109-151 consumes.  The reference's own eval tail
     (model.py:298-304) is ParallelWaveGAN leftover code that raises with hifigan.Generator; the intended semantics
@@ -175,7 +183,10 @@ def engine_forward(eng, x, force_duration=False, *, pad_to=None, zero_padded_mel
     Keyword-only extensions used by zerovox_b200.parallel so that a shard reproduces the unsharded batch: ``pad_to`` — an
     int, or a callable ``(local_L_max, mel_len_host) -> L`` — is the frame count to pad the batch to (>= its own maximum);
     ``zero_padded_mel`` overrides the reference's batch-size dependent zero-fill of padded mel frames (model.py:283-285
-    applies it iff a mel mask exists and B > 1 — B being the GLOBAL batch there)."""
+    applies it iff a mel mask exists and B > 1 — B being the GLOBAL batch there).  ``vocoder_groups`` = G > 1 vocodes the
+    batch in G consecutive utterance groups (the generator treats utterances independently: same samples) and calls
+    ``on_group(i, first, end, wav, mel, mel_len)`` after enqueuing each, so that a caller can ship finished waveforms (NCCL
+    gather, device-to-host copy) while the next group is still being computed."""
     dev = eng.device
     style = eng.spkemb(x["ref_mel"].to(dev, non_blocking=True))
     mask = x["phoneme_mask"].to(dev, non_blocking=True) if "phoneme_mask" in x else None
@@ -199,7 +210,17 @@ def engine_forward(eng, x, force_duration=False, *, pad_to=None, zero_padded_mel
     if zero_pad is None:
         zero_pad = ((not force_duration) or "mel_mask" in x) and feats.shape[0] > 1
     _, mel = eng.decode(feats, style, mask=dec_mask, mel_len=r["mel_len"], zero_padded_mel=bool(zero_pad), want_blc=False)
-    wav = eng.vocode(mel).squeeze(1)
+    B = mel.shape[0]
+    if vocoder_groups and int(vocoder_groups) > 1 and B > 1:
+        wav = torch.empty((B, L * eng.cfg.hop_length), device=dev, dtype=torch.float32)
+        for i, (g0, g1) in enumerate(group_bounds(B, vocoder_groups)):
+            eng.vocode(mel[g0:g1], out=wav[g0:g1])
+            if on_group is not None:
+                on_group(i, g0, g1, wav, mel, r["mel_len"])
+    else:
+        wav = eng.vocode(mel).squeeze(1)
+        if on_group is not None:
+            on_group(0, 0, B, wav, mel, r["mel_len"])
     return wav, mel, r["mel_len"], r["log_duration"]
 
 
