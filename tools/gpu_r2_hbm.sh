@@ -1,0 +1,15 @@
+#!/bin/bash
+# Round 2: ncu --set full of the HBM-bound kernels north_star names, at their DECODER-sized launches of a configs[1] step
+# (layer_norm_kernel: launches 15..17 are the decoder's SCLN; attn_softmax_warp_kernel<8>: the decoder's; the gather: its one launch).
+set -x
+mkdir -p gpurun_out
+timeout 300 ncu --set full --clock-control none --profile-from-start off -k regex:layer_norm_kernel --launch-skip 14 -c 3 \
+    -o gpurun_out/ncu_ln python tools/prof_step.py > gpurun_out/ncu_ln.log 2>&1
+timeout 300 ncu --set full --clock-control none --profile-from-start off -k regex:attn_softmax_warp_kernel --launch-skip 4 -c 3 \
+    -o gpurun_out/ncu_sm python tools/prof_step.py > gpurun_out/ncu_sm.log 2>&1
+timeout 300 ncu --set full --clock-control none --profile-from-start off -k regex:length_regulate_gather_kernel -c 1 \
+    -o gpurun_out/ncu_lr python tools/prof_step.py > gpurun_out/ncu_lr.log 2>&1
+timeout 300 ncu --set full --clock-control none --profile-from-start off -k "regex:conv_post_cl_kernel|se_scale_add_relu_kernel|hw_sum_partial_kernel" -c 5 \
+    -o gpurun_out/ncu_misc python tools/prof_step.py > gpurun_out/ncu_misc.log 2>&1
+for k in ln sm lr misc; do ncu -i gpurun_out/ncu_$k.ncu-rep --page raw --csv > gpurun_out/ncu_hbm_${k}_raw.csv 2>/dev/null; rm -f gpurun_out/ncu_$k.ncu-rep; done
+python tools/ncu_summary.py gpurun_out/ncu_hbm_*_raw.csv > gpurun_out/ncu_hbm_summary.json; cat gpurun_out/ncu_hbm_summary.json | head -80

@@ -17,6 +17,8 @@ WANT = {
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
     "launch__registers_per_thread": "regs",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+    "lts__t_sector_hit_rate.pct": "l2_hit_pct",
 }
 UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0, "second": 1.0,
         "msecond": 1e-3, "usecond": 1e-6, "nsecond": 1e-9}
@@ -54,6 +56,8 @@ def main():
                 s["avg_" + key] = sum(e[key]) / len(e[key])
         if "dram_read" in e and "dram_write" in e:
             s["avg_dram_traffic_bytes"] = (sum(e["dram_read"]) + sum(e["dram_write"])) / e["launches"]
+            if "duration" in e:   # achieved HBM bandwidth of the kernel (DRAM bytes moved / kernel duration), GB/s
+                s["avg_dram_gbs"] = (sum(e["dram_read"]) + sum(e["dram_write"])) / sum(e["duration"]) / 1e9
         summ[k] = s
     json.dump(summ, sys.stdout, indent=1)
     print()

@@ -27,7 +27,19 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
     return d;
 }
 
+__device__ __forceinline__ uint64_t desc_sw(uint32_t saddr, uint32_t sbo_bytes, uint64_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+
+// mode 2: 32-byte swizzle (rows of 32 B = one K = 8 step, 8-row atoms of 256 B); mode 3: 64-byte swizzle (rows of 64 B, 512 B atoms)
 // mode 0: no-swizzle, every MMA reads a different row offset of A (the vocoder pattern); 1: 128B swizzle (GEMM pattern)
+__device__ int g_lbo_a = 1024, g_lbo_b = 0;   // no-swizzle mode: K-half distance of A / B in 16-byte rows (0: B uses N)
 __global__ void __launch_bounds__(128) bench(int N, int mode, int reps, int same_a, long long* out) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -45,19 +57,33 @@ __global__ void __launch_bounds__(128) bench(int N, int mode, int reps, int same
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     if (threadIdx.x == 0) {
         const uint32_t sA = sb, sW = sb + 128 * 1024;
-        const int Rp = 1024;
-        long long t0 = clock64();
-        for (int r = 0; r < reps; ++r) {
-            uint64_t da, db;
+        const int Rp = g_lbo_a;
+        // eight operand descriptor pairs built BEFORE the timed loop: the loop body is eight back-to-back tcgen05.mma with
+        // register operands, so the figure is the tensor pipe's, not the issuing thread's address arithmetic
+        uint64_t da[8], db[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
             if (mode == 0) {
-                const int row = same_a ? 0 : (r * 5) % 512;
-                da = desc_nosw(sA + row * 16, Rp);
-                db = desc_nosw(sW, N);
+                const int row = same_a ? 0 : (r * 37) % 512;
+                da[r] = desc_nosw(sA + row * 16, Rp);
+                db[r] = desc_nosw(sW, g_lbo_b ? g_lbo_b : N);
+            } else if (mode == 2) {
+                const int row = same_a ? 0 : (r * 37) % 512;
+                da[r] = desc_sw(sA + row * 32, 256, 6);
+                db[r] = desc_sw(sW, 256, 6);
+            } else if (mode == 3) {
+                const int row = same_a ? 0 : (r * 37) % 512;
+                da[r] = desc_sw(sA + row * 64, 512, 4) + (uint64_t)(2 * (r & 1));
+                db[r] = desc_sw(sW, 512, 4) + (uint64_t)(2 * (r & 1));
             } else {
-                da = desc_sw128(sA + (same_a ? 0 : ((r & 3) * 16384))) + (uint64_t)(2 * (r & 3));
-                db = desc_sw128(sW) + (uint64_t)(2 * (r & 3));
+                da[r] = desc_sw128(sA + (same_a ? 0 : ((r & 3) * 16384))) + (uint64_t)(2 * (r & 3));
+                db[r] = desc_sw128(sW) + (uint64_t)(2 * (r & 3));
             }
-            umma_tf32(tmem, da, db, idesc, r ? 1u : 0u);
+        }
+        long long t0 = clock64();
+        for (int r = 0; r < reps; r += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) umma_tf32(tmem, da[u], db[u], idesc, (r | u) ? 1u : 0u);
         }
         umma_commit(bar);
         mbar_wait(bar, 0);
@@ -112,6 +138,50 @@ int peak_mode() {
 
 int main(int argc, char** argv) {
     if (argc > 1 && std::string(argv[1]) == "--peak") return peak_mode();
+    if (argc > 1 && std::string(argv[1]) == "--swz") {
+        long long* d;
+        cudaMalloc(&d, 8);
+        cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        const int reps = 4096;
+        for (int mode : {2, 3})
+            for (int same = 0; same < 2; ++same)
+                for (int N : {16, 32, 64, 96, 128, 256}) {
+                    long long best = 1LL << 60;
+                    for (int it = 0; it < 3; ++it) {
+                        bench<<<148, 128, 202 * 1024 + 1024>>>(N, mode, reps, same, d);
+                        long long h = 0;
+                        if (cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { printf("error\n"); return 1; }
+                        if (h < best) best = h;
+                    }
+                    printf("layout=%s a=%s N=%3d : %.1f cycles/MMA\n", mode == 2 ? "sw32" : "sw64", same ? "same" : "moving (any row)", N,
+                           (double)best / reps);
+                }
+        return 0;
+    }
+    if (argc > 1 && std::string(argv[1]) == "--lbo") {
+        // no-swizzle K-major operands: does the distance between the two K-halves (bank alignment) change the MMA cost?
+        long long* d;
+        cudaMalloc(&d, 8);
+        cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        const int reps = 4096;
+        for (int lboa : {1024, 1025, 1026, 1028, 1032, 1040, 128, 132, 2324, 1162, 585}) {
+            for (int lbob : {0, 40, 104, 132, 129, 352}) {
+                for (int N : {64, 128}) {
+                    cudaMemcpyToSymbol(g_lbo_a, &lboa, 4);
+                    cudaMemcpyToSymbol(g_lbo_b, &lbob, 4);
+                    long long best = 1LL << 60;
+                    for (int it = 0; it < 3; ++it) {
+                        bench<<<148, 128, 202 * 1024 + 1024>>>(N, 0, reps, 0, d);
+                        long long h = 0;
+                        if (cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { printf("error\n"); return 1; }
+                        if (h < best) best = h;
+                    }
+                    printf("nosw lbo_a=%4d lbo_b=%4d N=%3d : %.1f cycles/MMA\n", lboa, lbob ? lbob : N, N, (double)best / reps);
+                }
+            }
+        }
+        return 0;
+    }
     long long* d;
     cudaMalloc(&d, 8);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -631,7 +631,8 @@ class Engine {
                             pairw.push_back(nullptr);
                             return upload(tap_major(t));
                         }
-                        pairw.push_back(pair_ok ? upload(voc_pair_pack_weight(t.data.data(), cout, rk)) : nullptr);
+                        pairw.push_back(pair_ok ? upload(voc_pair_pack_weight(t.data.data(), W("_meldec." + key + ".bias", {cout}).data.data(),
+                                                                              cout, rk)) : nullptr);
                         poly.push_back(upload(voc_poly_pack_weight(t.data.data(), cout, rk, dil)));
                         return upload(voc_pack_weight(t.data.data(), cout, cout, rk));
                     };

@@ -50,6 +50,9 @@ struct TcParams {
     int xr_wrap8;             // extra descriptor units when the tap index wraps to the next filter row (2-D mode)
     int row_w;                // accumulator rows per tile row (= TW except in 2-D tap-reuse mode)
     int mt, a_bytes;          // MMA M tiles (128 positions each) per CTA tile, bytes of the activation tile
+    int nbuf;                 // TMEM accumulator buffers: 2 (epilogue of tile i overlaps the MMAs of tile i+1) or 1 (mt * BN = 512 columns:
+                              // two full-width M tiles share every weight tile — half the L2 -> SM weight traffic per MMA, the bound of
+                              // the long-K convs — and the epilogue, short against a K = 4752 main loop, runs between tiles)
     int spin;                 // single-thread roles spin on their barriers (small tiles)
     int ug, unit_bytes;       // k-steps grouped per pipeline stage (small-N problems: fewer barrier round trips / commits)
     uint32_t idesc;
@@ -263,11 +266,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 int sa = 0;
                 uint32_t pa = 0;
                 for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++cnt) {
-                    const int buf = (int)(cnt & 1u);
-                    mbar_wait_sel(p.spin, tempty_bar(buf), ((cnt >> 1) & 1u) ^ 1u);
+                    const int buf = p.nbuf == 2 ? (int)(cnt & 1u) : 0;
+                    mbar_wait_sel(p.spin, tempty_bar(buf), ((p.nbuf == 2 ? (cnt >> 1) : cnt) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
                     uint32_t acc_tap = 0u;   // 0 for the first tap of the tile (fresh accumulators), 1 afterwards
+                    // M tiles that lie entirely past the row's end are not computed (a 256-wide last tile of a row costs what a
+                    // 128-wide one costs)
+                    const int mt_eff = (p.xr == 1 && p.mt == 2 && decode_tile(p, t).x0 + BM >= p.Wo) ? 1 : p.mt;   // (1-D rows only)
                     for (int dy = 0; dy < p.xr_ky; ++dy)
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait_sel(p.spin, afull_bar(sa), pa);
@@ -280,7 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 mbar_wait_sel(p.spin, full_bar(stage), phase);
                                 uint32_t blo = desc_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);
                                 for (int j = 0; j < ng; ++j, blo += (uint32_t)(p.b_tile_stride >> 4)) {
-                                    for (int mi = 0; mi < p.mt; ++mi) {   // M tile mi = the same tile entered 128 rows further down
+                                    for (int mi = 0; mi < mt_eff; ++mi) {   // M tile mi = the same tile entered 128 rows further down
                                         const uint32_t am = alo + (uint32_t)(mi * BM * 8);
 #pragma unroll
                                         for (int k = 0; k < BK / 8; ++k)
@@ -302,8 +308,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             } else
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 for (int s0 = 0; s0 < ksteps; s0 += phase_len, ++cnt) {
-                    const int buf = (int)(cnt & 1u);
-                    const uint32_t par = (cnt >> 1) & 1u;
+                    const int buf = p.nbuf == 2 ? (int)(cnt & 1u) : 0;
+                    const uint32_t par = (p.nbuf == 2 ? (cnt >> 1) : cnt) & 1u;
                     mbar_wait_sel(p.spin, tempty_bar(buf), par ^ 1u);
                     tc_fence_after();
                     if (ZVX_DBG_PTR(p) && blockIdx.x == 0 && cnt < 16) ZVX_DBG_PTR(p)[16 + cnt] = clock64();
@@ -376,8 +382,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int e = 0; e < 16; ++e) acc[ci][e] = 0.f;
                 for (int s0 = 0; s0 < ksteps; s0 += phase_len, ++cnt) {
-                    const int buf = (int)(cnt & 1u);
-                    mbar_wait(tfull_bar(buf), (cnt >> 1) & 1u);
+                    const int buf = p.nbuf == 2 ? (int)(cnt & 1u) : 0;
+                    mbar_wait(tfull_bar(buf), (p.nbuf == 2 ? (cnt >> 1) : cnt) & 1u);
                     tc_fence_after();
                     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ACC_STRIDE);
 #pragma unroll
@@ -427,12 +433,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
                 continue;
             }
-            const int buf = (int)(cnt & 1u);
-            const uint32_t par = (cnt >> 1) & 1u;
+            const int buf = p.nbuf == 2 ? (int)(cnt & 1u) : 0;
+            const uint32_t par = (p.nbuf == 2 ? (cnt >> 1) : cnt) & 1u;
             ++cnt;
             mbar_wait(tfull_bar(buf), par);
             tc_fence_after();
-            for (int mi = 0; mi < p.mt; ++mi) {
+            const int mt_epi = (p.xr == 1 && p.mt == 2 && c.x0 + BM >= p.Wo) ? 1 : p.mt;   // (M tile never computed: nothing to store)
+            for (int mi = 0; mi < mt_epi; ++mi) {
             if (mi > 0) {
                 r = mi * BM + q * 32 + lane;
                 ty = r / p.row_w; tx = r - ty * p.row_w;
@@ -759,6 +766,13 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
         if (xr1_mtmax >= 2 && 2 * p.BN <= ACC_STRIDE && a.N <= 128 && t2 * 100 <= t1 * 104 &&
             t2 * a.Ho * a.IMG * p.tiles_n >= 4LL * num_sms())
             p.mt = 2;
+        // long-K, full-width convs (decoder FFN k = 9: K = 9 * 528, N = 1024) are bound by the L2 -> SM fetch of the weight tiles
+        // (32 KB per tap per k-chunk): two M tiles behind one weight stage halve it.  The two 256-column accumulators take the
+        // whole TMEM (single-buffered).  Row tails cost nothing extra: an M tile entirely past the row's end is skipped.
+        static const int xr1_wide = env_int("ZVX_XR1_WIDE", 1);
+        if (xr1_wide && p.mt == 1 && 2 * p.BN <= TMEM_COLS && (long long)a.K * a.ksx >= 2048 &&
+            (long long)cdiv(a.Wo, 2 * BM) * a.Ho * a.IMG * p.tiles_n >= 2LL * num_sms())
+            p.mt = 2;
         p.TW = BM * p.mt; p.TH = 1; best = 0;
     }
     if (xr2) { p.TW = xr2_tw; p.TH = xr2_th * xr2_mt; p.mt = xr2_mt; best = 0; }
@@ -806,6 +820,7 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     }
     p.stages = std::min(MAX_STAGES, (SMEM_LIMIT - 2048) / p.stage_bytes);
     p.row_w = p.TW;
+    p.nbuf = (p.mt * p.BN > ACC_STRIDE) ? 1 : 2;
     if (xr || xr2) {
         p.xr = xr ? 1 : 2; p.xr_na = xr ? 3 : xr2_na; p.xr_halo = halo;
         if (xr) {

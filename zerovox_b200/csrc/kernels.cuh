@@ -129,7 +129,7 @@ std::vector<float> voc_poly_pack_weight(const float* w, int C, int k, int dil);
 // choice for C in {8, 16, 32}; returns false (nothing launched) outside its plan, callers then fall back to voc_poly_tc.
 bool voc_pair_supported(int C, int k, const int* dils, int nd);
 bool voc_pair_tc(const VocResArgs& a, cudaStream_t st);
-std::vector<float> voc_pair_pack_weight(const float* w, int C, int k);
+std::vector<float> voc_pair_pack_weight(const float* w, const float* bias, int C, int k);
 
 // conv_post on channel-last input: wav[b,t] = tanh(bias + sum_{j,c} w[j][c] * lrelu(x[b, t+j-(k-1)/2, c], slope))
 void conv_post_cl(const float* x, long long x_bs, const float* w /*[k][C]*/, const float* bias, int B, int T, int C,

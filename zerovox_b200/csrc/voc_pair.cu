@@ -29,6 +29,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <type_traits>
 
@@ -40,6 +41,7 @@ constexpr int EPI_THREADS = 256;         // 8 loader / epilogue warps; lane 0 of
 constexpr int NT = EPI_THREADS;          // (no dedicated issuer warp: 2 x 8 warps per SM leave 128 registers per thread)
 constexpr int MAX_STEPS = VocResArgs::MAX_STEPS;
 constexpr int SMEM_PER_SM = 227 * 1024;
+constexpr int MAX_SCHED = 480;           // MMAs of one launch (8 steps x 57 at C = 32, k = 11) + 8 entries of read-ahead padding
 
 struct PairPlan {
     int nsteps, P, lgP, S, G, Rtot, R, TT, lo;
@@ -50,16 +52,43 @@ struct PairPlan {
     int wbuf_bytes, nwbuf;
     int sched_off[MAX_STEPS + 1];
     int sched_total;
-    uint32_t offA, offW, offZero, offBar, offSched;   // offZero: 256 zero rows of 16 B (operands of the accumulator-clearing MMA)
+    uint32_t offA, offW, offOnes, offBar;   // offOnes: 128 rows (1, 1, 0, 0) then 128 zero rows (accumulator-initialising MMA)
     int smem_bytes, ctas;
+    int wait_ns;                // suspend-time hint of the epilogue warps' barrier waits
+    // The tcgen05.mma list in issue order, per step, ready to use: x = A descriptor low word minus the tile's base (row offset
+    // | LBO << 16), y = the same for B (relative to the weight buffer), z = instruction descriptor, w = accumulator column.  It
+    // travels as a kernel PARAMETER: the issuing thread reads an entry from the constant bank straight into uniform registers
+    // (one LDCU.128) and needs three uniform adds per MMA — read from shared memory every MMA cost four R2UR moves plus the
+    // unpacking, and the single issuing thread, not the tensor pipe (64 cycles per N = 128 MMA), set the pace (~110-150 cycles).
+    uint4 sched[MAX_SCHED];
 };
 
 // leaky ReLU for slopes in (0, 1]: max(v, v*s)
 __device__ __forceinline__ float lrelu(float v, float s) { return fmaxf(v, v * s); }
 // fp32 -> tf32 round-to-nearest, ties away from zero (= cvt.rna.tf32.f32 for finite values) with two integer instructions
 __device__ __forceinline__ float rna_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+// Operand values are read by the tensor core as TF32 = the fp32 bits with the low 13 mantissa bits IGNORED: adding half a
+// TF32 ulp to the bit pattern makes that truncation a round-to-nearest (ties away) — one integer add, no mask.
+__device__ __forceinline__ float half_ulp_up(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 __device__ __forceinline__ float4 act4(float4 v, float s) {
-    return make_float4(rna_tf32(lrelu(v.x, s)), rna_tf32(lrelu(v.y, s)), rna_tf32(lrelu(v.z, s)), rna_tf32(lrelu(v.w, s)));
+    return make_float4(half_ulp_up(lrelu(v.x, s)), half_ulp_up(lrelu(v.y, s)), half_ulp_up(lrelu(v.z, s)), half_ulp_up(lrelu(v.w, s)));
+}
+// Lean barrier wait for the epilogue warps: try_wait with a suspend-time hint (the warp sleeps in hardware instead of spinning
+// through the issue slots of the co-resident CTA); a protocol bug traps after ~2^22 wake-ups instead of hanging the GPU.
+__device__ __forceinline__ void wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t done;
+    int spins = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity), "r"(ns)
+            : "memory");
+        if (done) return;
+        if (++spins > (1 << 22)) __trap();
+    }
 }
 
 // Row (16-byte units inside one channel-chunk plane) of sample tau in the residue-major layout of dilation d, or -1 when
@@ -73,7 +102,7 @@ __device__ __forceinline__ int layout_row(int tau, int d, uint32_t mg, int P, in
 }
 
 template <int C, int CTAS>
-__global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const VocResArgs a, const PairPlan p) {
+__global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const __grid_constant__ VocResArgs a, const __grid_constant__ PairPlan p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const uint32_t sb = smem_u32(smem);
@@ -91,9 +120,12 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const VocResArgs a, 
 #ifdef ZVX_DEBUG   // clock64 checkpoints of one CTA's thread 0 (ZVX_VOC_DBG=1): setup | load | per step: MMAs done, epilogue done
     const bool dbg = a.dbg && tid == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == gridDim.y / 2;
     int dbg_i = 0;
+    int dbg_j = 32;
 #define ZVX_STAMP() do { if (dbg) a.dbg[dbg_i++] = clock64(); } while (0)
+#define ZVX_STAMP2() do { if (dbg && dbg_j < 64) a.dbg[dbg_j++] = clock64(); } while (0)   // issuer: waits over | MMAs issued
 #else
 #define ZVX_STAMP() do { } while (0)
+#define ZVX_STAMP2() do { } while (0)
 #endif
     ZVX_STAMP();
 
@@ -105,28 +137,11 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const VocResArgs a, 
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(slot, 128);
-    // MMA schedule (host-built once per block shape): global {A offset | B offset << 16, D column | accumulate << 8 | N << 16}
-    // -> shared {A descriptor low word, B descriptor low word, D column | accumulate << 8, instruction descriptor}
-    {
-        const uint2* __restrict__ gs = reinterpret_cast<const uint2*>(a.sched);
-        uint4* ss = reinterpret_cast<uint4*>(smem + p.offSched);
-        for (int i = tid; i < p.sched_total; i += NT) {
-            const uint2 e = __ldg(gs + i);
-            int st = 0;
-            while (st + 1 < p.nsteps && i >= p.sched_off[st + 1]) ++st;
-            const uint32_t sWs = sb + p.offW + (uint32_t)((p.nwbuf == 2 ? (st & 1) : 0) * p.wbuf_bytes);
-            uint32_t alo = (((sA & 0x3FFFFu) >> 4) + (e.x & 0xFFFFu)) | ((uint32_t)Rtot << 16);
-            uint32_t blo = (((sWs & 0x3FFFFu) >> 4) + (e.x >> 16)) | ((uint32_t)p.ZC << 16);
-            if (e.y & 0x200u) alo = blo = (((sb + p.offZero) & 0x3FFFFu) >> 4) | (128u << 16);   // clear: 0 x 0, K-halves 128 rows apart
-            const uint32_t n = e.y >> 16;
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            ss[i] = make_uint4(alo, blo, e.y & 0x1FFu, idesc);
-        }
-    }
     // the whole operand tile starts as zeros: guard rows and layout rows no step writes only feed halo outputs, but must
     // stay finite
     for (int idx = tid; idx < CQ * Rtot; idx += NT) st_shared_v4(sA + (uint32_t)idx * 16u, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (int idx = tid; idx < 256; idx += NT) st_shared_v4(sb + p.offZero + (uint32_t)idx * 16u, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int idx = tid; idx < 256; idx += NT)
+        st_shared_v4(sb + p.offOnes + (uint32_t)idx * 16u, idx < 128 ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f));
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -146,21 +161,36 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const VocResArgs a, 
         mbar_wait_spin(w_bar(buf), (uint32_t)((p.nwbuf == 2 ? (s >> 1) : s) & 1));
         mbar_wait_spin(op_bar, (uint32_t)(s & 1));   // operand of step s written (and the accumulator of step s-1 drained)
         tc_fence_after();
+        ZVX_STAMP2();
         // double-buffered weights: the other buffer was last read by the MMAs of step s-1, complete since the epilogue of
         // s-1 has run
         if (p.nwbuf == 2 && s + 1 < p.nsteps) load_w(s + 1);
-        const uint4* tab = reinterpret_cast<const uint4*>(smem + p.offSched);
-        constexpr uint64_t DESC_HI = ((uint64_t)(128 >> 4) | ((uint64_t)1 << 14)) << 32;   // SBO = 128 B, version 1
-        auto issue = [&](const uint4 e) {
-            umma_tf32(tmem_base + (e.z & 0xFFu), DESC_HI | e.x, DESC_HI | e.y, e.w, (e.z >> 8) & 1u);
-        };
+        constexpr uint32_t DESC_HI = (uint32_t)(128 >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
+        constexpr uint32_t IDESC0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);   // f32 += tf32 x tf32, M = 128
+        const uint32_t a_rows = (sA & 0x3FFFFu) >> 4;
+        const uint32_t w_rows = ((sb + p.offW + (uint32_t)(buf * p.wbuf_bytes)) & 0x3FFFFu) >> 4;
+        {   // accumulator := bias.  A = 128 rows (1, 1, 0, 0) with the zero rows as second K-half; B = the bias block at the end
+            // of the step's weight image, rows (hi(b[co]), lo(b[co]), 0, 0), second K-half = the same zero rows
+            const uint32_t ones = ((sb + p.offOnes) & 0x3FFFFu) >> 4, bias_rows = w_rows + (uint32_t)(CQ * p.ZC);
+            umma_tf32_lo(tmem_base, ones | (128u << 16), bias_rows | ((ones + 128u - bias_rows) << 16), DESC_HI, IDESC0 | (128u << 14), 0u);
+        }
         const int i1 = p.sched_off[s + 1];
         int i = p.sched_off[s];
-        for (; i + 4 <= i1; i += 4) {   // four entries in registers before the first MMA: MMAs go back to back
-            const uint4 e0 = tab[i], e1 = tab[i + 1], e2 = tab[i + 2], e3 = tab[i + 3];
+        auto issue = [&](const uint4 e) {   // (row offsets stay below 2^14: no carry into the LBO field)
+            umma_tf32_lo(tmem_base + e.w, a_rows + e.x, w_rows + e.y, DESC_HI, e.z, 1u);
+        };
+        // entries are fetched one group of four ahead of the MMAs that use them (the asm statements are memory barriers to the
+        // compiler: without the explicit prefetch every MMA would wait for its own constant-bank load)
+        uint4 n0 = p.sched[i], n1 = p.sched[i + 1], n2 = p.sched[i + 2], n3 = p.sched[i + 3];
+        for (; i + 4 <= i1; i += 4) {
+            const uint4 e0 = n0, e1 = n1, e2 = n2, e3 = n3;
+            n0 = p.sched[i + 4]; n1 = p.sched[i + 5]; n2 = p.sched[i + 6]; n3 = p.sched[i + 7];   // (the table is padded by 8)
             issue(e0); issue(e1); issue(e2); issue(e3);
         }
-        for (; i < i1; ++i) issue(tab[i]);
+        if (i < i1) issue(n0);
+        if (i + 1 < i1) issue(n1);
+        if (i + 2 < i1) issue(n2);
+        ZVX_STAMP2();
         umma_commit(mma_bar);
     };
     if (tid == 0) load_w(0);
@@ -173,6 +203,7 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const VocResArgs a, 
         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64);
         const int n = q * 32 + lane;
         const int tau0 = P * n + g * NPH;            // first owned sample (d = 1 ownership)
+        const bool interior = tbase >= 0 && tbase + 130 * P <= a.T;   // every sample any layout of this tile holds is inside the utterance
         float4 xo[16];
         {   // input tile: coalesced global loads staged raw in the d = 1 layout; every thread takes the samples it owns into
             // registers (the residual stream); then the operand lrelu(x) is written in the layout of the first step
@@ -217,7 +248,6 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const VocResArgs a, 
         for (int s = 0; s < p.nsteps; ++s) {
             const int kind = a.steps[s].kind;
             const bool last = (s == p.nsteps - 1);
-            const float4* __restrict__ bias = reinterpret_cast<const float4*>(a.steps[s].b);
             // sample of (this thread's row, sub-index g*NPH + ri) in the layout of THIS step: tau = ds*(qs*P + r) + rho
             const int ds = p.ld[s];
             int tau_first, tau_step;
@@ -233,14 +263,43 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const VocResArgs a, 
                 if (lane == 0) issue_step(s);
                 __syncwarp();
             }
+            if (s + 2 >= p.nsteps) {
+                // While the MMAs of the last two steps run (the residual stream is final after step nsteps-3's epilogue):
+                // x <- x * out_scale + acc_in (the MRF running sum, hifigan.py:119-125), one batch of 8 float4 per MMA phase —
+                // the global-load latency hides behind the tensor pipe instead of stalling the final epilogue.
+                auto fold = [&](auto h_tag) {
+                    constexpr int h = decltype(h_tag)::value;
+                    float4 sa[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int idx = h * 8 + j, ri = idx / CQ, cq = idx % CQ;
+                        const int tau = tau0 + ri, t = tbase + tau;
+                        sa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (a.acc_in && t >= 0 && t < a.T && tau >= p.lo && tau < p.lo + p.TT)
+                            sa[j] = *(reinterpret_cast<const float4*>(a.acc_in + (long long)b * a.acc_in_bs + (long long)t * C) + cq);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4& x4 = xo[h * 8 + j];
+                        x4.x = fmaf(x4.x, a.out_scale, sa[j].x); x4.y = fmaf(x4.y, a.out_scale, sa[j].y);
+                        x4.z = fmaf(x4.z, a.out_scale, sa[j].z); x4.w = fmaf(x4.w, a.out_scale, sa[j].w);
+                    }
+                };
+                if (last) fold(std::integral_constant<int, 1>{}); else fold(std::integral_constant<int, 0>{});
+            }
             ZVX_STAMP();
-            mbar_wait(mma_bar, (uint32_t)(s & 1));   // suspending wait: leaves the issue slots to the co-resident CTA
+            wait_sleep(mma_bar, (uint32_t)(s & 1), (uint32_t)p.wait_ns);   // sleeping wait: leaves the issue slots to the co-resident CTA
             tc_fence_after();
             ZVX_STAMP();
             if (tid == 0 && p.nwbuf == 1 && s + 1 < p.nsteps) load_w(s + 1);   // single weight buffer: this step's MMAs have read it
 
-            auto epilogue = [&](auto mode_tag) {
-                constexpr int MODE = decltype(mode_tag)::value;   // 0: first conv of a pair, 1: residual step, 2: last step
+            // The accumulator already holds conv + bias (the step's first MMA initialises it with the bias).  Variants, all
+            // straight-line: MODE 0 first conv of a pair / 1 residual step / 2 last step; SCAT: the thread's samples (MODE 0) or
+            // the produced operand (MODE 1) are in a dilated layout -> index arithmetic + predicated stores; INTERIOR: the whole
+            // tile lies inside the utterance -> no zero-padding selects.
+            auto epilogue = [&](auto mode_tag, auto scat_tag, auto int_tag) {
+                constexpr int MODE = decltype(mode_tag)::value;
+                constexpr bool SCAT = decltype(scat_tag)::value, INTERIOR = decltype(int_tag)::value;
                 uint32_t vbuf[2][16];
                 tmem_ld16(tcol, vbuf[0]);
 #pragma unroll
@@ -255,37 +314,39 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const VocResArgs a, 
                     const int ri = idx / CQ, cq = idx % CQ;
                     const int tau = tau_first + ri * tau_step;
                     const int t = tbase + tau;
-                    const bool inside = (t >= 0) && (t < a.T);
-                    const float4 bb = __ldg(bias + cq);
-                    float4 c4;
-                    c4.x = __uint_as_float(v[0]) + bb.x; c4.y = __uint_as_float(v[1]) + bb.y;
-                    c4.z = __uint_as_float(v[2]) + bb.z; c4.w = __uint_as_float(v[3]) + bb.w;
+                    const bool inside = INTERIOR || ((t >= 0) && (t < a.T));
+                    const float4 c4 = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                    const int own_row = (g * NPH + ri) * S + G + n;   // the thread's own position in the d = 1 layout
                     if constexpr (MODE == 0) {
-                        // first conv of a pair: bias, lrelu, TF32 -> operand of the d = 1 conv (zero outside the utterance:
-                        // that conv's padding)
-                        const int row = (ds == 1) ? (g * NPH + ri) * S + G + n
-                                                  : ((tau >> lgP) < 128 ? (tau & (P - 1)) * S + G + (tau >> lgP) : -1);
+                        // first conv of a pair: lrelu, TF32 -> operand of the d = 1 conv (zero outside the utterance: its padding)
                         float4 o = act4(c4, a.mid_slope);
                         if (!inside) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (row >= 0) st_shared_v4(sA + (uint32_t)((cq * Rtot + row) * 16), o);
+                        if constexpr (SCAT) {
+                            const bool ok = (tau >> lgP) < 128;
+                            const int row = (tau & (P - 1)) * S + G + (tau >> lgP);
+                            if (ok) st_shared_v4(sA + (uint32_t)((cq * Rtot + row) * 16), o);
+                        } else {
+                            st_shared_v4(sA + (uint32_t)((cq * Rtot + own_row) * 16), o);
+                        }
                     } else if constexpr (MODE == 1) {
-                        // residual step: x += conv + bias (fp32, registers), next operand = lrelu(x) in TF32, stored in the
-                        // layout of the next step's dilation
+                        // residual step: x += conv (fp32, registers), next operand = lrelu(x) in TF32, stored in the layout of the
+                        // next step's dilation
                         float4 x4 = xo[idx];
-                        x4.x = inside ? x4.x + c4.x : x4.x; x4.y = inside ? x4.y + c4.y : x4.y;
-                        x4.z = inside ? x4.z + c4.z : x4.z; x4.w = inside ? x4.w + c4.w : x4.w;
+                        if (inside) { x4.x += c4.x; x4.y += c4.y; x4.z += c4.z; x4.w += c4.w; }
                         xo[idx] = x4;   // stays 0 outside the utterance
-                        const int row = (dn == 1) ? (g * NPH + ri) * S + G + n : layout_row(tau, dn, mgn, P, lgP, S, G);
-                        if (row >= 0) st_shared_v4(sA + (uint32_t)((cq * Rtot + row) * 16), act4(x4, a.in_slope));
+                        const float4 o = act4(x4, a.in_slope);
+                        if constexpr (SCAT) {
+                            const int row = layout_row(tau, dn, mgn, P, lgP, S, G);
+                            if (row >= 0) st_shared_v4(sA + (uint32_t)((cq * Rtot + row) * 16), o);
+                        } else {
+                            st_shared_v4(sA + (uint32_t)((cq * Rtot + own_row) * 16), o);
+                        }
                     } else {
-                        // last step: x += conv + bias, then the MRF bookkeeping and the store (channel-last rows)
+                        // last step: out = lrelu(x * out_scale + acc_in + conv * out_scale) — xo already holds the first two terms
                         if (inside && tau >= p.lo && tau < p.lo + p.TT) {
-                            float4 sa = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (a.acc_in) sa = *(reinterpret_cast<const float4*>(a.acc_in + (long long)b * a.acc_in_bs + (long long)t * C) + cq);
                             float4 y;
-                            y.x = xo[idx].x + c4.x; y.y = xo[idx].y + c4.y; y.z = xo[idx].z + c4.z; y.w = xo[idx].w + c4.w;
-                            y.x = fmaf(y.x, a.out_scale, sa.x); y.y = fmaf(y.y, a.out_scale, sa.y);
-                            y.z = fmaf(y.z, a.out_scale, sa.z); y.w = fmaf(y.w, a.out_scale, sa.w);
+                            y.x = fmaf(c4.x, a.out_scale, xo[idx].x); y.y = fmaf(c4.y, a.out_scale, xo[idx].y);
+                            y.z = fmaf(c4.z, a.out_scale, xo[idx].z); y.w = fmaf(c4.w, a.out_scale, xo[idx].w);
                             float* op = a.out + (long long)b * a.out_bs + (long long)t * C;
                             reinterpret_cast<float4*>(op)[cq] = make_float4(lrelu(y.x, a.out_slope), lrelu(y.y, a.out_slope),
                                                                            lrelu(y.z, a.out_slope), lrelu(y.w, a.out_slope));
@@ -298,9 +359,15 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const VocResArgs a, 
                     if (lane == 0) mbar_arrive(op_bar);
                 }
             };
-            if (kind == 0) epilogue(std::integral_constant<int, 0>{});
-            else if (!last) epilogue(std::integral_constant<int, 1>{});
-            else epilogue(std::integral_constant<int, 2>{});
+            using T_ = std::true_type;
+            using F_ = std::false_type;
+            auto run = [&](auto mode_tag, bool scat) {
+                if (scat) { if (interior) epilogue(mode_tag, T_{}, T_{}); else epilogue(mode_tag, T_{}, F_{}); }
+                else { if (interior) epilogue(mode_tag, F_{}, T_{}); else epilogue(mode_tag, F_{}, F_{}); }
+            };
+            if (kind == 0) run(std::integral_constant<int, 0>{}, ds != 1);
+            else if (!last) run(std::integral_constant<int, 1>{}, dn != 1);
+            else run(std::integral_constant<int, 2>{}, false);
             ZVX_STAMP();
         }
     }
@@ -350,23 +417,23 @@ bool make_plan(const VocResArgs& a, PairPlan* out) {
     if (CQ == 1) return false;
     const int planes = planes_of(C, k);
     p.ZC = planes * C;
-    const int wbytes = CQ * p.ZC * 16;
-    for (int s = 0; s < ns; ++s) p.n16[s] = CQ * p.ZC;
+    const int wbytes = CQ * p.ZC * 16 + 128 * 16;           // tap planes + the bias block (128 rows)
+    for (int s = 0; s < ns; ++s) p.n16[s] = CQ * p.ZC + 128;
+    p.wait_ns = env_int("ZVX_PAIR_WAIT_NS", 2000);
     p.wbuf_bytes = (int)round_up(wbytes, 128);
-    // MMA schedule size: per step, one accumulator-clearing MMA, then the P + k - 1 offsets x C/8 k-chunks
-    const int per_step = 1 + (P + k - 1) * (C / 8);
+    // MMA schedule size: per step the P + k - 1 offsets x C/8 k-chunks (after the bias-initialising MMA the kernel issues itself)
+    const int per_step = (P + k - 1) * (C / 8);
     for (int s = 0; s <= ns; ++s) p.sched_off[s] = s * per_step;
-    p.sched_total = (ns * per_step + 1) & ~1;
+    p.sched_total = ns * per_step;
+    if (p.sched_total + 8 > MAX_SCHED) return false;
     auto layout = [&](int nwbuf) {
         uint32_t o = 0;
         p.nwbuf = nwbuf;
         p.offA = o; o += (uint32_t)(CQ * p.Rtot * 16);
         p.offW = o; o += (uint32_t)(nwbuf * p.wbuf_bytes);
-        p.offZero = o; o += 256 * 16;
+        p.offOnes = o; o += 256 * 16;
         p.offBar = o; o += 48;
-        o = (uint32_t)round_up(o, 16);
-        p.offSched = o; o += (uint32_t)p.sched_total * 16;
-        p.smem_bytes = (int)o + 128;
+        p.smem_bytes = (int)round_up(o, 16) + 128;
     };
     // two CTAs per SM when both fit (double-buffered weights first), else one CTA with double-buffered weights
     const int per_cta2 = (SMEM_PER_SM - 2 * 1024) / 2;
@@ -378,58 +445,50 @@ bool make_plan(const VocResArgs& a, PairPlan* out) {
         else { layout(2); p.ctas = 1; if (p.smem_bytes > SMEM_PER_SM - 1024) { layout(1); } }
     }
     if (p.smem_bytes > SMEM_PER_SM - 1024) return false;
+    // The tcgen05.mma list.  Offset w of the sub-index only reaches the output sub-indices [w - c, w + c]: edge offsets issue
+    // N = (#r) * C columns at accumulator column r_lo * C; all of them accumulate onto the bias the step's first MMA wrote.
+    {
+        const int e = (C == 8) ? 1 : 0;
+        auto fdiv = [](int x, int y) { return (x >= 0) ? x / y : -((-x + y - 1) / y); };
+        int i = 0;
+        for (int s = 0; s < ns; ++s) {
+            const int d = p.ld[s];
+            for (int w = -c; w <= P - 1 + c; ++w) {
+                int r_lo = std::max(0, w - c), r_hi = std::min(P - 1, w + c);
+                if (C == 8) {   // N and the accumulator column must be multiples of 16: even r_lo, odd r_hi — a borrowed
+                    if (r_lo & 1) --r_lo;        // neighbour's tap is a zero plane of the weight image
+                    if (!(r_hi & 1)) ++r_hi;
+                }
+                if (!(r_lo >= 0 && r_hi <= P - 1 && r_lo - w >= -c - e && r_hi - w <= c + e)) return false;
+                const int al = fdiv(w, P), rp = w - al * P;
+                const uint32_t ncols = (uint32_t)((r_hi - r_lo + 1) * C);
+                for (int pp = 0; pp < C / 8; ++pp) {
+                    const uint32_t ao = (uint32_t)((2 * pp) * p.Rtot + rp * p.S + p.G + al * d);
+                    const uint32_t bo = (uint32_t)((2 * pp) * p.ZC + (r_lo - w + c + e) * C);
+                    if (ao + 4096u >= 16384u || bo + 8192u >= 16384u) return false;   // + the largest base (shared memory < 228 KB)... 
+                    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                    p.sched[i++] = make_uint4(ao | ((uint32_t)p.Rtot << 16), bo | ((uint32_t)p.ZC << 16), idesc, (uint32_t)(r_lo * C));
+                }
+            }
+            if (i != p.sched_off[s + 1]) return false;
+        }
+    }
     *out = p;
     return true;
 }
 
-// The tcgen05.mma list of one block shape in issue order: x = A offset | B offset << 16 (16-byte units relative to the
-// operand bases), y = accumulator column | accumulate << 8 | N << 16.
-std::vector<uint2> build_schedule(const VocResArgs& a, const PairPlan& p) {
-    const int C = a.C, P = p.P, k = a.k, c = (k - 1) / 2, e = (C == 8) ? 1 : 0;
-    auto fdiv = [](int x, int y) { return (x >= 0) ? x / y : -((-x + y - 1) / y); };
-    std::vector<uint2> t;
-    for (int s = 0; s < p.nsteps; ++s) {
-        const int d = p.ld[s];
-        // Offset w only reaches the output sub-indices [w - c, w + c]: no single MMA need cover the whole accumulator, so the
-        // step opens with one N = 128 MMA of zero operands that clears it (flag 0x200) and every real MMA accumulates.
-        t.push_back(make_uint2(0u, 0x200u | (128u << 16)));
-        for (int w = -c; w <= P - 1 + c; ++w) {
-            int r_lo = std::max(0, w - c), r_hi = std::min(P - 1, w + c);
-            if (C == 8) {   // N and the accumulator column must be multiples of 16: even r_lo, odd r_hi — a borrowed neighbour's
-                if (r_lo & 1) --r_lo;            // tap is a zero plane of the weight image
-                if (!(r_hi & 1)) ++r_hi;
-            }
-            ZVX_REQUIRE(r_lo >= 0 && r_hi <= P - 1 && r_lo - w >= -c - e && r_hi - w <= c + e, "voc_pair: column range out of plan");
-            const int al = fdiv(w, P), rp = w - al * P;
-            const uint32_t ncols = (uint32_t)((r_hi - r_lo + 1) * C);
-            for (int pp = 0; pp < C / 8; ++pp) {
-                const uint32_t ao = (uint32_t)((2 * pp) * p.Rtot + rp * p.S + p.G + al * d);
-                const uint32_t bo = (uint32_t)((2 * pp) * p.ZC + (r_lo - w + c + e) * C);
-                t.push_back(make_uint2(ao | (bo << 16), (uint32_t)(r_lo * C) | (1u << 8) | (ncols << 16)));
-            }
-        }
-        ZVX_REQUIRE((int)t.size() == p.sched_off[s + 1], "voc_pair: schedule size mismatch");
-    }
-    for (const uint2& en : t) ZVX_REQUIRE((en.x & 0xFFFFu) < 16384u && (en.x >> 16) < 16384u, "voc_pair: operand offset out of range");
-    if (t.size() & 1) t.push_back(make_uint2(0u, 0u));
-    return t;
-}
-
-// Device copies of the schedules, one per (device, block shape); built on first use.
-const uint2* schedule_for(const VocResArgs& a, const PairPlan& p) {
-    static std::map<std::string, uint2*> cache;
-    int dev = 0;
-    ZVX_CUDA_CHECK(cudaGetDevice(&dev));
-    std::string key = std::to_string(dev) + ":" + std::to_string(a.C) + ":" + std::to_string(a.k);
-    for (int s = 0; s < a.nsteps; ++s) key += ":" + std::to_string(a.steps[s].dil);
+// Plans (tile geometry + MMA list) are pure functions of the block shape: built once per (C, k, dilations).
+const PairPlan* plan_for(const VocResArgs& a) {
+    static std::map<std::string, std::unique_ptr<PairPlan>> cache;
+    std::string key = std::to_string(a.C) + ":" + std::to_string(a.k) + ":" + std::to_string(a.nsteps);
+    for (int s = 0; s < a.nsteps && s < MAX_STEPS; ++s) key += ":" + std::to_string(a.steps[s].dil) + "/" + std::to_string(a.steps[s].kind);
     auto it = cache.find(key);
-    if (it != cache.end()) return it->second;
-    const std::vector<uint2> t = build_schedule(a, p);
-    uint2* d = nullptr;
-    ZVX_CUDA_CHECK(cudaMalloc(&d, t.size() * sizeof(uint2)));
-    ZVX_CUDA_CHECK(cudaMemcpy(d, t.data(), t.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-    cache[key] = d;
-    return d;
+    if (it == cache.end()) {
+        std::unique_ptr<PairPlan> p(new PairPlan());
+        if (!make_plan(a, p.get())) p.reset();
+        it = cache.emplace(key, std::move(p)).first;
+    }
+    return it->second.get();
 }
 
 template <int C, int CTAS>
@@ -455,20 +514,19 @@ bool voc_pair_supported(int C, int k, const int* dils, int nd) {
         a.steps[a.nsteps].dil = dils[i]; a.steps[a.nsteps++].kind = 0;
         a.steps[a.nsteps].dil = 1; a.steps[a.nsteps++].kind = 1;
     }
-    PairPlan p;
-    return make_plan(a, &p);
+    return plan_for(a) != nullptr;
 }
 
 // Steps must carry the images of voc_pair_pack_weight in `w_pair`.  Returns false (nothing launched) outside the plan.
 bool voc_pair_tc(const VocResArgs& a, cudaStream_t st) {
     if (a.B == 0 || a.T == 0) return true;
-    PairPlan p;
-    if (!make_plan(a, &p)) return false;
+    const PairPlan* pp = plan_for(a);
+    if (!pp) return false;
+    const PairPlan& p = *pp;
     for (int s = 0; s < a.nsteps; ++s)
         if (!a.steps[s].w_pair) return false;
     ZVX_REQUIRE(a.x && a.out && a.B <= 65535, "voc_pair_tc: bad arguments");
-    VocResArgs b = a;
-    b.sched = schedule_for(a, p);
+    const VocResArgs& b = a;
     switch (a.C * 10 + p.ctas) {
         case 81: launch<8, 1>(b, p, st); break;
         case 82: launch<8, 2>(b, p, st); break;
@@ -481,8 +539,9 @@ bool voc_pair_tc(const VocResArgs& a, cudaStream_t st) {
 }
 
 // Weight image of one conv for voc_pair_kernel, TF32-rounded: the dilation-free trimmed Toeplitz array
-// [cq][plane][co][4 ci] with plane z + c + e <-> tap j = c - z (zero planes at both ends when C = 8).
-std::vector<float> voc_pair_pack_weight(const float* w, int C, int k) {
+// [cq][plane][co][4 ci] with plane z + c + e <-> tap j = c - z (zero planes at both ends when C = 8), followed by the
+// bias block (128 rows of 4 floats).
+std::vector<float> voc_pair_pack_weight(const float* w, const float* bias, int C, int k) {
     auto rn = [](float v) {
         uint32_t u;
         memcpy(&u, &v, 4);
@@ -491,7 +550,19 @@ std::vector<float> voc_pair_pack_weight(const float* w, int C, int k) {
         return v;
     };
     const int CQ = C / 4, c = (k - 1) / 2, e = (C == 8) ? 1 : 0, planes = planes_of(C, k);
-    std::vector<float> o((size_t)CQ * planes * C * 4, 0.f);
+    std::vector<float> o((size_t)CQ * planes * C * 4 + 128 * 4, 0.f);
+    // bias block: row (r, co) = (hi, lo, 0, 0) with hi = the bias truncated to TF32 (what the tensor core reads), lo = the
+    // TF32-rounded remainder: ones(1, 1, 0, 0) x this row = the bias to ~2^-21 relative
+    for (int row = 0; row < 128; ++row) {
+        const float bv = bias[row % C];
+        uint32_t u;
+        memcpy(&u, &bv, 4);
+        u &= ~0x1FFFu;
+        float hi;
+        memcpy(&hi, &u, 4);
+        o[(size_t)CQ * planes * C * 4 + (size_t)row * 4 + 0] = hi;
+        o[(size_t)CQ * planes * C * 4 + (size_t)row * 4 + 1] = rn(bv - hi);
+    }
     for (int z = -c; z <= c; ++z) {
         const int j = c - z;
         for (int co = 0; co < C; ++co)
