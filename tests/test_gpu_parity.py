@@ -5,8 +5,9 @@ Tolerances (stated per stage, fp32 unless marked):
   * integer outputs (mel_len, forced durations, LengthRegulator indices and gathered rows): bit-exact;
   * fp32 FMA path (tensor_core_policy=0; encoder + variance predictors always): |err| <= 2e-4 * max|ref| + 2e-5;
   * TF32 tensor-core path (policy 1; decoder / vocoder / speaker net; operands rounded to nearest TF32, fp32
-    accumulation): mel |err| <= 5e-3 * max|ref|, wav |err| <= 2e-2 (CPU emulation of TF32 operand rounding in the
-    oracle's decoder, tools/diag_tf32_oracle.py: rel-RMS ~5e-4, max-abs ~7e-4 * max|ref|);
+    accumulation): mel |err| <= 3.5e-3 * max|ref|, wav |err| <= 1.8e-2, rel-RMS <= 3e-3 — at most 2x the worst values
+    measured on B200 over this file's cases (mel 1.9e-3 * max, wav 9.4e-3: the tiny random-weight models are the worst; at
+    the benchmarked sizes, tests/test_gpu_fullsize.py, mel 1.75e-3 * max / wav 7.4e-3 / rel-RMS 9.5e-4);
   * pitch / energy buckets and predicted durations: exact wherever the oracle's float input to the rounding step is
     more than 1e-3 away from a rounding boundary (reported otherwise).
   * end-to-end runs under policy 1: the speaker net runs in TF32, so its style vector differs from the reference's by
@@ -39,16 +40,19 @@ def rel_err(a, b):
     return (a - b).abs().max().item(), b.abs().max().item()
 
 
-def check(name, got, ref, rtol, atol=2e-5):
+def check(name, got, ref, rtol, atol=2e-5, rms=None):
     err, mag = rel_err(got, ref)
-    ok = err <= rtol * mag + atol
-    print(f"  {name:28s} max|diff|={err:.3e} max|ref|={mag:.3e} tol={rtol * mag + atol:.3e} {'ok' if ok else 'FAIL'}")
-    assert ok, f"{name}: {err:.3e} > {rtol * mag + atol:.3e}"
+    a, b = torch.as_tensor(got).double().cpu(), torch.as_tensor(ref).double().cpu()
+    rel_rms = float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp(min=1e-30)) if a.numel() else 0.0
+    ok = err <= rtol * mag + atol and (rms is None or rel_rms <= rms)
+    print(f"  {name:28s} max|diff|={err:.3e} max|ref|={mag:.3e} tol={rtol * mag + atol:.3e} rel-RMS={rel_rms:.2e} "
+          f"{'ok' if ok else 'FAIL'}")
+    assert ok, f"{name}: {err:.3e} > {rtol * mag + atol:.3e} (rel-RMS {rel_rms:.2e}, bar {rms})"
 
 
 FP32 = dict(rtol=2e-4)
-TC_MEL = dict(rtol=5e-3)
-TC_WAV = dict(rtol=0.0, atol=2e-2)
+TC_MEL = dict(rtol=3.5e-3, rms=3e-3)
+TC_WAV = dict(rtol=0.0, atol=1.8e-2, rms=3e-3)
 
 
 def tol(policy, kind):
@@ -325,9 +329,9 @@ def test_full_size_properties_config2(medium, policy):
         wav1, mel1, len1, _ = model(xi, force_duration=True)
     n = int(len1[0])
     assert n == int(mel_len[i])
-    check("mel batch-invariance", mel1[0, :, :n], mel[i, :, :n], rtol=1e-2 if policy else 1e-4)
+    check("mel batch-invariance", mel1[0, :, :n], mel[i, :, :n], rtol=3e-3 if policy else 1e-4)   # measured 1.5e-3 * max
     keep = (n - 16) * cfg.hop_length
-    check("wav batch-invariance", wav1[0, :keep], wav[i, :keep], rtol=0.0, atol=2e-2 if policy else 1e-4)
+    check("wav batch-invariance", wav1[0, :keep], wav[i, :keep], rtol=0.0, atol=1.6e-2 if policy else 1e-4)   # measured 7.8e-3
     # speaker embedding has unit norm
     style = model._spkemb(x["ref_mel"][:4].to(DEV))
     np.testing.assert_allclose(style.norm(dim=-1).cpu().numpy(), 1.0, atol=1e-5)

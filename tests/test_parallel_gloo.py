@@ -186,7 +186,7 @@ def _worker(rank, world, port, cases, q):
             dist.broadcast_object_list(box, src=0)
             host = torch.zeros(B * T * 7 * HOP + 64) if rank == 0 else None
             rb = sharded_forward(fake_model, x, force_duration=forced, device="cpu", hop_length=HOP, n_mels=NMEL,
-                                 ragged=True, spec=box[0], vocoder_groups=3, host_out=host)
+                                 ragged=True, spec=box[0], vocoder_groups=(3 if B % 2 else -3), host_out=host)
             if rank == 0:
                 o = 0
                 for i, n in enumerate(ref[2].tolist()):     # host_out: the valid waveforms back to back, utterance order

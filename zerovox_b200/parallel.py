@@ -266,9 +266,11 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
 
     # ---- forward on the block, at the global frame count; results shipped group by group --------------------------------
     from .tts.model import group_bounds
-    G = max(1, int(vocoder_groups or 1))
+    G = int(vocoder_groups or 1)   # > 1: equal groups; < -1: halving groups (tts.model.group_bounds)
+    if G == 0 or G == -1:
+        G = 1
     cuda = dev.type == "cuda"
-    side = torch.cuda.Stream(dev) if cuda and (G > 1 or host_out is not None) else None
+    side = torch.cuda.Stream(dev) if cuda and (G != 1 or host_out is not None) else None
     root = 0 if (group is None or not multi) else dist.get_global_rank(group, 0)
     lens_box, st = {}, {"groups_done": 0}
 
@@ -386,7 +388,7 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
         ship(parts)
         st["groups_done"] += 1
 
-    kw = dict(vocoder_groups=G, on_group=on_group) if (G > 1) else {}
+    kw = dict(vocoder_groups=G, on_group=on_group) if (G != 1) else {}
     if n_mine > 0:
         wav, mel, mel_len, logd = model(xs, force_duration=has_dur, pad_to=pad_to, zero_padded_mel=bool(zero_pad), **kw)
         L = mel.shape[2]

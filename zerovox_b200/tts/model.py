@@ -169,9 +169,21 @@ class ZeroVox(nn.Module):
 # rebinds them on the reference's own ZeroVox class)
 # ---------------------------------------------------------------------------------------------------------------------
 def group_bounds(n: int, groups: int) -> list[tuple[int, int]]:
-    """Consecutive, nearly equal utterance groups (the vocoder's delivery units): [(first, end), ...]."""
-    groups = max(1, min(int(groups or 1), n))
-    return [(n * i // groups, n * (i + 1) // groups) for i in range(groups)]
+    """Consecutive utterance groups (the vocoder's delivery units): [(first, end), ...].  groups > 0: that many nearly equal
+    groups; groups < 0: |groups| groups of halving size (n/2, n/4, ..., the last two equal) — the transfer of a group hides
+    behind the vocoding of ALL later groups, so only the small last group's transfer is exposed."""
+    g = int(groups or 1)
+    if g >= 0:
+        g = max(1, min(g, n))
+        return [(n * i // g, n * (i + 1) // g) for i in range(g)]
+    g = max(1, min(-g, n))
+    cuts, left = [0], n
+    for i in range(g - 1):
+        take = max(1, left // 2) if left > (g - 1 - i) else 1
+        cuts.append(cuts[-1] + take)
+        left -= take
+    cuts.append(n)
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
 
 
 def engine_forward(eng, x, force_duration=False, *, pad_to=None, zero_padded_mel=None, vocoder_groups=None, on_group=None):
@@ -211,7 +223,7 @@ def engine_forward(eng, x, force_duration=False, *, pad_to=None, zero_padded_mel
         zero_pad = ((not force_duration) or "mel_mask" in x) and feats.shape[0] > 1
     _, mel = eng.decode(feats, style, mask=dec_mask, mel_len=r["mel_len"], zero_padded_mel=bool(zero_pad), want_blc=False)
     B = mel.shape[0]
-    if vocoder_groups and int(vocoder_groups) > 1 and B > 1:
+    if vocoder_groups and abs(int(vocoder_groups)) > 1 and B > 1:
         wav = torch.empty((B, L * eng.cfg.hop_length), device=dev, dtype=torch.float32)
         for i, (g0, g1) in enumerate(group_bounds(B, vocoder_groups)):
             eng.vocode(mel[g0:g1], out=wav[g0:g1])
