@@ -142,8 +142,9 @@ class ClockSampler:
 # engine profiling class -> kernel names in profiles/*_ncu_summary.json (tools/ncu_summary.py)
 NCU_KERNELS = {"gemm_tf32_tcgen05": ("gemm_tc_kernel<0, 0>", "gemm_tc_kernel<1, 0>"),
                "gemm_3xtf32_tcgen05": ("gemm_tc_kernel<1, 1>",),
-               "vocoder_pair_tcgen05": ("voc_poly_kernel<32>", "voc_poly_kernel<16>", "voc_poly_kernel<8>",
-                                        "voc_stage_kernel<32>", "voc_stage_kernel<16>", "voc_stage_kernel<8>")}
+               "vocoder_pair_tcgen05": ("voc_pair_kernel<32, 2>", "voc_pair_kernel<32, 1>", "voc_pair_kernel<16, 2>", "voc_pair_kernel<16, 1>",
+                                        "voc_pair_kernel<8, 2>", "voc_pair_kernel<8, 1>", "voc_poly_kernel<32>", "voc_poly_kernel<16>",
+                                        "voc_poly_kernel<8>")}
 
 
 def ncu_traffic(cls):

@@ -206,6 +206,17 @@ int zvx_trim_silence(zvx_frontend* h, const float* wav, int B, int64_t n_stride,
                      int frame_length, int hop_length, int64_t* start, int64_t* len, int64_t* start_len_host,
                      void* stream);
 
+/* Sample-rate conversion of the prompt: the `sr=` argument of librosa.load in ZeroVoxTTS.get_speakerref (synthesize.py:113-121;
+ * the packaged prompts are 24 kHz, the models 22.05 kHz).  Band-limited polyphase resampling with a Kaiser-windowed sinc
+ * (resampy "kaiser_best" design: 64 zero crossings, beta 14.7697, roll-off 0.9476), exact taps per rational phase.  librosa's
+ * default (soxr_hq) is a different filter of the same class: parity with it is a stated tolerance, not bit-exactness
+ * (DESIGN.md section 2).  wav_in fp32 [B, n_in_stride], len_in device int64 [B] or NULL (= n_in_stride each);
+ * wav_out fp32 [B, n_out_stride], the first n_out samples of every row are written (n_out = zvx_resample_num_samples of the
+ * longest row; rows are zero-extended past their own length). */
+int64_t zvx_resample_num_samples(int64_t n_in, int sr_in, int sr_out);
+int zvx_resample(zvx_frontend* h, const float* wav_in, int B, int64_t n_in_stride, const int64_t* len_in, int sr_in, int sr_out,
+                 float* wav_out, int64_t n_out_stride, int64_t n_out, void* stream);
+
 /* get_mel_from_wav (mels.py:356-394), fused: reflect pad, Hann STFT magnitude, Slaney mel filterbank, log(clip), energy.
  * wav fp32 [B, n_stride]; wav_start / wav_len device int64 [B] select the window of each row (NULL = 0 / the rest of the
  * row) — the outputs of zvx_trim_silence plug in directly.  mel_BTC fp32 [B, n_frames, num_mels] (the reference's `spec`

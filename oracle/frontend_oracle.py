@@ -130,6 +130,53 @@ def trim(y: np.ndarray, top_db: float = 40.0, frame_length: int = 2048, hop_leng
     return y[start:end], (start, end)
 
 
+def trim_bounds_independent(y: np.ndarray, top_db: float = 40.0, frame_length: int = 2048, hop_length: int = 512):
+    """A second, independently formulated statement of librosa.effects.trim's published rule, used to cross-check `trim`
+    (oracle/make_goldens_frontend.py): frame POWER by a cumulative sum in float64 instead of gathering frames, and the
+    threshold as a power ratio  P_frame > P_max * 10^(-top_db/10)  instead of a difference of decibels.  Frames whose power sits
+    within a float32 rounding of the threshold may legitimately differ between the two; the generator reports them."""
+    y = np.asarray(y, dtype=np.float64)
+    yp = np.pad(y, (frame_length // 2, frame_length // 2))
+    cs = np.concatenate([[0.0], np.cumsum(yp * yp)])
+    n_frames = 1 + (len(yp) - frame_length) // hop_length
+    starts = hop_length * np.arange(n_frames)
+    power = (cs[starts + frame_length] - cs[starts]) / frame_length
+    pmax = max(power.max(), 1e-10)
+    loud = np.flatnonzero(np.maximum(power, 1e-10) > pmax * 10.0 ** (-top_db / 10.0))
+    if loud.size == 0:
+        return 0, 0
+    return int(loud[0]) * hop_length, min(len(y), (int(loud[-1]) + 1) * hop_length)
+
+
+def resample(y: np.ndarray, sr_in: int, sr_out: int) -> np.ndarray:
+    """The `sr=` conversion of librosa.load (synthesize.py:113-121) as band-limited interpolation with the Kaiser-windowed sinc
+    of resampy's published "kaiser_best" design (64 zero crossings, beta 14.769656459379492, roll-off 0.9475937167399596),
+    evaluated directly in float64 — the arithmetic csrc/frontend.cu tabulates per rational phase.  Output length
+    ceil(n * sr_out / sr_in) (librosa.resample).  PARITY with librosa's default soxr_hq: unpinned (soxr is absent); both are
+    > 100 dB band-limited interpolators, tests bound the difference against analytic band-limited signals instead."""
+    import math
+    y = np.asarray(y, dtype=np.float64)
+    g = math.gcd(int(sr_in), int(sr_out))
+    up, down = sr_out // g, sr_in // g
+    num_zeros, beta, rolloff = 64.0, 14.769656459379492, 0.9475937167399596
+    scale = min(1.0, sr_out / sr_in)
+    kh = int(math.ceil(num_zeros / scale))
+    n_out = -(-len(y) * sr_out // sr_in)
+    m = np.arange(n_out, dtype=np.int64)
+    i0 = (m * down) // up
+    frac = ((m * down) % up) / up
+    out = np.zeros(n_out)
+    i0b = np.i0(beta)
+    for j in range(2 * kh):
+        k = i0 - kh + 1 + j
+        u = (frac + kh - 1 - j) * scale
+        w = np.where(np.abs(u) < num_zeros,
+                     scale * rolloff * np.sinc(rolloff * u) * np.i0(beta * np.sqrt(np.clip(1.0 - (u / num_zeros) ** 2, 0.0, None))) / i0b, 0.0)
+        ok = (k >= 0) & (k < len(y))
+        out[ok] += w[ok] * y[k[ok]]
+    return out.astype(np.float32)
+
+
 def speaker_prompt_mel(wav: np.ndarray, **mel_kwargs) -> np.ndarray:
     """synthesize.py:123-138: trim -> get_mel_from_wav -> [1, n_frames, num_mels] (the `_spkemb` input)."""
     wav, _ = trim(wav, top_db=40)

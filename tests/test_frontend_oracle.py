@@ -71,6 +71,53 @@ def test_trim_invariants():
     assert fo.trim(wav, top_db=200.0)[1] == (0, n)
 
 
+def test_trim_two_independent_formulations_agree():
+    """librosa is absent, so `trim` cannot be pinned to librosa itself; it is cross-checked against a second statement of the
+    same published rule written differently (float64 cumulative-sum frame power, power-ratio threshold instead of a dB
+    difference) on 40 signals: speech-like envelopes with varying lead / tail, noise floors around the threshold, clicks."""
+    rng = np.random.default_rng(0)
+    checked = 0
+    for s_ in range(40):
+        n = int(rng.integers(6000, 60000))
+        w = make_speech_like(n, seed=s_, lead=float(rng.uniform(0, .3)), tail=float(rng.uniform(0, .3)))
+        if s_ % 4 == 1:
+            w = w + rng.normal(0, 10 ** rng.uniform(-4.5, -2.0), n).astype(np.float32)    # noise floor near / above -40 dB
+        if s_ % 4 == 2:
+            w[int(rng.integers(0, n))] += 0.9                                               # a click
+        for top_db, fl, hop in ((40.0, 2048, 512), (20.0, 1024, 256)):
+            a = fo.trim(w, top_db=top_db, frame_length=fl, hop_length=hop)[1]
+            b = fo.trim_bounds_independent(w, top_db=top_db, frame_length=fl, hop_length=hop)
+            if a != b:   # only legitimate when a frame's power sits within float32 rounding of the threshold
+                yp = np.pad(w.astype(np.float64), (fl // 2, fl // 2))
+                pw = np.array([np.mean(yp[i * hop:i * hop + fl] ** 2) for i in range(1 + (len(yp) - fl) // hop)])
+                thr = max(pw.max(), 1e-10) * 10 ** (-top_db / 10)
+                assert np.min(np.abs(pw / thr - 1.0)) < 1e-5, (s_, a, b)
+            checked += 1
+    assert checked == 80
+
+
+def test_resample_oracle_is_band_limited_interpolation():
+    """The `sr=` conversion of librosa.load (synthesize.py:113-121).  soxr is absent, so parity with librosa's soxr_hq is a
+    stated tolerance: both are band-limited interpolators, and for a band-limited input the exact answer is known — sinusoids
+    below 0.85 x the output Nyquist frequency, sampled analytically at the output rate."""
+    from scipy.signal import resample_poly
+    for sr_in, sr_out in ((24000, 22050), (16000, 22050), (44100, 22050)):
+        n = sr_in
+        t_in = np.arange(n) / sr_in
+        freqs = [110.0, 997.0, 3501.0, 0.70 * min(sr_in, sr_out) / 2, 0.85 * min(sr_in, sr_out) / 2]
+        x = sum(np.sin(2 * np.pi * f * t_in + i) / len(freqs) for i, f in enumerate(freqs))
+        y = fo.resample(x.astype(np.float32), sr_in, sr_out)
+        assert len(y) == -(-n * sr_out // sr_in)                       # ceil(n * ratio), librosa.resample
+        t_out = np.arange(len(y)) / sr_out
+        ref = sum(np.sin(2 * np.pi * f * t_out + i) / len(freqs) for i, f in enumerate(freqs))
+        mid = slice(200, -200)                                          # the truncated ends are not band-limited
+        assert np.abs(y[mid] - ref[mid]).max() < 2e-6, (sr_in, sr_out, np.abs(y[mid] - ref[mid]).max())
+        g = np.gcd(sr_in, sr_out)
+        z = resample_poly(x, sr_out // g, sr_in // g)                   # another band-limited resampler (Kaiser beta = 5 FIR)
+        assert np.abs(z[mid] - y[mid]).max() < 5e-3
+    assert len(fo.resample(np.zeros(0, dtype=np.float32), 24000, 22050)) == 0
+
+
 # ------------------------------------------------------------------------------------------------ tokeniser
 def _cases(golden_dir):
     with open(os.path.join(golden_dir, "tokeniser.json"), encoding="utf-8") as f:

@@ -108,6 +108,27 @@ def test_trim_matches_oracle(fe):
     assert (hs[0], hs[0] + hl[0]) == (a, e)
 
 
+@pytest.mark.parametrize("sr_in,sr_out", [(24000, 22050), (16000, 22050), (44100, 22050), (22050, 24000)])
+def test_resample_matches_oracle(fe, sr_in, sr_out):
+    """zvx_resample (the `sr=` of librosa.load, synthesize.py:113-121) against the float64 oracle of the same filter: fp32
+    accumulation of ~140 taps -> 3e-6; ragged rows are zero-extended; and against the analytic band-limited answer."""
+    n = 30011
+    rng = np.random.default_rng(1)
+    wavs = np.stack([make_speech_like(n, seed=3), rng.normal(0, 0.2, n).astype(np.float32),
+                     np.sin(2 * np.pi * 1234.5 * np.arange(n) / sr_in).astype(np.float32)])
+    lens = [n, 20000, n]
+    out = fe.resample(torch.from_numpy(wavs).to(DEV), sr_in, sr_out, wav_len=torch.tensor(lens, device=DEV)).cpu().numpy()
+    assert out.shape == (3, -(-n * sr_out // sr_in))
+    for b in range(3):
+        ref = fo.resample(wavs[b, :lens[b]], sr_in, sr_out)
+        assert np.abs(out[b, :len(ref)] - ref).max() < 3e-6
+        assert np.abs(out[b, len(ref) + 80:]).max() < 1e-6 if len(ref) + 80 < out.shape[1] else True
+    t_out = np.arange(out.shape[1]) / sr_out
+    assert np.abs(out[2] - np.sin(2 * np.pi * 1234.5 * t_out))[200:-200].max() < 2e-5
+    same = fe.resample(torch.from_numpy(wavs).to(DEV), sr_out, sr_out)
+    assert same.shape == wavs.shape and torch.equal(same.cpu(), torch.from_numpy(wavs))
+
+
 def test_speaker_prompt_mel_and_speaker_embed_mirror():
     """ZeroVoxTTS.speaker_embed (synthesize.py:123-143) through the mirror: trim -> mel -> `_spkemb`, against the
     oracle composition (speaker net in fp32 FMA, policy 0, so the only differences are the front-end's)."""
@@ -132,6 +153,12 @@ def test_speaker_prompt_mel_and_speaker_embed_mirror():
     assert err < 2e-4 and abs(style.norm().item() - 1.0) < 1e-5
     assert tts.transcript2phonemids("this is a test.") == fo.transcript2phonemids(fo.Symbols(cfg.phones, cfg.puncts),
                                                                                   "this is a test.")
+    # a 24 kHz prompt (every packaged prompt of the reference): resampled on the GPU first, like librosa.load(sr=22050)
+    wav24 = make_speech_like(24000 * 2, seed=6, sr=24000)
+    style24 = tts.speaker_embed(wav24, sampling_rate=24000)
+    with torch.no_grad():
+        ref24 = zo.speaker_embed(cfg, w, torch.from_numpy(fo.speaker_prompt_mel(fo.resample(wav24, 24000, 22050))))
+    assert (style24.cpu() - ref24).abs().max().item() < 2e-4
 
 
 def test_get_mel_from_wav_mirror_signature():

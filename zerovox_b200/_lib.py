@@ -97,6 +97,8 @@ SYMBOLS = {
     "zvx_mel_num_frames": (C.c_int64, [_P, C.c_int64]),
     "zvx_trim_silence": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, C.c_float, C.c_int, C.c_int, _P, _P, _P, _P]),
     "zvx_mel_spectrogram": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, _P, C.c_int, _P, _P, _P]),
+    "zvx_resample_num_samples": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
+    "zvx_resample": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P, C.c_int, C.c_int, _P, C.c_int64, C.c_int64, _P]),
     "zvx_symbols_create": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(_P)]),
     "zvx_symbols_destroy": (None, [_P]),
     "zvx_symbols_last_error": (C.c_char_p, [_P]),

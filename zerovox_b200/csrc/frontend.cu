@@ -6,6 +6,7 @@
 // mel filterbank, log(clip(., 1e-5)) and the per-frame spectral energy — the waveform is read once, nothing intermediate
 // touches HBM.  Independent of the model weights, so it has its own small handle (zvx_frontend).
 #include <cmath>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -224,6 +225,44 @@ trim_bounds_kernel(const float* __restrict__ rms, const unsigned* __restrict__ r
     }
 }
 
+// ------------------------------------------------------------------------------------------------ resampler
+// Band-limited sample-rate conversion of the speaker prompt (what `librosa.load(path, sr=sampling_rate)` does in front of the
+// path, synthesize.py:113-121: the packaged prompts are 24 kHz, the models 22.05 kHz).  One thread per output sample m:
+//   t = m * down / up (input samples),  y[m] = sum_j w[phase][j] * x[floor(t) - KH + 1 + j],   phase = (m * down) mod up,
+// w = the Kaiser-windowed sinc of resampy's published "kaiser_best" design (64 zero crossings, beta 14.7697, roll-off
+// 0.9476), time-scaled by min(1, sr_out / sr_in) and tabulated exactly (no table interpolation) per rational phase.
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ x, long long x_stride, const long long* __restrict__ x_len,
+                                                       const float* __restrict__ tab, int up, int down, int taps, int kh,
+                                                       float* __restrict__ y, long long y_stride, long long n_out) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (m >= n_out) return;
+    const long long n_in = x_len ? min(max(x_len[b], 0LL), x_stride) : x_stride;
+    const long long num = m * down, i0 = num / up;
+    const int phase = (int)(num - i0 * up);
+    const float* __restrict__ w = tab + (long long)phase * taps;
+    const float* __restrict__ xb = x + (long long)b * x_stride;
+    const long long k0 = i0 - kh + 1;
+    float acc = 0.f;
+    for (int j = 0; j < taps; ++j) {
+        const long long k = k0 + j;
+        if (k >= 0 && k < n_in) acc = fmaf(__ldg(w + j), __ldg(xb + k), acc);
+    }
+    y[(long long)b * y_stride + m] = acc;
+}
+
+struct ResampleTable { int up = 1, down = 1, taps = 0, kh = 0; float* tab = nullptr; };
+
+static double bessel_i0(double x) {   // power series, converges fast for the argument range of a Kaiser window
+    double s = 1.0, term = 1.0;
+    for (int k = 1; k < 200; ++k) {
+        term *= (x / (2.0 * k)) * (x / (2.0 * k));
+        s += term;
+        if (term < 1e-18 * s) break;
+    }
+    return s;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static std::string g_fe_create_error;
 
@@ -235,6 +274,7 @@ struct Frontend {
     std::vector<void*> owned;
     float* rms = nullptr; size_t rms_cap = 0;
     unsigned* rmax = nullptr; size_t rmax_cap = 0;
+    std::map<std::pair<int, int>, ResampleTable> rs_tabs;   // per (sr_in, sr_out), built on first use
 
     template <typename T> T* upload(const std::vector<T>& h) {
         T* d = nullptr;
@@ -331,6 +371,48 @@ struct Frontend {
         ZVX_POST_LAUNCH();
     }
 
+    const ResampleTable& resample_table(int sr_in, int sr_out) {
+        auto it = rs_tabs.find({sr_in, sr_out});
+        if (it != rs_tabs.end()) return it->second;
+        ZVX_REQUIRE(sr_in >= 1000 && sr_out >= 1000 && sr_in <= 768000 && sr_out <= 768000, "zvx_resample: sampling rate out of range");
+        int a = sr_in, b = sr_out;
+        while (b) { const int t = a % b; a = b; b = t; }
+        ResampleTable r;
+        r.up = sr_out / a; r.down = sr_in / a;
+        ZVX_REQUIRE(r.up <= 4096, "zvx_resample: rate ratio needs more than 4096 filter phases");
+        const double num_zeros = 64.0, beta = 14.769656459379492, rolloff = 0.9475937167399596;
+        const double scale = std::min(1.0, (double)sr_out / sr_in);
+        r.kh = (int)std::ceil(num_zeros / scale);
+        r.taps = 2 * r.kh;
+        std::vector<float> h((size_t)r.up * r.taps);
+        const double i0b = bessel_i0(beta), pi = 3.14159265358979323846;
+        for (int ph = 0; ph < r.up; ++ph)
+            for (int j = 0; j < r.taps; ++j) {
+                const double u = ((double)ph / r.up + r.kh - 1 - j) * scale;   // (t - k) * scale, k = floor(t) - kh + 1 + j
+                double w = 0.0;
+                if (std::fabs(u) < num_zeros) {
+                    const double xs = pi * rolloff * u, sinc = std::fabs(xs) < 1e-12 ? 1.0 : std::sin(xs) / xs;
+                    const double q = u / num_zeros;
+                    w = scale * rolloff * sinc * bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - q * q))) / i0b;
+                }
+                h[(size_t)ph * r.taps + j] = (float)w;
+            }
+        r.tab = upload(h);
+        return rs_tabs.emplace(std::make_pair(sr_in, sr_out), r).first->second;
+    }
+
+    void resample(const float* in, int B, long long n_in_stride, const long long* len_in, int sr_in, int sr_out, float* out,
+                  long long n_out_stride, long long n_out, cudaStream_t st) {
+        ZVX_REQUIRE(in && out, "zvx_resample: null pointer");
+        ZVX_REQUIRE(B >= 1 && B <= 65535 && n_in_stride >= 1 && n_out >= 0 && n_out <= n_out_stride, "zvx_resample: bad sizes");
+        ZVX_CUDA_CHECK(cudaSetDevice(device));
+        if (n_out == 0) return;
+        const ResampleTable& r = resample_table(sr_in, sr_out);
+        resample_kernel<<<dim3(cdiv(n_out, 256), B), 256, 0, st>>>(in, n_in_stride, len_in, r.tab, r.up, r.down, r.taps, r.kh, out,
+                                                                    n_out_stride, n_out);
+        ZVX_POST_LAUNCH();
+    }
+
     void trim(const float* wav, int B, long long n_stride, const long long* wav_len, float top_db, int frame_length,
               int hop, long long* start, long long* len, long long* host_out, cudaStream_t st) {
         ZVX_REQUIRE(wav && start && len, "zvx_trim_silence: null pointer");
@@ -424,6 +506,17 @@ int zvx_trim_silence(zvx_frontend* h, const float* wav, int B, int64_t n_stride,
                      void* stream) {
     ZVX_FE_GUARD(h, h->fe->trim(wav, B, n_stride, (const long long*)wav_len, top_db, frame_length, hop_length,
                                 (long long*)start, (long long*)len, (long long*)start_len_host, (cudaStream_t)stream));
+}
+
+int64_t zvx_resample_num_samples(int64_t n_in, int sr_in, int sr_out) {
+    if (n_in <= 0 || sr_in <= 0 || sr_out <= 0) return 0;
+    return (n_in * (int64_t)sr_out + sr_in - 1) / sr_in;   // ceil(n * ratio), as librosa.resample sizes its output
+}
+
+int zvx_resample(zvx_frontend* h, const float* wav_in, int B, int64_t n_in_stride, const int64_t* len_in, int sr_in, int sr_out,
+                 float* wav_out, int64_t n_out_stride, int64_t n_out, void* stream) {
+    ZVX_FE_GUARD(h, h->fe->resample(wav_in, B, n_in_stride, (const long long*)len_in, sr_in, sr_out, wav_out, n_out_stride, n_out,
+                                    (cudaStream_t)stream));
 }
 
 int zvx_mel_spectrogram(zvx_frontend* h, const float* wav, int B, int64_t n_stride, const int64_t* wav_start,

@@ -103,9 +103,16 @@ __global__ void __launch_bounds__(256) hw_sum_partial_kernel(const float* __rest
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r0 < nr) {
         const float4* p = reinterpret_cast<const float4*>(x) + (long long)b * HW * C4 + c4;
-        for (int i = lo + r0; i < hi; i += nr) {
-            const float4 v = __ldg(p + (long long)i * C4);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        // four independent loads in flight per thread (one per iteration left the kernel latency-bound at 0.54 of the HBM
+        // peak, profiles/r02_ncu_hbm_kernels.csv); fixed summation order
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = lo + r0; i < hi; i += 4 * nr) {
+            const float4 v0 = __ldg(p + (long long)i * C4);
+            const float4 v1 = (i + nr < hi) ? __ldg(p + (long long)(i + nr) * C4) : z4;
+            const float4 v2 = (i + 2 * nr < hi) ? __ldg(p + (long long)(i + 2 * nr) * C4) : z4;
+            const float4 v3 = (i + 3 * nr < hi) ? __ldg(p + (long long)(i + 3 * nr) * C4) : z4;
+            acc.x += (v0.x + v1.x) + (v2.x + v3.x); acc.y += (v0.y + v1.y) + (v2.y + v3.y);
+            acc.z += (v0.z + v1.z) + (v2.z + v3.z); acc.w += (v0.w + v1.w) + (v2.w + v3.w);
         }
     }
     red[threadIdx.x] = acc;

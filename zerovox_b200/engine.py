@@ -112,6 +112,25 @@ def _ptr(t: torch.Tensor | None):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+class _nvtx:
+    """NVTX range around one stage call: `nsys` / `ncu --nvtx` timelines show zvx_spkemb / zvx_encode /
+    zvx_length_regulate / zvx_decode / zvx_vocode per forward.  Costs two driver calls; no-op when NVTX is unavailable."""
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        try:
+            torch.cuda.nvtx.range_push(self.name)
+        except Exception:  # noqa: BLE001
+            self.name = None
+
+    def __exit__(self, *exc):
+        if self.name is not None:
+            torch.cuda.nvtx.range_pop()
+
+
 class Engine:
     """One engine handle bound to one CUDA device (not thread-safe, like the reference)."""
 
@@ -127,7 +146,8 @@ class Engine:
         self.cfg = cfg
         self._c_cfg = cfg.to_c()
         self._h = C.c_void_p()
-        rc = self.lib.zvx_create(C.byref(self._c_cfg), self.device.index, C.byref(self._h))
+        with torch.cuda.device(self.device):   # the C side does cudaSetDevice: keep the caller's current device untouched
+            rc = self.lib.zvx_create(C.byref(self._c_cfg), self.device.index, C.byref(self._h))
         if rc != 0:
             raise RuntimeError("zvx_create: " + self.lib.zvx_last_error(None).decode())
 
@@ -160,8 +180,9 @@ class Engine:
                 continue
             t = v.detach().to(torch.float32).contiguous()
             shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
-            self._check(self.lib.zvx_set_weight(self._h, (prefix + k).encode(), _ptr(t), shape, t.dim()),
-                        f"zvx_set_weight({prefix + k})")
+            with torch.cuda.device(self.device):
+                self._check(self.lib.zvx_set_weight(self._h, (prefix + k).encode(), _ptr(t), shape, t.dim()),
+                            f"zvx_set_weight({prefix + k})")
 
     def load_weights(self, state_dict: Mapping[str, torch.Tensor], prefix: str = ""):
         """set_weights + finalize (the engine-level load_state_dict)."""
@@ -169,7 +190,8 @@ class Engine:
         self.finalize()
 
     def finalize(self):
-        self._check(self.lib.zvx_finalize_weights(self._h), "zvx_finalize_weights")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.zvx_finalize_weights(self._h), "zvx_finalize_weights")
 
     # ------------------------------------------------------------------ stages
     def spkemb(self, ref_mel: torch.Tensor) -> torch.Tensor:
@@ -179,7 +201,7 @@ class Engine:
         if M != self.cfg.n_mels:
             raise RuntimeError(f"ref_mel has {M} mel channels, model expects {self.cfg.n_mels}")
         out = torch.empty((B, 1, self.cfg.hidden), device=self.device, dtype=torch.float32)
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _nvtx("zvx_spkemb"):
             self._check(self.lib.zvx_spkemb(self._h, _ptr(x), B, T, _ptr(out), self._stream()), "zvx_spkemb")
         return out
 
@@ -207,7 +229,7 @@ class Engine:
         }
         lmax = C.c_int(0)
         host = (C.c_int64 * B)()
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _nvtx("zvx_encode"):
             self._check(self.lib.zvx_encode(
                 self._h, _ptr(ph), _ptr(pu), _ptr(pm), _ptr(st), _ptr(fd), B, T, _ptr(out["pitch"]),
                 _ptr(out["energy"]), _ptr(out["log_duration"]), _ptr(out["duration_rounded"]), _ptr(out["mel_len"]),
@@ -226,7 +248,7 @@ class Engine:
         B, T, H = x.shape
         feats = torch.empty((B, L_max, H), device=self.device, dtype=torch.float32)
         idx = torch.empty((B, L_max), device=self.device, dtype=torch.int32) if want_index else None
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _nvtx("zvx_length_regulate"):
             if frame0:
                 self._check(self.lib.zvx_length_regulate_chunk(self._h, _ptr(x), _ptr(d), B, T, int(frame0), L_max,
                                                                _ptr(feats), _ptr(idx), self._stream()),
@@ -263,7 +285,7 @@ class Engine:
         ml = None if mel_len is None else self._dev(mel_len, torch.int64, "mel_len")
         blc = torch.empty((B, L, self.cfg.n_mels), device=self.device, dtype=torch.float32) if want_blc else None
         bcl = torch.empty((B, self.cfg.n_mels, L), device=self.device, dtype=torch.float32) if want_bcl else None
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _nvtx("zvx_decode"):
             self._check(self.lib.zvx_decode(self._h, _ptr(f), _ptr(m), _ptr(ml), _ptr(st), B, L,
                                             1 if zero_padded_mel else 0, _ptr(blc), _ptr(bcl), self._stream()),
                         "zvx_decode")
@@ -283,7 +305,7 @@ class Engine:
                     out.numel() != B * L * self.cfg.hop_length:
                 raise RuntimeError("vocode(out=): need a contiguous fp32 tensor of B * L * hop elements on the engine's device")
             wav = out
-        with torch.cuda.device(self.device):
+        with torch.cuda.device(self.device), _nvtx("zvx_vocode"):
             self._check(self.lib.zvx_vocode(self._h, _ptr(m), B, L, _ptr(wav), self._stream()), "zvx_vocode")
         return wav
 

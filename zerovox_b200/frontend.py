@@ -19,8 +19,9 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device):
+    """torch's current stream ON THE HANDLE'S DEVICE (not on whatever device happens to be current)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class MelFrontend:
@@ -38,12 +39,14 @@ class MelFrontend:
             self.device = torch.device("cuda", torch.cuda.current_device())
         c = _lib.ZvxMelConfig()
         c.abi_version = _lib.ZVX_ABI_VERSION
+        self.sampling_rate = int(sampling_rate)
         c.sampling_rate, c.fft_size, c.hop_size = int(sampling_rate), int(fft_size), int(hop_size)
         c.win_length = int(win_length if win_length is not None else fft_size)
         c.num_mels, c.fmin, c.fmax, c.clip_val = int(num_mels), float(fmin or 0), float(fmax), 1e-5
         self.num_mels, self.hop_size = c.num_mels, c.hop_size
         self._h = C.c_void_p()
-        rc = self.lib.zvx_frontend_create(C.byref(c), self.device.index, C.byref(self._h))
+        with torch.cuda.device(self.device):   # the C side does cudaSetDevice: keep the caller's current device untouched
+            rc = self.lib.zvx_frontend_create(C.byref(c), self.device.index, C.byref(self._h))
         if rc != 0:
             raise RuntimeError("zvx_frontend_create: " + self.lib.zvx_frontend_last_error(None).decode())
 
@@ -76,9 +79,10 @@ class MelFrontend:
         start = torch.empty(B, dtype=torch.int64, device=self.device)
         length = torch.empty(B, dtype=torch.int64, device=self.device)
         host = (C.c_int64 * (2 * B))()
-        self._check(self.lib.zvx_trim_silence(self._h, _ptr(wav), B, n, _ptr(wav_len), float(top_db), int(frame_length),
-                                              int(hop_length), _ptr(start), _ptr(length), host, _stream()),
-                    "zvx_trim_silence")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.zvx_trim_silence(self._h, _ptr(wav), B, n, _ptr(wav_len), float(top_db), int(frame_length),
+                                                  int(hop_length), _ptr(start), _ptr(length), host, _stream(self.device)),
+                        "zvx_trim_silence")
         return start, length, list(host[:B]), list(host[B:])
 
     def mel(self, wav: torch.Tensor, wav_start: torch.Tensor | None = None, wav_len: torch.Tensor | None = None,
@@ -93,9 +97,25 @@ class MelFrontend:
             n_frames = self.num_frames(n)
         mel = torch.empty((B, n_frames, self.num_mels), dtype=torch.float32, device=self.device)
         energy = torch.empty((B, n_frames), dtype=torch.float32, device=self.device) if with_energy else None
-        self._check(self.lib.zvx_mel_spectrogram(self._h, _ptr(wav), B, n, _ptr(wav_start), _ptr(wav_len), int(n_frames),
-                                                 _ptr(mel), _ptr(energy), _stream()), "zvx_mel_spectrogram")
+        with torch.cuda.device(self.device):
+            self._check(self.lib.zvx_mel_spectrogram(self._h, _ptr(wav), B, n, _ptr(wav_start), _ptr(wav_len), int(n_frames),
+                                                     _ptr(mel), _ptr(energy), _stream(self.device)), "zvx_mel_spectrogram")
         return (mel, energy) if with_energy else mel
+
+    def resample(self, wav: torch.Tensor, sr_in: int, sr_out: int | None = None, wav_len: torch.Tensor | None = None):
+        """The `sr=` conversion of librosa.load (synthesize.py:113-121) on the GPU: wav [B, n] (or [n]) at ``sr_in`` ->
+        [B, ceil(n * sr_out / sr_in)] at ``sr_out`` (default: this front-end's sampling rate)."""
+        sr_out = int(sr_out or self.sampling_rate)
+        wav = self._wav(wav)
+        if int(sr_in) == sr_out:
+            return wav
+        B, n = wav.shape
+        n_out = int(self.lib.zvx_resample_num_samples(n, int(sr_in), sr_out))
+        out = torch.empty((B, n_out), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.zvx_resample(self._h, _ptr(wav), B, n, _ptr(wav_len), int(sr_in), sr_out, _ptr(out), n_out, n_out,
+                                              _stream(self.device)), "zvx_resample")
+        return out
 
     def speaker_prompt_mel(self, wav: torch.Tensor, top_db: float = 40.0) -> torch.Tensor:
         """synthesize.py:123-138 for a batch of prompts [B, n]: trim each row, then its log-mel; rows are zero-filled

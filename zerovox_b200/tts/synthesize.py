@@ -2,7 +2,8 @@
 the hot path — ``speaker_embed`` (synthesize.py:123-143), ``transcript2phonemids`` (145-190), ``text2phonemeids``
 (192-213), ``tts_ex`` / ``tts`` (215-243) — with the GPU front-end and the native tokeniser underneath.
 
-Not mirrored (outside the path, SURVEY.md §8f / DESIGN.md §9): audio file loading + resampling (librosa.load), the NeMo /
+Not mirrored (outside the path, SURVEY.md §8f / DESIGN.md §9): audio file decoding (librosa.load; its `sr=` resampling IS
+built: `speaker_embed(wav, sampling_rate=)`), the NeMo /
 uroman text normaliser (pass any callable with ``normalize(text) -> (transcript, _)`` as ``normalizer``), the HuggingFace
 download in ``load_model`` (local directory / cache layouts are read, nothing is fetched) and the torchinfo ``summary``.
 """
@@ -51,13 +52,17 @@ class ZeroVoxTTS:
         self._frontend = MelFrontend(sampling_rate, fft_size, hop_length, win_length, n_mel_channels, mel_fmin, mel_fmax,
                                      device=infer_device)
 
-    def speaker_embed(self, wav):
+    def speaker_embed(self, wav, sampling_rate=None):
         """synthesize.py:123-143: trim(top_db=40) -> log-mel -> `_spkemb`; the prompt goes to the GPU once and only the
-        trimmed length (16 bytes) comes back before the style vector."""
+        trimmed length (16 bytes) comes back before the style vector.  ``sampling_rate`` (extension): the rate of ``wav`` when it
+        is not the model's — the conversion `librosa.load(..., sr=)` does in get_speakerref (synthesize.py:113-121; the packaged
+        prompts are 24 kHz) then runs on the GPU first."""
         if not isinstance(wav, torch.Tensor):
             wav = torch.from_numpy(np.ascontiguousarray(wav, dtype=np.float32))
         wav = wav.to(self._infer_device)
         with torch.no_grad():
+            if sampling_rate is not None and int(sampling_rate) != int(self._sampling_rate):
+                wav = self._frontend.resample(wav, int(sampling_rate), int(self._sampling_rate))[0]
             x = self._frontend.speaker_prompt_mel(wav, top_db=40)
             return self._model._spkemb(x)
 
