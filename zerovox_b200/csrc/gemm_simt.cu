@@ -381,26 +381,13 @@ __global__ void __launch_bounds__(256) gemm_skinny_stream_kernel(const GemmArgs 
                 __syncthreads();
             }
             if (n < a.N) {
-                // the column's weight slice goes to registers first (<= 9 independent 128-bit loads per lane in flight: the loop
-                // was bound by one load latency per 128 k's), then the FMAs run from registers and shared memory
                 const float4* __restrict__ wrow = reinterpret_cast<const float4*>(a.W + (long long)n * a.ldw + k0);
-                constexpr int WMAX = (SKS_KC / 4 + 31) / 32;
-                float4 wreg[WMAX];
+                for (int k4 = lane; k4 < kc4; k4 += 32) {
+                    const float4 w = __ldg(wrow + k4);
 #pragma unroll
-                for (int i = 0; i < WMAX; ++i) {
-                    const int k4 = lane + 32 * i;
-                    wreg[i] = (k4 < kc4) ? __ldg(wrow + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int i = 0; i < WMAX; ++i) {
-                    const int k4 = lane + 32 * i;
-                    if (k4 < kc4) {
-                        const float4 w = wreg[i];
-#pragma unroll
-                        for (int m = 0; m < 32; ++m) {
-                            const float4 x = As4[m * pitch + k4];
-                            acc[m] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[m]))));
-                        }
+                    for (int m = 0; m < 32; ++m) {
+                        const float4 x = As4[m * pitch + k4];
+                        acc[m] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[m]))));
                     }
                 }
             }
