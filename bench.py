@@ -60,6 +60,7 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-config4", action="store_true")
+    p.add_argument("--e2e-groups-extra", default="", help="N > 1: further delivery-group settings to time, e.g. '-3,2,4' (reported)")
     p.add_argument("--e2e-groups", type=int, default=0,
                    help="N > 1 e2e: vocoder delivery groups per rank (gather + D2H of group i overlap the vocoding of group i+1); "
                         "negative = groups of halving size; 0 = -4 when N >= 4 (rank 0 then has >= 100 MB to copy out), else 2")
@@ -368,7 +369,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     W = max(args.warmup, 3)
-    if args.e2e_groups <= 0:
+    if args.e2e_groups == 0:
         args.e2e_groups = -4 if world >= 4 else 2
     w = syn.make_weights(cfg, seed=0)
     model = build_model(cfg, w, device=dev, tensor_core_policy=args.policy)
@@ -489,6 +490,15 @@ def main():
             for _ in range(args.steps):
                 step_e2e(1)
             e2e["ms_unpipelined"] = (time.perf_counter() - t0) / args.steps * 1e3
+            e2e["extra"] = {}
+            for gs in [int(v) for v in args.e2e_groups_extra.split(",") if v.strip()]:
+                for _ in range(2):
+                    step_e2e(gs)
+                dist.barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    step_e2e(gs)
+                e2e["extra"][str(gs)] = (time.perf_counter() - t0) / args.steps * 1e3
 
     # ---- config 4 variant (N > 1): ragged T_i ~ U{64..192}, alternating EN / DE weight sets, sharded ------------------
     c4 = None
@@ -559,6 +569,7 @@ def main():
                                 "delivery": "pipelined" if best == e2e["ms"] else "one gather-v after the forward",
                                 "delivery_groups": args.e2e_groups, "ms_per_step_pipelined": e2e["ms"],
                                 "ms_per_step_unpipelined": e2e["ms_unpipelined"],
+                                "ms_per_step_other_group_settings_rank0": e2e.get("extra") or None,
                                 "note": "pipelined = every rank vocodes in delivery_groups utterance groups; the gather-v and the D2H copy "
                                         "of a group overlap the next group's kernels (sharded_forward(vocoder_groups=, host_out=))"})
     if world > 1:

@@ -179,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (warp == 0) {
         // ================================================================ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tx_bytes = (uint32_t)(p.a_bytes + p.b_tile_bytes) * (SPLIT ? 2u : 1u);
@@ -258,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         __syncwarp();
     } else if (warp == 1) {
         // ================================================================ MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             uint32_t cnt = 0;   // accumulation phases issued so far (one per tile unless SPLIT)

@@ -89,6 +89,19 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
+// One elected lane of a converged warp (elect.sync).  Single-thread roles branch on THIS instead of `lane == 0`: ptxas then knows
+// that exactly one thread is active inside and emits tcgen05 / TMA instructions (which execute once per warp on the uniform
+// datapath) directly, instead of wrapping each one in a loop over the active threads (ELECT / PLOP3 / BRA.U.ANY per instruction:
+// ~5 extra instructions and a branch per MMA — the issue loop of narrow-N tiles was bound by it, profiles/r02_ncu_gemm_spk32_*).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const __grid_constan
         ZVX_STAMP2();
         umma_commit(mma_bar);
     };
-    if (tid == 0) load_w(0);
+    if (warp == 0 && elect_one()) load_w(0);
     {
         // ================================================================ loader + epilogue warps (0..7)
         // Thread (q, lane, g) reads accumulator row n = 32q + lane, columns [64g, 64g + 64) = the NPH sub-indices
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const __grid_constan
             const int dn = last ? 1 : p.ld[s + 1];
             const uint32_t mgn = last ? 0u : p.mg[s + 1];
             if (warp == 0) {
-                if (lane == 0) issue_step(s);
+                if (elect_one()) issue_step(s);
                 __syncwarp();
             }
             if (s + 2 >= p.nsteps) {
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const __grid_constan
             wait_sleep(mma_bar, (uint32_t)(s & 1), (uint32_t)p.wait_ns);   // sleeping wait: leaves the issue slots to the co-resident CTA
             tc_fence_after();
             ZVX_STAMP();
-            if (tid == 0 && p.nwbuf == 1 && s + 1 < p.nsteps) load_w(s + 1);   // single weight buffer: this step's MMAs have read it
+            if (warp == 0 && p.nwbuf == 1 && s + 1 < p.nsteps && elect_one()) load_w(s + 1);   // single weight buffer: this step's MMAs have read it
 
             // The accumulator already holds conv + bias (the step's first MMA initialises it with the bias).  Variants, all
             // straight-line: MODE 0 first conv of a pair / 1 residual step / 2 last step; SCAT: the thread's samples (MODE 0) or

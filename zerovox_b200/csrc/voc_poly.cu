@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(NT) voc_poly_kernel(const VocResArgs a, const 
 
     if (warp == EPI_THREADS / 32) {
         // ================================================================ MMA issuer + weight streamer (one thread)
-        if (lane == 0) {
+        if (elect_one()) {
             auto load_w = [&](int s) {
                 const uint32_t bytes = (uint32_t)p.n16[s] * 16u;
                 mbar_arrive_expect_tx(w_bar(s & 1), bytes);

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NT) voc_resblock_kernel(const VocResArgs a, co
     for (int s = 0; s < p.nsteps; ++s) {
         const int dil = a.steps[s].dil;
         const int mt = p.mt[s];
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             // all taps of the conv for every M tile: D[m] (+)= A[rows m*128 + j*dil ...] x W[j]
             const uint64_t da0 = nosw_desc(sA, (uint32_t)p.Rp), db0 = nosw_desc(sW, (uint32_t)p.Np);
             for (int m = 0; m < mt; ++m) {
