@@ -461,44 +461,53 @@ def main():
                     len_host.copy_(ml, non_blocking=True)
                 torch.cuda.synchronize(dev)
         else:
+            # N > 1, two deliveries of the same call, several group settings each; the headline is the fastest, all are stated:
+            #  "funnel": rank 0 uploads the global batch, NCCL scatter, NCCL gather-v, rank 0 copies all waveforms to the host
+            #  "shared": inputs and waveforms live in page-locked host windows mapped by every rank (SharedHostBatch /
+            #            SharedHostBuffer): every rank moves its own block over its own PCIe link, no scatter, tails over NCCL
+            from zerovox_b200.parallel import SharedHostBatch, SharedHostBuffer
             h2d = d2h = 0
             wav_host = None
             if rank == 0:
                 h2d = sum(xg_host[k].numel() * xg_host[k].element_size() for k in keys)
                 wav_host = torch.empty(sum(e - s for s, e in last["r"].wav_segments()), dtype=torch.float32).pin_memory()
                 d2h = wav_host.numel() * 4
+            shared_x = SharedHostBatch(xg_host if rank == 0 else None)
+            win = SharedHostBuffer(4 * world * args.batch * spec[7] * cfg.hop_length)
 
-            def step_e2e(groups=args.e2e_groups):
-                # pinned host inputs in, the valid samples of every utterance out to pinned host memory (rank-major, back to
-                # back; lengths are host-known): the copies ride the side stream group by group
-                step_sharded(xg_host if rank == 0 else None, groups=groups, host_out=wav_host)
+            def step_e2e(groups=args.e2e_groups, shared=True):
+                # host inputs in, the valid samples of every utterance out to host memory (rank-major; lengths are
+                # host-known): the copies ride the side stream group by group
+                if shared:
+                    step_sharded(shared_x, groups=groups, host_out=win)
+                else:
+                    step_sharded(xg_host if rank == 0 else None, groups=groups, host_out=wav_host)
                 torch.cuda.synchronize(dev)
-        for _ in range(2):
-            step_e2e()
-        if dist:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        t_e2e = (time.perf_counter() - t0) / args.steps
-        e2e = {"ms": t_e2e * 1e3, "h2d": h2d, "d2h": d2h}
-        if world > 1 and args.e2e_groups != 1:           # the same path without the pipelined delivery
+
+        def time_e2e(**kw):
             for _ in range(2):
-                step_e2e(1)
-            dist.barrier()
+                step_e2e(**kw)
+            if dist:
+                dist.barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                step_e2e(1)
-            e2e["ms_unpipelined"] = (time.perf_counter() - t0) / args.steps * 1e3
-            e2e["extra"] = {}
-            for gs in [int(v) for v in args.e2e_groups_extra.split(",") if v.strip()]:
-                for _ in range(2):
-                    step_e2e(gs)
-                dist.barrier()
-                t0 = time.perf_counter()
-                for _ in range(args.steps):
-                    step_e2e(gs)
-                e2e["extra"][str(gs)] = (time.perf_counter() - t0) / args.steps * 1e3
+                step_e2e(**kw)
+            return (time.perf_counter() - t0) / args.steps * 1e3
+
+        e2e = {"h2d": h2d, "d2h": d2h}
+        if world == 1:
+            e2e["ms"] = time_e2e()
+        else:
+            variants = {}
+            extra = [int(v) for v in args.e2e_groups_extra.split(",") if v.strip()]
+            rbs = {}
+            for shared in (True, False):
+                for gs in dict.fromkeys([1, args.e2e_groups] + extra):
+                    variants[("shared" if shared else "funnel") + f"_groups{gs}"] = time_e2e(groups=gs, shared=shared)
+                rbs[shared] = last["r"]
+            e2e["variants"] = variants
+            if rank == 0:                                  # both deliveries hold the same samples, bit for bit
+                e2e["deliveries_identical"] = all(torch.equal(rbs[True].host_wav(i), rbs[False].host_wav(i)) for i in range(Bg))
 
     # ---- config 4 variant (N > 1): ragged T_i ~ U{64..192}, alternating EN / DE weight sets, sharded ------------------
     c4 = None
@@ -524,16 +533,17 @@ def main():
 
     # ---- max over ranks -------------------------------------------------------------------------------------------------
     if dist:
-        t = torch.tensor([ms, e2e["ms"] if e2e else 0.0, ms_rep or 0.0, c4["ms"] if c4 else 0.0,
-                          (e2e or {}).get("ms_unpipelined", 0.0)], device=dev, dtype=torch.float64)
+        vkeys = sorted((e2e or {}).get("variants", {}))
+        t = torch.tensor([ms, ms_rep or 0.0, c4["ms"] if c4 else 0.0] + [e2e["variants"][k] for k in vkeys],
+                         device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_rep = float(t[0]), float(t[2])
+        ms, ms_rep = float(t[0]), float(t[1])
         if e2e:
-            e2e["ms"] = float(t[1])
-            if "ms_unpipelined" in e2e:
-                e2e["ms_unpipelined"] = float(t[4])
+            e2e["variants"] = {k: float(t[3 + i]) for i, k in enumerate(vkeys)}
+            e2e["best"] = min(e2e["variants"], key=e2e["variants"].get)
+            e2e["ms"] = e2e["variants"][e2e["best"]]
         if c4:
-            c4["ms"] = float(t[3])
+            c4["ms"] = float(t[2])
         fr = torch.tensor([float(frames_local)], device=dev, dtype=torch.float64)
         dist.all_reduce(fr, op=dist.ReduceOp.SUM)
         frames_replicas = int(fr[0])
@@ -562,16 +572,15 @@ def main():
     if e2e:
         line["e2e"] = {"value": audio_seconds(frames, cfg) / (e2e["ms"] / 1e3), "unit": UNIT,
                        "ms_per_step": e2e["ms"], "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]}
-        if "ms_unpipelined" in e2e:
-            # two delivery modes of the same call were timed; the headline is the faster one, both are stated
-            best = min(e2e["ms"], e2e["ms_unpipelined"])
-            line["e2e"].update({"value": audio_seconds(frames, cfg) / (best / 1e3), "ms_per_step": best,
-                                "delivery": "pipelined" if best == e2e["ms"] else "one gather-v after the forward",
-                                "delivery_groups": args.e2e_groups, "ms_per_step_pipelined": e2e["ms"],
-                                "ms_per_step_unpipelined": e2e["ms_unpipelined"],
-                                "ms_per_step_other_group_settings_rank0": e2e.get("extra") or None,
-                                "note": "pipelined = every rank vocodes in delivery_groups utterance groups; the gather-v and the D2H copy "
-                                        "of a group overlap the next group's kernels (sharded_forward(vocoder_groups=, host_out=))"})
+        if "variants" in e2e:
+            line["e2e"].update({
+                "delivery": e2e["best"], "ms_per_step_by_delivery": e2e["variants"],
+                "deliveries_bit_identical": e2e.get("deliveries_identical"),
+                "note": "shared = inputs and waveforms in page-locked host windows mapped by every rank (zerovox_b200.parallel."
+                        "SharedHostBatch / SharedHostBuffer): each rank moves its own block over its own PCIe link, tails and "
+                        "completion over NCCL; funnel = everything through rank 0's GPU (upload, NCCL scatter, NCCL gather-v, "
+                        "one D2H); groupsG = every rank vocodes in G utterance groups (negative: halving sizes) and a group's "
+                        "delivery overlaps the next group's kernels; byte counts are the totals over all ranks"})
     if world > 1:
         r = last["r"]
         ph = {}

@@ -66,3 +66,27 @@ def test_sharded_forward_single_gpu_matches_forward(forced):
     for i, n in enumerate(mel_len.tolist()):
         assert torch.equal(vw[i, : n * cfg.hop_length], wav[i, : n * cfg.hop_length]) and not vw[i, n * cfg.hop_length:].any()
         assert torch.equal(vm[i, :, :n], mel[i, :, :n]) and not vm[i, :, n:].any()
+
+
+def test_shared_host_window_single_gpu():
+    """SharedHostBatch / SharedHostBuffer with one rank: the window is page-locked (cudaHostRegister), the forward uploads
+    from it and the waveforms land in it group by group."""
+    from zerovox_b200.parallel import SharedHostBatch, SharedHostBuffer
+    cfg = zo.ZeroVoxConfig.tiny()
+    w = zo.make_weights(cfg, seed=1, dur_bias=float(np.log(4.0)))
+    model = build_model(cfg, w, device=DEV)
+    x = zo.make_inputs(cfg, 4, 9, 24, seed=3, ragged=True, dur_lo=1, dur_hi=5)
+    with torch.no_grad():
+        wav, mel, mel_len, logd = model(dict(x), force_duration=True)
+        batch = SharedHostBatch(dict(x))
+        assert batch.window.registered and batch.x["ref_mel"].is_pinned()
+        win = SharedHostBuffer(4 * 4 * int(mel_len.max()) * cfg.hop_length)
+        rb = sharded_forward(model, batch, force_duration=True, device=DEV, hop_length=cfg.hop_length, n_mels=cfg.n_mels,
+                             ragged=True, vocoder_groups=2, host_out=win)
+        torch.cuda.synchronize()
+    for i, n in enumerate(mel_len.tolist()):
+        assert torch.equal(rb.host_wav(i), wav[i, : n * cfg.hop_length].cpu())
+        assert torch.equal(rb.wav(i), wav[i, : n * cfg.hop_length])          # one rank: also on the device
+        assert torch.equal(rb.mel(i), mel[i, :, :n])
+    win.close()
+    batch.window.close()

@@ -16,7 +16,8 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from zerovox_b200.parallel import mixed_language_forward, partition, sharded_forward  # noqa: E402
+from zerovox_b200.parallel import (SharedHostBatch, SharedHostBuffer, mixed_language_forward, partition,  # noqa: E402
+                                   sharded_forward)
 
 HOP, NMEL = 4, 6
 
@@ -198,6 +199,24 @@ def _worker(rank, world, port, cases, q):
                 assert torch.equal(rb.log_duration(), ref[3])
             else:
                 assert rb is None
+            # host-to-host through shared host windows: every rank uploads its own block and writes its own waveforms
+            shared_x = SharedHostBatch(x, register=False)
+            win = SharedHostBuffer(4 * (world * (-(-B // world)) * T * 7 * HOP + 64), register=False)
+            win.tensor().zero_()
+            dist.barrier()
+            rb = sharded_forward(fake_model, shared_x, force_duration=forced, device="cpu", hop_length=HOP, n_mels=NMEL,
+                                 ragged=True, vocoder_groups=(2 if B % 2 else 1), host_out=win)
+            if rank == 0:
+                assert not rb.wav_on_device and rb.host is not None
+                for i, n in enumerate(ref[2].tolist()):
+                    assert torch.equal(rb.host_wav(i), ref[0][i, : n * HOP]), f"shared host window, utterance {i}"
+                    assert torch.equal(rb.mel(i), ref[1][i, :, :n])
+                assert torch.equal(rb.log_duration(), ref[3])
+                with pytest.raises(RuntimeError):
+                    rb.wav(0)
+            else:
+                assert rb is None
+            dist.barrier()
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         q.put((rank, repr(e)))

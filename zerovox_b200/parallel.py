@@ -10,6 +10,13 @@ gathered buffer (``gather-v``: one grouped ncclSend / ncclRecv, no staging copy,
 which is how the host logic is tested — the ragged pack / unpack then use plain tensor slicing instead of the CUDA
 kernels of csrc/ragged.cu).
 
+Host-to-host delivery.  When the batch comes from and the waveforms go back to HOST memory, funnelling everything through
+rank 0's GPU makes rank 0's one PCIe link carry world x the bytes (8 GPUs, configs[1]: 202 MB of waveforms per step = 4 ms,
+a fifth of the step).  :class:`SharedHostBuffer` is a page-locked host window mapped by every rank of the group;
+with ``host_out=SharedHostBuffer`` every rank writes its own waveforms to the host over its OWN PCIe link (only the small
+mel / log-duration tails still travel to rank 0 over NCCL, which is also the completion fence), and with
+``x=SharedHostBatch`` every rank uploads its own block of the global batch from the window (no scatter).
+
 Control plane: one broadcast of 12 int64 (shapes, flags, the global frame count when durations are forced) unless every
 rank passes ``spec``; with predicted durations one all-gather of the per-utterance frame counts, which also yields the
 global frame count.
@@ -24,6 +31,9 @@ an utterance's own length; ``tails="padded"`` also ships the padded tails, repro
 from __future__ import annotations
 
 import ctypes as C
+import os
+import shutil
+import tempfile
 from dataclasses import dataclass, field
 from typing import Callable, Mapping, Sequence
 
@@ -84,6 +94,115 @@ def _ragged_copy(pack: bool, padded: torch.Tensor, packed: torch.Tensor, lens_de
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# host memory shared by the ranks of a box
+# ---------------------------------------------------------------------------------------------------------------------
+def _group_info(group):
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if not multi:
+        return False, 0, 1, 0
+    return True, dist.get_rank(group), dist.get_world_size(group), (0 if group is None else dist.get_global_rank(group, 0))
+
+
+class SharedHostBuffer:
+    """``nbytes`` of host memory mapped by every rank of ``group`` (one process per GPU on ONE box) and page-locked for DMA
+    in each of them, so that every GPU reads / writes it over its own PCIe link.  Collective: every rank of the group
+    constructs it in the same order.  Backed by an unlinked tmpfs file (/dev/shm, else the temp directory); with CUDA the
+    mapping is registered with ``cudaHostRegister`` (non-blocking copies then go straight to / from it); without
+    (gloo tests) it is plain shared memory.
+
+    ``tensor(dtype, numel, offset_bytes)`` returns a view.  Ordering is the caller's: a rank may read what another wrote
+    only after something that orders the two (sharded_forward's tail exchange does that for the waveforms)."""
+
+    def __init__(self, nbytes: int, group=None, register: bool | None = None):
+        multi, rank, world, root = _group_info(group)
+        self.nbytes = nbytes = max(int(nbytes), 16)
+        self.group, self.rank, self.world = group, rank, world
+        path = None
+        if rank == 0:
+            d = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > nbytes + (64 << 20) else None
+            fd, path = tempfile.mkstemp(prefix="zvx_host_", dir=d)
+            os.ftruncate(fd, nbytes)
+            os.close(fd)
+        if multi:
+            box = [path]
+            dist.broadcast_object_list(box, src=root, group=group)
+            path = box[0]
+        try:
+            self.bytes = torch.from_file(path, shared=True, size=nbytes, dtype=torch.uint8)
+        finally:
+            if multi:
+                dist.barrier(group=group)              # every rank has mapped it
+            if rank == 0:
+                os.unlink(path)
+        self.registered = False
+        if register is None:
+            register = torch.cuda.is_available()
+        if register:
+            rc = torch.cuda.cudart().cudaHostRegister(self.bytes.data_ptr(), nbytes, 0)
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister of the shared host window failed: {rc}")
+            self.registered = True
+
+    def tensor(self, dtype=torch.float32, numel: int | None = None, offset_bytes: int = 0) -> torch.Tensor:
+        item = torch.empty((), dtype=dtype).element_size()
+        if numel is None:
+            numel = (self.nbytes - offset_bytes) // item
+        if offset_bytes % item or offset_bytes + numel * item > self.nbytes:
+            raise ValueError("view outside the shared host window")
+        return self.bytes[offset_bytes: offset_bytes + numel * item].view(dtype)
+
+    def close(self):
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.bytes.data_ptr())
+            self.registered = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SharedHostBatch:
+    """The global input batch in a :class:`SharedHostBuffer`: rank 0 passes the batch dict (host tensors), the other
+    ranks ``None``; every rank then holds ``.x`` — the same dict as views of the shared window — and
+    ``sharded_forward(model, batch)`` lets every rank upload its own block of utterances (no NCCL scatter, no 8x traffic on
+    rank 0's PCIe link).  Rank 0 refills the window in place for the next batch (``.x[name].copy_(...)``; same shapes) and
+    publishes it with whatever tells the other ranks that a batch is ready (the header broadcast does when ``spec`` is not
+    used)."""
+
+    def __init__(self, x: Mapping[str, torch.Tensor] | None, group=None, register: bool | None = None):
+        multi, rank, world, root = _group_info(group)
+        meta = None
+        if rank == 0:
+            meta, off = [], 0
+            for k, v in x.items():
+                if isinstance(v, torch.Tensor):
+                    meta.append((k, v.dtype, tuple(v.shape), off))
+                    off = -(-(off + v.numel() * v.element_size()) // 256) * 256
+            meta = (meta, off)
+        if multi:
+            box = [meta]
+            dist.broadcast_object_list(box, src=root, group=group)
+            meta = box[0]
+        fields, total = meta
+        self.window = SharedHostBuffer(total, group=group, register=register)
+        self.x = {}
+        for k, dt, shape, off in fields:
+            n = 1
+            for d in shape:
+                n *= d
+            self.x[k] = self.window.tensor(dt, n, off).view(shape)
+            if rank == 0:
+                self.x[k].copy_(x[k])
+        if multi:
+            dist.barrier(group=group)                  # filled before anyone reads
+
+    def nbytes(self) -> int:
+        return sum(v.numel() * v.element_size() for v in self.x.values())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # the gathered result on rank 0
 # ---------------------------------------------------------------------------------------------------------------------
 @dataclass
@@ -105,9 +224,20 @@ class RaggedBatch:
     gather_bytes: int = 0                              # bytes received from the other ranks
     scatter_bytes: int = 0                             # bytes sent to the other ranks
     events: dict = field(default_factory=dict)
+    host: torch.Tensor | None = None                   # host_out delivery: the host buffer (fp32, 1-D) ...
+    host_wav_off: list[int] | None = None              # ... and every utterance's offset in it
+    wav_on_device: bool = True                         # False: SharedHostBuffer delivery — peers' waveforms exist on the host only
 
     def wav(self, i: int) -> torch.Tensor:
+        if not self.wav_on_device:
+            raise RuntimeError("the waveforms were delivered to the shared host buffer only: use host_wav(i)")
         return self.buf[self.wav_off[i]: self.wav_off[i] + self.lens[i] * self.hop]
+
+    def host_wav(self, i: int) -> torch.Tensor:
+        """Utterance i's valid samples in the host buffer (after the caller has synchronised the stream)."""
+        if self.host is None:
+            raise RuntimeError("no host_out was given")
+        return self.host[self.host_wav_off[i]: self.host_wav_off[i] + self.lens[i] * self.hop]
 
     def mel(self, i: int) -> torch.Tensor:
         return self.buf[self.mel_off[i]: self.mel_off[i] + self.lens[i] * self.n_mels].view(self.n_mels, self.lens[i])
@@ -123,6 +253,8 @@ class RaggedBatch:
         """The tuple of ``ZeroVox.forward`` for the whole batch: (wav [B, L*hop], mel [B, n_mels, L], mel_len int64 [B],
         log_duration [B, T]); zeros past every utterance's shipped length."""
         dev = self.buf.device
+        if not self.wav_on_device:
+            raise RuntimeError("the waveforms were delivered to the shared host buffer only: use host_wav(i)")
         wav = torch.empty((self.B, self.L * self.hop), dtype=torch.float32, device=dev)
         mel = torch.empty((self.B, self.n_mels, self.L), dtype=torch.float32, device=dev)
         lens_d = torch.tensor(self.lens, dtype=torch.int64, device=dev)
@@ -169,7 +301,8 @@ def _row_layout(T, T_ref, n_mels_in, has_mask, has_dur, Lm):
 def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force_duration: bool = False,
                     group=None, device: torch.device | str | None = None, hop_length: int = 256, n_mels: int = 80,
                     tails: str = "valid", ragged: bool = False, spec: Sequence[int] | None = None,
-                    events: dict | None = None, vocoder_groups: int = 1, host_out: torch.Tensor | None = None):
+                    events: dict | None = None, vocoder_groups: int = 1,
+                    host_out: "torch.Tensor | SharedHostBuffer | None" = None):
     """Run ``model(x_shard, force_duration=..., pad_to=..., zero_padded_mel=...)`` on every rank of ``group`` for the
     global batch ``x`` held by rank 0 (other ranks pass ``x=None``).  ``model`` is a ``ZeroVox`` (or any callable with
     that signature returning ``(wav [n, L*hop], mel [n, n_mels, L], mel_len int64 [n], log_duration [n, T])``).
@@ -184,6 +317,12 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
     stream, overlapping the next group's kernels); with ``host_out`` (rank 0: a pinned fp32 buffer) the gathered waveforms
     are also copied to the host group by group — rank-major, utterance order, valid samples back to back — so that only the
     last group's transfer is exposed.
+
+    Host-to-host without the rank-0 funnel: ``host_out`` = a :class:`SharedHostBuffer` given by EVERY rank makes each rank
+    copy its own waveforms to the host itself (fixed slots of ``ceil(B / world) * L * hop`` samples per rank, valid samples
+    of the rank's utterances back to back; ``RaggedBatch.host_wav(i)``); the waveforms of the other ranks then never reach
+    rank 0's GPU (``RaggedBatch.wav_on_device`` is False).  ``x`` = a :class:`SharedHostBatch` given by every rank replaces
+    the scatter by each rank uploading its own block from the shared window.
     """
     if tails not in ("valid", "padded"):
         raise ValueError("tails must be 'valid' or 'padded'")
@@ -201,6 +340,12 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
             e = torch.cuda.Event(enable_timing=True)
             e.record()
             events[name] = e
+
+    shared_in = isinstance(x, SharedHostBatch)
+    shared_out = isinstance(host_out, SharedHostBuffer)
+    if shared_in:
+        x = x.x
+    host_t = host_out.tensor(torch.float32) if shared_out else host_out
 
     # ---- header -------------------------------------------------------------------------------------------------
     all_lens = None                                    # rank 0, forced durations: frames of every utterance
@@ -237,7 +382,14 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
     # ---- ONE scatter of the inputs, packed on the device as one row per utterance --------------------------------------
     fields, row_bytes = _row_layout(T, T_ref, n_mels_in, has_mask, has_dur, Lm if has_mm else 0)
     scatter_bytes = 0
-    if multi:
+    if multi and shared_in:
+        # every rank uploads its own block from the shared host window (the model's forward does the H2D, as at N = 1)
+        blk = parts[rank]
+        xs = {k: v[blk.start: blk.stop] for k, v in x.items() if isinstance(v, torch.Tensor)}
+        if not has_dur:
+            xs.pop("duration", None)
+        mark("packed")
+    elif multi:
         recv = torch.empty((nb, row_bytes), dtype=torch.uint8, device=dev)
         send = None
         if rank == 0:
@@ -270,7 +422,7 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
     if G == 0 or G == -1:
         G = 1
     cuda = dev.type == "cuda"
-    side = torch.cuda.Stream(dev) if cuda and (G != 1 or host_out is not None) else None
+    side = torch.cuda.Stream(dev) if cuda and (G != 1 or host_t is not None) else None
     root = 0 if (group is None or not multi) else dist.get_global_rank(group, 0)
     lens_box, st = {}, {"groups_done": 0}
 
@@ -290,6 +442,10 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
         st["F"] = F = sum(st["my_ship"])
         st["my_size"] = -(-(F * (hop_length + n_mels) + n_mine * T) // _ALIGN) * _ALIGN
         st["L"] = L
+        slot = nb * L * hop_length                     # shared host window: a rank's fixed slot (L is global)
+        st["host_base"] = rank * slot
+        if shared_out and host_t.numel() < world * slot:
+            raise ValueError(f"the shared host window holds {host_t.numel()} samples, {world} slots of {slot} are needed")
         if rank == 0:
             if has_dur:
                 true_all = [int(v) for v in all_lens]
@@ -302,17 +458,23 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
             buf = torch.empty(total, dtype=torch.float32, device=dev)
             st["out"] = RaggedBatch(buf=buf, B=B, T=T, L=L, hop=hop_length, n_mels=n_mels, lens=ship_all, mel_len_host=true_all,
                                     wav_off=wav_off, mel_off=mel_off, logd_off=logd_off, seg=seg,
-                                    gather_bytes=4 * sum(x_[2] for x_ in seg[1:]), scatter_bytes=scatter_bytes,
+                                    gather_bytes=4 * sum(x_[2] - (x_[1] if shared_out else 0) for x_ in seg[1:]),
+                                    scatter_bytes=scatter_bytes,
                                     events=events if events is not None else {})
             st["mine"] = buf[:st["my_size"]]
-            # host offsets of every rank's waveform segment (rank-major, contiguous)
+            # host offsets of every rank's waveform segment: rank-major — contiguous, or fixed slots in a shared window
             ho, acc = [], 0
-            for (_, w, _) in seg:
-                ho.append(acc)
+            for r_, (_, w, _) in enumerate(seg):
+                ho.append(r_ * slot if shared_out else acc)
                 acc += w
             st["host_seg"] = ho
-            if host_out is not None and host_out.numel() < acc:
-                raise ValueError(f"host_out holds {host_out.numel()} samples, the gathered waveforms need {acc}")
+            if host_t is not None:
+                if not shared_out and host_t.numel() < acc:
+                    raise ValueError(f"host_out holds {host_t.numel()} samples, the gathered waveforms need {acc}")
+                st["out"].host = host_t
+                st["out"].host_wav_off = [ho[r_] + st["out"].wav_off[i] - seg[r_][0]
+                                          for r_, blk in enumerate(partition(B, world)) for i in blk]
+                st["out"].wav_on_device = not (shared_out and multi)
         else:
             st["mine"] = torch.empty(st["my_size"], dtype=torch.float32, device=dev)
         if n_mine > 0:
@@ -334,7 +496,7 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
             ops = []
             if multi:
                 for (r, a0, a1, is_wav) in parts:
-                    if a1 <= a0:
+                    if a1 <= a0 or (shared_out and is_wav):
                         continue
                     if rank == 0 and r != 0:
                         s0 = st["out"].seg[r][0]
@@ -345,11 +507,16 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
             if ops:
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
-            if rank == 0 and host_out is not None:
+            if shared_out:                             # every rank: its own waveforms, over its own PCIe link
+                for (r, a0, a1, is_wav) in parts:
+                    if is_wav and r == rank and a1 > a0:
+                        h0 = st["host_base"]
+                        host_t[h0 + a0: h0 + a1].copy_(st["mine"][a0:a1], non_blocking=True)
+            elif rank == 0 and host_t is not None:
                 for (r, a0, a1, is_wav) in parts:
                     if is_wav and a1 > a0:
                         s0, h0 = st["out"].seg[r][0], st["host_seg"][r]
-                        host_out[h0 + a0: h0 + a1].copy_(st["out"].buf[s0 + a0: s0 + a1], non_blocking=True)
+                        host_t[h0 + a0: h0 + a1].copy_(st["out"].buf[s0 + a0: s0 + a1], non_blocking=True)
         if side is None:
             body()
         else:
@@ -377,7 +544,9 @@ def sharded_forward(model: Callable, x: Mapping[str, torch.Tensor] | None, force
         if g1 > g0:
             _ragged_copy(True, wav[g0:g1].to(torch.float32).contiguous(), st["mine"], st["lens_d"][g0:g1], st["w_offs"][g0:g1],
                          st["my_ship"][g0:g1], st["wl"][g0:g1], 1, hop_length)
-        if rank == 0:
+        if shared_out:
+            parts = [(rank, st["cum"][g0], st["cum"][g1], True)]
+        elif rank == 0:
             parts = []
             for r in range(world):
                 rng = peer_wav_range(r, i)
