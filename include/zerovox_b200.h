@@ -266,9 +266,20 @@ int zvx_ragged_unpack(const float* packed, const int64_t* lens, const int64_t* o
                       void* stream);
 const char* zvx_ragged_last_error(void);
 
+/* Fused scaled-dot-product attention of the FFT blocks (fs2.py:101-163: bmm, / temperature, masked_fill(-inf), softmax, bmm)
+ * as ONE tcgen05 kernel; the engine's decoder calls the same kernel.  qk fp32 [B*L, 2*n_head*d_k] row-major (Q in the first
+ * n_head*d_k columns, K in the rest; head h in columns h*d_k..), vt = V transposed per utterance: vt[(b*n_head*d_k + h*d_k + c)
+ * * vt_pitch + j]; key_mask (optional, uint8 [B, L]): non-zero = key j of utterance b is masked; out fp32 [B*L, n_head*d_k].
+ * d_k % 8 == 0, d_k <= 384, vt_pitch % 4 == 0, 16-byte aligned pointers.  Products in TF32, softmax and accumulation in fp32. */
+int zvx_attention(const float* qk, const float* vt, int64_t vt_pitch, const uint8_t* key_mask, int B, int L, int n_head, int d_k,
+                  float temperature, float* out, void* stream);
+const char* zvx_attention_last_error(void);
+
 /* Runtime options of a handle (the release library reads no environment variables).
  *   "score_workspace_bytes": budget of the attention-score workspace; longer inputs are processed in chunks of query rows
- *                            (exact: the softmax is per row).  Default 4 GiB. */
+ *                            (exact: the softmax is per row).  Default 4 GiB.  Only used when the fused kernel is off.
+ *   "fused_attention":       1 (default) = the TF32 policy's attention runs as one kernel (zvx_attention); 0 = QK^T, softmax
+ *                            and PV as three kernels with the score matrix in HBM / L2 (A/B and debugging). */
 int zvx_set_option(zvx_handle* h, const char* name, int64_t value);
 
 /* Workspace control: bytes of engine-owned scratch currently reserved on the device. */

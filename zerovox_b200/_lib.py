@@ -110,6 +110,8 @@ SYMBOLS = {
     "zvx_ragged_unpack": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int,
                                     _P]),
     "zvx_ragged_last_error": (C.c_char_p, []),
+    "zvx_attention": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
+    "zvx_attention_last_error": (C.c_char_p, []),
     "zvx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "zvx_workspace_bytes": (C.c_int64, [_P]),
     "zvx_launch_count": (C.c_int64, [_P]),

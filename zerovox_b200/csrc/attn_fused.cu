@@ -1,0 +1,464 @@
+// Fused scaled-dot-product attention of the decoder's FFT blocks (fs2.py:101-163: bmm -> / temperature -> masked_fill(-inf)
+// -> softmax -> bmm) on tcgen05, without the score matrix ever leaving the SM.
+//
+//   out[b, q, h*dk + c] = sum_j softmax_j( <Q[b,q,h,:], K[b,j,h,:]> / temperature  |  key j not masked ) * V[b,j,h,c]
+//
+// One CTA tile = 128 query rows of one (utterance, head); keys are visited in blocks of 128:
+//   warp 0      TMA producer : Q and K k-chunks (128 rows x 32 fp32, 128B swizzle) for S = Q K^T, then the block's V^T chunks
+//                              (dk channel rows x 32 keys) into a 4-stage ring — in exactly the order the issuer consumes them;
+//   warp 1      MMA issuer   : S(j+1) = Q K_{j+1}^T is issued as soon as the softmax warps have read S(j) out of TMEM, and
+//                              O += P(j) V_j as soon as P(j) is in shared memory: the tensor pipe runs QK^T of the next block
+//                              while the softmax of this one is computed (TMEM: S 128 columns + O round16(dk) columns);
+//   warps 2..5  softmax      : one query row per thread (TMEM lane = row: no cross-thread reduction).  Online softmax with a
+//                              LAZY reference maximum: the row's reference m only moves when the block maximum exceeds it by
+//                              more than 2^8 in the exponent, and only then is the O accumulator rescaled in TMEM
+//                              (tcgen05.ld / st) — exact in real arithmetic, the final division by the row sum l uses the same m.
+//                              P = exp2((s - m) * log2e / T) is rounded to TF32 (round-to-nearest, what the TMA unit does for the
+//                              unfused PV product) and written to shared memory in the K-major 128B-swizzled layout the MMA reads.
+// Q|K come row-major [B*L, 2H] (one GEMM), V transposed per utterance Vt[b][c][t] (row pitch Lp) — the layouts the unfused
+// path already uses (engine.cu fft_block).
+#include "kernels.cuh"
+#include "tc_ptx.cuh"
+
+#include <cuda.h>
+
+#include <cmath>
+#include <mutex>
+#include <string>
+
+namespace zvx {
+
+namespace {
+
+constexpr int AT_THREADS = 192;          // producer warp, issuer warp, 4 softmax warps
+constexpr int KB = 128;                  // keys per block = columns of S
+constexpr int QT = 128;                  // query rows per tile (MMA M)
+constexpr int CH = 32;                   // fp32 per 128-byte swizzle row
+constexpr int P_CHUNK_BYTES = QT * CH * 4;           // 16 KB: 128 rows x 32 keys
+constexpr int P_BYTES = (KB / CH) * P_CHUNK_BYTES;   // 64 KB
+constexpr int AT_STAGES = 4;
+constexpr int QK_STAGE_BYTES = 2 * QT * CH * 4;      // Q chunk + K chunk
+constexpr int S_COL = 0, O_COL = KB;     // TMEM columns
+constexpr float LAZY_EXP2 = 8.f;         // the reference maximum moves when a block maximum exceeds it by 2^8
+
+struct AttnParams {
+    int B, L, n_head, dk, H;
+    int qtiles, num_tiles, nkb;
+    int kchunks, last_ksteps;
+    int NV, n_lo, n_hi;
+    int stage_bytes;
+    uint32_t idesc_qk, idesc_lo, idesc_hi;
+    float sc;                            // log2(e) / temperature
+    float* out;
+    const uint8_t* mask;
+    int mask_ld;
+};
+
+__device__ __forceinline__ uint64_t at_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// keys of block j that take part: chunks of 32 that contain at least one key < L
+__device__ __forceinline__ int valid_chunks(const AttnParams& p, int j) {
+    const int left = p.L - j * KB;
+    return left >= KB ? KB / CH : (left + CH - 1) / CH;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                  const __grid_constant__ CUtensorMap mapVlo, const __grid_constant__ CUtensorMap mapVhi, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sP = smem_u32(smem);
+    const uint32_t sStage = sP + P_BYTES;
+    const uint32_t bars = sStage + (uint32_t)(AT_STAGES * p.stage_bytes);
+    auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(AT_STAGES + s); };
+    const uint32_t s_full = bars + 8u * (2 * AT_STAGES + 0), s_empty = bars + 8u * (2 * AT_STAGES + 1);
+    const uint32_t p_full = bars + 8u * (2 * AT_STAGES + 2), pv_done = bars + 8u * (2 * AT_STAGES + 3);
+    const uint32_t o_empty = bars + 8u * (2 * AT_STAGES + 4);
+    const uint32_t tmem_slot = bars + 8u * (2 * AT_STAGES + 5);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem + P_BYTES + AT_STAGES * p.stage_bytes + 8 * (2 * AT_STAGES + 5));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&mapQ);
+        prefetch_tmap(&mapK);
+        prefetch_tmap(&mapVlo);
+        prefetch_tmap(&mapVhi);
+        for (int s = 0; s < AT_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 4);
+        mbar_init(p_full, 4);
+        mbar_init(pv_done, 1);
+        mbar_init(o_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    const uint32_t DESC_HI = (uint32_t)(at_sw128_desc(0) >> 32);
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int qt = t % p.qtiles, z = t / p.qtiles, h = z % p.n_head, b = z / p.n_head;
+                auto load_qk = [&](int j) {
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait_spin(empty_bar(stage), phase ^ 1u);
+                        const uint32_t fb = full_bar(stage), dst = sStage + (uint32_t)(stage * p.stage_bytes);
+                        mbar_arrive_expect_tx(fb, (uint32_t)QK_STAGE_BYTES);
+                        tma_load_4d(&mapQ, fb, dst, kc * CH, qt * QT, h, b);
+                        tma_load_4d(&mapK, fb, dst + (uint32_t)(QT * CH * 4), kc * CH, j * KB, h, b);
+                        if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                };
+                auto load_v = [&](int j) {
+                    const int nc = valid_chunks(p, j);
+                    for (int c = 0; c < nc; ++c) {
+                        mbar_wait_spin(empty_bar(stage), phase ^ 1u);
+                        const uint32_t fb = full_bar(stage), dst = sStage + (uint32_t)(stage * p.stage_bytes);
+                        mbar_arrive_expect_tx(fb, (uint32_t)(p.NV * CH * 4));
+                        tma_load_4d(&mapVlo, fb, dst, j * KB + c * CH, 0, h, b);
+                        if (p.n_hi) tma_load_4d(&mapVhi, fb, dst + (uint32_t)(p.n_lo * CH * 4), j * KB + c * CH, p.n_lo, h, b);
+                        if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                };
+                load_qk(0);
+                for (int j = 0; j < p.nkb; ++j) {
+                    if (j + 1 < p.nkb) load_qk(j + 1);
+                    load_v(j);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t g = 0, tcount = 0;          // key blocks / tiles this CTA has started
+            const uint32_t dS = tmem_base + S_COL, dO = tmem_base + O_COL;
+            const uint32_t p_lo0 = (uint32_t)(at_sw128_desc(sP) & 0xFFFFFFFFull);
+            const uint32_t st_lo0 = (uint32_t)(at_sw128_desc(sStage) & 0xFFFFFFFFull);
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+                auto issue_qk = [&](uint32_t gq) {
+                    if (gq > 0) mbar_wait_spin(s_empty, (gq - 1) & 1u);   // S(gq-1) has been read out of TMEM
+                    tc_fence_after();
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait_spin(full_bar(stage), phase);
+                        const uint32_t a = st_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4), bb = a + (uint32_t)((QT * CH * 4) >> 4);
+                        const int nk = (kc == p.kchunks - 1) ? p.last_ksteps : CH / 8;
+                        for (int k = 0; k < nk; ++k)
+                            umma_tf32_lo(dS, a + 2 * k, bb + 2 * k, DESC_HI, p.idesc_qk, (kc | k) ? 1u : 0u);
+                        umma_commit(empty_bar(stage));
+                        if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(s_full);
+                };
+                auto issue_pv = [&](int j, uint32_t gq) {
+                    mbar_wait_spin(p_full, gq & 1u);                      // P(gq) is in shared memory (and O rescaled if needed)
+                    if (j == 0 && tcount > 0) mbar_wait_spin(o_empty, (tcount - 1) & 1u);   // previous tile's O has been read
+                    tc_fence_after();
+                    const int nc = valid_chunks(p, j);
+                    for (int c = 0; c < nc; ++c) {
+                        mbar_wait_spin(full_bar(stage), phase);
+                        const uint32_t a = p_lo0 + (uint32_t)((c * P_CHUNK_BYTES) >> 4);
+                        const uint32_t bb = st_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);
+                        const uint32_t bh = bb + (uint32_t)((p.n_lo * CH * 4) >> 4);
+#pragma unroll
+                        for (int k = 0; k < CH / 8; ++k) {
+                            const uint32_t acc = (j | c | k) ? 1u : 0u;
+                            umma_tf32_lo(dO, a + 2 * k, bb + 2 * k, DESC_HI, p.idesc_lo, acc);
+                            if (p.n_hi) umma_tf32_lo(dO + (uint32_t)p.n_lo, a + 2 * k, bh + 2 * k, DESC_HI, p.idesc_hi, acc);
+                        }
+                        umma_commit(empty_bar(stage));
+                        if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    umma_commit(pv_done);
+                };
+                issue_qk(g);
+                for (int j = 0; j < p.nkb; ++j) {
+                    if (j + 1 < p.nkb) issue_qk(g + (uint32_t)j + 1u);
+                    issue_pv(j, g + (uint32_t)j);
+                }
+                g += (uint32_t)p.nkb;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================================================ softmax warps: one query row per thread
+        const int quarter = warp & 3;                      // the TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t prow = sP + (uint32_t)(row * 128);
+        const uint32_t sw = (uint32_t)(row & 7);
+        uint32_t g = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            const int qt = t % p.qtiles, z = t / p.qtiles, h = z % p.n_head, b = z / p.n_head;
+            const int q = qt * QT + row;
+            const uint8_t* km = p.mask ? p.mask + (long long)b * p.mask_ld : nullptr;
+            float m_ref = -INFINITY, l = 0.f;
+            for (int j = 0; j < p.nkb; ++j) {
+                const uint32_t gq = g + (uint32_t)j;
+                // key validity of the block (bounds + padding mask), one bit per key, the same words in every lane
+                uint32_t vw[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int key = j * KB + i * 32 + lane;
+                    const bool ok = key < p.L && !(km && km[key]);
+                    vw[i] = __ballot_sync(0xFFFFFFFFu, ok);
+                }
+                const bool all_valid = (vw[0] & vw[1] & vw[2] & vw[3]) == 0xFFFFFFFFu;
+
+                mbar_wait_hint(s_full, gq & 1u, 64);
+                tc_fence_after();
+                float v[KB];
+#pragma unroll
+                for (int i = 0; i < KB / 16; ++i) tmem_ld16(trow + (uint32_t)(S_COL + i * 16), reinterpret_cast<uint32_t*>(v + i * 16));
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty);                 // the issuer may overwrite S with the next block's scores
+
+                float mb = -INFINITY;
+                if (all_valid) {
+#pragma unroll
+                    for (int i = 0; i < KB; ++i) mb = fmaxf(mb, v[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KB; ++i) {
+                        if (!((vw[i >> 5] >> (i & 31)) & 1u)) v[i] = -INFINITY;
+                        mb = fmaxf(mb, v[i]);
+                    }
+                }
+                // lazy reference maximum (in units of the exponent: s * sc)
+                float factor = 1.f;
+                bool rescale = false;
+                if (mb * p.sc > m_ref * p.sc + LAZY_EXP2 || (m_ref == -INFINITY && mb > -INFINITY)) {
+                    if (m_ref != -INFINITY) {
+                        factor = exp2f((m_ref - mb) * p.sc);
+                        rescale = j > 0;
+                    }
+                    m_ref = mb;
+                }
+                const float off = (m_ref == -INFINITY) ? 0.f : m_ref * p.sc;
+                float sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < KB; ++i) {
+                    const float e = exp2f(fmaf(v[i], p.sc, -off));
+                    sum += e;
+                    v[i] = rn_tf32(e);
+                }
+                l = fmaf(l, factor, sum);
+
+                // P buffer free and O stable: the previous block's PV product has completed
+                if (gq > 0) mbar_wait_hint(pv_done, (gq - 1) & 1u, 64);
+                tc_fence_after();
+                if (__any_sync(0xFFFFFFFFu, rescale)) {
+                    for (int c = 0; c < p.NV; c += 16) {
+                        uint32_t o[16];
+                        tmem_ld16(trow + (uint32_t)(O_COL + c), o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                        tmem_st16(trow + (uint32_t)(O_COL + c), o);
+                    }
+                    tmem_wait_st();
+                }
+#pragma unroll
+                for (int c = 0; c < KB / CH; ++c)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        st_shared_v4(prow + (uint32_t)(c * P_CHUNK_BYTES) + (((uint32_t)u ^ sw) << 4),
+                                     make_float4(v[c * CH + u * 4], v[c * CH + u * 4 + 1], v[c * CH + u * 4 + 2], v[c * CH + u * 4 + 3]));
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+            }
+            g += (uint32_t)p.nkb;
+            // ---- epilogue: O / l -> out[b, q, h*dk + :]
+            mbar_wait_hint(pv_done, (g - 1) & 1u, 64);
+            tc_fence_after();
+            const float inv = 1.f / l;
+            float* orow = p.out + ((long long)b * p.L + q) * p.H + (long long)h * p.dk;
+            for (int c = 0; c < p.dk; c += 16) {
+                uint32_t o[16];
+                tmem_ld16(trow + (uint32_t)(O_COL + c), o);
+                tmem_wait_ld();
+                if (q < p.L) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        if (c + i < p.dk)
+                            *reinterpret_cast<float4*>(orow + c + i) =
+                                make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, __uint_as_float(o[i + 2]) * inv,
+                                            __uint_as_float(o[i + 3]) * inv);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn at_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        else
+            cudaGetLastError();
+    });
+    if (!fn) throw Error("cuTensorMapEncodeTiled is not available from this driver");
+    return fn;
+}
+
+// 4-D fp32 view, dim 0 contiguous; TFLOAT32 element type (round-to-nearest in flight), 128B swizzle, zero fill out of bounds
+CUtensorMap at_map(const float* base, const long long dims[4], const long long strides_elems[3], int box0, int box1) {
+    CUtensorMap m;
+    cuuint64_t gd[4], gs[3];
+    cuuint32_t bx[4] = {(cuuint32_t)box0, (cuuint32_t)box1, 1, 1}, es[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) gd[i] = (cuuint64_t)std::max<long long>(dims[i], 1);
+    long long prev = 16;
+    for (int i = 0; i < 3; ++i) {
+        long long s = strides_elems[i] * 4;
+        if (dims[i + 1] <= 1 && s <= 0) s = prev;
+        gs[i] = (cuuint64_t)s;
+        prev = std::max<long long>(s, 16);
+    }
+    const CUresult rc = at_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), gd, gs, bx, es,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "attention: cuTensorMapEncodeTiled failed (%d): dims %lld %lld %lld %lld box %d %d", (int)rc,
+                 dims[0], dims[1], dims[2], dims[3], box0, box1);
+        throw Error(buf);
+    }
+    return m;
+}
+
+uint32_t at_idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(QT >> 4) << 24); }
+
+int at_num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        ZVX_CUDA_CHECK(cudaGetDevice(&dev));
+        ZVX_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return n;
+}
+
+}  // namespace
+
+bool attn_fused_supported(const AttnFusedArgs& a) {
+    const int NV = (a.dk + 15) / 16 * 16;
+    auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    return a.dk % 8 == 0 && a.dk >= 16 && NV <= 384 && (NV <= 256 || NV - 128 >= 16) && a.H % 4 == 0 && a.Lp % 4 == 0 &&
+           a.Lp >= a.L && a.L >= 1 && a.B >= 1 && al16(a.qk) && al16(a.vt) && al16(a.out);
+}
+
+void attn_fused(const AttnFusedArgs& a, cudaStream_t st) {
+    ZVX_REQUIRE(attn_fused_supported(a), "attn_fused: unsupported shape / alignment");
+    AttnParams p{};
+    p.B = a.B; p.L = a.L; p.n_head = a.n_head; p.dk = a.dk; p.H = a.H;
+    p.qtiles = cdiv(a.L, QT);
+    p.num_tiles = p.qtiles * a.n_head * a.B;
+    p.nkb = cdiv(a.L, KB);
+    p.kchunks = cdiv(a.dk, CH);
+    p.last_ksteps = (a.dk - (p.kchunks - 1) * CH) / 8;
+    p.NV = (a.dk + 15) / 16 * 16;
+    if (p.NV <= 256) { p.n_lo = p.NV; p.n_hi = 0; }
+    else { p.n_hi = 128; p.n_lo = p.NV - 128; }
+    p.stage_bytes = std::max(QK_STAGE_BYTES, (int)round_up((long long)p.NV * CH * 4, 1024));
+    p.idesc_qk = at_idesc(KB);
+    p.idesc_lo = at_idesc(p.n_lo);
+    p.idesc_hi = at_idesc(p.n_hi ? p.n_hi : 16);
+    p.sc = 1.4426950408889634f / a.temperature;
+    p.out = a.out; p.mask = a.key_mask; p.mask_ld = a.mask_ld;
+
+    const long long H2 = 2LL * a.H;
+    const long long qdims[4] = {a.dk, a.L, a.n_head, a.B};
+    const long long qstr[3] = {H2, a.dk, (long long)a.L * H2};
+    const CUtensorMap mapQ = at_map(a.qk, qdims, qstr, CH, QT);
+    const CUtensorMap mapK = at_map(a.qk + a.H, qdims, qstr, CH, KB);
+    const long long vdims[4] = {a.L, a.dk, a.n_head, a.B};
+    const long long vstr[3] = {a.Lp, (long long)a.dk * a.Lp, (long long)a.H * a.Lp};
+    const CUtensorMap mapVlo = at_map(a.vt, vdims, vstr, CH, p.n_lo);
+    const CUtensorMap mapVhi = p.n_hi ? at_map(a.vt, vdims, vstr, CH, p.n_hi) : mapVlo;
+
+    const size_t smem = 1024 + (size_t)P_BYTES + (size_t)AT_STAGES * p.stage_bytes + 8 * (2 * AT_STAGES + 6);
+    static std::once_flag once;
+    std::call_once(once, [] {
+        ZVX_CUDA_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    });
+    ZVX_REQUIRE(smem <= 227 * 1024, "attn_fused: shared memory");
+    const int grid = std::min(p.num_tiles, at_num_sms());
+    attn_fused_kernel<<<grid, AT_THREADS, smem, st>>>(mapQ, mapK, mapVlo, mapVhi, p);
+    ZVX_POST_LAUNCH();
+}
+
+}  // namespace zvx
+
+namespace { thread_local std::string g_attn_error; }
+
+extern "C" {
+
+int zvx_attention(const float* qk, const float* vt, int64_t vt_pitch, const uint8_t* key_mask, int B, int L, int n_head, int d_k,
+                  float temperature, float* out, void* stream) {
+    try {
+        zvx::AttnFusedArgs a;
+        a.qk = qk; a.vt = vt; a.out = out; a.key_mask = key_mask; a.mask_ld = L; a.B = B; a.L = L; a.n_head = n_head; a.dk = d_k;
+        a.H = n_head * d_k; a.Lp = (int)vt_pitch; a.temperature = temperature;
+        if (!zvx::attn_fused_supported(a)) throw zvx::Error("zvx_attention: unsupported shape / alignment (d_k % 8, pitches % 4, 16-byte bases)");
+        zvx::attn_fused(a, (cudaStream_t)stream);
+        return 0;
+    } catch (const std::exception& e) {
+        g_attn_error = e.what();
+        return 1;
+    }
+}
+
+const char* zvx_attention_last_error(void) { return g_attn_error.c_str(); }
+
+}  // extern "C"
+

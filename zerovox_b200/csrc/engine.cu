@@ -806,6 +806,16 @@ class Engine {
             }
             gemm_tc_prof(v, st);
             if (split) tf32_split_lo(qkv, sc.lo_qkv, rows * 2 * H + (long long)B * H * Lp, st);
+            // TF32 policy: ONE kernel for S = QK^T, the masked softmax and PV — the score matrix never leaves the SM
+            // (attn_fused.cu).  The 3xTF32 policy (encoder, T <= a few hundred) keeps the three-kernel path below.
+            AttnFusedArgs fa;
+            fa.qk = qk; fa.vt = vt; fa.out = att; fa.key_mask = mask; fa.mask_ld = L; fa.B = B; fa.L = L; fa.n_head = n_head;
+            fa.dk = dk; fa.H = H; fa.Lp = Lp; fa.temperature = temperature;
+            if (!split && kFusedAttention && attn_fused_supported(fa)) {
+                prof.begin(ZVX_PROF_GEMM_TC, fa.flops(), fa.bytes(), st);
+                attn_fused(fa, st);
+                prof.end(st);
+            } else {
             // Utterances are independent, so the three attention kernels run over slices of the batch whose score
             // matrices (plus their Q / K / V rows) fit in L2: the softmax and the PV product then read what the kernel
             // before them wrote from L2 instead of DRAM (the whole-batch score tensor is 172 MB at configs[1], moved
@@ -842,6 +852,7 @@ class Engine {
                 pv.C = att + (r0 + q0) * H; pv.c_simg = (long long)L * H; pv.c_sy = dk; pv.c_sx = H; pv.c_sn = 1;
                 if (split) { pv.A_lo = sc.lo_S; pv.W_lo = sc.lo_qkv + rows * 2 * H + (long long)b0 * H * Lp; }
                 gemm_tc_prof(pv, st);
+            }
             }
             }
         } else {
@@ -1345,12 +1356,17 @@ class Engine {
             kScoreBytes = value;
             return 0;
         }
+        if (n == "fused_attention") {
+            kFusedAttention = value != 0;
+            return 0;
+        }
         throw Error("zvx_set_option: unknown option '" + n + "'");
     }
 
     static constexpr int kMaxBatch = 65536;
     // attention-score workspace budget: longer sequences are processed in chunks of query rows (exact)
     long long kScoreBytes = 4LL << 30;   // zvx_set_option("score_workspace_bytes")
+    bool kFusedAttention = true;         // zvx_set_option("fused_attention"): 0 = QK^T / softmax / PV as three kernels
     // attention batch-slice budget (score bytes per slice); 0 = whole batch per launch.  Default set by measurement.
     static constexpr long long kAttnSliceBytes = 0;
 

@@ -135,6 +135,21 @@ std::vector<float> voc_pair_pack_weight(const float* w, const float* bias, int C
 void conv_post_cl(const float* x, long long x_bs, const float* w /*[k][C]*/, const float* bias, int B, int T, int C,
                   int k, float slope, float* wav, cudaStream_t st);
 
+// ---- fused attention (attn_fused.cu) ------------------------------------------------------------------
+// out[b, q, h*dk + c] = sum_j softmax_j(<Q[b,q,h,:], K[b,j,h,:]> / temperature | key j not masked) V[b,j,h,c]   (fs2.py:101-163)
+// qk: [B*L, 2H] row-major, Q in columns [0, H), K in [H, 2H), head h in columns h*dk..; vt: V transposed per utterance,
+// vt[(b*H + h*dk + c) * Lp + j]; key_mask (optional): key_mask[b*mask_ld + j] != 0 masks key j of utterance b.
+struct AttnFusedArgs {
+    const float* qk = nullptr; const float* vt = nullptr; float* out = nullptr;
+    const uint8_t* key_mask = nullptr; int mask_ld = 0;
+    int B = 0, L = 0, n_head = 1, dk = 0, H = 0, Lp = 0;
+    float temperature = 1.f;
+    double flops() const { return 4.0 * B * n_head * (double)L * L * dk; }
+    double bytes() const { return 4.0 * 4.0 * B * (double)L * H; }
+};
+bool attn_fused_supported(const AttnFusedArgs& a);
+void attn_fused(const AttnFusedArgs& a, cudaStream_t st);
+
 // ---- ResNetSE34V2 (kernels_spk.cu), channel-last [B, H, W, C] ---------------------------------------
 // InstanceNorm1d over time (no affine, biased var, eps 1e-5): ref_mel [B,T,n_mels] -> out [B, n_mels(H), T(W)]
 void instance_norm_time(const float* ref_mel, int B, int T, int n_mels, float* out, cudaStream_t st);
