@@ -9,7 +9,8 @@
 //   warp 1      MMA issuer   : S(j+1) = Q K_{j+1}^T is issued as soon as the softmax warps have read S(j) out of TMEM, and
 //                              O += P(j) V_j as soon as P(j) is in shared memory: the tensor pipe runs QK^T of the next block
 //                              while the softmax of this one is computed (TMEM: S 128 columns + O round16(dk) columns);
-//   warps 2..5  softmax      : one query row per thread (TMEM lane = row: no cross-thread reduction).  Online softmax with a
+//   warps 2..9  softmax      : a query row per pair of threads (TMEM lane = row; warps w and w + 4 split the row's 128 scores and
+//                              exchange the block maximum through shared memory).  Online softmax with a
 //                              LAZY reference maximum: the row's reference m only moves when the block maximum exceeds it by
 //                              more than 2^8 in the exponent, and only then is the O accumulator rescaled in TMEM
 //                              (tcgen05.ld / st) — exact in real arithmetic, the final division by the row sum l uses the same m.
@@ -30,7 +31,7 @@ namespace zvx {
 
 namespace {
 
-constexpr int AT_THREADS = 192;          // producer warp, issuer warp, 4 softmax warps
+constexpr int AT_THREADS = 320;          // producer warp, issuer warp, 8 softmax warps
 constexpr int KB = 128;                  // keys per block = columns of S
 constexpr int QT = 128;                  // query rows per tile (MMA M)
 constexpr int CH = 32;                   // fp32 per 128-byte swizzle row
@@ -52,6 +53,8 @@ struct AttnParams {
     float* out;
     const uint8_t* mask;
     int mask_ld;
+    int dbg_skip;                        // -DZVX_DEBUG experiments (wrong results): 1 = reload no Q after the first key block
+    long long* dbg;                      // -DZVX_DEBUG: wait-cycle counters of CTA 0's roles (tools/attn_bench.py)
 };
 
 __device__ __forceinline__ uint64_t at_sw128_desc(uint32_t saddr) {
@@ -64,14 +67,32 @@ __device__ __forceinline__ uint64_t at_sw128_desc(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-        : "memory");
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+// 2^x, MUFU.EX2 directly (2 ulp; arguments here are <= 8, results below 2^-126 flush to zero)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// -DZVX_DEBUG: cycles a role of CTA 0 spends in a wait, accumulated per wait site
+#ifdef ZVX_DEBUG
+#define AT_TIMED(acc, stmt) do { const long long t0_ = clock64(); stmt; (acc) += clock64() - t0_; } while (0)
+#else
+#define AT_TIMED(acc, stmt) do { stmt; } while (0)
+#endif
+
+// -DZVX_DEBUG: time stamps of CTA 0's first tile, dbg[16 + role*64 + j*4 + k] (role 0 producer, 1 issuer, 2 softmax warp 2)
+#ifdef ZVX_DEBUG
+#define AT_STAMP(cond, role, j, k) do { if (p.dbg && blockIdx.x == 0 && (cond) && (j) < 16) p.dbg[16 + (role) * 64 + (j) * 4 + (k)] = clock64(); } while (0)
+#else
+#define AT_STAMP(cond, role, j, k) do { } while (0)
+#endif
 
 // keys of block j that take part: chunks of 32 that contain at least one key < L
 __device__ __forceinline__ int valid_chunks(const AttnParams& p, int j) {
@@ -107,10 +128,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             mbar_init(empty_bar(s), 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(s_empty, 4);
-        mbar_init(p_full, 4);
+        mbar_init(s_empty, 8);
+        mbar_init(p_full, 8);
         mbar_init(pv_done, 1);
-        mbar_init(o_empty, 4);
+        mbar_init(o_empty, 8);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -125,14 +146,20 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
+            long long w_empty = 0;
+            const long long t_start = clock64();
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const int qt = t % p.qtiles, z = t / p.qtiles, h = z % p.n_head, b = z / p.n_head;
+                const bool first = t == (int)blockIdx.x;
                 auto load_qk = [&](int j) {
                     for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait_spin(empty_bar(stage), phase ^ 1u);
+                        AT_TIMED(w_empty, mbar_wait_spin(empty_bar(stage), phase ^ 1u));
+                        if (kc == 0) AT_STAMP(first, 0, j, 0);
+                        if (kc == p.kchunks - 1) AT_STAMP(first, 0, j, 1);
                         const uint32_t fb = full_bar(stage), dst = sStage + (uint32_t)(stage * p.stage_bytes);
-                        mbar_arrive_expect_tx(fb, (uint32_t)QK_STAGE_BYTES);
-                        tma_load_4d(&mapQ, fb, dst, kc * CH, qt * QT, h, b);
+                        const bool skip_q = (ZVX_DBG_SKIP(p) & 1) && j > 0;
+                        mbar_arrive_expect_tx(fb, (uint32_t)(skip_q ? QK_STAGE_BYTES / 2 : QK_STAGE_BYTES));
+                        if (!skip_q) tma_load_4d(&mapQ, fb, dst, kc * CH, qt * QT, h, b);
                         tma_load_4d(&mapK, fb, dst + (uint32_t)(QT * CH * 4), kc * CH, j * KB, h, b);
                         if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
                     }
@@ -140,7 +167,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 auto load_v = [&](int j) {
                     const int nc = valid_chunks(p, j);
                     for (int c = 0; c < nc; ++c) {
-                        mbar_wait_spin(empty_bar(stage), phase ^ 1u);
+                        AT_TIMED(w_empty, mbar_wait_spin(empty_bar(stage), phase ^ 1u));
+                        if (c == 0) AT_STAMP(first, 0, j, 2);
+                        if (c == nc - 1) AT_STAMP(first, 0, j, 3);
                         const uint32_t fb = full_bar(stage), dst = sStage + (uint32_t)(stage * p.stage_bytes);
                         mbar_arrive_expect_tx(fb, (uint32_t)(p.NV * CH * 4));
                         tma_load_4d(&mapVlo, fb, dst, j * KB + c * CH, 0, h, b);
@@ -154,6 +183,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     load_v(j);
                 }
             }
+            if (ZVX_DBG_PTR(p) && blockIdx.x == 0) { ZVX_DBG_PTR(p)[0] = clock64() - t_start; ZVX_DBG_PTR(p)[1] = w_empty; }
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -162,15 +192,19 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             int stage = 0;
             uint32_t phase = 0;
             uint32_t g = 0, tcount = 0;          // key blocks / tiles this CTA has started
+            long long w_sempty = 0, w_pfull = 0, w_oempty = 0, w_full_qk = 0, w_full_v = 0;
+            const long long t_start = clock64();
             const uint32_t dS = tmem_base + S_COL, dO = tmem_base + O_COL;
             const uint32_t p_lo0 = (uint32_t)(at_sw128_desc(sP) & 0xFFFFFFFFull);
             const uint32_t st_lo0 = (uint32_t)(at_sw128_desc(sStage) & 0xFFFFFFFFull);
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+                const bool first = tcount == 0;
                 auto issue_qk = [&](uint32_t gq) {
-                    if (gq > 0) mbar_wait_spin(s_empty, (gq - 1) & 1u);   // S(gq-1) has been read out of TMEM
+                    if (gq > 0) AT_TIMED(w_sempty, mbar_wait_spin(s_empty, (gq - 1) & 1u));   // S(gq-1) has been read out of TMEM
                     tc_fence_after();
+                    AT_STAMP(first, 1, (int)(gq - g), 0);
                     for (int kc = 0; kc < p.kchunks; ++kc) {
-                        mbar_wait_spin(full_bar(stage), phase);
+                        AT_TIMED(w_full_qk, mbar_wait_spin(full_bar(stage), phase));
                         const uint32_t a = st_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4), bb = a + (uint32_t)((QT * CH * 4) >> 4);
                         const int nk = (kc == p.kchunks - 1) ? p.last_ksteps : CH / 8;
                         for (int k = 0; k < nk; ++k)
@@ -179,14 +213,16 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                         if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
                     }
                     umma_commit(s_full);
+                    AT_STAMP(first, 1, (int)(gq - g), 1);
                 };
                 auto issue_pv = [&](int j, uint32_t gq) {
-                    mbar_wait_spin(p_full, gq & 1u);                      // P(gq) is in shared memory (and O rescaled if needed)
-                    if (j == 0 && tcount > 0) mbar_wait_spin(o_empty, (tcount - 1) & 1u);   // previous tile's O has been read
+                    AT_TIMED(w_pfull, mbar_wait_spin(p_full, gq & 1u));   // P(gq) is in shared memory (and O rescaled if needed)
+                    if (j == 0 && tcount > 0) AT_TIMED(w_oempty, mbar_wait_spin(o_empty, (tcount - 1) & 1u));   // previous tile's O has been read
                     tc_fence_after();
+                    AT_STAMP(first, 1, j, 2);
                     const int nc = valid_chunks(p, j);
                     for (int c = 0; c < nc; ++c) {
-                        mbar_wait_spin(full_bar(stage), phase);
+                        AT_TIMED(w_full_v, mbar_wait_spin(full_bar(stage), phase));
                         const uint32_t a = p_lo0 + (uint32_t)((c * P_CHUNK_BYTES) >> 4);
                         const uint32_t bb = st_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);
                         const uint32_t bh = bb + (uint32_t)((p.n_lo * CH * 4) >> 4);
@@ -200,6 +236,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                         if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
                     }
                     umma_commit(pv_done);
+                    AT_STAMP(first, 1, j, 3);
                 };
                 issue_qk(g);
                 for (int j = 0; j < p.nkb; ++j) {
@@ -208,90 +245,113 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 }
                 g += (uint32_t)p.nkb;
             }
+            if (ZVX_DBG_PTR(p) && blockIdx.x == 0) {
+                long long* d = ZVX_DBG_PTR(p);
+                d[2] = clock64() - t_start; d[3] = w_sempty; d[4] = w_pfull; d[5] = w_oempty; d[6] = w_full_qk; d[7] = w_full_v;
+            }
         }
         __syncwarp();
     } else {
-        // ================================================================ softmax warps: one query row per thread
-        const int quarter = warp & 3;                      // the TMEM lane quarter this warp may access
+        // ================================================================ softmax warps: a query row per PAIR of threads
+        // Warps w and w + 4 own the same TMEM lane quarter (hardware rule: warp id % 4) and split the row's 128 scores /
+        // the O columns in halves; they exchange the block maximum through shared memory (one named barrier per block), so
+        // both halves keep the same reference maximum; the partial row sums only meet in the epilogue.
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t prow = sP + (uint32_t)(row * 128);
+        const uint32_t prow = sP + (uint32_t)(row * 128) + (uint32_t)(half * (KB / 2 / CH) * P_CHUNK_BYTES);
         const uint32_t sw = (uint32_t)(row & 7);
+        volatile float* xmax = reinterpret_cast<volatile float*>(smem + P_BYTES + AT_STAGES * p.stage_bytes + 128);   // [2][2][128]
+        volatile float* xsum = xmax + 2 * 2 * QT;                                                                       // [2][128]
+        const int NVh = p.NV >> 1;                         // O columns of this half: [half * NVh, half * NVh + NVh)
         uint32_t g = 0;
+        long long w_sfull = 0, w_pv = 0, w_bar = 0, w_epi = 0;
+        const long long t_start = clock64();
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             const int qt = t % p.qtiles, z = t / p.qtiles, h = z % p.n_head, b = z / p.n_head;
             const int q = qt * QT + row;
             const uint8_t* km = p.mask ? p.mask + (long long)b * p.mask_ld : nullptr;
+            auto key_ok = [&](int j, int i) {
+                const int key = j * KB + half * (KB / 2) + i * 32 + lane;
+                return key < p.L && !(km && km[key]);
+            };
             float m_ref = -INFINITY, l = 0.f;
+            bool ok0 = key_ok(0, 0), ok1 = key_ok(0, 1);
             for (int j = 0; j < p.nkb; ++j) {
                 const uint32_t gq = g + (uint32_t)j;
-                // key validity of the block (bounds + padding mask), one bit per key, the same words in every lane
-                uint32_t vw[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int key = j * KB + i * 32 + lane;
-                    const bool ok = key < p.L && !(km && km[key]);
-                    vw[i] = __ballot_sync(0xFFFFFFFFu, ok);
-                }
-                const bool all_valid = (vw[0] & vw[1] & vw[2] & vw[3]) == 0xFFFFFFFFu;
+                // key validity of this half of the block (bounds + padding mask), one bit per key, the same words in every lane
+                const uint32_t vw0 = __ballot_sync(0xFFFFFFFFu, ok0), vw1 = __ballot_sync(0xFFFFFFFFu, ok1);
+                const bool all_valid = (vw0 & vw1) == 0xFFFFFFFFu;
 
-                mbar_wait_hint(s_full, gq & 1u, 64);
+                AT_TIMED(w_sfull, mbar_wait_hint(s_full, gq & 1u, 32));
+                AT_STAMP(g == 0 && threadIdx.x == 64, 2, j, 0);
                 tc_fence_after();
-                float v[KB];
+                float v[KB / 2];
 #pragma unroll
-                for (int i = 0; i < KB / 16; ++i) tmem_ld16(trow + (uint32_t)(S_COL + i * 16), reinterpret_cast<uint32_t*>(v + i * 16));
+                for (int i = 0; i < KB / 32; ++i)
+                    tmem_ld16(trow + (uint32_t)(S_COL + half * (KB / 2) + i * 16), reinterpret_cast<uint32_t*>(v + i * 16));
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_empty);                 // the issuer may overwrite S with the next block's scores
+                AT_STAMP(g == 0 && threadIdx.x == 64, 2, j, 1);
+                if (j + 1 < p.nkb) { ok0 = key_ok(j + 1, 0); ok1 = key_ok(j + 1, 1); }   // (the loads fly during the arithmetic)
 
-                float mb = -INFINITY;
+                float mb0 = -INFINITY, mb1 = -INFINITY;
                 if (all_valid) {
 #pragma unroll
-                    for (int i = 0; i < KB; ++i) mb = fmaxf(mb, v[i]);
+                    for (int i = 0; i < KB / 2; i += 2) { mb0 = fmaxf(mb0, v[i]); mb1 = fmaxf(mb1, v[i + 1]); }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < KB; ++i) {
-                        if (!((vw[i >> 5] >> (i & 31)) & 1u)) v[i] = -INFINITY;
-                        mb = fmaxf(mb, v[i]);
+                    for (int i = 0; i < KB / 2; i += 2) {
+                        if (!(((i < 32 ? vw0 : vw1) >> (i & 31)) & 1u)) v[i] = -INFINITY;
+                        if (!(((i < 32 ? vw0 : vw1) >> ((i + 1) & 31)) & 1u)) v[i + 1] = -INFINITY;
+                        mb0 = fmaxf(mb0, v[i]); mb1 = fmaxf(mb1, v[i + 1]);
                     }
                 }
+                float mb = fmaxf(mb0, mb1);
+                xmax[((gq & 1u) * 2 + (uint32_t)half) * QT + row] = mb;
+                AT_TIMED(w_bar, asm volatile("bar.sync 1, 256;" ::: "memory"));
+                mb = fmaxf(mb, xmax[((gq & 1u) * 2 + (uint32_t)(half ^ 1)) * QT + row]);
                 // lazy reference maximum (in units of the exponent: s * sc)
                 float factor = 1.f;
                 bool rescale = false;
-                if (mb * p.sc > m_ref * p.sc + LAZY_EXP2 || (m_ref == -INFINITY && mb > -INFINITY)) {
+                if (mb * p.sc > m_ref * p.sc + LAZY_EXP2) {          // (also the first finite maximum: m_ref = -inf)
                     if (m_ref != -INFINITY) {
-                        factor = exp2f((m_ref - mb) * p.sc);
+                        factor = ex2_approx((m_ref - mb) * p.sc);
                         rescale = j > 0;
                     }
                     m_ref = mb;
                 }
                 const float off = (m_ref == -INFINITY) ? 0.f : m_ref * p.sc;
-                float sum = 0.f;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                for (int i = 0; i < KB; ++i) {
-                    const float e = exp2f(fmaf(v[i], p.sc, -off));
-                    sum += e;
-                    v[i] = rn_tf32(e);
+                for (int i = 0; i < KB / 2; i += 4) {
+                    const float e0 = ex2_approx(fmaf(v[i], p.sc, -off)), e1 = ex2_approx(fmaf(v[i + 1], p.sc, -off));
+                    const float e2 = ex2_approx(fmaf(v[i + 2], p.sc, -off)), e3 = ex2_approx(fmaf(v[i + 3], p.sc, -off));
+                    s0 += e0; s1 += e1; s2 += e2; s3 += e3;
+                    v[i] = rn_tf32(e0); v[i + 1] = rn_tf32(e1); v[i + 2] = rn_tf32(e2); v[i + 3] = rn_tf32(e3);
                 }
-                l = fmaf(l, factor, sum);
+                l = fmaf(l, factor, (s0 + s1) + (s2 + s3));
 
                 // P buffer free and O stable: the previous block's PV product has completed
-                if (gq > 0) mbar_wait_hint(pv_done, (gq - 1) & 1u, 64);
+                AT_STAMP(g == 0 && threadIdx.x == 64, 2, j, 2);
+                if (gq > 0) AT_TIMED(w_pv, mbar_wait_hint(pv_done, (gq - 1) & 1u, 32));
                 tc_fence_after();
                 if (__any_sync(0xFFFFFFFFu, rescale)) {
-                    for (int c = 0; c < p.NV; c += 16) {
-                        uint32_t o[16];
-                        tmem_ld16(trow + (uint32_t)(O_COL + c), o);
+                    for (int c = half * NVh; c < (half + 1) * NVh; c += 8) {
+                        uint32_t o[8];
+                        tmem_ld8(trow + (uint32_t)(O_COL + c), o);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-                        tmem_st16(trow + (uint32_t)(O_COL + c), o);
+                        for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                        tmem_st8(trow + (uint32_t)(O_COL + c), o);
                     }
                     tmem_wait_st();
                 }
 #pragma unroll
-                for (int c = 0; c < KB / CH; ++c)
+                for (int c = 0; c < KB / 2 / CH; ++c)
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         st_shared_v4(prow + (uint32_t)(c * P_CHUNK_BYTES) + (((uint32_t)u ^ sw) << 4),
@@ -300,21 +360,27 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
+                AT_STAMP(g == 0 && threadIdx.x == 64, 2, j, 3);
             }
             g += (uint32_t)p.nkb;
-            // ---- epilogue: O / l -> out[b, q, h*dk + :]
-            mbar_wait_hint(pv_done, (g - 1) & 1u, 64);
+            // ---- epilogue: O / l -> out[b, q, h*dk + :], this half's columns; the two partial row sums meet here
+            xsum[half * QT + row] = l;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float inv = 1.f / (l + xsum[(half ^ 1) * QT + row]);
+            AT_TIMED(w_epi, mbar_wait_hint(pv_done, (g - 1) & 1u, 32));
             tc_fence_after();
-            const float inv = 1.f / l;
             float* orow = p.out + ((long long)b * p.L + q) * p.H + (long long)h * p.dk;
-            for (int c = 0; c < p.dk; c += 16) {
-                uint32_t o[16];
-                tmem_ld16(trow + (uint32_t)(O_COL + c), o);
+            const int c_end = min((half + 1) * NVh, p.dk);
+            for (int c = half * NVh; c < c_end; c += 32) {
+                uint32_t o[32];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (c + i * 8 < c_end) tmem_ld8(trow + (uint32_t)(O_COL + c + i * 8), o + i * 8);
                 tmem_wait_ld();
                 if (q < p.L) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        if (c + i < p.dk)
+                    for (int i = 0; i < 32; i += 4)
+                        if (c + i < c_end)
                             *reinterpret_cast<float4*>(orow + c + i) =
                                 make_float4(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv, __uint_as_float(o[i + 2]) * inv,
                                             __uint_as_float(o[i + 3]) * inv);
@@ -323,6 +389,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(o_empty);
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // xsum is rewritten by the next tile
+        }
+        if (ZVX_DBG_PTR(p) && blockIdx.x == 0 && threadIdx.x == 64) {
+            long long* d = ZVX_DBG_PTR(p);
+            d[8] = clock64() - t_start; d[9] = w_sfull; d[10] = w_pv; d[11] = w_bar; d[12] = w_epi;
         }
     }
     tc_fence_before();
@@ -415,6 +486,15 @@ void attn_fused(const AttnFusedArgs& a, cudaStream_t st) {
     p.idesc_hi = at_idesc(p.n_hi ? p.n_hi : 16);
     p.sc = 1.4426950408889634f / a.temperature;
     p.out = a.out; p.mask = a.key_mask; p.mask_ld = a.mask_ld;
+    p.dbg = nullptr;
+    p.dbg_skip = env_int("ZVX_ATTN_EXP", 0);
+    static const bool dbg_on = env_set("ZVX_ATTN_DBG");   // debug builds: wait-cycle counters of CTA 0, printed after every launch
+    static long long* dbg_buf = nullptr;
+    if (dbg_on) {
+        if (!dbg_buf) ZVX_CUDA_CHECK(cudaMalloc(&dbg_buf, 256 * sizeof(long long)));
+        ZVX_CUDA_CHECK(cudaMemsetAsync(dbg_buf, 0, 256 * sizeof(long long), st));
+        p.dbg = dbg_buf;
+    }
 
     const long long H2 = 2LL * a.H;
     const long long qdims[4] = {a.dk, a.L, a.n_head, a.B};
@@ -426,7 +506,7 @@ void attn_fused(const AttnFusedArgs& a, cudaStream_t st) {
     const CUtensorMap mapVlo = at_map(a.vt, vdims, vstr, CH, p.n_lo);
     const CUtensorMap mapVhi = p.n_hi ? at_map(a.vt, vdims, vstr, CH, p.n_hi) : mapVlo;
 
-    const size_t smem = 1024 + (size_t)P_BYTES + (size_t)AT_STAGES * p.stage_bytes + 8 * (2 * AT_STAGES + 6);
+    const size_t smem = 1024 + (size_t)P_BYTES + (size_t)AT_STAGES * p.stage_bytes + 128 + 6 * QT * 4;   // barriers, max / sum exchange
     static std::once_flag once;
     std::call_once(once, [] {
         ZVX_CUDA_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -435,6 +515,21 @@ void attn_fused(const AttnFusedArgs& a, cudaStream_t st) {
     const int grid = std::min(p.num_tiles, at_num_sms());
     attn_fused_kernel<<<grid, AT_THREADS, smem, st>>>(mapQ, mapK, mapVlo, mapVhi, p);
     ZVX_POST_LAUNCH();
+    if (dbg_on) {
+        long long hst[256];
+        ZVX_CUDA_CHECK(cudaMemcpyAsync(hst, dbg_buf, sizeof(hst), cudaMemcpyDeviceToHost, st));
+        ZVX_CUDA_CHECK(cudaStreamSynchronize(st));
+        fprintf(stderr, "[attn dbg] CTA0 cycles: producer total %lld wait_empty %lld | issuer total %lld wait s_empty %lld p_full %lld "
+                        "o_empty %lld full(qk) %lld full(v) %lld | softmax total %lld wait s_full %lld pv_done %lld bar %lld epi %lld\n",
+                hst[0], hst[1], hst[2], hst[3], hst[4], hst[5], hst[6], hst[7], hst[8], hst[9], hst[10], hst[11], hst[12]);
+        const long long t0 = hst[16 + 64];   // issuer: QK(0) issue start
+        for (int j = 0; j < std::min(p.nkb, 16); ++j) {
+            const long long* a = hst + 16 + j * 4;
+            fprintf(stderr, "[attn dbg] blk %2d | load qk %6lld..%6lld v %6lld..%6lld | issue qk %6lld..%6lld pv %6lld..%6lld | softmax s_full %6lld "
+                            "s_empty %6lld computed %6lld p_full %6lld\n", j, a[0] - t0, a[1] - t0, a[2] - t0, a[3] - t0, a[64] - t0, a[65] - t0,
+                    a[66] - t0, a[67] - t0, a[128] - t0, a[129] - t0, a[130] - t0, a[131] - t0);
+        }
+    }
 }
 
 }  // namespace zvx
