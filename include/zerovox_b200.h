@@ -270,7 +270,7 @@ const char* zvx_ragged_last_error(void);
  * as ONE tcgen05 kernel; the engine's decoder calls the same kernel.  qk fp32 [B*L, 2*n_head*d_k] row-major (Q in the first
  * n_head*d_k columns, K in the rest; head h in columns h*d_k..), vt = V transposed per utterance: vt[(b*n_head*d_k + h*d_k + c)
  * * vt_pitch + j]; key_mask (optional, uint8 [B, L]): non-zero = key j of utterance b is masked; out fp32 [B*L, n_head*d_k].
- * d_k % 8 == 0, d_k <= 384, vt_pitch % 4 == 0, 16-byte aligned pointers.  Products in TF32, softmax and accumulation in fp32. */
+ * d_k % 8 == 0, d_k <= 288, vt_pitch % 4 == 0, 16-byte aligned pointers.  Products in TF32, softmax and accumulation in fp32. */
 int zvx_attention(const float* qk, const float* vt, int64_t vt_pitch, const uint8_t* key_mask, int B, int L, int n_head, int d_k,
                   float temperature, float* out, void* stream);
 const char* zvx_attention_last_error(void);

@@ -32,14 +32,14 @@ namespace zvx {
 namespace {
 
 constexpr int AT_THREADS = 320;          // producer warp, issuer warp, 8 softmax warps
-constexpr int KB = 128;                  // keys per block = columns of S
+constexpr int KB = 112;                  // keys per block = columns of S: S + P + O = 112 + 112 + 272 TMEM columns
 constexpr int QT = 128;                  // query rows per tile (MMA M)
 constexpr int CH = 32;                   // fp32 per 128-byte swizzle row
-constexpr int P_CHUNK_BYTES = QT * CH * 4;           // 16 KB: 128 rows x 32 keys
-constexpr int P_BYTES = (KB / CH) * P_CHUNK_BYTES;   // 64 KB
-constexpr int AT_STAGES = 4;
-constexpr int QK_STAGE_BYTES = 2 * QT * CH * 4;      // Q chunk + K chunk
-constexpr int S_COL = 0, O_COL = KB;     // TMEM columns
+constexpr int HK = KB / 2;               // keys per softmax thread
+constexpr int AT_STAGES = 6;             // no P buffer in shared memory: the whole 227 KB is operand ring
+constexpr int Q_CHUNK_BYTES = QT * CH * 4, K_CHUNK_BYTES = KB * CH * 4;
+constexpr int QK_STAGE_BYTES = Q_CHUNK_BYTES + K_CHUNK_BYTES;
+constexpr int S_COL = 0, P_COL = KB, O_COL = 2 * KB;   // TMEM columns
 constexpr float LAZY_EXP2 = 8.f;         // the reference maximum moves when a block maximum exceeds it by 2^8
 
 struct AttnParams {
@@ -67,6 +67,24 @@ __device__ __forceinline__ uint64_t at_sw128_desc(uint32_t saddr) {
     return d;
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows x 8 tf32) is read from TMEM columns [a_tmem, a_tmem + 8), lane = row
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -94,10 +112,12 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 #define AT_STAMP(cond, role, j, k) do { } while (0)
 #endif
 
-// keys of block j that take part: chunks of 32 that contain at least one key < L
+// K = 8 steps of block j's PV product (keys < L, rounded up to 8: the rest of P is zero, of V zero-filled)
+__device__ __forceinline__ int valid_ksteps(const AttnParams& p, int j) { return (min(p.L - j * KB, KB) + 7) / 8; }
+// chunks of 32 keys (one V^T load each) that contain at least one key < L
 __device__ __forceinline__ int valid_chunks(const AttnParams& p, int j) {
-    const int left = p.L - j * KB;
-    return left >= KB ? KB / CH : (left + CH - 1) / CH;
+    const int left = min(p.L - j * KB, KB);
+    return (left + CH - 1) / CH;
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -105,8 +125,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                   const __grid_constant__ CUtensorMap mapVlo, const __grid_constant__ CUtensorMap mapVhi, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t sP = smem_u32(smem);
-    const uint32_t sStage = sP + P_BYTES;
+    const uint32_t sStage = smem_u32(smem);
     const uint32_t bars = sStage + (uint32_t)(AT_STAGES * p.stage_bytes);
     auto full_bar = [&](int s) { return bars + 8u * (uint32_t)s; };
     auto empty_bar = [&](int s) { return bars + 8u * (uint32_t)(AT_STAGES + s); };
@@ -115,7 +134,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
     const uint32_t o_empty = bars + 8u * (2 * AT_STAGES + 4);
     const uint32_t tmem_slot = bars + 8u * (2 * AT_STAGES + 5);
     volatile uint32_t* tmem_slot_ptr =
-        reinterpret_cast<volatile uint32_t*>(smem + P_BYTES + AT_STAGES * p.stage_bytes + 8 * (2 * AT_STAGES + 5));
+        reinterpret_cast<volatile uint32_t*>(smem + AT_STAGES * p.stage_bytes + 8 * (2 * AT_STAGES + 5));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -158,9 +177,9 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                         if (kc == p.kchunks - 1) AT_STAMP(first, 0, j, 1);
                         const uint32_t fb = full_bar(stage), dst = sStage + (uint32_t)(stage * p.stage_bytes);
                         const bool skip_q = (ZVX_DBG_SKIP(p) & 1) && j > 0;
-                        mbar_arrive_expect_tx(fb, (uint32_t)(skip_q ? QK_STAGE_BYTES / 2 : QK_STAGE_BYTES));
+                        mbar_arrive_expect_tx(fb, (uint32_t)(skip_q ? K_CHUNK_BYTES : QK_STAGE_BYTES));
                         if (!skip_q) tma_load_4d(&mapQ, fb, dst, kc * CH, qt * QT, h, b);
-                        tma_load_4d(&mapK, fb, dst + (uint32_t)(QT * CH * 4), kc * CH, j * KB, h, b);
+                        tma_load_4d(&mapK, fb, dst + (uint32_t)Q_CHUNK_BYTES, kc * CH, j * KB, h, b);
                         if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
                     }
                 };
@@ -194,8 +213,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             uint32_t g = 0, tcount = 0;          // key blocks / tiles this CTA has started
             long long w_sempty = 0, w_pfull = 0, w_oempty = 0, w_full_qk = 0, w_full_v = 0;
             const long long t_start = clock64();
-            const uint32_t dS = tmem_base + S_COL, dO = tmem_base + O_COL;
-            const uint32_t p_lo0 = (uint32_t)(at_sw128_desc(sP) & 0xFFFFFFFFull);
+            const uint32_t dS = tmem_base + S_COL, dO = tmem_base + O_COL, dP = tmem_base + P_COL;
             const uint32_t st_lo0 = (uint32_t)(at_sw128_desc(sStage) & 0xFFFFFFFFull);
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
                 const bool first = tcount == 0;
@@ -205,7 +223,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     AT_STAMP(first, 1, (int)(gq - g), 0);
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         AT_TIMED(w_full_qk, mbar_wait_spin(full_bar(stage), phase));
-                        const uint32_t a = st_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4), bb = a + (uint32_t)((QT * CH * 4) >> 4);
+                        const uint32_t a = st_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4), bb = a + (uint32_t)(Q_CHUNK_BYTES >> 4);
                         const int nk = (kc == p.kchunks - 1) ? p.last_ksteps : CH / 8;
                         for (int k = 0; k < nk; ++k)
                             umma_tf32_lo(dS, a + 2 * k, bb + 2 * k, DESC_HI, p.idesc_qk, (kc | k) ? 1u : 0u);
@@ -220,17 +238,17 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     if (j == 0 && tcount > 0) AT_TIMED(w_oempty, mbar_wait_spin(o_empty, (tcount - 1) & 1u));   // previous tile's O has been read
                     tc_fence_after();
                     AT_STAMP(first, 1, j, 2);
-                    const int nc = valid_chunks(p, j);
+                    const int nc = valid_chunks(p, j), nks = valid_ksteps(p, j);
                     for (int c = 0; c < nc; ++c) {
                         AT_TIMED(w_full_v, mbar_wait_spin(full_bar(stage), phase));
-                        const uint32_t a = p_lo0 + (uint32_t)((c * P_CHUNK_BYTES) >> 4);
+                        const uint32_t a = dP + (uint32_t)(c * CH);                 // P columns of this chunk's keys
                         const uint32_t bb = st_lo0 + (uint32_t)((stage * p.stage_bytes) >> 4);
                         const uint32_t bh = bb + (uint32_t)((p.n_lo * CH * 4) >> 4);
-#pragma unroll
-                        for (int k = 0; k < CH / 8; ++k) {
+                        const int nk = min(CH / 8, nks - c * (CH / 8));
+                        for (int k = 0; k < nk; ++k) {
                             const uint32_t acc = (j | c | k) ? 1u : 0u;
-                            umma_tf32_lo(dO, a + 2 * k, bb + 2 * k, DESC_HI, p.idesc_lo, acc);
-                            if (p.n_hi) umma_tf32_lo(dO + (uint32_t)p.n_lo, a + 2 * k, bh + 2 * k, DESC_HI, p.idesc_hi, acc);
+                            umma_tf32_ts(dO, a + 8 * k, bb + 2 * k, DESC_HI, p.idesc_lo, acc);
+                            if (p.n_hi) umma_tf32_ts(dO + (uint32_t)p.n_lo, a + 8 * k, bh + 2 * k, DESC_HI, p.idesc_hi, acc);
                         }
                         umma_commit(empty_bar(stage));
                         if (++stage == AT_STAGES) { stage = 0; phase ^= 1u; }
@@ -260,9 +278,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
         const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        const uint32_t prow = sP + (uint32_t)(row * 128) + (uint32_t)(half * (KB / 2 / CH) * P_CHUNK_BYTES);
-        const uint32_t sw = (uint32_t)(row & 7);
-        volatile float* xmax = reinterpret_cast<volatile float*>(smem + P_BYTES + AT_STAGES * p.stage_bytes + 128);   // [2][2][128]
+        volatile float* xmax = reinterpret_cast<volatile float*>(smem + AT_STAGES * p.stage_bytes + 128);   // [2][2][128]
         volatile float* xsum = xmax + 2 * 2 * QT;                                                                       // [2][128]
         const int NVh = p.NV >> 1;                         // O columns of this half: [half * NVh, half * NVh + NVh)
         uint32_t g = 0;
@@ -273,8 +289,8 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
             const int q = qt * QT + row;
             const uint8_t* km = p.mask ? p.mask + (long long)b * p.mask_ld : nullptr;
             auto key_ok = [&](int j, int i) {
-                const int key = j * KB + half * (KB / 2) + i * 32 + lane;
-                return key < p.L && !(km && km[key]);
+                const int key = j * KB + half * HK + i * 32 + lane;
+                return i * 32 + lane < HK && key < p.L && !(km && km[key]);
             };
             float m_ref = -INFINITY, l = 0.f;
             bool ok0 = key_ok(0, 0), ok1 = key_ok(0, 1);
@@ -282,15 +298,17 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 const uint32_t gq = g + (uint32_t)j;
                 // key validity of this half of the block (bounds + padding mask), one bit per key, the same words in every lane
                 const uint32_t vw0 = __ballot_sync(0xFFFFFFFFu, ok0), vw1 = __ballot_sync(0xFFFFFFFFu, ok1);
-                const bool all_valid = (vw0 & vw1) == 0xFFFFFFFFu;
+                const bool all_valid = vw0 == 0xFFFFFFFFu && vw1 == (0xFFFFFFFFu >> (64 - HK));
 
                 AT_TIMED(w_sfull, mbar_wait_hint(s_full, gq & 1u, 32));
                 AT_STAMP(g == 0 && threadIdx.x == 64, 2, j, 0);
                 tc_fence_after();
-                float v[KB / 2];
+                float v[HK];
+                static_assert(HK % 16 == 8, "56 columns per thread: three x16 loads and one x8");
 #pragma unroll
-                for (int i = 0; i < KB / 32; ++i)
-                    tmem_ld16(trow + (uint32_t)(S_COL + half * (KB / 2) + i * 16), reinterpret_cast<uint32_t*>(v + i * 16));
+                for (int i = 0; i < HK / 16; ++i)
+                    tmem_ld16(trow + (uint32_t)(S_COL + half * HK + i * 16), reinterpret_cast<uint32_t*>(v + i * 16));
+                tmem_ld8(trow + (uint32_t)(S_COL + half * HK + HK - 8), reinterpret_cast<uint32_t*>(v + HK - 8));
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
@@ -301,10 +319,10 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 float mb0 = -INFINITY, mb1 = -INFINITY;
                 if (all_valid) {
 #pragma unroll
-                    for (int i = 0; i < KB / 2; i += 2) { mb0 = fmaxf(mb0, v[i]); mb1 = fmaxf(mb1, v[i + 1]); }
+                    for (int i = 0; i < HK; i += 2) { mb0 = fmaxf(mb0, v[i]); mb1 = fmaxf(mb1, v[i + 1]); }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < KB / 2; i += 2) {
+                    for (int i = 0; i < HK; i += 2) {
                         if (!(((i < 32 ? vw0 : vw1) >> (i & 31)) & 1u)) v[i] = -INFINITY;
                         if (!(((i < 32 ? vw0 : vw1) >> ((i + 1) & 31)) & 1u)) v[i + 1] = -INFINITY;
                         mb0 = fmaxf(mb0, v[i]); mb1 = fmaxf(mb1, v[i + 1]);
@@ -327,7 +345,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                 const float off = (m_ref == -INFINITY) ? 0.f : m_ref * p.sc;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                for (int i = 0; i < KB / 2; i += 4) {
+                for (int i = 0; i < HK; i += 4) {
                     const float e0 = ex2_approx(fmaf(v[i], p.sc, -off)), e1 = ex2_approx(fmaf(v[i + 1], p.sc, -off));
                     const float e2 = ex2_approx(fmaf(v[i + 2], p.sc, -off)), e3 = ex2_approx(fmaf(v[i + 3], p.sc, -off));
                     s0 += e0; s1 += e1; s2 += e2; s3 += e3;
@@ -350,13 +368,12 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constan
                     }
                     tmem_wait_st();
                 }
+                // P goes to TMEM (the PV product reads its A operand there: lane = query row, column = key)
 #pragma unroll
-                for (int c = 0; c < KB / 2 / CH; ++c)
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        st_shared_v4(prow + (uint32_t)(c * P_CHUNK_BYTES) + (((uint32_t)u ^ sw) << 4),
-                                     make_float4(v[c * CH + u * 4], v[c * CH + u * 4 + 1], v[c * CH + u * 4 + 2], v[c * CH + u * 4 + 3]));
-                fence_proxy_async();
+                for (int i = 0; i < HK / 16; ++i)
+                    tmem_st16(trow + (uint32_t)(P_COL + half * HK + i * 16), reinterpret_cast<const uint32_t*>(v + i * 16));
+                tmem_st8(trow + (uint32_t)(P_COL + half * HK + HK - 8), reinterpret_cast<const uint32_t*>(v + HK - 8));
+                tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
@@ -464,7 +481,7 @@ int at_num_sms() {
 bool attn_fused_supported(const AttnFusedArgs& a) {
     const int NV = (a.dk + 15) / 16 * 16;
     auto al16 = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
-    return a.dk % 8 == 0 && a.dk >= 16 && NV <= 384 && (NV <= 256 || NV - 128 >= 16) && a.H % 4 == 0 && a.Lp % 4 == 0 &&
+    return a.dk % 8 == 0 && a.dk >= 16 && NV <= 512 - 2 * KB && (NV <= 256 || NV - 128 >= 16) && a.H % 4 == 0 && a.Lp % 4 == 0 &&
            a.Lp >= a.L && a.L >= 1 && a.B >= 1 && al16(a.qk) && al16(a.vt) && al16(a.out);
 }
 
@@ -506,7 +523,7 @@ void attn_fused(const AttnFusedArgs& a, cudaStream_t st) {
     const CUtensorMap mapVlo = at_map(a.vt, vdims, vstr, CH, p.n_lo);
     const CUtensorMap mapVhi = p.n_hi ? at_map(a.vt, vdims, vstr, CH, p.n_hi) : mapVlo;
 
-    const size_t smem = 1024 + (size_t)P_BYTES + (size_t)AT_STAGES * p.stage_bytes + 128 + 6 * QT * 4;   // barriers, max / sum exchange
+    const size_t smem = 1024 + (size_t)AT_STAGES * p.stage_bytes + 128 + 6 * QT * 4;   // barriers, max / sum exchange
     static std::once_flag once;
     std::call_once(once, [] {
         ZVX_CUDA_CHECK(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
