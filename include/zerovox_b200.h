@@ -273,13 +273,26 @@ const char* zvx_ragged_last_error(void);
  * d_k % 8 == 0, d_k <= 288, vt_pitch % 4 == 0, 16-byte aligned pointers.  Products in TF32, softmax and accumulation in fp32. */
 int zvx_attention(const float* qk, const float* vt, int64_t vt_pitch, const uint8_t* key_mask, int B, int L, int n_head, int d_k,
                   float temperature, float* out, void* stream);
+/* The same with the kernel chosen by the caller: variant 0 = as zvx_attention (the CTA-pair kernel when an utterance has at least
+ * two 128-row query tiles); 1 = single-CTA kernel (tcgen05.mma.cta_group::1, operands re-streamed per key block); 2 = CTA-pair
+ * kernel (two SMs of a TPC run every product as one tcgen05.mma.cta_group::2, M = 256; Q resident in shared memory, each SM
+ * fetches half of every K / V block).  Both compute the same function (tests/test_gpu_attention.py runs every case on both).
+ * workspace (optional, device memory, 16-byte aligned, zvx_attention_workspace_bytes(B, L, n_head) bytes): the tile list is then
+ * built on the device from key_mask — key blocks past an utterance's last unmasked key are not visited (exact), a ragged batch
+ * is balanced over the SMs — and with skip_masked_queries != 0 the query rows past that position are NOT computed and NOT
+ * written (the FFT block zero-fills masked positions right after, fs2.py:226-229; the engine's decoder runs this way). */
+int zvx_attention_ex(const float* qk, const float* vt, int64_t vt_pitch, const uint8_t* key_mask, int B, int L, int n_head, int d_k,
+                     float temperature, float* out, int variant, int skip_masked_queries, void* workspace, int64_t workspace_bytes,
+                     void* stream);
+int64_t zvx_attention_workspace_bytes(int B, int L, int n_head);
 const char* zvx_attention_last_error(void);
 
 /* Runtime options of a handle (the release library reads no environment variables).
  *   "score_workspace_bytes": budget of the attention-score workspace; longer inputs are processed in chunks of query rows
  *                            (exact: the softmax is per row).  Default 4 GiB.  Only used when the fused kernel is off.
  *   "fused_attention":       1 (default) = the TF32 policy's attention runs as one kernel (zvx_attention); 0 = QK^T, softmax
- *                            and PV as three kernels with the score matrix in HBM / L2 (A/B and debugging). */
+ *                            and PV as three kernels with the score matrix in HBM / L2 (A/B and debugging); 2 / 3 = one kernel,
+ *                            always the single-CTA / the CTA-pair variant (zvx_attention_ex variants 1 / 2). */
 int zvx_set_option(zvx_handle* h, const char* name, int64_t value);
 
 /* Workspace control: bytes of engine-owned scratch currently reserved on the device. */

@@ -111,6 +111,8 @@ SYMBOLS = {
                                     _P]),
     "zvx_ragged_last_error": (C.c_char_p, []),
     "zvx_attention": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
+    "zvx_attention_ex": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, C.c_int, C.c_int, _P, C.c_int64, _P]),
+    "zvx_attention_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "zvx_attention_last_error": (C.c_char_p, []),
     "zvx_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "zvx_workspace_bytes": (C.c_int64, [_P]),

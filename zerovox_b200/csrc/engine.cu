@@ -748,7 +748,21 @@ class Engine {
         float *lo_qkv = nullptr, *lo_S = nullptr;   // 3xTF32 split: low parts of the attention operands
         long long qkv_elems = 0, S_elems = 0;
         int Lq_max = 0, ldS = 0;
+        AttnPlan plan;                              // fused attention: tile list of this mask (one per stack of FFT blocks)
+        bool has_plan = false;
     };
+
+    // Tile list of the fused attention kernel for a stack of FFT blocks that share `mask` (attn_fused.cu attn_plan): masked key
+    // blocks and the query tiles of masked positions are left out — fft_block zero-fills masked rows after each layer norm.
+    void plan_attention(FFTScratch& s, int B, int L, int n_head, const uint8_t* mask, cudaStream_t st) {
+        AttnFusedArgs fa;
+        fa.key_mask = mask; fa.mask_ld = L; fa.B = B; fa.L = L; fa.n_head = n_head; fa.dk = H / n_head; fa.H = H;
+        fa.Lp = (int)round_up(L, 4); fa.variant = kAttentionVariant;
+        if (!kFusedAttention || !mask || H % n_head) return;
+        int* w = ws.get<int>((long long)(attn_plan_bytes(B, L, n_head) / sizeof(int)));
+        attn_plan(fa, /*skip_masked_queries=*/true, w, s.plan, st);
+        s.has_plan = true;
+    }
 
     FFTScratch fft_scratch(int B, int L, int n_head, int prec) {
         FFTScratch s;
@@ -810,7 +824,8 @@ class Engine {
             // (attn_fused.cu).  The 3xTF32 policy (encoder, T <= a few hundred) keeps the three-kernel path below.
             AttnFusedArgs fa;
             fa.qk = qk; fa.vt = vt; fa.out = att; fa.key_mask = mask; fa.mask_ld = L; fa.B = B; fa.L = L; fa.n_head = n_head;
-            fa.dk = dk; fa.H = H; fa.Lp = Lp; fa.temperature = temperature;
+            fa.dk = dk; fa.H = H; fa.Lp = Lp; fa.temperature = temperature; fa.variant = kAttentionVariant;
+            fa.plan = sc.has_plan ? &sc.plan : nullptr;
             if (!split && kFusedAttention && attn_fused_supported(fa)) {
                 prof.begin(ZVX_PROF_GEMM_TC, fa.flops(), fa.bytes(), st);
                 attn_fused(fa, st);
@@ -1056,7 +1071,8 @@ class Engine {
         }
         float* x = ws.get<float>((long long)B * L * H);
         add_posenc(features, pos_table(true, L), B, L, H, x, st);
-        const FFTScratch sc = fft_scratch(B, L, cfg.dec_heads, tc);
+        FFTScratch sc = fft_scratch(B, L, cfg.dec_heads, tc);
+        plan_attention(sc, B, L, cfg.dec_heads, mask, st);
         for (int i = 0; i < cfg.dec_layers; ++i) {
             const float* gb1 = gb ? gb + (long long)(2 * i) * 2 * H : nullptr;
             const float* gb2 = gb ? gb + (long long)(2 * i + 1) * 2 * H : nullptr;
@@ -1357,7 +1373,9 @@ class Engine {
             return 0;
         }
         if (n == "fused_attention") {
+            ZVX_REQUIRE(value >= 0 && value <= 3, "zvx_set_option: fused_attention must be 0..3");
             kFusedAttention = value != 0;
+            kAttentionVariant = value >= 2 ? (int)value - 1 : 0;
             return 0;
         }
         throw Error("zvx_set_option: unknown option '" + n + "'");
@@ -1367,6 +1385,7 @@ class Engine {
     // attention-score workspace budget: longer sequences are processed in chunks of query rows (exact)
     long long kScoreBytes = 4LL << 30;   // zvx_set_option("score_workspace_bytes")
     bool kFusedAttention = true;         // zvx_set_option("fused_attention"): 0 = QK^T / softmax / PV as three kernels
+    int kAttentionVariant = 0;           // AttnFusedArgs::variant (0 = the kernel chooses)
     // attention batch-slice budget (score bytes per slice); 0 = whole batch per launch.  Default set by measurement.
     static constexpr long long kAttnSliceBytes = 0;
 

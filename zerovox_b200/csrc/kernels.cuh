@@ -139,14 +139,24 @@ void conv_post_cl(const float* x, long long x_bs, const float* w /*[k][C]*/, con
 // out[b, q, h*dk + c] = sum_j softmax_j(<Q[b,q,h,:], K[b,j,h,:]> / temperature | key j not masked) V[b,j,h,c]   (fs2.py:101-163)
 // qk: [B*L, 2H] row-major, Q in columns [0, H), K in [H, 2H), head h in columns h*dk..; vt: V transposed per utterance,
 // vt[(b*H + h*dk + c) * Lp + j]; key_mask (optional): key_mask[b*mask_ld + j] != 0 masks key j of utterance b.
+// Device-built tile list of one (mask, shape): key blocks that are entirely masked are never visited (exact: they contribute
+// exp(-inf) = 0), and with skip_masked_queries the query tiles past an utterance's last unmasked position are left out as well —
+// their output rows are NOT written; the FFT block zero-fills them after the layer norm (fs2.py:226, 229).  The list is what
+// balances a ragged batch over the SMs.  One plan serves every layer that shares the mask.
+struct AttnPlan { const int* dev = nullptr; int rows_per_tile = 0; int variant = 0; };
 struct AttnFusedArgs {
     const float* qk = nullptr; const float* vt = nullptr; float* out = nullptr;
     const uint8_t* key_mask = nullptr; int mask_ld = 0;
     int B = 0, L = 0, n_head = 1, dk = 0, H = 0, Lp = 0;
     float temperature = 1.f;
+    int variant = 0;   // 0 = choose; 1 = single-CTA kernel; 2 = CTA-pair kernel (cta_group::2, Q resident)
+    const AttnPlan* plan = nullptr;
     double flops() const { return 4.0 * B * n_head * (double)L * L * dk; }
     double bytes() const { return 4.0 * 4.0 * B * (double)L * H; }
 };
+size_t attn_plan_bytes(int B, int L, int n_head);
+// ws: attn_plan_bytes() bytes, 16-byte aligned; uses a.key_mask / mask_ld / B / L / n_head / dk / variant
+void attn_plan(const AttnFusedArgs& a, bool skip_masked_queries, int* ws, AttnPlan& plan, cudaStream_t st);
 bool attn_fused_supported(const AttnFusedArgs& a);
 void attn_fused(const AttnFusedArgs& a, cudaStream_t st);
 
