@@ -48,6 +48,8 @@ struct AttnParams {
     int kchunks, last_ksteps;
     int NV, n_lo, n_hi;
     int stage_bytes, stages;
+    int narrow_last;                     // pair kernel: the last k-chunk of Q / K is 8 columns wide, 32-byte swizzle (d_k % 32 == 8)
+    int q_bytes;                         // pair kernel: resident Q tile
     uint32_t idesc_qk, idesc_lo, idesc_hi;
     float sc;                            // log2(e) / temperature
     float* out;
@@ -66,6 +68,18 @@ __device__ __forceinline__ uint64_t at_sw128_desc(uint32_t saddr) {
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// K-major operand whose rows hold ONE k-step (8 tf32 = 32 bytes, 32-byte swizzle; 8-row groups 256 bytes apart): the last k-chunk
+// of a head dimension with d_k % 32 == 8 takes a quarter of the shared memory of a 128-byte-swizzled chunk
+__device__ __forceinline__ uint64_t at_sw32_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;
     return d;
 }
 
@@ -563,10 +577,11 @@ constexpr int AP_MAX_STAGES = 8;
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-                 const __grid_constant__ CUtensorMap mapVlo, const __grid_constant__ CUtensorMap mapVhi, const AttnParams p) {
+                 const __grid_constant__ CUtensorMap mapVlo, const __grid_constant__ CUtensorMap mapVhi,
+                 const __grid_constant__ CUtensorMap mapQ8, const __grid_constant__ CUtensorMap mapK8, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int q_bytes = p.kchunks * Q_CHUNK_BYTES;
+    const int q_bytes = p.q_bytes;
     const uint32_t sQ = smem_u32(smem);
     const uint32_t sRing = sQ + (uint32_t)q_bytes;
     const int bar_off = q_bytes + p.stages * p.stage_bytes;
@@ -588,6 +603,8 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         prefetch_tmap(&mapK);
         prefetch_tmap(&mapVlo);
         prefetch_tmap(&mapVhi);
+        prefetch_tmap(&mapQ8);
+        prefetch_tmap(&mapK8);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);          // the leader's producer arrives (expect_tx of both CTAs' bytes)
             mbar_init(empty_bar(s), 1);         // one multicast commit
@@ -606,7 +623,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    const uint32_t DESC_HI = (uint32_t)(at_sw128_desc(0) >> 32);
+    const uint32_t DESC_HI = (uint32_t)(at_sw128_desc(0) >> 32), DESC_HI32 = (uint32_t)(at_sw32_desc(0) >> 32);
 
     if (warp == 0) {
         // ================================================================ TMA producer (both CTAs, the same sequence)
@@ -623,8 +640,10 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                 const int qt = tq.qt, h = tq.h, b = tq.b;
                 if (tc > 0) mbar_wait_spin(q_empty, (tc - 1) & 1u);       // every QK^T of the previous tile has completed
                 if (leader) mbar_arrive_expect_tx(q_full, (uint32_t)(2 * q_bytes));
-                for (int kc = 0; kc < p.kchunks; ++kc)
+                const int nfull = p.kchunks - p.narrow_last;
+                for (int kc = 0; kc < nfull; ++kc)
                     tma_load_4d_pair(&mapQ, L_qfull, sQ + (uint32_t)(kc * Q_CHUNK_BYTES), kc * CH, qt * QT, h, b);
+                if (p.narrow_last) tma_load_4d_pair(&mapQ8, L_qfull, sQ + (uint32_t)(nfull * Q_CHUNK_BYTES), nfull * CH, qt * QT, h, b);
             };
             const int t0 = first_tile<true>(), dt = tile_stride<true>();
             if (t0 < ntiles) load_q(t0, 0);
@@ -638,10 +657,12 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                         if (kc + 2 >= p.kchunks) AT_STAMP(tcount == 0, 0, j, 1);
                         const int nch = min(2, p.kchunks - kc);
                         const uint32_t dst = sRing + (uint32_t)(stage * p.stage_bytes);
-                        if (leader) mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(2 * nch * KH_CHUNK_BYTES));
+                        const bool narrow = p.narrow_last && kc + nch == p.kchunks;   // the stage's last chunk is the 8-column one
+                        if (leader)
+                            mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(2 * (nch * KH_CHUNK_BYTES - (narrow ? KH_CHUNK_BYTES * 3 / 4 : 0))));
                         for (int c = 0; c < nch; ++c)
-                            tma_load_4d_pair(&mapK, L_full0 + 8u * (uint32_t)stage, dst + (uint32_t)(c * KH_CHUNK_BYTES), (kc + c) * CH,
-                                             j * KB + (int)rank * (KB / 2), h, b);
+                            tma_load_4d_pair((narrow && c == nch - 1) ? &mapK8 : &mapK, L_full0 + 8u * (uint32_t)stage,
+                                             dst + (uint32_t)(c * KH_CHUNK_BYTES), (kc + c) * CH, j * KB + (int)rank * (KB / 2), h, b);
                         advance();
                     }
                 };
@@ -698,9 +719,11 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                         for (int c = 0; c < nch; ++c) {
                             const uint32_t a = q_lo0 + (uint32_t)(((kc + c) * Q_CHUNK_BYTES) >> 4);
                             const uint32_t bb = ring_lo0 + (uint32_t)((stage * p.stage_bytes + c * KH_CHUNK_BYTES) >> 4);
-                            const int nk = (kc + c == p.kchunks - 1) ? p.last_ksteps : CH / 8;
+                            const bool lastc = kc + c == p.kchunks - 1;
+                            const int nk = lastc ? p.last_ksteps : CH / 8;
+                            const uint32_t dhi = (lastc && p.narrow_last) ? DESC_HI32 : DESC_HI;
                             for (int k = 0; k < nk; ++k)
-                                umma_pair_tf32_ss(dS, a + 2 * k, bb + 2 * k, DESC_HI, p.idesc_qk, (kc | c | k) ? 1u : 0u);
+                                umma_pair_tf32_ss(dS, a + 2 * k, bb + 2 * k, dhi, p.idesc_qk, (kc | c | k) ? 1u : 0u);
                         }
                         umma_commit_pair(empty_bar(stage));
                         advance();
@@ -828,7 +851,8 @@ EncodeTiledFn at_encode_fn() {
 }
 
 // 4-D fp32 view, dim 0 contiguous; TFLOAT32 element type (round-to-nearest in flight), 128B swizzle, zero fill out of bounds
-CUtensorMap at_map(const float* base, const long long dims[4], const long long strides_elems[3], int box0, int box1) {
+CUtensorMap at_map(const float* base, const long long dims[4], const long long strides_elems[3], int box0, int box1,
+                   CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     CUtensorMap m;
     cuuint64_t gd[4], gs[3];
     cuuint32_t bx[4] = {(cuuint32_t)box0, (cuuint32_t)box1, 1, 1}, es[4] = {1, 1, 1, 1};
@@ -841,7 +865,7 @@ CUtensorMap at_map(const float* base, const long long dims[4], const long long s
         prev = std::max<long long>(s, 16);
     }
     const CUresult rc = at_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), gd, gs, bx, es,
-                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
         char buf[256];
@@ -903,7 +927,7 @@ bool at_single_supported(const AttnFusedArgs& a) {
 
 // The pair kernel's plan: value columns rounded up to 32 (tcgen05.mma.cta_group::2 with A from TMEM: N % 32 == 0), split in at
 // most two MMAs; Q resident, the rest of the 227 KB as operand ring.
-struct PairPlan { int NV, n_lo, n_hi, stage_bytes, stages, q_bytes; size_t smem; };
+struct PairPlan { int NV, n_lo, n_hi, stage_bytes, stages, q_bytes, narrow_last; size_t smem; };
 constexpr int AP_AUX_BYTES = 256 + 6 * QT * 4;   // barriers; max / sum exchange
 
 bool at_pair_plan(const AttnFusedArgs& a, PairPlan& pl) {
@@ -913,7 +937,8 @@ bool at_pair_plan(const AttnFusedArgs& a, PairPlan& pl) {
     if (pl.NV <= 256) { pl.n_lo = pl.NV; pl.n_hi = 0; }
     else { pl.n_hi = 128; pl.n_lo = pl.NV - 128; }
     const int kchunks = cdiv(a.dk, CH);
-    pl.q_bytes = kchunks * Q_CHUNK_BYTES;
+    pl.narrow_last = (a.dk % CH == 8) ? 1 : 0;
+    pl.q_bytes = kchunks * Q_CHUNK_BYTES - (pl.narrow_last ? Q_CHUNK_BYTES * 3 / 4 : 0);
     pl.stage_bytes = (int)round_up((long long)std::max(2 * KH_CHUNK_BYTES, (pl.NV / 2) * CH * 4), 1024);
     const long long room = 227LL * 1024 - 1024 - pl.q_bytes - AP_AUX_BYTES;
     pl.stages = (int)std::min<long long>(AP_MAX_STAGES, room / pl.stage_bytes);
@@ -990,13 +1015,21 @@ void attn_pair_launch(const AttnFusedArgs& a, const PairPlan& pl, cudaStream_t s
     p.qtiles = cdiv(cdiv(a.L, QT), 2);                  // pairs of q tiles
     p.num_tiles = p.qtiles * a.n_head * a.B;
     p.NV = pl.NV; p.n_lo = pl.n_lo; p.n_hi = pl.n_hi;
-    p.stage_bytes = pl.stage_bytes; p.stages = pl.stages;
+    p.stage_bytes = pl.stage_bytes; p.stages = pl.stages; p.narrow_last = pl.narrow_last; p.q_bytes = pl.q_bytes;
     p.idesc_qk = at_idesc(KB, 2 * QT);
     p.idesc_lo = at_idesc(p.n_lo, 2 * QT);
     p.idesc_hi = at_idesc(p.n_hi ? p.n_hi : 32, 2 * QT);
     at_use_plan(a, p, 2 * QT);
     CUtensorMap mapQ, mapK, mapVlo, mapVhi;
     at_maps(a, QT, KB / 2, p.n_lo / 2, p.n_hi / 2, mapQ, mapK, mapVlo, mapVhi);
+    CUtensorMap mapQ8 = mapQ, mapK8 = mapK;
+    if (p.narrow_last) {
+        const long long H2 = 2LL * a.H;
+        const long long qdims[4] = {a.dk, a.L, a.n_head, a.B};
+        const long long qstr[3] = {H2, a.dk, (long long)a.L * H2};
+        mapQ8 = at_map(a.qk, qdims, qstr, 8, QT, CU_TENSOR_MAP_SWIZZLE_32B);
+        mapK8 = at_map(a.qk + a.H, qdims, qstr, 8, KB / 2, CU_TENSOR_MAP_SWIZZLE_32B);
+    }
     const int clusters = std::min(p.num_tiles, at_pair_clusters(pl.smem));
     ZVX_REQUIRE(clusters >= 1, "attn_fused: no CTA pair can be resident");
     cudaLaunchConfig_t cfg = {};
@@ -1009,7 +1042,7 @@ void attn_pair_launch(const AttnFusedArgs& a, const PairPlan& pl, cudaStream_t s
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     at_dbg_begin(p, st);
-    ZVX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_pair_kernel, mapQ, mapK, mapVlo, mapVhi, p));
+    ZVX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_pair_kernel, mapQ, mapK, mapVlo, mapVhi, mapQ8, mapK8, p));
     ZVX_POST_LAUNCH();
     at_dbg_end(p, st);
 }
