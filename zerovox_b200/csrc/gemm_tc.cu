@@ -822,7 +822,9 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
     p.row_w = p.TW;
     p.nbuf = (p.mt * p.BN > ACC_STRIDE) ? 1 : 2;
     if (xr || xr2) {
-        p.xr = xr ? 1 : 2; p.xr_na = xr ? 3 : xr2_na; p.xr_halo = halo;
+        // full-width two-M-tile rows (FFN k = 9): an activation buffer lasts ksx x 1024 tensor cycles, two of them are plenty, and
+        // the third one's 34 KB buy a fourth 32 KB weight stage (A/B on one box: decoder 5.50 -> 5.42 ms)
+        p.xr = xr ? 1 : 2; p.xr_na = xr ? ((p.mt == 2 && p.BN > 128) ? 2 : 3) : xr2_na; p.xr_halo = halo;
         if (xr) {
             p.xr_a_tx = (p.mt * BM + halo) * BK * 4;
             p.xr_a_bytes = (int)round_up(p.xr_a_tx, 1024);

@@ -1,4 +1,4 @@
-// Inline-PTX wrappers shared by the tcgen05 kernels (gemm_tc.cu, voc_poly.cu, voc_res.cu, conv_rs.cu): mbarrier, TMA, tcgen05 MMA / TMEM.
+// Inline-PTX wrappers shared by the tcgen05 kernels (gemm_tc.cu, attn_fused.cu, voc_pair.cu, voc_poly.cu, voc_res.cu): mbarrier, TMA, tcgen05 MMA / TMEM.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -171,6 +171,94 @@ __device__ __forceinline__ float rn_tf32(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
+}
+
+// ---- cluster / CTA-pair (cta_group::2) forms ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// single polling thread, barrier completed by arrivals from both CTAs of the pair
+__device__ __forceinline__ void mbar_wait_spin_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    long long t0 = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) __trap();
+    }
+}
+// TMA load issued by either CTA of a pair into ITS shared memory; the bytes are counted on `bar`, a shared::cluster address
+// (the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// completion of all prior MMAs of the pair -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3)
+                 : "memory");
+}
+// D[256 x N] (+)= A[256 x 8] * B[N x 8]^T over the CTA pair: rows 0..127 of A / D belong to the leader, 128..255 to its peer;
+// each CTA holds N / 2 rows of B at the descriptor's address in its own shared memory.  Issued by the leader only.
+__device__ __forceinline__ void umma_pair_tf32_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the same with A read from TMEM columns [a_tmem, a_tmem + 8) of each CTA (lane = its row)
+__device__ __forceinline__ void umma_pair_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// executed by the same warp of BOTH CTAs of the pair
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem_addr, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem_addr), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+
+// consumer warps -> MMA issuer.  CTA-pair kernels: the issuer lives in the leader CTA, `bar` is its barrier's shared::cluster address.
+template <bool PAIR> __device__ __forceinline__ void arrive_issuer(uint32_t bar) {
+    // (default semantics, release at CTA scope: the data handed over lives in TMEM and is ordered by the tcgen05 fences either side;
+    // .release.cluster made every arrival wait for the thread's outstanding global traffic: 1-6 k cycles, profiles/r02_attn_pair_*)
+    if (PAIR) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+    else mbar_arrive(bar);
 }
 
 }  // namespace
