@@ -454,10 +454,19 @@ def main():
             h2d = sum(x_host[k].numel() * x_host[k].element_size() for k in keys)
             d2h = wav_host.numel() * 4 + len_host.numel() * 8
 
-            def step_e2e():
+            from zerovox_b200.tts.model import host_delivery
+            deliver = host_delivery(wav_host, torch.cuda.Stream(device=dev))
+
+            def step_e2e(groups=1):
+                # groups != 1: the vocoder runs in utterance groups (same samples) and every finished group's waveforms go to the
+                # host on a side stream while the next group is computed (ZeroVox.forward(vocoder_groups=, on_group=))
                 with torch.no_grad():
-                    wav, _, ml, _ = model({k: x_host[k] for k in keys}, force_duration=True)  # forward() does the H2D
-                    wav_host.copy_(wav, non_blocking=True)
+                    if groups == 1:
+                        wav, _, ml, _ = model({k: x_host[k] for k in keys}, force_duration=True)  # forward() does the H2D
+                        wav_host.copy_(wav, non_blocking=True)
+                    else:
+                        wav, _, ml, _ = model({k: x_host[k] for k in keys}, force_duration=True, vocoder_groups=groups,
+                                              on_group=deliver)
                     len_host.copy_(ml, non_blocking=True)
                 torch.cuda.synchronize(dev)
         else:
@@ -496,7 +505,15 @@ def main():
 
         e2e = {"h2d": h2d, "d2h": d2h}
         if world == 1:
-            e2e["ms"] = time_e2e()
+            variants = {("whole_batch" if gs == 1 else f"groups{gs}"): time_e2e(groups=gs) for gs in (1, 2, -3, -4)}
+            e2e["variants"] = variants
+            e2e["best"] = min(variants, key=variants.get)
+            e2e["ms"] = variants[e2e["best"]]
+            step_e2e(groups=1)
+            ref_wav = wav_host.clone()
+            step_e2e(groups=-4)
+            e2e["deliveries_identical"] = bool(torch.equal(ref_wav, wav_host))
+            del ref_wav
         else:
             variants = {}
             extra = [int(v) for v in args.e2e_groups_extra.split(",") if v.strip()]
@@ -576,7 +593,11 @@ def main():
             line["e2e"].update({
                 "delivery": e2e["best"], "ms_per_step_by_delivery": e2e["variants"],
                 "deliveries_bit_identical": e2e.get("deliveries_identical"),
-                "note": "shared = inputs and waveforms in page-locked host windows mapped by every rank (zerovox_b200.parallel."
+                "note": "whole_batch = forward, then one device-to-host copy of the waveforms; groupsG = the vocoder runs in G "
+                        "utterance groups (negative: halving sizes, zerovox_b200.tts.model.group_bounds) and a finished group's "
+                        "waveforms are copied to the host on a side stream while the next group is computed "
+                        "(ZeroVox.forward(vocoder_groups=, on_group=host_delivery(...)))" if world == 1 else
+                        "shared = inputs and waveforms in page-locked host windows mapped by every rank (zerovox_b200.parallel."
                         "SharedHostBatch / SharedHostBuffer): each rank moves its own block over its own PCIe link, tails and "
                         "completion over NCCL; funnel = everything through rank 0's GPU (upload, NCCL scatter, NCCL gather-v, "
                         "one D2H); groupsG = every rank vocodes in G utterance groups (negative: halving sizes) and a group's "

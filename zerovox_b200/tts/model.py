@@ -186,6 +186,27 @@ def group_bounds(n: int, groups: int) -> list[tuple[int, int]]:
     return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
 
 
+def host_delivery(wav_host: torch.Tensor, stream: "torch.cuda.Stream | None" = None):
+    """``on_group`` callback for ``forward(..., vocoder_groups=G)``: copies every finished utterance group of the padded
+    waveform batch to ``wav_host`` (page-locked, [B, >= L*hop]) on a side stream, so that the device-to-host transfer of group i
+    runs while group i + 1 is vocoded; with groups of halving size only the last, small group's copy is exposed.  The caller
+    synchronises (``callback.stream.synchronize()`` or a device synchronise) before reading ``wav_host``."""
+    side = stream
+
+    def on_group(i, g0, g1, wav, mel, mel_len):
+        nonlocal side
+        if side is None:
+            side = torch.cuda.Stream(device=wav.device)
+            on_group.stream = side
+        side.wait_stream(torch.cuda.current_stream(wav.device))
+        with torch.cuda.stream(side):
+            wav_host[g0:g1, : wav.shape[1]].copy_(wav[g0:g1], non_blocking=True)
+        wav.record_stream(side)
+
+    on_group.stream = side
+    return on_group
+
+
 def engine_forward(eng, x, force_duration=False, *, pad_to=None, zero_padded_mel=None, vocoder_groups=None, on_group=None):
     """Batched eval forward (model.py:260-306).  Returns (wav [B, L_max*hop], mel [B, n_mels, L_max], mel_len int64 [B],
     log_duration [B, T]) — the tuple utils/export_hifigan.py:109-151 consumes.  The reference's own eval tail
