@@ -70,6 +70,7 @@ CASES = [
     (37, 300, 2, 264, True, 1.0),     # pair kernel: 148 pair tiles on 74 clusters (Q replaced between tiles), odd q-tile count
     (1, 257, 2, 128, True, 1.0),      # pair kernel: second pair holds one row
     (9, 640, 2, 264, True, 1.0),      # ragged: utterances with 2..5 q tiles and 2..6 key blocks in one tile list
+    (1100, 150, 1, 32, True, 1.0),    # more utterances than the plan kernel has threads (its scan runs in rounds of 1024)
 ]
 
 
