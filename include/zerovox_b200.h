@@ -115,6 +115,16 @@ int zvx_encode(zvx_handle* h, const int32_t* phoneme, const int32_t* puncts,
                int B, int T, float* pitch, float* energy, float* log_dur, int32_t* dur_rounded,
                int64_t* mel_len, float* xprime, int64_t* mel_len_host, int* L_max_out, void* stream);
 
+/* zvx_spkemb followed by zvx_encode as ONE call — ZeroVox.forward's `style_embed = self._spkemb(x["ref_mel"])` and
+ * `self._phoneme_encoder(x, style_embed, ...)` (model.py:263-265).  Same results as the two calls; the speaker net is enqueued on
+ * an engine-owned side stream and joins the caller's stream right before the style vector is first needed (after the encoder's
+ * FFT blocks, fs2.py:740-741), so the two independent kernel sequences share the GPU.  ref_mel fp32 [B, T_ref, n_mels]; style out
+ * fp32 [B, hidden] (valid in `stream` order after the call, like every other output); the rest as zvx_encode. */
+int zvx_spkemb_encode(zvx_handle* h, const float* ref_mel, int T_ref, float* style, const int32_t* phoneme, const int32_t* puncts,
+                      const uint8_t* phoneme_mask, const int32_t* forced_dur, int B, int T, float* pitch, float* energy,
+                      float* log_dur, int32_t* dur_rounded, int64_t* mel_len, float* xprime, int64_t* mel_len_host,
+                      int* L_max_out, void* stream);
+
 /* LengthRegulator.forward + pad (fs2.py:403-459): features[b, f, :] = xprime[b, i, :] where i is
  * the phoneme whose run covers frame f, zero for f >= mel_len[b].  src_index (nullable) receives
  * i (or -1) — bit-exact integer arithmetic. */

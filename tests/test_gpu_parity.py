@@ -101,6 +101,25 @@ def test_speaker_embedding(tiny, medium, which, B, T_ref, policy):
     np.testing.assert_allclose(got.norm(dim=-1).cpu().numpy(), 1.0, atol=1e-5)
 
 
+@pytest.mark.parametrize("which,B,T,T_ref,forced", [("tiny", 3, 11, 24, False), ("medium", 4, 33, 131, True), ("medium", 32, 128, 440, True)])
+def test_spkemb_encode_equals_the_two_calls(tiny, medium, which, B, T, T_ref, forced):
+    """zvx_spkemb_encode (speaker net on the engine's side stream next to the encoder's FFT blocks, joined where the style
+    vector enters) gives what zvx_spkemb followed by zvx_encode gives, bit for bit — twice in a row (the side stream, its
+    events and the speaker net's own workspace are reused)."""
+    case = tiny if which == "tiny" else medium
+    x = to_dev(zo.make_inputs(case.cfg, B, T, T_ref, seed=13, ragged=True))
+    eng = case.model(1)._shared_ctx.get(torch.device(DEV))
+    fd = x["duration"] if forced else None
+    style = eng.spkemb(x["ref_mel"])
+    r = eng.encode(x["phoneme"], x["puncts"], style, x["phoneme_mask"], fd)
+    for _ in range(2):
+        style2, r2 = eng.spkemb_encode(x["ref_mel"], x["phoneme"], x["puncts"], x["phoneme_mask"], fd)
+        assert torch.equal(style2, style)
+        for k in ("pitch", "energy", "log_duration", "duration_rounded", "mel_len", "xprime"):
+            assert torch.equal(r2[k], r[k]), k
+        assert r2["L_max"] == r["L_max"] and r2["mel_len_host"] == r["mel_len_host"]
+
+
 @pytest.mark.parametrize("which,B,T,ragged", [("tiny", 3, 11, True), ("tiny", 1, 1, False), ("tiny", 2, 30, False),
                                               ("medium", 2, 12, True), ("medium", 4, 33, True)])
 def test_encoder_and_variance_adaptor(tiny, medium, which, B, T, ragged):
@@ -400,11 +419,21 @@ def test_longform_decoder_attention_chunks(medium):
     eng = medium.model(1)._shared_ctx.get(torch.device(DEV))
     full, _ = eng.decode(feats.to(DEV), style.to(DEV), mask=mask.to(DEV), want_bcl=False)
     check("long-form mel vs oracle", full, ref, **TC_MEL)
+    # the three-kernel attention (fused_attention = 0: QK^T GEMM, softmax, PV GEMM with the scores in HBM) on a second engine,
+    # unchunked and with the score budget forced small
     eng2 = engine_mod.Engine(eng.cfg, torch.device(DEV))
-    eng2.set_option("score_workspace_bytes", 2 * 2 * 500 * 1900 * 4)   # ~500 query rows per chunk
+    eng2.set_option("fused_attention", 0)
     eng2.load_weights({k: v for k, v in medium.w.items() if k.startswith("_mel_decoder.")})
+    unfused, _ = eng2.decode(feats.to(DEV), style.to(DEV), mask=mask.to(DEV), want_bcl=False)
+    check("three-kernel attention vs oracle", unfused, ref, **TC_MEL)
+    eng2.set_option("score_workspace_bytes", 2 * 2 * 500 * 1900 * 4)   # ~500 query rows per chunk
     part, _ = eng2.decode(feats.to(DEV), style.to(DEV), mask=mask.to(DEV), want_bcl=False)
-    check("chunked attention vs unchunked", part, full, rtol=0.0, atol=1e-5)
+    check("chunked attention vs unchunked", part, unfused, rtol=0.0, atol=1e-5)
+    # each variant of the fused kernel on its own
+    for variant, name in ((2, "single-CTA"), (3, "CTA-pair")):
+        eng2.set_option("fused_attention", variant)
+        one, _ = eng2.decode(feats.to(DEV), style.to(DEV), mask=mask.to(DEV), want_bcl=False)
+        check(f"fused attention ({name}) vs oracle", one, ref, **TC_MEL)
 
 
 def test_longform_config5_properties(medium):

@@ -81,6 +81,8 @@ SYMBOLS = {
     "zvx_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
     "zvx_finalize_weights": (C.c_int, [_P]),
     "zvx_spkemb": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "zvx_spkemb_encode": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P,
+                                    C.POINTER(C.c_int), _P]),
     "zvx_encode": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P,
                              C.POINTER(C.c_int), _P]),
     "zvx_length_regulate": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

@@ -193,6 +193,9 @@ class Engine {
 
     ~Engine() {
         cudaSetDevice(dev);
+        if (side_stream) { cudaStreamSynchronize(side_stream); cudaStreamDestroy(side_stream); }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         for (void* p : owned) cudaFree(p);
         if (pinned_len) cudaFreeHost(pinned_len);
     }
@@ -777,7 +780,12 @@ class Engine {
         const long long max_q = kScoreBytes / ((long long)B * n_head * s.ldS * (long long)sizeof(float));
         s.Lq_max = (int)std::max<long long>(1, std::min<long long>(L, max_q));
         s.S_elems = (long long)B * n_head * s.Lq_max * s.ldS;
-        s.S = ws.get<float>(s.S_elems);
+        // the score matrix only exists on the unfused paths (3xTF32 attention, fused_attention = 0, shapes the fused kernel rejects)
+        AttnFusedArgs fa;
+        fa.B = B; fa.L = L; fa.n_head = n_head; fa.dk = H / n_head; fa.H = H; fa.Lp = (int)round_up(L, 4); fa.variant = kAttentionVariant;
+        const bool fused = prec == P_TF32 && tc_enabled(prec) && kFusedAttention && H % n_head == 0 && (H / n_head) % 4 == 0 &&
+                           (long long)B * L >= tc_min_rows() && attn_fused_supported(fa);
+        s.S = fused ? nullptr : ws.get<float>(s.S_elems);
         if (prec == P_EXACT && tc_enabled(prec)) {
             s.lo_qkv = ws.get<float>(s.qkv_elems);
             s.lo_S = ws.get<float>(s.S_elems);
@@ -831,6 +839,7 @@ class Engine {
                 attn_fused(fa, st);
                 prof.end(st);
             } else {
+            ZVX_REQUIRE(S, "fft_block: no score workspace was planned for the unfused attention path");
             // Utterances are independent, so the three attention kernels run over slices of the batch whose score
             // matrices (plus their Q / K / V rows) fit in L2: the softmax and the PV product then read what the kernel
             // before them wrote from L2 instead of DRAM (the whole-batch score tensor is 172 MB at configs[1], moved
@@ -871,6 +880,7 @@ class Engine {
             }
             }
         } else {
+        ZVX_REQUIRE(S, "fft_block: no score workspace was planned for the unfused attention path");
         linear(x, (int)rows, H, ly.wqkv, ly.bqkv, 3 * H, qkv, tc, st);
         for (int q0 = 0; q0 < L; q0 += Lq_max) {
             const int Lq = std::min(Lq_max, L - q0);
@@ -931,16 +941,16 @@ class Engine {
     int spkemb(const float* ref_mel, int B, int T, float* style, cudaStream_t st) {
         check_ready(SEC_SPK);
         ZVX_REQUIRE(B >= 0 && T >= 8, "zvx_spkemb: need T_ref >= 8 frames");
-        ws.reset();
+        ws_spk.reset();   // the speaker net owns a workspace: it may run next to the encoder (spkemb_encode)
         const int M = cfg.n_mels;
         const int* nf = cfg.resnet_num_filters;
         const int tc = P_TF32;
-        float* x0 = ws.get<float>((long long)B * M * T);
+        float* x0 = ws_spk.get<float>((long long)B * M * T);
         instance_norm_time(ref_mel, B, T, M, x0, st);
         long long big = (long long)B * M * T * nf[0];
         float* buf[4];
-        for (int i = 0; i < 4; ++i) buf[i] = ws.get<float>(big);
-        float* gate = ws.get<float>((long long)B * 1024);
+        for (int i = 0; i < 4; ++i) buf[i] = ws_spk.get<float>(big);
+        float* gate = ws_spk.get<float>((long long)B * 1024);
         float* x = buf[0];
         stem_conv3x3(x0, stem_w, stem_b, stem_s, stem_sh, B, M, T, nf[0], x, st);
         int Hh = M, Ww = T;
@@ -964,7 +974,7 @@ class Engine {
             c2.scale = b.bn2_s; c2.shift = b.bn2_b;
             gemm(c2, tc, st);
             const int S = hw_mean_splits(B, Ho * Wo);
-            float* pooled = ws.get<float>((long long)B * S * b.planes);
+            float* pooled = ws_spk.get<float>((long long)B * S * b.planes);
             hw_sum_partial(t2, B, Ho * Wo, b.planes, S, pooled, st);
             se_excite(pooled, S, Ho * Wo, b.se_w1, b.se_b1, b.se_w2, b.se_b2, B, b.planes, b.red, gate, st);
             const float* res = x;
@@ -986,11 +996,11 @@ class Engine {
         // attentive statistics pooling head (ResNetSE34V2.py:196-208)
         const int C3 = nf[3];
         ZVX_REQUIRE(Hh * C3 == spk_D, "speaker net: unexpected feature-map height");
-        float* flat = ws.get<float>((long long)B * Ww * spk_D);
-        float* a1 = ws.get<float>((long long)B * Ww * 128);
-        float* lg = ws.get<float>((long long)B * Ww * spk_D);
+        float* flat = ws_spk.get<float>((long long)B * Ww * spk_D);
+        float* a1 = ws_spk.get<float>((long long)B * Ww * 128);
+        float* lg = ws_spk.get<float>((long long)B * Ww * spk_D);
         const int asp = cfg.resnet_encoder_type == 1;
-        float* stats = ws.get<float>((long long)B * spk_D * 2);
+        float* stats = ws_spk.get<float>((long long)B * spk_D * 2);
         spk_flatten(x, B, Hh, Ww, C3, flat, st);
         linear(flat, B * Ww, spk_D, att_w0, att_b0, 128, a1, tc, st, nullptr, 1, att_bn_s, att_bn_b);
         linear(a1, B * Ww, 128, att_w3, att_b3, spk_D, lg, tc, st);
@@ -1002,7 +1012,8 @@ class Engine {
 
     int encode(const int32_t* phoneme, const int32_t* puncts, const uint8_t* mask, const float* style,
                const int32_t* forced, int B, int T, float* pitch, float* energy, float* log_dur, int32_t* dur,
-               int64_t* mel_len, float* xprime, int64_t* mel_len_host, int* L_max_out, cudaStream_t st) {
+               int64_t* mel_len, float* xprime, int64_t* mel_len_host, int* L_max_out, cudaStream_t st,
+               cudaEvent_t style_ready = nullptr) {
         check_ready(SEC_ENC);
         ZVX_REQUIRE(B >= 1 && T >= 1, "zvx_encode: empty batch");
         ZVX_REQUIRE(B <= kMaxBatch, "zvx_encode: batch too large");
@@ -1016,6 +1027,7 @@ class Engine {
         const FFTScratch sc = fft_scratch(B, T, cfg.enc_heads, P_EXACT);
         for (int i = 0; i < cfg.enc_layers; ++i)
             fft_block(x, B, T, cfg.enc_heads, enc[(size_t)i], mask, false, nullptr, nullptr, 0, P_EXACT, sc, st);
+        if (style_ready) ZVX_CUDA_CHECK(cudaStreamWaitEvent(st, style_ready, 0));   // (spkemb_encode: produced on the side stream)
         add_batch_vector(x, style, B, T, H, st);  // all positions, padded ones too (fs2.py:740-741)
         variance_predictor(x, B, T, vp[0], mask, log_dur, st);
         variance_predictor(x, B, T, vp[1], mask, pitch, st);
@@ -1037,6 +1049,28 @@ class Engine {
             if (mel_len_host) std::memcpy(mel_len_host, pinned_len, sizeof(int64_t) * B);
         }
         return 0;
+    }
+
+    // ZeroVox.forward's first two module calls as ONE call (model.py:263-265): the speaker net and the encoder's FFT blocks do not
+    // depend on each other — the style vector enters after the last encoder layer (fs2.py:740-741) — so the speaker net is enqueued
+    // on an engine-owned side stream and the caller's stream waits for it right before that addition.  The encoder's kernels are
+    // small (B*T rows: one wave or less of tiles, launch-latency class); next to the speaker net's they fill SMs that would idle.
+    int spkemb_encode(const float* ref_mel, int T_ref, float* style, const int32_t* phoneme, const int32_t* puncts,
+                      const uint8_t* mask, const int32_t* forced, int B, int T, float* pitch, float* energy, float* log_dur,
+                      int32_t* dur, int64_t* mel_len, float* xprime, int64_t* mel_len_host, int* L_max_out, cudaStream_t st) {
+        check_ready(SEC_SPK);
+        check_ready(SEC_ENC);
+        if (!side_stream) {
+            ZVX_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+            ZVX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            ZVX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
+        ZVX_CUDA_CHECK(cudaEventRecord(ev_fork, st));                     // the inputs are ready in the caller's stream order
+        ZVX_CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+        spkemb(ref_mel, B, T_ref, style, side_stream);
+        ZVX_CUDA_CHECK(cudaEventRecord(ev_join, side_stream));
+        return encode(phoneme, puncts, mask, style, forced, B, T, pitch, energy, log_dur, dur, mel_len, xprime, mel_len_host,
+                      L_max_out, st, ev_join);
     }
 
     int length_regulate(const float* xprime, const int32_t* dur, int B, int T, int frame0, int L_max, float* features,
@@ -1401,6 +1435,9 @@ class Engine {
     bool sec_ready[4] = {false, false, false, false};
     std::string sec_err[4];
     Workspace ws;
+    Workspace ws_spk;                    // the speaker net's own (spkemb_encode runs it next to the encoder)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     Profiler prof;
     bool split_on = !env_set("ZVX_NO_SPLIT");   // 3xTF32 for P_EXACT contractions (switchable in debug builds only)
     std::map<const float*, const float*> w_lo;
@@ -1489,6 +1526,15 @@ int zvx_spkemb(zvx_handle* h, const float* ref_mel, int B, int T_ref, float* sty
     ZVX_GUARD(h, return h->eng->spkemb(ref_mel, B, T_ref, style, (cudaStream_t)stream));
 }
 
+int zvx_spkemb_encode(zvx_handle* h, const float* ref_mel, int T_ref, float* style, const int32_t* phoneme, const int32_t* puncts,
+                      const uint8_t* phoneme_mask, const int32_t* forced_dur, int B, int T, float* pitch, float* energy,
+                      float* log_dur, int32_t* dur_rounded, int64_t* mel_len, float* xprime, int64_t* mel_len_host,
+                      int* L_max_out, void* stream) {
+    ZVX_GUARD(h, return h->eng->spkemb_encode(ref_mel, T_ref, style, phoneme, puncts, phoneme_mask, forced_dur, B, T, pitch,
+                                              energy, log_dur, dur_rounded, mel_len, xprime, mel_len_host, L_max_out,
+                                              (cudaStream_t)stream));
+}
+
 int zvx_encode(zvx_handle* h, const int32_t* phoneme, const int32_t* puncts, const uint8_t* phoneme_mask,
                const float* style, const int32_t* forced_dur, int B, int T, float* pitch, float* energy,
                float* log_dur, int32_t* dur_rounded, int64_t* mel_len, float* xprime, int64_t* mel_len_host,
@@ -1575,7 +1621,7 @@ int zvx_debug_gemm(zvx_handle* h, const zvx_gemm_desc* d, int use_tc, void* stre
 
 int zvx_set_option(zvx_handle* h, const char* name, int64_t value) { ZVX_GUARD(h, return h->eng->set_option(name, value)); }
 
-int64_t zvx_workspace_bytes(const zvx_handle* h) { return (h && h->eng) ? h->eng->ws.bytes() : 0; }
+int64_t zvx_workspace_bytes(const zvx_handle* h) { return (h && h->eng) ? h->eng->ws.bytes() + h->eng->ws_spk.bytes() : 0; }
 
 int64_t zvx_launch_count(const zvx_handle* h) {
     (void)h;

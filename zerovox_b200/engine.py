@@ -205,6 +205,42 @@ class Engine:
             self._check(self.lib.zvx_spkemb(self._h, _ptr(x), B, T, _ptr(out), self._stream()), "zvx_spkemb")
         return out
 
+    def spkemb_encode(self, ref_mel, phoneme, puncts, phoneme_mask=None, forced_duration=None):
+        """``spkemb`` followed by ``encode`` as one C-ABI call (zvx_spkemb_encode): the speaker net runs on an engine-owned side
+        stream next to the encoder's FFT blocks and joins the caller's stream where the style vector is first needed.  Returns
+        (style [B, 1, hidden], the dict of :meth:`encode` with ``L_max`` / ``mel_len_host``)."""
+        x = self._dev(ref_mel, torch.float32, "ref_mel")
+        B, Tr, M = x.shape
+        if M != self.cfg.n_mels:
+            raise RuntimeError(f"ref_mel has {M} mel channels, model expects {self.cfg.n_mels}")
+        ph = self._dev(phoneme, torch.int32, "phoneme")
+        pu = self._dev(puncts, torch.int32, "puncts")
+        if ph.shape[0] != B:
+            raise RuntimeError("ref_mel batch size does not match phoneme batch size")
+        T = ph.shape[1]
+        pm = None if phoneme_mask is None else self._dev(phoneme_mask, torch.uint8, "phoneme_mask")
+        fd = None if forced_duration is None else self._dev(forced_duration, torch.int32, "duration")
+        dev, f32 = self.device, torch.float32
+        style = torch.empty((B, 1, self.cfg.hidden), device=dev, dtype=f32)
+        out = {
+            "pitch": torch.empty((B, T), device=dev, dtype=f32),
+            "energy": torch.empty((B, T), device=dev, dtype=f32),
+            "log_duration": torch.empty((B, T), device=dev, dtype=f32),
+            "duration_rounded": torch.empty((B, T), device=dev, dtype=torch.int32),
+            "mel_len": torch.empty((B,), device=dev, dtype=torch.int64),
+            "xprime": torch.empty((B, T, self.cfg.hidden), device=dev, dtype=f32),
+        }
+        lmax = C.c_int(0)
+        host = (C.c_int64 * B)()
+        with torch.cuda.device(self.device), _nvtx("zvx_spkemb_encode"):
+            self._check(self.lib.zvx_spkemb_encode(
+                self._h, _ptr(x), Tr, _ptr(style), _ptr(ph), _ptr(pu), _ptr(pm), _ptr(fd), B, T, _ptr(out["pitch"]),
+                _ptr(out["energy"]), _ptr(out["log_duration"]), _ptr(out["duration_rounded"]), _ptr(out["mel_len"]),
+                _ptr(out["xprime"]), C.cast(host, C.c_void_p), C.byref(lmax), self._stream()), "zvx_spkemb_encode")
+        out["L_max"] = int(lmax.value)
+        out["mel_len_host"] = list(host)
+        return style, out
+
     def encode(self, phoneme, puncts, style, phoneme_mask=None, forced_duration=None, need_lengths=True):
         """FS2Encoder.forward up to the LengthRegulator.  Returns a dict of device tensors plus ``L_max`` (int)
         and ``mel_len_host`` (list[int]) when ``need_lengths`` (costs the engine's single stream sync)."""

@@ -221,11 +221,11 @@ def engine_forward(eng, x, force_duration=False, *, pad_to=None, zero_padded_mel
     ``on_group(i, first, end, wav, mel, mel_len)`` after enqueuing each, so that a caller can ship finished waveforms (NCCL
     gather, device-to-host copy) while the next group is still being computed."""
     dev = eng.device
-    style = eng.spkemb(x["ref_mel"].to(dev, non_blocking=True))
     mask = x["phoneme_mask"].to(dev, non_blocking=True) if "phoneme_mask" in x else None
     forced = x["duration"].to(dev, non_blocking=True) if force_duration else None
-    r = eng.encode(x["phoneme"].to(dev, non_blocking=True), x["puncts"].to(dev, non_blocking=True), style, mask,
-                   forced, need_lengths=True)
+    # model.py:263-265 as one call: the speaker net runs on a side stream next to the encoder's FFT blocks
+    style, r = eng.spkemb_encode(x["ref_mel"].to(dev, non_blocking=True), x["phoneme"].to(dev, non_blocking=True),
+                                 x["puncts"].to(dev, non_blocking=True), mask, forced)
     L = r["L_max"]
     if pad_to is not None:
         L = max(L, int(pad_to(L, r["mel_len_host"]) if callable(pad_to) else pad_to))
