@@ -1060,6 +1060,11 @@ class Engine {
                       int32_t* dur, int64_t* mel_len, float* xprime, int64_t* mel_len_host, int* L_max_out, cudaStream_t st) {
         check_ready(SEC_SPK);
         check_ready(SEC_ENC);
+        if (prof.on) {   // the per-launch profiler times kernels one at a time: keep everything in the caller's stream order
+            spkemb(ref_mel, B, T_ref, style, st);
+            return encode(phoneme, puncts, mask, style, forced, B, T, pitch, energy, log_dur, dur, mel_len, xprime, mel_len_host,
+                          L_max_out, st);
+        }
         if (!side_stream) {
             ZVX_CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
             ZVX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
