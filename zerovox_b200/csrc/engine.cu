@@ -196,6 +196,8 @@ class Engine {
         if (side_stream) { cudaStreamSynchronize(side_stream); cudaStreamDestroy(side_stream); }
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_vp_x) cudaEventDestroy(ev_vp_x);
+        if (ev_vp_done) cudaEventDestroy(ev_vp_done);
         for (void* p : owned) cudaFree(p);
         if (pinned_len) cudaFreeHost(pinned_len);
     }
@@ -916,12 +918,13 @@ class Engine {
     }
 
     void variance_predictor(const float* x, int B, int T, const VarPredictor& v, const uint8_t* mask, float* out,
-                            cudaStream_t st) {
+                            cudaStream_t st, cudaEvent_t x_consumed = nullptr) {
         const int F = cfg.vp_filter_size, K = cfg.vp_kernel_size;
         const long long rows = (long long)B * T;
         float* c1 = ws.get<float>(rows * F);
         float* c2 = ws.get<float>(rows * F);
         conv1d_cl(x, B, T, H, v.wc1, v.bc1, F, K, (K - 1) / 2, c1, P_EXACT, st, nullptr, 1);
+        if (x_consumed) ZVX_CUDA_CHECK(cudaEventRecord(x_consumed, st));   // (the only read of x)
         NormArgs n;
         n.x = c1; n.out = c1; n.rows = (int)rows; n.C = F; n.gamma = v.ln1_g; n.beta = v.ln1_b; n.eps = 1e-5f;
         layer_norm(n, st);
@@ -951,6 +954,8 @@ class Engine {
         float* buf[4];
         for (int i = 0; i < 4; ++i) buf[i] = ws_spk.get<float>(big);
         float* gate = ws_spk.get<float>((long long)B * 1024);
+        int* ticket = ws_spk.get<int>(B);   // se_squeeze_excite: one ticket counter per utterance, self-resetting
+        ZVX_CUDA_CHECK(cudaMemsetAsync(ticket, 0, sizeof(int) * (size_t)B, st));
         float* x = buf[0];
         stem_conv3x3(x0, stem_w, stem_b, stem_s, stem_sh, B, M, T, nf[0], x, st);
         int Hh = M, Ww = T;
@@ -975,8 +980,7 @@ class Engine {
             gemm(c2, tc, st);
             const int S = hw_mean_splits(B, Ho * Wo);
             float* pooled = ws_spk.get<float>((long long)B * S * b.planes);
-            hw_sum_partial(t2, B, Ho * Wo, b.planes, S, pooled, st);
-            se_excite(pooled, S, Ho * Wo, b.se_w1, b.se_b1, b.se_w2, b.se_b2, B, b.planes, b.red, gate, st);
+            se_squeeze_excite(t2, B, Ho * Wo, b.planes, S, pooled, ticket, b.se_w1, b.se_b1, b.se_w2, b.se_b2, b.red, gate, st);
             const float* res = x;
             if (b.wd) {
                 GemmArgs dn;
@@ -1029,11 +1033,32 @@ class Engine {
             fft_block(x, B, T, cfg.enc_heads, enc[(size_t)i], mask, false, nullptr, nullptr, 0, P_EXACT, sc, st);
         if (style_ready) ZVX_CUDA_CHECK(cudaStreamWaitEvent(st, style_ready, 0));   // (spkemb_encode: produced on the side stream)
         add_batch_vector(x, style, B, T, H, st);  // all positions, padded ones too (fs2.py:740-741)
-        variance_predictor(x, B, T, vp[0], mask, log_dur, st);
-        variance_predictor(x, B, T, vp[1], mask, pitch, st);
+        if (style_ready && side_stream) {
+            // The duration and the pitch predictor read the same x (fs2.py:667-671) and are chains of one-wave-or-less launches
+            // (B*T / 128 x 2 tiles): the duration predictor runs on the side stream — idle again once the style vector is there —
+            // with its own split scratch; the pitch embedding may only be added to x once the duration predictor's first conv
+            // has read it.
+            if (!ev_vp_x) {
+                ZVX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_vp_x, cudaEventDisableTiming));
+                ZVX_CUDA_CHECK(cudaEventCreateWithFlags(&ev_vp_done, cudaEventDisableTiming));
+            }
+            ZVX_CUDA_CHECK(cudaEventRecord(ev_fork, st));
+            ZVX_CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+            float* lo_main = lo_buf;
+            lo_buf = lo_main ? ws.get<float>(lo_cap) : nullptr;
+            variance_predictor(x, B, T, vp[0], mask, log_dur, side_stream, ev_vp_x);
+            ZVX_CUDA_CHECK(cudaEventRecord(ev_vp_done, side_stream));
+            lo_buf = lo_main;
+            variance_predictor(x, B, T, vp[1], mask, pitch, st);
+            ZVX_CUDA_CHECK(cudaStreamWaitEvent(st, ev_vp_x, 0));
+        } else {
+            variance_predictor(x, B, T, vp[0], mask, log_dur, st);
+            variance_predictor(x, B, T, vp[1], mask, pitch, st);
+        }
         bucket_embed_add(x, pitch, pitch_emb, B * T, H, cfg.ve_n_bins, nullptr, st);
         variance_predictor(x, B, T, vp[2], mask, energy, st);
         bucket_embed_add(x, energy, energy_emb, B * T, H, cfg.ve_n_bins, nullptr, st);
+        if (style_ready && side_stream) ZVX_CUDA_CHECK(cudaStreamWaitEvent(st, ev_vp_done, 0));
         duration_round(log_dur, forced, dur, B * T, st);
         int32_t* cum = ws.get<int32_t>((long long)B * T);
         duration_scan(dur, B, T, cum, mel_len, st);
@@ -1442,7 +1467,7 @@ class Engine {
     Workspace ws;
     Workspace ws_spk;                    // the speaker net's own (spkemb_encode runs it next to the encoder)
     cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_vp_x = nullptr, ev_vp_done = nullptr;
     Profiler prof;
     bool split_on = !env_set("ZVX_NO_SPLIT");   // 3xTF32 for P_EXACT contractions (switchable in debug builds only)
     std::map<const float*, const float*> w_lo;

@@ -172,6 +172,10 @@ void hw_sum_partial(const float* x, int B, int HW, int C, int S, float* out, cud
 // SE excitation: p = (sum_s partial[b,s,:]) / HW; y = sigmoid(W2 relu(W1 p + b1) + b2), W1 [R,C], W2 [C,R]
 void se_excite(const float* partial, int S, int HW, const float* w1, const float* b1, const float* w2, const float* b2,
                int B, int C, int R, float* y, cudaStream_t st);
+// hw_sum_partial + se_excite as one launch (the last block of an utterance runs the excitation); ticket [B] ints, zero before
+// the first launch, left zero
+void se_squeeze_excite(const float* x, int B, int HW, int C, int S, float* partial, int* ticket, const float* w1,
+                       const float* b1, const float* w2, const float* b2, int R, float* y, cudaStream_t st);
 // out = relu(x * y[b,c] + res)
 void se_scale_add_relu(const float* x, const float* y, const float* res, int B, int HW, int C, float* out,
                        cudaStream_t st);

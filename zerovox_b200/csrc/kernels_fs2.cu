@@ -40,7 +40,11 @@ void embed_posenc(const int32_t* phoneme, const int32_t* puncts, const float* ph
 // ------------------------------------------------------------------------------------------------
 constexpr int NORM_MAXV = 8;  // float4 per lane -> C <= 32*4*8 = 1024
 
-__global__ void __launch_bounds__(256) layer_norm_kernel(const NormArgs a) {
+// NV = float4 per lane the row needs (ceil(C / 128)): the 528-wide rows of the FFT blocks take 5, the 256-wide rows of the variance
+// predictors 2 — sized for 1024 columns the kernel held 68 registers and 24 warps per SM (profiles/r02_ncu_hbm_kernels.csv: warps
+// active 35 %, 0.62 of the HBM peak); fewer live registers = more rows in flight per SM.
+template <int NV>
+__global__ void __launch_bounds__(256, NV <= 2 ? 6 : NV <= 5 ? 5 : 3) layer_norm_kernel(const NormArgs a) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= a.rows) return;
@@ -58,10 +62,10 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const NormArgs a) {
     const int C4 = a.C >> 2;
     const float4* xr = reinterpret_cast<const float4*>(a.x + (long long)row * a.C);
     const float4* rr = a.res ? reinterpret_cast<const float4*>(a.res + (long long)row * a.C) : nullptr;
-    float4 v[NORM_MAXV];
+    float4 v[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c4 = lane + i * 32;
         if (c4 < C4) {
             v[i] = xr[c4];
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const NormArgs a) {
     const float mu = warp_sum(s) / (float)a.C;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c4 = lane + i * 32;
         if (c4 < C4) {
             float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const NormArgs a) {
     float dot = 0.f;
     float4* o = a.dot_w ? nullptr : reinterpret_cast<float4*>(a.out + (long long)row * a.C);
 #pragma unroll
-    for (int i = 0; i < NORM_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
         const int c4 = lane + i * 32;
         if (c4 < C4) {
             const float4 g = __ldg(reinterpret_cast<const float4*>(gp) + c4);
@@ -136,7 +140,11 @@ void layer_norm(const NormArgs& a, cudaStream_t st) {
     ZVX_REQUIRE(a.C % 4 == 0 && a.C <= 128 * NORM_MAXV, "layer_norm: C must be a multiple of 4 and <= 1024");
     ZVX_REQUIRE(!a.scln || (a.gb && (a.gb_ld % 4) == 0 && a.C > 1), "layer_norm: SCLN needs per-batch affine rows");
     const int warps_per_block = 8;
-    layer_norm_kernel<<<cdiv(a.rows, warps_per_block), warps_per_block * 32, 0, st>>>(a);
+    const int nv = cdiv(a.C, 128);
+    const dim3 grid(cdiv(a.rows, warps_per_block)), block(warps_per_block * 32);
+    if (nv <= 2) layer_norm_kernel<2><<<grid, block, 0, st>>>(a);
+    else if (nv <= 5) layer_norm_kernel<5><<<grid, block, 0, st>>>(a);
+    else layer_norm_kernel<NORM_MAXV><<<grid, block, 0, st>>>(a);
     ZVX_POST_LAUNCH();
 }
 

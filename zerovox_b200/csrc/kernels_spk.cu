@@ -94,8 +94,8 @@ void stem_conv3x3(const float* in, const float* w, const float* bias, const floa
 // SE squeeze (AdaptiveAvgPool2d(1), ResNetSE34V2.py:63-64): x [B, HW, C] -> sums over HW, split into S partial sums so
 // that the whole GPU streams the tensor once: grid (S, B); block = 256 threads = (256 / (C/4)) rows x C/4 float4 columns.
 // out[b][s][c] = sum over the s-th slice of HW (deterministic order); se_excite adds the S partials and divides.
-__global__ void __launch_bounds__(256) hw_sum_partial_kernel(const float* __restrict__ x, int HW, int C4, int rows_per,
-                                                             float* __restrict__ out) {
+__device__ __forceinline__ void hw_sum_partial_body(const float* __restrict__ x, int HW, int C4, int rows_per,
+                                                    float* __restrict__ out) {
     __shared__ float4 red[256];
     const int s = blockIdx.x, b = blockIdx.y, S = gridDim.x;
     const int c4 = threadIdx.x % C4, r0 = threadIdx.x / C4, nr = 256 / C4;
@@ -126,6 +126,11 @@ __global__ void __launch_bounds__(256) hw_sum_partial_kernel(const float* __rest
     }
 }
 
+__global__ void __launch_bounds__(256) hw_sum_partial_kernel(const float* __restrict__ x, int HW, int C4, int rows_per,
+                                                             float* __restrict__ out) {
+    hw_sum_partial_body(x, HW, C4, rows_per, out);
+}
+
 int hw_mean_splits(int B, int HW) {
     return std::max(1, std::min(cdiv(HW, 32), cdiv(4 * 148, std::max(B, 1))));
 }
@@ -137,19 +142,16 @@ void hw_sum_partial(const float* x, int B, int HW, int C, int S, float* out, cud
     ZVX_POST_LAUNCH();
 }
 
-// SE excitation (ResNetSE34V2.py:55-60, 65): one block per utterance.
-__global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict__ p, int S, float inv_hw,
-                                                        const float* __restrict__ w1, const float* __restrict__ b1,
-                                                        const float* __restrict__ w2, const float* __restrict__ b2,
-                                                        int C, int R, float* __restrict__ y) {
-    extern __shared__ float sh[];  // [C] pooled, [R] hidden
-    float* ps = sh;
-    float* hs = sh + C;
-    const int b = blockIdx.x;
+// SE excitation (ResNetSE34V2.py:55-60, 65) for utterance b from the S partial sums: called by every thread of one block.
+__device__ __forceinline__ void se_excite_block(const float* p, int b, int S, float inv_hw, const float* __restrict__ w1,
+                                                const float* __restrict__ b1, const float* __restrict__ w2,
+                                                const float* __restrict__ b2, int C, int R, float* __restrict__ y, float* sh) {
+    float* ps = sh;        // [C] pooled
+    float* hs = sh + C;    // [R] hidden
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float t = 0.f;
-        for (int s = 0; s < S; ++s) t += p[((long long)b * S + s) * C + c];
+        for (int s = 0; s < S; ++s) t += __ldcg(p + ((long long)b * S + s) * C + c);   // fixed order; written by other blocks: L2
         ps[c] = t * inv_hw;
     }
     __syncthreads();
@@ -167,10 +169,53 @@ __global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict_
     }
 }
 
+__global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict__ p, int S, float inv_hw,
+                                                        const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2,
+                                                        int C, int R, float* __restrict__ y) {
+    extern __shared__ float sh[];
+    se_excite_block(p, blockIdx.x, S, inv_hw, w1, b1, w2, b2, C, R, y, sh);
+}
+
 void se_excite(const float* p, int S, int HW, const float* w1, const float* b1, const float* w2, const float* b2, int B,
                int C, int R, float* y, cudaStream_t st) {
     if (B == 0) return;
     se_excite_kernel<<<B, 256, (C + R) * sizeof(float), st>>>(p, S, 1.f / (float)HW, w1, b1, w2, b2, C, R, y);
+    ZVX_POST_LAUNCH();
+}
+
+// Squeeze and excitation in ONE launch: grid (S, B) streams the tensor as hw_sum_partial does; the block of utterance b
+// that finishes last (a ticket per utterance, release / acquire fences around it) adds the S partials in index order —
+// the gate does not depend on which block that is — and runs the two small linears.  `ticket` [B] must be zero at
+// the first launch; the last block leaves it zero again.
+__global__ void __launch_bounds__(256) se_squeeze_excite_kernel(const float* __restrict__ x, int HW, int C4, int rows_per,
+                                                                float* __restrict__ partial, int* __restrict__ ticket,
+                                                                const float* __restrict__ w1, const float* __restrict__ b1,
+                                                                const float* __restrict__ w2, const float* __restrict__ b2,
+                                                                int R, float* __restrict__ y) {
+    extern __shared__ float sh[];
+    __shared__ int last;
+    hw_sum_partial_body(x, HW, C4, rows_per, partial);
+    __threadfence();   // this block's partial before its ticket
+    __syncthreads();
+    const int b = blockIdx.y, S = gridDim.x;
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket + b, 1);
+        last = (t == S - 1);
+        if (last) ticket[b] = 0;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();   // every other block's partial after the ticket
+    se_excite_block(partial, b, S, 1.f / (float)HW, w1, b1, w2, b2, 4 * C4, R, y, sh);
+}
+
+void se_squeeze_excite(const float* x, int B, int HW, int C, int S, float* partial, int* ticket, const float* w1,
+                       const float* b1, const float* w2, const float* b2, int R, float* y, cudaStream_t st) {
+    if (B == 0) return;
+    ZVX_REQUIRE(C % 4 == 0 && C / 4 <= 256, "se_squeeze_excite: C must be a multiple of 4, <= 1024");
+    se_squeeze_excite_kernel<<<dim3(S, B), 256, (C + R) * sizeof(float), st>>>(x, HW, C / 4, cdiv(HW, S), partial, ticket, w1, b1,
+                                                                                w2, b2, R, y);
     ZVX_POST_LAUNCH();
 }
 
