@@ -57,6 +57,8 @@ def parse():
     p.add_argument("--policy", type=int, default=1, help="0 = all fp32 FMA, 1 = TF32 tensor cores where allowed")
     p.add_argument("--cpu-sample-batch", type=int, default=0, help="utterances in the CPU sample (0 = the full batch)")
     p.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: stop timing after this many seconds")
+    p.add_argument("--pdl", type=int, default=0, choices=[0, 1],
+                   help="1 = launch the hot kernels with programmatic dependent launch (A/B of zvx_set_option('pdl'))")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-config4", action="store_true")
@@ -374,6 +376,7 @@ def main():
     w = syn.make_weights(cfg, seed=0)
     model = build_model(cfg, w, device=dev, tensor_core_policy=args.policy)
     eng = model._shared_ctx.get(dev)
+    eng.set_option("pdl", args.pdl)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     keys = ("phoneme", "puncts", "duration", "ref_mel")
 

@@ -302,7 +302,12 @@ const char* zvx_attention_last_error(void);
  *                            (exact: the softmax is per row).  Default 4 GiB.  Only used when the fused kernel is off.
  *   "fused_attention":       1 (default) = the TF32 policy's attention runs as one kernel (zvx_attention); 0 = QK^T, softmax
  *                            and PV as three kernels with the score matrix in HBM / L2 (A/B and debugging); 2 / 3 = one kernel,
- *                            always the single-CTA / the CTA-pair variant (zvx_attention_ex variants 1 / 2). */
+ *                            always the single-CTA / the CTA-pair variant (zvx_attention_ex variants 1 / 2).
+ *   "pdl":                   1 = the hot kernels are launched with programmatic stream serialisation: the set-up of launch
+ *                            N+1 (barriers, TMEM, shared-memory clearing) overlaps the tail of launch N; every kernel waits
+ *                            for its predecessor's completion before its first global access, so results are those of plain
+ *                            stream order.  0 (default) = plain launches — measured 0.6 % faster on configs[1].
+ *                            Process-wide. */
 int zvx_set_option(zvx_handle* h, const char* name, int64_t value);
 
 /* Workspace control: bytes of engine-owned scratch currently reserved on the device. */

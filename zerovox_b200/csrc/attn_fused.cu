@@ -510,6 +510,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
+    pdl_trigger();
     if (threadIdx.x == 0) {
         prefetch_tmap(&mapQ);
         prefetch_tmap(&mapK);
@@ -535,6 +536,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();   // (the tile list and Q / K / V come from the launches before this one)
     const uint32_t DESC_HI = (uint32_t)(at_sw128_desc(0) >> 32), DESC_HI32 = (uint32_t)(at_sw32_desc(0) >> 32);
 
     if (warp == 0) {
@@ -949,10 +951,12 @@ void attn_pair_launch(const AttnFusedArgs& a, const PairPlan& pl, cudaStream_t s
     cfg.blockDim = dim3(AT_THREADS);
     cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
     at_dbg_begin(p, st);
     ZVX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_pair_kernel, mapQ, mapK, mapVlo, mapVhi, mapQ8, mapK8, p));
     ZVX_POST_LAUNCH();

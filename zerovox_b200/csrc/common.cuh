@@ -62,6 +62,29 @@ extern long long g_launches;
         ZVX_CUDA_CHECK(cudaGetLastError());                                                  \
     } while (0)
 
+// Programmatic dependent launch (sm_90+), opt-in.  Every hot kernel is launched through launch_k — with the stream-serialisation
+// attribute when the option is on —, calls pdl_trigger() first thing — its successor in the stream may then be scheduled as soon as every CTA of this grid is running
+// or done, i.e. on the SMs this grid's last wave leaves idle — and pdl_wait() after its own set-up (barrier init, TMEM allocation,
+// shared-memory clearing, descriptor prefetch: nothing that touches global memory) — which returns when the predecessor grid has
+// COMPLETED and its writes are visible.  So the data dependences are exactly those of plain stream order; what overlaps is the
+// launch latency and the prologue of kernel N+1 with the tail of kernel N (273 launches per configs[1] step).
+// Without the attribute (the default: zvx_set_option("pdl", 0) — on configs[1] the plain launches measured 0.6 % FASTER, DESIGN.md
+// section 4d) both instructions are no-ops.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1u : 0u;
+    ZVX_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -1442,6 +1442,11 @@ class Engine {
             kAttentionVariant = value >= 2 ? (int)value - 1 : 0;
             return 0;
         }
+        if (n == "pdl") {   // programmatic dependent launch of the hot kernels (common.cuh); process-wide like the launch counter
+            ZVX_REQUIRE(value == 0 || value == 1, "zvx_set_option: pdl must be 0 or 1");
+            g_pdl = (int)value;
+            return 0;
+        }
         throw Error("zvx_set_option: unknown option '" + n + "'");
     }
 

@@ -138,6 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     auto aempty_bar = [&](int s) { return bars + 8u * (uint32_t)(2 * p.stages + 5 + p.xr_na + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_trigger();
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&mapA);
@@ -167,6 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();   // (barriers, TMEM and descriptors are set up: from here on the predecessor's output is read)
 
     const int ksteps = p.taps * p.kchunks;
     // shared-memory descriptor of the first operand stage: low word (address | LBO), and the word common to all (SBO = 1024 B,
@@ -650,6 +652,8 @@ int num_sms() {
 namespace {
 // lo = rn_tf32(x - trunc_tf32(x)): the part of x the tensor core drops when it reads raw fp32 bits as TF32
 __global__ void tf32_split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, long long n4) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const float4 v = __ldg(x + i);
@@ -662,7 +666,7 @@ void tf32_split_lo(const float* x, float* lo, long long n, cudaStream_t st) {
     if (n <= 0) return;
     ZVX_REQUIRE(aligned16(x) && aligned16(lo), "tf32_split_lo: unaligned");
     const long long n4 = (n + 3) / 4;   // buffers are padded to 16 bytes by the workspace / weight uploader
-    tf32_split_lo_kernel<<<cdiv(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(lo), n4);
+    launch_k(tf32_split_lo_kernel, dim3(cdiv(n4, 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(lo), n4);
     ZVX_POST_LAUNCH();
 }
 
@@ -899,9 +903,9 @@ void gemm_tc(const TcGemmArgs& a, cudaStream_t st) {
 #endif
     const int grid = std::min(p.num_tiles, num_sms());
     const bool general = a.scale || a.acc_mode || a.act_slope != 1.f || a.C2;
-    if (split) gemm_tc_kernel<true, true><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
-    else if (general) gemm_tc_kernel<true, false><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
-    else gemm_tc_kernel<false, false><<<grid, NUM_THREADS, smem, st>>>(mapA, mapB, mapAlo, mapBlo, p);
+    if (split) launch_k(gemm_tc_kernel<true, true>, dim3(grid), dim3(NUM_THREADS), smem, st, mapA, mapB, mapAlo, mapBlo, p);
+    else if (general) launch_k(gemm_tc_kernel<true, false>, dim3(grid), dim3(NUM_THREADS), smem, st, mapA, mapB, mapAlo, mapBlo, p);
+    else launch_k(gemm_tc_kernel<false, false>, dim3(grid), dim3(NUM_THREADS), smem, st, mapA, mapB, mapAlo, mapBlo, p);
     ZVX_POST_LAUNCH();
 #ifdef ZVX_DEBUG
     if (dbg) {

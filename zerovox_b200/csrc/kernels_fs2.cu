@@ -6,6 +6,7 @@
 namespace zvx {
 
 long long g_launches = 0;
+int g_pdl = 0;   // measured: no gain on configs[1] — opt-in with zvx_set_option("pdl", 1)
 
 // ------------------------------------------------------------------------------------------------
 // K1 embedding + position encoding (fs2.py:372-392)
@@ -45,6 +46,8 @@ constexpr int NORM_MAXV = 8;  // float4 per lane -> C <= 32*4*8 = 1024
 // active 35 %, 0.62 of the HBM peak); fewer live registers = more rows in flight per SM.
 template <int NV>
 __global__ void __launch_bounds__(256, NV <= 2 ? 6 : NV <= 5 ? 5 : 3) layer_norm_kernel(const NormArgs a) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= a.rows) return;
@@ -142,9 +145,9 @@ void layer_norm(const NormArgs& a, cudaStream_t st) {
     const int warps_per_block = 8;
     const int nv = cdiv(a.C, 128);
     const dim3 grid(cdiv(a.rows, warps_per_block)), block(warps_per_block * 32);
-    if (nv <= 2) layer_norm_kernel<2><<<grid, block, 0, st>>>(a);
-    else if (nv <= 5) layer_norm_kernel<5><<<grid, block, 0, st>>>(a);
-    else layer_norm_kernel<NORM_MAXV><<<grid, block, 0, st>>>(a);
+    if (nv <= 2) launch_k(layer_norm_kernel<2>, grid, block, 0, st, a);
+    else if (nv <= 5) launch_k(layer_norm_kernel<5>, grid, block, 0, st, a);
+    else launch_k(layer_norm_kernel<NORM_MAXV>, grid, block, 0, st, a);
     ZVX_POST_LAUNCH();
 }
 

@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(256) conv_post_cl_reg_kernel(const float* __re
     float* xs = sm;
     constexpr int half = (K - 1) / 2, pitch = C + 4, C4 = C >> 2, rows = CP_TILE + K - 1;
     const int t0 = blockIdx.x * CP_TILE, b = blockIdx.y;
+    pdl_trigger();
+    pdl_wait();
     const float* xb = x + (long long)b * x_bs;
 #pragma unroll
     for (int i = threadIdx.x; i < rows * C4; i += 256) {   // (every thread's 8-9 loads are in flight together)
@@ -307,7 +309,7 @@ void conv_post_cl(const float* x, long long x_bs, const float* w, const float* b
             ZVX_CUDA_CHECK(cudaFuncSetAttribute(conv_post_cl_reg_kernel<8, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr_reg = true;
         }
-        conv_post_cl_reg_kernel<8, 7><<<grid, 256, (size_t)(CP_TILE + 6) * 12 * sizeof(float), st>>>(x, x_bs, w, bias, T, slope, wav);
+        launch_k(conv_post_cl_reg_kernel<8, 7>, grid, dim3(256), (size_t)(CP_TILE + 6) * 12 * sizeof(float), st, x, x_bs, w, bias, T, slope, wav);
         ZVX_POST_LAUNCH();
         return;
     }

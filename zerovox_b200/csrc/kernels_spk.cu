@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(256) se_squeeze_excite_kernel(const float* __r
                                                                 int R, float* __restrict__ y) {
     extern __shared__ float sh[];
     __shared__ int last;
+    pdl_trigger();
+    pdl_wait();
     hw_sum_partial_body(x, HW, C4, rows_per, partial);
     __threadfence();   // this block's partial before its ticket
     __syncthreads();
@@ -214,8 +216,8 @@ void se_squeeze_excite(const float* x, int B, int HW, int C, int S, float* parti
                        const float* b1, const float* w2, const float* b2, int R, float* y, cudaStream_t st) {
     if (B == 0) return;
     ZVX_REQUIRE(C % 4 == 0 && C / 4 <= 256, "se_squeeze_excite: C must be a multiple of 4, <= 1024");
-    se_squeeze_excite_kernel<<<dim3(S, B), 256, (C + R) * sizeof(float), st>>>(x, HW, C / 4, cdiv(HW, S), partial, ticket, w1, b1,
-                                                                                w2, b2, R, y);
+    launch_k(se_squeeze_excite_kernel, dim3(S, B), dim3(256), (C + R) * sizeof(float), st, x, HW, C / 4, cdiv(HW, S), partial, ticket,
+             w1, b1, w2, b2, R, y);
     ZVX_POST_LAUNCH();
 }
 
@@ -223,6 +225,8 @@ void se_squeeze_excite(const float* x, int B, int HW, int C, int S, float* parti
 __global__ void se_scale_add_relu_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                          const float* __restrict__ res, long long n4, long long HWC4, int C4,
                                          float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
     const int b = (int)(i / HWC4);
@@ -243,7 +247,7 @@ void se_scale_add_relu(const float* x, const float* y, const float* res, int B, 
     ZVX_REQUIRE(C % 4 == 0, "se_scale_add_relu: C % 4");
     const long long n4 = (long long)B * HW * C / 4;
     if (n4 == 0) return;
-    se_scale_add_relu_kernel<<<cdiv(n4, 256), 256, 0, st>>>(x, y, res, n4, (long long)HW * C / 4, C / 4, out);
+    launch_k(se_scale_add_relu_kernel, dim3(cdiv(n4, 256)), dim3(256), 0, st, x, y, res, n4, (long long)HW * C / 4, C / 4, out);
     ZVX_POST_LAUNCH();
 }
 

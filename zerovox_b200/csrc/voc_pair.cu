@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const __grid_constan
 #define ZVX_STAMP2() do { } while (0)
 #endif
     ZVX_STAMP();
+    pdl_trigger();
 
     if (tid == 0) {
         mbar_init(mma_bar, 1);
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(NT, CTAS) voc_pair_kernel(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *slot_ptr;
+    pdl_wait();   // (tile cleared, barriers and TMEM set up while the previous launch drains)
     ZVX_STAMP();
 
     // ---- MMA issue + weight streaming: lane 0 of warp 0, between its epilogue duties ---------------------------------
@@ -500,7 +502,7 @@ void launch(const VocResArgs& a, const PairPlan& p, cudaStream_t st) {
         attr_done = 1;
     }
     dim3 grid(cdiv(a.T, p.TT), a.B);
-    voc_pair_kernel<C, CTAS><<<grid, NT, p.smem_bytes, st>>>(a, p);
+    launch_k(voc_pair_kernel<C, CTAS>, grid, dim3(NT), (size_t)p.smem_bytes, st, a, p);
     ZVX_POST_LAUNCH();
 }
 
