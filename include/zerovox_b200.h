@@ -306,7 +306,7 @@ const char* zvx_attention_last_error(void);
  *   "pdl":                   1 = the hot kernels are launched with programmatic stream serialisation: the set-up of launch
  *                            N+1 (barriers, TMEM, shared-memory clearing) overlaps the tail of launch N; every kernel waits
  *                            for its predecessor's completion before its first global access, so results are those of plain
- *                            stream order.  0 (default) = plain launches — measured 0.6 % faster on configs[1].
+ *                            stream order.  0 (default) = plain launches; measured difference on configs[1]: +-0.5 %.
  *                            Process-wide. */
 int zvx_set_option(zvx_handle* h, const char* name, int64_t value);
 

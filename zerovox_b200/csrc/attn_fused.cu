@@ -510,7 +510,6 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
-    pdl_trigger();
     if (threadIdx.x == 0) {
         prefetch_tmap(&mapQ);
         prefetch_tmap(&mapK);

@@ -138,7 +138,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     auto aempty_bar = [&](int s) { return bars + 8u * (uint32_t)(2 * p.stages + 5 + p.xr_na + s); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    pdl_trigger();
 
     if (threadIdx.x == 0) {
         prefetch_tmap(&mapA);
@@ -191,6 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 uint32_t pa = 0;
                 for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                     const Tile c = decode_tile(p, t);
+                    if (t + (int)gridDim.x >= p.num_tiles) pdl_trigger();   // last tile of this CTA: the next launch may move in behind it
                     for (int dy = 0; dy < p.xr_ky; ++dy)
                         for (int kc = 0; kc < p.kchunks; ++kc) {
                             mbar_wait_sel(p.spin, aempty_bar(sa), pa ^ 1u);
@@ -221,6 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             } else
             for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
                 const Tile c = decode_tile(p, t);
+                if (t + (int)gridDim.x >= p.num_tiles) pdl_trigger();
                 if (ZVX_DBG_PTR(p) && blockIdx.x == 0 && t / (int)gridDim.x < 16) ZVX_DBG_PTR(p)[t / gridDim.x] = clock64();
                 long long pwait = 0;
                 // (single-thread loop: its instruction latency bounds small tiles -> counters instead of divisions)

@@ -6,7 +6,7 @@
 namespace zvx {
 
 long long g_launches = 0;
-int g_pdl = 0;   // measured: no gain on configs[1] — opt-in with zvx_set_option("pdl", 1)
+int g_pdl = 0;   // measured: +-0.5 % on configs[1] — opt-in with zvx_set_option("pdl", 1)
 
 // ------------------------------------------------------------------------------------------------
 // K1 embedding + position encoding (fs2.py:372-392)
