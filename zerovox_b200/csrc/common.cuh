@@ -62,14 +62,15 @@ extern long long g_launches;
         ZVX_CUDA_CHECK(cudaGetLastError());                                                  \
     } while (0)
 
-// Programmatic dependent launch (sm_90+), opt-in.  Every hot kernel is launched through launch_k — with the stream-serialisation
-// attribute when the option is on —, calls pdl_trigger() (first thing; gemm_tc when a CTA starts its last tile) — its successor in the stream may then be scheduled as soon as every CTA of this grid is running
-// or done, i.e. on the SMs this grid's last wave leaves idle — and pdl_wait() after its own set-up (barrier init, TMEM allocation,
-// shared-memory clearing, descriptor prefetch: nothing that touches global memory) — which returns when the predecessor grid has
-// COMPLETED and its writes are visible.  So the data dependences are exactly those of plain stream order; what overlaps is the
-// launch latency and the prologue of kernel N+1 with the tail of kernel N (273 launches per configs[1] step).
-// Without the attribute (the default: zvx_set_option("pdl", 0) — measured on configs[1]: -0.6 % with every kernel triggering first
-// thing, +0.3 % with gemm_tc triggering at its last tile; DESIGN.md section 4d, profiles/r02_ab_pdl.txt) both instructions are no-ops.
+// Programmatic dependent launch (sm_90+), opt-in.  The hot kernels are launched through launch_k — with the stream-serialisation
+// attribute when the option is on.  Each calls pdl_trigger() (first thing; gemm_tc when a CTA starts its last tile): its successor
+// in the stream may then be scheduled as soon as every CTA of this grid has got that far or is done, i.e. on the SMs the grid's last
+// wave leaves idle.  And each calls pdl_wait() after its own set-up (barrier init, TMEM allocation, shared-memory clearing,
+// descriptor prefetch: nothing that touches global memory), which returns when the predecessor grid has COMPLETED and its writes
+// are visible.  So the data dependences are exactly those of plain stream order; what overlaps is the launch latency and the
+// prologue of kernel N+1 with the tail of kernel N.  Without the attribute both instructions are no-ops — the default
+// (zvx_set_option("pdl", 0)): measured on configs[1], -0.6 % with every kernel triggering first thing, +0.3 % with gemm_tc
+// triggering at its last tile (profiles/r02_ab_pdl.txt).
 extern int g_pdl;
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
