@@ -166,14 +166,10 @@ void instance_norm_time(const float* ref_mel, int B, int T, int n_mels, float* o
 // stem: Conv2d(1->C, 3x3, pad 1, bias) -> ReLU -> BN(scale, shift); in [B,H,W] -> out [B,H,W,C]
 void stem_conv3x3(const float* in, const float* w /*[9][C]*/, const float* bias, const float* scale,
                   const float* shift, int B, int H, int W, int C, float* out, cudaStream_t st);
-// SE squeeze: S partial sums over HW -> [B, S, C] (S = hw_mean_splits(B, HW)); se_excite finishes the mean
+// SE squeeze + excitation (ResNetSE34V2.py:52-67): S = hw_mean_splits(B, HW) partial sums over HW -> partial [B, S, C]; the block
+// of an utterance that finishes last forms p = (sum_s partial[b,s,:]) / HW and y = sigmoid(W2 relu(W1 p + b1) + b2), W1 [R,C],
+// W2 [C,R].  ticket [B] ints, zero before the first launch, left zero.
 int hw_mean_splits(int B, int HW);
-void hw_sum_partial(const float* x, int B, int HW, int C, int S, float* out, cudaStream_t st);
-// SE excitation: p = (sum_s partial[b,s,:]) / HW; y = sigmoid(W2 relu(W1 p + b1) + b2), W1 [R,C], W2 [C,R]
-void se_excite(const float* partial, int S, int HW, const float* w1, const float* b1, const float* w2, const float* b2,
-               int B, int C, int R, float* y, cudaStream_t st);
-// hw_sum_partial + se_excite as one launch (the last block of an utterance runs the excitation); ticket [B] ints, zero before
-// the first launch, left zero
 void se_squeeze_excite(const float* x, int B, int HW, int C, int S, float* partial, int* ticket, const float* w1,
                        const float* b1, const float* w2, const float* b2, int R, float* y, cudaStream_t st);
 // out = relu(x * y[b,c] + res)

@@ -93,7 +93,7 @@ void stem_conv3x3(const float* in, const float* w, const float* bias, const floa
 
 // SE squeeze (AdaptiveAvgPool2d(1), ResNetSE34V2.py:63-64): x [B, HW, C] -> sums over HW, split into S partial sums so
 // that the whole GPU streams the tensor once: grid (S, B); block = 256 threads = (256 / (C/4)) rows x C/4 float4 columns.
-// out[b][s][c] = sum over the s-th slice of HW (deterministic order); se_excite adds the S partials and divides.
+// out[b][s][c] = sum over the s-th slice of HW (deterministic order); the excitation adds the S partials and divides.
 __device__ __forceinline__ void hw_sum_partial_body(const float* __restrict__ x, int HW, int C4, int rows_per,
                                                     float* __restrict__ out) {
     __shared__ float4 red[256];
@@ -126,21 +126,9 @@ __device__ __forceinline__ void hw_sum_partial_body(const float* __restrict__ x,
     }
 }
 
-__global__ void __launch_bounds__(256) hw_sum_partial_kernel(const float* __restrict__ x, int HW, int C4, int rows_per,
-                                                             float* __restrict__ out) {
-    hw_sum_partial_body(x, HW, C4, rows_per, out);
-}
-
 int hw_mean_splits(int B, int HW) {
     // 8 CTAs of 256 threads per SM: with 4 (608 CTAs at B = 32) the squeeze ran at 0.54 of the HBM peak, too few loads in flight
     return std::max(1, std::min(cdiv(HW, 32), cdiv(8 * 148, std::max(B, 1))));
-}
-
-void hw_sum_partial(const float* x, int B, int HW, int C, int S, float* out, cudaStream_t st) {
-    if (B == 0) return;
-    ZVX_REQUIRE(C % 4 == 0 && C / 4 <= 256, "hw_sum_partial: C must be a multiple of 4, <= 1024");
-    hw_sum_partial_kernel<<<dim3(S, B), 256, 0, st>>>(x, HW, C / 4, cdiv(HW, S), out);
-    ZVX_POST_LAUNCH();
 }
 
 // SE excitation (ResNetSE34V2.py:55-60, 65) for utterance b from the S partial sums: called by every thread of one block.
@@ -170,22 +158,7 @@ __device__ __forceinline__ void se_excite_block(const float* p, int b, int S, fl
     }
 }
 
-__global__ void __launch_bounds__(256) se_excite_kernel(const float* __restrict__ p, int S, float inv_hw,
-                                                        const float* __restrict__ w1, const float* __restrict__ b1,
-                                                        const float* __restrict__ w2, const float* __restrict__ b2,
-                                                        int C, int R, float* __restrict__ y) {
-    extern __shared__ float sh[];
-    se_excite_block(p, blockIdx.x, S, inv_hw, w1, b1, w2, b2, C, R, y, sh);
-}
-
-void se_excite(const float* p, int S, int HW, const float* w1, const float* b1, const float* w2, const float* b2, int B,
-               int C, int R, float* y, cudaStream_t st) {
-    if (B == 0) return;
-    se_excite_kernel<<<B, 256, (C + R) * sizeof(float), st>>>(p, S, 1.f / (float)HW, w1, b1, w2, b2, C, R, y);
-    ZVX_POST_LAUNCH();
-}
-
-// Squeeze and excitation in ONE launch: grid (S, B) streams the tensor as hw_sum_partial does; the block of utterance b
+// Squeeze and excitation in ONE launch: grid (S, B) streams the tensor once (hw_sum_partial_body); the block of utterance b
 // that finishes last (a ticket per utterance, release / acquire fences around it) adds the S partials in index order —
 // the gate does not depend on which block that is — and runs the two small linears.  `ticket` [B] must be zero at
 // the first launch; the last block leaves it zero again.
