@@ -3,7 +3,7 @@
 // double precision on the CPU against a direct ResBlock1, so indexing errors are found without a GPU.
 //   nvcc -std=c++17 -O1 -o build/emul_voc_pair tools/emul_voc_pair.cu && build/emul_voc_pair
 #include "../zerovox_b200/csrc/voc_pair.cu"
-namespace zvx { long long g_launches = 0; }
+namespace zvx { long long g_launches = 0; int g_pdl = 0; }
 #include <cmath>
 #include <random>
 using namespace zvx;
